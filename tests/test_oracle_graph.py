@@ -1,0 +1,124 @@
+"""Oracle self-checks: KAT-1, closed-form backward vs autograd, analytic properties."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import init_ref
+from oracle.graph import GraphCfg, PARAM_KEYS, closed_form_grads, graph_forward, graph_grads
+
+
+def kat1(use_det):
+    I = np.array([[round(255 * (4 * y + x) / 15) / 255 for x in range(4)] for y in range(4)], np.float64)[..., None]
+    mus, A = init_ref.kernel_grid([2, 2], 2, False)
+    nu, ga = init_ref.experts(I, mus)
+    p = dict(pis=init_ref.pis(4, True).astype(np.float64), musX=mus, A_diagonal=A, A_corr=np.zeros_like(A),
+             gamma_e=ga, nu_e=nu.astype(np.float64))
+    jd = init_ref.gen_domain(I, 2).reshape(-1, 3)
+    cfg = GraphCfg(dim_domain=2, num_channels=1, use_determinant=use_det, train_inverse_cov=False,
+                   use_yuv=False, start_pis=4)
+    return p, jd, cfg
+
+
+def test_kat1_forward_and_grads():
+    p, jd, cfg = kat1(False)
+    tp = {k: torch.tensor(v, dtype=torch.float64) for k, v in p.items()}
+    out, g = graph_grads(tp, np.ones(4, bool), torch.tensor(jd[:, :2]), torch.tensor(jd[:, 2:]), cfg)
+    np.testing.assert_allclose(p["nu_e"][:, 0], [0.16666667, 0.3, 0.7, 0.83333333], rtol=5e-6)
+    np.testing.assert_allclose(out["S"][:4].detach(), [0.02635631, 0.07520154, 0.07520154, 0.02635631], rtol=2e-7)
+    np.testing.assert_allclose(out["w_full"][0, :4].detach(), [0.999753226, 0.952456584, 0.0474200211, 1.23379350e-4], rtol=1e-7)
+    assert int((~out["infl"]).sum()) == 28
+    np.testing.assert_allclose(out["r_pre"][:4, 0].detach(), [0.16662554, 0.17296877, 0.29364031, 0.29992597], atol=1e-8)
+    np.testing.assert_allclose(out["r_pre"][[5, 10, 15], 0].detach(), [0.198283915452, 0.801716084548, 0.833127688395], atol=1e-10)
+    np.testing.assert_array_equal(np.round(out["resq"][:4, 0].detach().numpy() * 255), [42, 44, 75, 76])
+    assert abs(float(out["loss"].detach()) - 0.015144070248) < 2e-9   # KAT inputs were float32-rounded
+    assert abs(float(out["mse_op"].detach()) - 1023.10237601) < 1e-4
+    assert abs(10 * np.log10(65536 / float(out["mse_op"].detach())) - 18.06561) < 1e-5
+    np.testing.assert_allclose(g["pis"], [-4.4520e-4, 4.7775e-4, 4.5346e-4, -4.8601e-4], rtol=2e-4)
+    np.testing.assert_allclose(g["nu_e"][:, 0], [0.0109761, 0.00629165, -0.00678173, -0.01146617], rtol=1e-5)
+    np.testing.assert_allclose(g["musX"], [(-0.00601605, 0.0011727), (-0.00913828, 0.00215535),
+                                           (0.00922202, -0.0020942), (0.00607877, -0.00119669)], rtol=1e-5)
+    np.testing.assert_allclose(torch.diagonal(g["A_diagonal"], dim1=1, dim2=2),
+                               [(7.37267938e-4, 1.44157150e-4), (5.16439388e-4, -6.60195321e-5),
+                                (5.31619440e-4, -6.96875999e-5), (7.52599965e-4, 1.48230052e-4)], rtol=5e-6)
+    np.testing.assert_allclose(g["A_corr"][:, 1, 0], [-2.80623275e-4, -7.57960392e-5, -7.78221117e-5, -2.77211053e-4], rtol=5e-6)
+    np.testing.assert_allclose(g["gamma_e"].reshape(-1), [-0.00712058, -0.00034182, -0.00801585, 0.00284964,
+                                                          -0.01479758, -0.00344201, -0.01858676, -0.01180799], rtol=1e-5)
+    assert float(g["A_diagonal"][:, 0, 1].abs().max()) == 0 and float(g["A_corr"][:, 0, 0].abs().max()) == 0
+
+
+def test_kat1_determinant():
+    p, jd, cfg = kat1(True)
+    tp = {k: torch.tensor(v, dtype=torch.float64) for k, v in p.items()}
+    out, g = graph_grads(tp, np.ones(4, bool), torch.tensor(jd[:, :2]), torch.tensor(jd[:, 2:]), cfg)
+    np.testing.assert_allclose(out["S"][:2].detach(), [0.15101053, 0.43087307], rtol=2e-7)
+    np.testing.assert_allclose(torch.diagonal(g["A_diagonal"], dim1=1, dim2=2),
+                               [(7.18717790e-4, 1.25607002e-4), (5.36345629e-4, -4.61132916e-5),
+                                (5.50513632e-4, -5.07934087e-5), (7.32349682e-4, 1.27979768e-4)], rtol=5e-6)
+    assert abs(float(out["loss"].detach()) - 0.015144070248) < 2e-9   # KAT inputs were float32-rounded
+
+
+def _rand_case(d, C, tic, det, yuv, seed, K=9, N=150, tg=True):
+    rs = np.random.RandomState(seed)
+    p = dict(pis=rs.uniform(0.05, 1, K), musX=rs.uniform(0, 1, (K, d)), gamma_e=rs.normal(0, .3, (K, d, C)),
+             nu_e=rs.uniform(0, 1, (K, C)))
+    Ad = np.zeros((K, d, d)); Ac = np.zeros((K, d, d))
+    for i in range(d):
+        Ad[:, i, i] = rs.uniform(2, 6, K)
+        for j in range(i):
+            Ac[:, i, j] = rs.normal(0, 1.0, K)
+        for j in range(i + 1, d):
+            Ac[:, i, j] = rs.normal(0, 1.0, K)     # must be ignored (upper part of A_corr)
+            Ad[:, i, j] = rs.normal(0, 1.0, K)     # must be ignored (off-diagonal of A_diagonal)
+    p["A_diagonal"], p["A_corr"] = Ad, Ac
+    p["pis"][1] = -0.1
+    x = rs.uniform(0, 1, (N, d)); t = rs.uniform(0, 1, (N, C))
+    kl = np.ones(K, bool); kl[3] = False
+    cfg = GraphCfg(dim_domain=d, num_channels=C, use_determinant=det, train_inverse_cov=tic, use_yuv=yuv,
+                   train_gammas=tg, start_pis=K)
+    return p, x, t, kl, cfg
+
+
+@pytest.mark.parametrize("d,C,tic,det,yuv,tg", [(2, 1, False, False, False, True), (2, 3, False, True, True, True),
+                                               (3, 3, False, True, False, True), (2, 1, True, False, True, True),
+                                               (3, 1, True, True, False, True), (2, 3, False, True, True, False)])
+def test_closed_form_matches_autograd(d, C, tic, det, yuv, tg):
+    p, x, t, kl, cfg = _rand_case(d, C, tic, det, yuv, seed=d * 10 + C, tg=tg)
+    tp = {k: torch.tensor(v, dtype=torch.float64) for k, v in p.items()}
+    out, g = graph_grads(tp, kl, torch.tensor(x), torch.tensor(t), cfg, pis_l1=0.2, u_l1=1e-3)
+    cf, extra = closed_form_grads(p, kl, x, t, cfg, pis_l1=0.2, u_l1=1e-3)
+    for k in PARAM_KEYS:
+        np.testing.assert_allclose(cf[k], g[k].numpy(), rtol=1e-9, atol=1e-14, err_msg=k)
+    np.testing.assert_allclose(extra["r_pre"], out["r_pre"].detach().numpy(), rtol=1e-12, atol=1e-14)
+    assert float(np.abs(cf["pis"][[1, 3]]).max()) == 0          # pruned / unlisted kernels get no gradient
+
+
+def test_einsum_broadcast_mode_equals_einsum():
+    for tic in (False, True):
+        p, x, t, kl, cfg = _rand_case(3, 3, tic, True, False, seed=5)
+        tp = {k: torch.tensor(v, dtype=torch.float64) for k, v in p.items()}
+        a = graph_forward(tp, kl, torch.tensor(x), torch.tensor(t), cfg)
+        cfg.einsum_mode = "broadcast"
+        b = graph_forward(tp, kl, torch.tensor(x), torch.tensor(t), cfg)
+        np.testing.assert_allclose(a["maha"].numpy(), b["maha"].numpy(), rtol=1e-12)
+
+
+def test_single_kernel_is_clipped_linear_expert():
+    rs = np.random.RandomState(0)
+    x = rs.uniform(0, 1, (50, 2)); t = rs.uniform(0, 1, (50, 1))
+    p = dict(pis=np.array([0.7]), musX=np.array([[.4, .6]]), A_diagonal=np.array([[[3., 0], [0, 4.]]]),
+             A_corr=np.array([[[0., 0], [1., 0]]]), gamma_e=np.array([[[0.9], [-1.4]]]), nu_e=np.array([[0.5]]))
+    cfg = GraphCfg(dim_domain=2, num_channels=1, train_inverse_cov=False, use_yuv=False, start_pis=1)
+    out = graph_forward({k: torch.tensor(v) for k, v in p.items()}, np.ones(1, bool), torch.tensor(x), torch.tensor(t), cfg)
+    np.testing.assert_allclose(out["res"][:, 0].numpy(), np.clip(0.5 + 0.9 * x[:, 0] - 1.4 * x[:, 1], 0, 1), atol=1e-12)
+
+
+def test_mirrored_kernels_gate_half_on_bisector_and_pruned_absent():
+    p = dict(pis=np.array([0.5, 0.5, 0.0]), musX=np.array([[.3, .5], [.7, .5], [.5, .5]]),
+             A_diagonal=np.tile(np.diag([5., 5.]), (3, 1, 1)), A_corr=np.zeros((3, 2, 2)),
+             gamma_e=np.zeros((3, 2, 1)), nu_e=np.array([[.2], [.8], [.9]]))
+    x = np.array([[.5, .1], [.5, .9]]); t = np.zeros((2, 1))
+    cfg = GraphCfg(dim_domain=2, num_channels=1, train_inverse_cov=False, use_yuv=False, start_pis=3)
+    out = graph_forward({k: torch.tensor(v) for k, v in p.items()}, np.ones(3, bool), torch.tensor(x), torch.tensor(t), cfg)
+    np.testing.assert_allclose(out["w"].numpy(), 0.5, atol=1e-12)
+    assert out["indices"].tolist() == [0, 1] and out["num_pi"] == 2
+    assert out["w_e_max"].tolist() == [0, 0]          # argmax tie -> lowest index

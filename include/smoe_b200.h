@@ -1,0 +1,201 @@
+/*
+ * smoe_b200.h -- C ABI of libsmoe_b200.so: the B200 (sm_100a) drop-in for the hot path of
+ * roljon/Steered-Mixture-of-Experts.
+ *
+ * The reference has no FFI: its seam is "Python `Smoe` methods <-> one TensorFlow
+ * `session.run`" (smoe.py:1702 for the forward/backward graph, smoe.py:1788 for the Adam
+ * `train_op`).  Every entry point below replaces one segment of that graph; the reference lines
+ * it replaces are cited per function.  Bindings a maintainer of the reference would add are
+ * shown in INTEGRATION.md (ctypes, as the reference is Python).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a positive cudaError_t, or a negative SMOE_E_* code;
+ *     smoe_last_error() returns a thread-local message for the last failure;
+ *   - the library never allocates, frees or retains caller-visible memory: all buffers are device
+ *     pointers owned by the caller (float32 / int32 / uint8, contiguous, 16-byte aligned);
+ *   - every launch is asynchronous on the `stream` argument (a cudaStream_t passed as void*);
+ *     there is no host synchronisation and no host read-back inside the library;
+ *   - the number of active kernels K lives on the device (`counts[0]`), so a training step
+ *     never needs a device->host copy to size a launch.
+ *
+ * Layouts (float32 unless noted; d = dim_domain in {2,3}, C = channels in {1,3},
+ * T = d(d+1)/2, P = d + T + 1 + C + d*C, PK = smoe_packed_stride(d,C)):
+ *   theta  [K_all][P]  the K_all-sized variables, one row per kernel:
+ *                      musX[d] | A lower-tri row-major (l,m), l>=m: diagonal entries are
+ *                      A_diagonal_var[l,l], strictly-lower entries are A_corr_var[l,m] | pis |
+ *                      nu_e[C] | gamma_e[d][C]
+ *   grads, adam_m, adam_v : same shape as theta
+ *   packed [K][PK]     compacted compute records (smoe_pack): musX[d] | Qm (upper-tri row-major
+ *                      of s*A*A^T, or s*A_sym when train_inverse_cov; s = log2(e)/2) |
+ *                      c0 = log2(pi * prod(diag A)/(2pi)^(d/2)) | nu_e[C] | gamma_e[d][C] | pad
+ *   image  [H][W]([T])[C]  target colours, the numpy layout of the reference's `image`
+ *   axes   ax0[H], ax1[W], ax2[T]  pixel coordinates per axis (np.linspace(0,1,n) cast to f32,
+ *                      smoe.py:2412 / the float32 feed at smoe.py:545)
+ *   pix    [tiles][SMOE_TPIX][SMOE_PIXREC]  per-pixel state written by the forward and streamed
+ *                      by the backward
+ */
+#ifndef SMOE_B200_H
+#define SMOE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMOE_ABI_VERSION 1
+#define SMOE_TPIX 1024     /* pixels per tile (compile-time constant of the kernels) */
+#define SMOE_PIXREC 8      /* floats per pixel record */
+#define SMOE_NSCAL 16      /* floats in the scalar block */
+
+#define SMOE_E_BADARG (-1)
+#define SMOE_E_UNSUPPORTED (-2)
+
+/* Static model configuration; field names follow Smoe.__init__ (smoe.py:38-41). */
+typedef struct smoe_cfg {
+    int32_t d;                 /* dim_domain: 2 (image) or 3 (video)                        */
+    int32_t C;                 /* channels: 1 or 3                                          */
+    int32_t precision;         /* output bit depth (smoe.py:825, 899, 931, 1053)            */
+    float   margin;            /* epsilon = margin / 2^precision (smoe.py:931)              */
+    int32_t use_determinant;   /* smoe.py:809-815                                           */
+    int32_t train_inverse_cov; /* maha = d^T A d with symmetric A (smoe.py:734-735, 793)    */
+    int32_t use_yuv;           /* loss weights 6/8,1/8,1/8 (smoe.py:933-935)                */
+    int32_t train_gammas;      /* smoe.py:841-848: gamma ignored in the forward when 0      */
+    int32_t only_y_gamma;      /* smoe.py:725-729                                           */
+    int32_t quantize_pis;      /* fake-quantise pis before the >0 mask (smoe.py:474-480)    */
+    float   pis_lb, pis_ub;    /* lower_bounds[3], upper_bounds[3]                          */
+    int32_t pis_bits;          /* bit_depths[3]                                             */
+    int32_t dense_exec;        /* 1: execute the expert/gradient part for every (pixel,
+                                  kernel) pair instead of skipping warps whose gates are all
+                                  below the threshold (results are identical)               */
+} smoe_cfg;
+
+/* One spatial batch (smoe.py:18-35 sliding_window / one rank's shard) of a resident image. */
+typedef struct smoe_batch {
+    int32_t dims[3];     /* extents of the resident image buffer (H, W, T); T = 1 when d == 2 */
+    int32_t origin[3];   /* first pixel of the batch inside the buffer                         */
+    int32_t extent[3];   /* batch extents                                                      */
+    int32_t tile[3];     /* tile extents, tile[0]*tile[1]*tile[2] == SMOE_TPIX                 */
+    float   inv_count;   /* 1 / number of pixels the loss means run over (smoe.py:927-937);
+                            N_batch on one GPU, N_total when pixels are sharded over ranks     */
+} smoe_batch;
+
+/* Adam hyper-parameters of the three optimizer groups (smoe.py:1102-1104, smoe_test.py:84-88):
+ * group 0 = {nu_e, gamma_e, musX}, 1 = {pis}, 2 = {A_diagonal, A_corr}.  alpha is the
+ * bias-corrected step lr*sqrt(1-beta2^t)/(1-beta1^t) of TF1's ApplyAdam; alpha == 0 skips the
+ * group (optimizer._lr == 0, smoe.py:1120-1144, or a non-trainable variable). */
+typedef struct smoe_adam {
+    float alpha[3], beta1[3], beta2[3], epsilon[3];
+    float grad_clip;     /* <= 0: off (grad_clip_value_abs, smoe.py:1152-1153) */
+    int32_t train_musx;  /* smoe.py:394 */
+    int32_t train_gammas;/* smoe.py:389 */
+} smoe_adam;
+
+int         smoe_abi_version(void);
+const char* smoe_last_error(void);
+int         smoe_param_count(int d, int C);      /* P  */
+int         smoe_packed_stride(int d, int C);    /* PK */
+int         smoe_num_tiles(const smoe_batch* b);
+size_t      smoe_pack_workspace_bytes(int K_all);
+size_t      smoe_backward_workspace_bytes(const smoe_cfg* cfg, int K_cap, int num_splits);
+
+/* pi-mask compaction + parameter staging.  Replaces smoe.py:474-480 (optional fake-quant of pis),
+ * 732-735 (A assembly), 738-753 (bool_mask = kernel_list & pis>0, indices, 5x boolean_mask) and
+ * 1012 (num_pi = count_nonzero(qpis>0)); stream compaction in ascending kernel index.
+ *   counts[0] = K (active), counts[1] = num_pi, counts[2] = kernels with pi*det <= 0 (unsupported
+ *   by the fast path, reported), counts[3] = 0
+ *   regsums[0] = sum of active pis, regsums[1] = sum of diag(A) over active kernels (for the
+ *   L1 terms of smoe.py:1027, 1044) */
+int smoe_pack(const smoe_cfg* cfg, const float* theta, const uint8_t* kernel_list, int K_all,
+              float* packed, int32_t* indices, int32_t* counts, float* regsums,
+              void* workspace, void* stream);
+
+/* Same staging for parameters that are FED over the compacted tensors (with_quantized_params,
+ * smoe.py:1688-1689: rparams A, musX, nu_e, gamma_e, pis of K rows each); no mask, K given. */
+int smoe_pack_fed(const smoe_cfg* cfg, const float* A /*[K][d][d]*/, const float* musX, const float* nu_e,
+                  const float* gamma_e, const float* pis, int K, float* packed, int32_t* counts,
+                  void* stream);
+
+/* Fused forward over one batch: Mahalanobis logits, gating with the un-renormalised threshold,
+ * experts, clip, output fake-quant, loss partials, per-pixel backward state.  Replaces
+ * smoe.py:777-858 (kernel values, gates, influence list, argmax, mixture, clip) and 899-937, 1053
+ * (fake-quant, diff, loss, mse).  The K x N gate matrix is never materialised.
+ *   res      [dims..][C]  fake-quantised reconstruction (written inside the batch rectangle)
+ *   res_pre  [dims..][C]  optional (may be NULL): mixture output before clip / quantisation
+ *   argmax   [dims..] int32, optional: original index of the kernel with the largest gate, -1
+ *            where no gate passed the threshold (host applies tf.argmax's all-zero convention)
+ *   infl     [K] uint8, optional: 1 where the kernel's gate passed the threshold for some pixel
+ *            (kernel_list_batch, smoe.py:829); must be zeroed by the caller
+ *   pix      optional: per-pixel state for smoe_backward
+ *   scalars  [SMOE_NSCAL]: [0..C) sum_n (|diff|-eps)^2 per channel, [4] sum diff^2,
+ *            [5] non-finite flag; accumulated (+=) so that batches/ranks can be summed; the
+ *            caller zeroes it */
+int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const float* packed, const int32_t* indices,
+                 const int32_t* counts, const float* image, const float* ax0, const float* ax1,
+                 const float* ax2, float* res, float* res_pre, int32_t* argmax, uint8_t* infl,
+                 float* pix, float* scalars, float* partials /*[num_sms*8][8]*/, int32_t* ticket,
+                 void* stream);
+
+/* Fused backward over one batch: recomputes the gates from the per-pixel state and reduces the
+ * per-kernel sufficient statistics (sum t, sum t*delta, sum t*delta*delta^T, sum m*w*g,
+ * sum m*w*g*x) over the pixels, kernel-stationary, deterministically (no float atomics).
+ * Replaces tf.gradients(loss_op, variables) at smoe.py:1148 for the data term.
+ *   raw_part [num_splits][K_cap][P]  partial statistics, one slab per pixel split */
+int smoe_backward(const smoe_cfg* cfg, const smoe_batch* batch, const float* packed, const int32_t* counts,
+                  int K_cap, const float* pix, const float* ax0, const float* ax1, const float* ax2,
+                  int num_splits, float* raw_part, void* stream);
+/* number of pixel splits that fills the GPU in whole waves for K_cap kernels and ntiles tiles */
+int smoe_suggest_splits(int K_cap, int ntiles);
+
+/* Fixed-order reduction of the pixel splits: raw[k][j] = sum_s raw_part[s][k][j].  (The buffer a
+ * multi-GPU run all-reduces with NCCL.) */
+int smoe_reduce_splits(const smoe_cfg* cfg, const int32_t* counts, int K_cap, int num_splits,
+                       const float* raw_part, float* raw, void* stream);
+
+/* Statistics -> variable gradients (chain rule through A assembly, pi, determinant; L1 terms of
+ * smoe.py:1027, 1044), scattered through `indices` and ACCUMULATED into the K_all-sized `grads`
+ * (assign_add, smoe.py:1150).  Also rewrites kernel_list[indices[k]] = infl[k] when infl != NULL
+ * (smoe.py:1763-1766). */
+int smoe_grad_finalize(const smoe_cfg* cfg, const float* raw, int num_splits, int K_cap, const float* theta,
+                       const int32_t* indices, const int32_t* counts, float pis_l1_over_norm, float u_l1,
+                       float* grads, void* stream);
+
+/* kernel_list[i] = 0 for all i, then kernel_list[indices[k]] = infl[k] (smoe.py:1763-1766). */
+int smoe_update_kernel_list(const int32_t* indices, const int32_t* counts, const uint8_t* infl,
+                            uint8_t* kernel_list, int K_all, void* stream);
+
+/* TF1 ApplyAdam on every K_all row (dense, pruned rows included), three groups.  Replaces
+ * session.run(train_op) at smoe.py:1788 (apply_gradients at smoe.py:1173-1193). */
+int smoe_adam_step(const smoe_cfg* cfg, const smoe_adam* hp, float* theta, const float* grads,
+                   float* adam_m, float* adam_v, int K_all, void* stream);
+
+/* custom_ssim (ops/image_ops_impl.py:235-293) as evaluated by the loss graph (smoe.py:993-1010):
+ * SYMMETRIC pad 5, 11-tap sigma-1.5 Gaussian window, VALID; out[c] = mean SSIM of channel c.
+ * a, b: [dims..][C].  workspace from smoe_ssim_workspace_bytes. */
+size_t smoe_ssim_workspace_bytes(int d, const int32_t dims[3], int C);
+int    smoe_ssim(int d, const int32_t dims[3], int C, const float* a, const float* b, double* out /*[C]*/,
+                 void* workspace, void* stream);
+
+/* sum over all elements of (a-b)^2 -> out[0] (double accumulation in fixed order);
+ * PSNR = 10 log10((2^p)^2 / (mean * (2^p)^2)) on the host (plotter.py:14-15, smoe.py:1053). */
+int smoe_sqerr(const float* a, const float* b, size_t n, double* out, void* workspace /* >= 8 KiB */, void* stream);
+
+/* Uniform quantiser of quantizer.py:58-75 / rescale of quantizer.py:124-130 on one tensor of
+ * `rows` x `cols` float32 (bounds per column, keepdims semantics of quantizer.py:8-19), IEEE
+ * round-to-nearest-even, no FMA contraction: codes are bit-exact with NumPy float32. */
+/* `f64` selects the arithmetic NumPy uses at that call site: 0 = float32 (min/max bounds, modes
+ * 0/1/3), 1 = float64 (fixed bounds built with np.ones(...)*python_float: mode 2 and quantised
+ * pis).  Bounds are passed as double in both cases (float32 values are exact in double); codes /
+ * out are float32 arrays when f64 == 0 and float64 arrays when f64 == 1, as in the reference. */
+int smoe_quantize(const float* x, const double* lb, const double* ub, int rows, int cols, double step,
+                  int f64, void* codes, void* stream);
+int smoe_rescale(const void* codes, const double* lb, const double* ub, int rows, int cols, double step,
+                 int f64, void* out, void* stream);
+/* per-column min / max over rows (np.amin / np.amax axis=0, quantizer.py:8-19), as double */
+int smoe_colminmax(const float* x, int rows, int cols, double* lb, double* ub, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMOE_B200_H */

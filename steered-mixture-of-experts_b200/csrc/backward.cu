@@ -1,0 +1,502 @@
+// Fused SMoE backward (smoe_backward, smoe_reduce_splits, smoe_grad_finalize, smoe_adam_step).
+// Replaces tf.gradients(loss_op, variables) + assign_add + ApplyAdam (smoe.py:1148-1150, 1173-1193).
+//
+// Kernel-stationary: a thread owns ONE kernel (its record and 2*P accumulators live in
+// registers), a CTA owns 256 consecutive kernels and a 1/num_splits share of the pixel tiles.
+// Pixel state written by the forward ([tile][1024][8] floats: tile-centred x, 1/S, gr, g_c)
+// arrives by TMA bulk copies (32 KB per tile, double buffered) and is broadcast to all threads
+// from shared memory, so the per-kernel reductions over pixels happen in registers with no
+// shuffles and no atomics.  Per (pixel, kernel): recompute the gate (T+d FFMA + ex2), then
+//     t = w (m gE - gr)            [SURVEY 8a-8: dL/dlog(n_w)]
+// and accumulate the sufficient statistics  sum t, sum t x', sum t x' x'^T, sum m w g_c,
+// sum m w g_c x'  in tile-centred coordinates; at the end of each tile they are folded into
+// kernel-centred moments (sum t delta, sum t delta delta^T) so that no cancellation against
+// the absolute position builds up.  The chain rule to (mu, A, pi, nu, gamma) is applied once
+// per kernel in smoe_grad_finalize from these P numbers -- for both maha forms.
+// The expert part (gE, sum m w g ...) is skipped for a warp when none of its 32 kernels passes
+// the threshold at that pixel (exact zeros; cfg.dense_exec = 1 executes everything).
+#include "smoe_common.cuh"
+
+namespace smoe {
+
+template <int D, int C>
+struct BRec {
+    static constexpr int T = tri(D);
+    static constexpr int GN = T + D + 1;
+    static constexpr int EN = C + D * C;
+    static constexpr int RC = GN + EN;
+    static constexpr int OQ = 0, OL = T, OC = T + D, ONU = GN, OGA = GN + C;
+};
+
+struct BwdArgs {
+    smoe_cfg cfg;
+    smoe_batch b;
+    const float* packed;
+    const int32_t* counts;
+    const float* pix;
+    const float* ax[3];
+    float* raw_part;
+    int K_cap, num_splits, ntiles, nt1, nt2;
+    float tau;
+};
+
+template <int D, int C>
+__global__ void __launch_bounds__(kThreads, 2) backward_kernel(const BwdArgs a) {
+    using R = BRec<D, C>;
+    constexpr int T = tri(D);
+    constexpr int P = nparam(D, C), PK = pstride(D, C);
+    constexpr uint32_t kTileBytes = SMOE_TPIX * SMOE_PIXREC * 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* buf0 = reinterpret_cast<float*>(smem_raw);
+    float* buf1 = buf0 + SMOE_TPIX * SMOE_PIXREC;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(buf1 + SMOE_TPIX * SMOE_PIXREC);
+
+    const int tid = threadIdx.x;
+    const int K = a.counts[0];
+    if ((int)blockIdx.x * kThreads >= K) return;
+    const int k = blockIdx.x * kThreads + tid;
+    const bool active = k < K;
+    const int split = blockIdx.y;
+
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    uint32_t phase0 = 0, phase1 = 0;
+    auto issue = [&](int tile, int buf) {
+        fence_proxy_async();
+        mbar_expect_tx(&bar[buf], kTileBytes);
+        tma_load_1d(buf ? buf1 : buf0, a.pix + (size_t)tile * SMOE_TPIX * SMOE_PIXREC, kTileBytes, &bar[buf]);
+    };
+
+    // own kernel record (global -> registers)
+    float mu[D], Qm[D][D], c0, nu[C], ga[D][C];
+    {
+        const float* rec = a.packed + (size_t)(active ? k : 0) * PK;
+#pragma unroll
+        for (int l = 0; l < D; ++l) mu[l] = rec[off_mu(D, C) + l];
+#pragma unroll
+        for (int l = 0; l < D; ++l)
+#pragma unroll
+            for (int m = l; m < D; ++m) Qm[l][m] = Qm[m][l] = rec[off_A(D, C) + ut(D, l, m)];
+        c0 = active ? rec[off_pi(D, C)] : -INFINITY;
+#pragma unroll
+        for (int c = 0; c < C; ++c) nu[c] = rec[off_nu(D, C) + c];
+#pragma unroll
+        for (int l = 0; l < D; ++l)
+#pragma unroll
+            for (int c = 0; c < C; ++c) ga[l][c] = rec[off_ga(D, C) + l * C + c];
+    }
+
+    float G0 = 0.f, G1[D], G2[T], GNu[C], GGa[D][C];
+#pragma unroll
+    for (int l = 0; l < D; ++l) G1[l] = 0.f;
+#pragma unroll
+    for (int q = 0; q < T; ++q) G2[q] = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        GNu[c] = 0.f;
+#pragma unroll
+        for (int l = 0; l < D; ++l) GGa[l][c] = 0.f;
+    }
+
+    if (tid == 0) {
+        if (split < a.ntiles) issue(split, 0);
+        if (split + a.num_splits < a.ntiles) issue(split + a.num_splits, 1);
+    }
+    int it = 0;
+    for (int tile = split; tile < a.ntiles; tile += a.num_splits, ++it) {
+        const int buf = it & 1;
+        // tile centre, exactly as the forward derives it
+        int tt[3];
+        tt[2] = tile % a.nt2;
+        tt[1] = (tile / a.nt2) % a.nt1;
+        tt[0] = tile / (a.nt2 * a.nt1);
+        float ctr[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            int lo = a.b.origin[i] + tt[i] * a.b.tile[i];
+            int hi = min(lo + a.b.tile[i], a.b.origin[i] + a.b.extent[i]) - 1;
+            ctr[i] = (i < D) ? 0.5f * (a.ax[i][lo] + a.ax[i][hi]) : 0.f;
+        }
+        // tile-centred record in registers
+        float f[R::RC], mup[D];
+        {
+            float v[D];
+            float qc = c0;
+#pragma unroll
+            for (int l = 0; l < D; ++l) mup[l] = mu[l] - ctr[l];
+#pragma unroll
+            for (int l = 0; l < D; ++l) {
+                v[l] = 0.f;
+#pragma unroll
+                for (int m = 0; m < D; ++m) v[l] = fmaf(Qm[l][m], mup[m], v[l]);
+            }
+#pragma unroll
+            for (int l = 0; l < D; ++l) qc = fmaf(-mup[l], v[l], qc);
+#pragma unroll
+            for (int l = 0; l < D; ++l) {
+                f[R::OL + l] = 2.f * v[l];
+#pragma unroll
+                for (int m = l; m < D; ++m) f[R::OQ + ut(D, l, m)] = (l == m) ? -Qm[l][m] : -2.f * Qm[l][m];
+            }
+            f[R::OC] = qc;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float n = nu[c];
+#pragma unroll
+                for (int l = 0; l < D; ++l) {
+                    n = fmaf(ga[l][c], ctr[l], n);
+                    f[R::OGA + l * C + c] = ga[l][c];
+                }
+                f[R::ONU + c] = n;
+            }
+        }
+        float M0 = 0.f, M1[D], M2[T], N0[C], N1[D][C];
+#pragma unroll
+        for (int l = 0; l < D; ++l) M1[l] = 0.f;
+#pragma unroll
+        for (int q = 0; q < T; ++q) M2[q] = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            N0[c] = 0.f;
+#pragma unroll
+            for (int l = 0; l < D; ++l) N1[l][c] = 0.f;
+        }
+
+        if (buf) { mbar_wait(&bar[1], phase1); phase1 ^= 1; } else { mbar_wait(&bar[0], phase0); phase0 ^= 1; }
+        const float4* px = reinterpret_cast<const float4*>(buf ? buf1 : buf0);
+#pragma unroll 4
+        for (int j = 0; j < SMOE_TPIX; ++j) {
+            const float4 p0 = px[2 * j], p1 = px[2 * j + 1];
+            const float xx[3] = {p0.x, p0.y, p0.z};
+            float x[D];
+#pragma unroll
+            for (int l = 0; l < D; ++l) x[l] = xx[l];
+            const float invS = p0.w, gr = p1.x;
+            const float g[3] = {p1.y, p1.z, p1.w};
+            // gate logit (Horner), gate
+            float q = f[R::OC];
+#pragma unroll
+            for (int l = 0; l < D; ++l) {
+                float tq = f[R::OL + l];
+#pragma unroll
+                for (int m = l; m < D; ++m) tq = fmaf(f[R::OQ + ut(D, l, m)], x[m], tq);
+                q = fmaf(tq, x[l], q);
+            }
+            const float w = ex2f(q) * invS;
+            float t = -w * gr;
+            const bool pass = w > a.tau;
+            if (__any_sync(0xffffffffu, pass) || a.cfg.dense_exec) {
+                const float wm = pass ? w : 0.f;
+                float gE = 0.f;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    float E = f[R::ONU + c];
+#pragma unroll
+                    for (int l = 0; l < D; ++l) E = fmaf(f[R::OGA + l * C + c], x[l], E);
+                    gE = fmaf(g[c], E, gE);
+                    const float vc = wm * g[c];
+                    N0[c] += vc;
+#pragma unroll
+                    for (int l = 0; l < D; ++l) N1[l][c] = fmaf(vc, x[l], N1[l][c]);
+                }
+                t = fmaf(wm, gE, t);
+            }
+            M0 += t;
+#pragma unroll
+            for (int l = 0; l < D; ++l) {
+                const float u = t * x[l];
+                M1[l] += u;
+#pragma unroll
+                for (int m = l; m < D; ++m) M2[ut(D, l, m)] = fmaf(u, x[m], M2[ut(D, l, m)]);
+            }
+        }
+        __syncthreads();       // everyone is done with this buffer
+        if (tid == 0 && tile + 2 * a.num_splits < a.ntiles) issue(tile + 2 * a.num_splits, buf);
+
+        // fold tile-centred statistics into kernel-centred ones
+        G0 += M0;
+#pragma unroll
+        for (int l = 0; l < D; ++l) G1[l] += fmaf(-mup[l], M0, M1[l]);
+#pragma unroll
+        for (int l = 0; l < D; ++l)
+#pragma unroll
+            for (int m = l; m < D; ++m) {
+                float dd = M2[ut(D, l, m)];
+                dd = fmaf(-mup[l], M1[m], dd);
+                dd = fmaf(-mup[m], M1[l], dd);
+                dd = fmaf(mup[l] * mup[m], M0, dd);
+                G2[ut(D, l, m)] += dd;
+            }
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            GNu[c] += N0[c];
+#pragma unroll
+            for (int l = 0; l < D; ++l) GGa[l][c] += fmaf(ctr[l], N0[c], N1[l][c]);
+        }
+    }
+
+    if (active) {
+        float* out = a.raw_part + ((size_t)split * a.K_cap + k) * P;
+#pragma unroll
+        for (int l = 0; l < D; ++l) out[off_mu(D, C) + l] = G1[l];
+#pragma unroll
+        for (int q = 0; q < T; ++q) out[off_A(D, C) + q] = G2[q];     // upper-tri order of the symmetric D
+        out[off_pi(D, C)] = G0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) out[off_nu(D, C) + c] = GNu[c];
+#pragma unroll
+        for (int l = 0; l < D; ++l)
+#pragma unroll
+            for (int c = 0; c < C; ++c) out[off_ga(D, C) + l * C + c] = GGa[l][c];
+    }
+}
+
+// raw[k][j] = sum_s raw_part[s][k][j], fixed order
+__global__ void __launch_bounds__(256) reduce_splits_kernel(const int32_t* __restrict__ counts, int K_cap, int P,
+                                                            int num_splits, const float* __restrict__ part,
+                                                            float* __restrict__ raw) {
+    size_t n = (size_t)counts[0] * P;
+    size_t stride = (size_t)K_cap * P;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int sp = 0; sp < num_splits; ++sp) s += part[sp * stride + i];
+        raw[i] = s;
+    }
+}
+
+struct Nudged { float nmin, nmax, scale, inv_scale; };
+
+// statistics -> variable gradients, one thread per active kernel
+template <int D, int C>
+__global__ void __launch_bounds__(256) grad_finalize_kernel(smoe_cfg cfg, const float* __restrict__ raw, int num_splits,
+                                                            int K_cap, const float* __restrict__ theta,
+                                                            const int32_t* __restrict__ indices,
+                                                            const int32_t* __restrict__ counts, float l1, float u_l1,
+                                                            Nudged nq, float* __restrict__ grads) {
+    constexpr int T = tri(D);
+    constexpr int P = nparam(D, C);
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= counts[0]) return;
+    float s[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) s[j] = 0.f;
+    for (int sp = 0; sp < num_splits; ++sp) {
+        const float* r = raw + ((size_t)sp * K_cap + k) * P;
+#pragma unroll
+        for (int j = 0; j < P; ++j) s[j] += r[j];
+    }
+    const int row = indices[k];
+    const float* th = theta + (size_t)row * P;
+    float* gr = grads + (size_t)row * P;
+    float A[D][D];
+#pragma unroll
+    for (int l = 0; l < D; ++l)
+#pragma unroll
+        for (int m = 0; m < D; ++m) A[l][m] = (m <= l) ? th[off_A(D, C) + lt(l, m)] : 0.f;
+    float V[D], Dm[D][D];
+#pragma unroll
+    for (int l = 0; l < D; ++l) V[l] = s[off_mu(D, C) + l];
+#pragma unroll
+    for (int l = 0; l < D; ++l)
+#pragma unroll
+        for (int m = l; m < D; ++m) Dm[l][m] = Dm[m][l] = s[off_A(D, C) + ut(D, l, m)];
+    const float M0 = s[off_pi(D, C)];
+    // pi
+    float pi = th[off_pi(D, C)];
+    float ste = 1.f;
+    if (cfg.quantize_pis) {
+        ste = (pi >= nq.nmin && pi <= nq.nmax) ? 1.f : 0.f;
+        float cq = fminf(fmaxf(pi, nq.nmin), nq.nmax);
+        float kq = floorf(__fadd_rn(__fmul_rn(__fsub_rn(cq, nq.nmin), nq.inv_scale), 0.5f));
+        pi = __fadd_rn(__fmul_rn(kq, nq.scale), nq.nmin);
+    }
+    gr[off_pi(D, C)] += (M0 / pi + l1) * ste;
+    // mu and A
+    float gmu[D], gA[D][D];
+    if (cfg.train_inverse_cov) {
+        // maha = delta^T As delta, As = diag + L + L^T
+#pragma unroll
+        for (int l = 0; l < D; ++l) {
+            float acc = 0.f;
+#pragma unroll
+            for (int m = 0; m < D; ++m) acc = fmaf((m <= l) ? A[l][m] : A[m][l], V[m], acc);
+            gmu[l] = acc;
+        }
+#pragma unroll
+        for (int l = 0; l < D; ++l)
+#pragma unroll
+            for (int m = 0; m <= l; ++m) gA[l][m] = (l == m) ? -0.5f * Dm[l][l] : -Dm[l][m];
+    } else {
+        // maha = |A^T delta|^2 : dmu = A (A^T V), dA = -(D A) on the lower triangle
+        float AtV[D];
+#pragma unroll
+        for (int m = 0; m < D; ++m) {
+            float acc = 0.f;
+#pragma unroll
+            for (int l = m; l < D; ++l) acc = fmaf(A[l][m], V[l], acc);
+            AtV[m] = acc;
+        }
+#pragma unroll
+        for (int l = 0; l < D; ++l) {
+            float acc = 0.f;
+#pragma unroll
+            for (int m = 0; m <= l; ++m) acc = fmaf(A[l][m], AtV[m], acc);
+            gmu[l] = acc;
+        }
+#pragma unroll
+        for (int l = 0; l < D; ++l)
+#pragma unroll
+            for (int m = 0; m <= l; ++m) {
+                float acc = 0.f;
+#pragma unroll
+                for (int j = m; j < D; ++j) acc = fmaf(Dm[l][j], A[j][m], acc);
+                gA[l][m] = -acc;
+            }
+    }
+#pragma unroll
+    for (int l = 0; l < D; ++l) {
+        gr[off_mu(D, C) + l] += gmu[l];
+#pragma unroll
+        for (int m = 0; m <= l; ++m) {
+            float gv = gA[l][m];
+            if (l == m) {
+                gv += u_l1;                                             // smoe.py:1044
+                if (cfg.use_determinant) gv += M0 / A[l][l];            // smoe.py:810
+            }
+            gr[off_A(D, C) + lt(l, m)] += gv;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        gr[off_nu(D, C) + c] += s[off_nu(D, C) + c];
+#pragma unroll
+        for (int l = 0; l < D; ++l) {
+            float gv = s[off_ga(D, C) + l * C + c];
+            if (!cfg.train_gammas) gv = 0.f;
+            if (cfg.use_yuv && cfg.only_y_gamma && c > 0) gv = 0.f;
+            gr[off_ga(D, C) + l * C + c] += gv;
+        }
+    }
+}
+
+// TF1 ApplyAdam: m += (g-m)(1-b1); v += (g^2-v)(1-b2); var -= alpha*m/(sqrt(v)+eps)
+template <int D, int C>
+__global__ void __launch_bounds__(256) adam_kernel(smoe_adam hp, float* __restrict__ theta, const float* __restrict__ grads,
+                                                   float* __restrict__ am, float* __restrict__ av, size_t n) {
+    constexpr int P = nparam(D, C);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(i % P);
+        int grp;
+        bool on = true;
+        if (j < off_A(D, C)) { grp = 0; on = hp.train_musx != 0; }
+        else if (j < off_pi(D, C)) grp = 2;
+        else if (j == off_pi(D, C)) grp = 1;
+        else if (j < off_ga(D, C)) grp = 0;
+        else { grp = 0; on = hp.train_gammas != 0; }
+        const float alpha = hp.alpha[grp];
+        if (!on || alpha == 0.f) continue;
+        float g = grads[i];
+        if (hp.grad_clip > 0.f) g = fminf(fmaxf(g, -hp.grad_clip), hp.grad_clip);
+        float m = am[i], v = av[i];
+        m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), 1.f - hp.beta1[grp]));
+        v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), 1.f - hp.beta2[grp]));
+        am[i] = m;
+        av[i] = v;
+        theta[i] = __fsub_rn(theta[i], __fdiv_rn(__fmul_rn(m, alpha), __fadd_rn(__fsqrt_rn(v), hp.epsilon[grp])));
+    }
+}
+
+}  // namespace smoe
+
+using namespace smoe;
+
+extern "C" {
+
+size_t smoe_backward_workspace_bytes(const smoe_cfg* cfg, int K_cap, int num_splits) {
+    return (size_t)num_splits * K_cap * nparam(cfg->d, cfg->C) * sizeof(float);
+}
+
+int smoe_backward(const smoe_cfg* cfg, const smoe_batch* batch, const float* packed, const int32_t* counts, int K_cap,
+                  const float* pix, const float* ax0, const float* ax1, const float* ax2, int num_splits,
+                  float* raw_part, void* stream) {
+    SMOE_REQUIRE(cfg && batch && packed && counts && pix && ax0 && ax1 && raw_part, "null argument");
+    SMOE_REQUIRE(K_cap > 0 && num_splits > 0 && num_splits <= 65535, "bad K_cap / num_splits");
+    BwdArgs a;
+    a.cfg = *cfg;
+    a.b = *batch;
+    a.packed = packed; a.counts = counts; a.pix = pix; a.raw_part = raw_part;
+    a.ax[0] = ax0; a.ax[1] = ax1; a.ax[2] = ax2 ? ax2 : ax0;
+    a.K_cap = K_cap;
+    a.num_splits = num_splits;
+    a.nt1 = (batch->extent[1] + batch->tile[1] - 1) / batch->tile[1];
+    a.nt2 = (batch->extent[2] + batch->tile[2] - 1) / batch->tile[2];
+    a.ntiles = smoe_num_tiles(batch);
+    a.tau = 0.5f / (float)(1 << cfg->precision);
+    dim3 grid((K_cap + kThreads - 1) / kThreads, num_splits);
+    size_t sm = 2 * (size_t)SMOE_TPIX * SMOE_PIXREC * 4 + 64;
+    cudaStream_t st = (cudaStream_t)stream;
+    // partial slabs of splits that own no tile, and rows k >= K, are never read
+#define CALL(D, C)                                                                                        \
+    {                                                                                                     \
+        cudaFuncSetAttribute(backward_kernel<D, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+        backward_kernel<D, C><<<grid, kThreads, sm, st>>>(a);                                             \
+    }
+    SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
+#undef CALL
+    return check_launch("smoe_backward");
+}
+
+int smoe_reduce_splits(const smoe_cfg* cfg, const int32_t* counts, int K_cap, int num_splits, const float* raw_part,
+                       float* raw, void* stream) {
+    SMOE_REQUIRE(cfg && counts && raw_part && raw && K_cap > 0 && num_splits > 0, "bad argument");
+    int P = nparam(cfg->d, cfg->C);
+    size_t n = (size_t)K_cap * P;
+    int nb = (int)((n + 255) / 256);
+    if (nb > 148 * 16) nb = 148 * 16;
+    reduce_splits_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(counts, K_cap, P, num_splits, raw_part, raw);
+    return check_launch("smoe_reduce_splits");
+}
+
+int smoe_grad_finalize(const smoe_cfg* cfg, const float* raw, int num_splits, int K_cap, const float* theta,
+                       const int32_t* indices, const int32_t* counts, float pis_l1_over_norm, float u_l1, float* grads,
+                       void* stream) {
+    SMOE_REQUIRE(cfg && raw && theta && indices && counts && grads && K_cap > 0 && num_splits > 0, "bad argument");
+    Nudged nq = {0, 0, 1, 1};
+    if (cfg->quantize_pis) {
+        float qmax = (float)((1 << cfg->pis_bits) - 1);
+        float scale = (cfg->pis_ub - cfg->pis_lb) / qmax;
+        float zp = 0.f - cfg->pis_lb / scale;
+        float nzp = zp < 0.f ? 0.f : (zp > qmax ? qmax : floorf(zp + 0.5f));
+        nq.nmin = (0.f - nzp) * scale;
+        nq.nmax = (qmax - nzp) * scale;
+        nq.scale = scale;
+        nq.inv_scale = 1.0f / scale;
+    }
+    int nb = (K_cap + 255) / 256;
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(D, C)                                                                                              \
+    grad_finalize_kernel<D, C><<<nb, 256, 0, st>>>(*cfg, raw, num_splits, K_cap, theta, indices, counts,        \
+                                                   pis_l1_over_norm, u_l1, nq, grads);
+    SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
+#undef CALL
+    return check_launch("smoe_grad_finalize");
+}
+
+int smoe_adam_step(const smoe_cfg* cfg, const smoe_adam* hp, float* theta, const float* grads, float* adam_m,
+                   float* adam_v, int K_all, void* stream) {
+    SMOE_REQUIRE(cfg && hp && theta && grads && adam_m && adam_v && K_all > 0, "bad argument");
+    size_t n = (size_t)K_all * nparam(cfg->d, cfg->C);
+    int nb = (int)((n + 255) / 256);
+    if (nb > 148 * 8) nb = 148 * 8;
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(D, C) adam_kernel<D, C><<<nb, 256, 0, st>>>(*hp, theta, grads, adam_m, adam_v, n);
+    SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
+#undef CALL
+    return check_launch("smoe_adam_step");
+}
+
+}  // extern "C"

@@ -1,0 +1,304 @@
+// GPU metrics and quantiser (smoe_ssim, smoe_sqerr, smoe_quantize, smoe_rescale, smoe_colminmax,
+// smoe_suggest_splits).  HBM-bound pieces; reported in GB/s.
+//
+// SSIM follows ops/image_ops_impl.py:77-293 as the loss graph calls it (smoe.py:993-1010):
+// SYMMETRIC pad by 5 on every domain axis, 11-tap sigma-1.5 Gaussian window (the reference's
+// softmax-normalised 11^d window is the outer product of the normalised 1-D windows), VALID
+// correlation of x, y, x*x+y*y, x*y, K1=.01, K2=.03, mean over positions per channel.
+// Implemented as separable passes (innermost axis first) over a 4-plane workspace; the last
+// pass fuses the SSIM formula and a fixed-order block reduction (no atomics).
+#include <math.h>
+#include "smoe_common.cuh"
+
+namespace smoe {
+
+__constant__ float c_win[11];
+
+__device__ __forceinline__ int reflect_sym(int i, int n) {
+    // numpy / tf "SYMMETRIC": -1 -> 0, -2 -> 1, n -> n-1, n+1 -> n-2
+    while (i < 0 || i >= n) i = i < 0 ? -i - 1 : 2 * n - 1 - i;
+    return i;
+}
+
+// planes: 0: E[x], 1: E[y], 2: E[x^2+y^2], 3: E[xy]
+template <bool FIRST, bool LAST>
+__global__ void __launch_bounds__(256) ssim_pass_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                        const float* __restrict__ src, float* __restrict__ dst,
+                                                        int n0, int n1, int n2, int C, int axis, float c1, float c2,
+                                                        double* __restrict__ partial) {
+    const size_t total = (size_t)n0 * n1 * n2 * C;
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    float ssim = 0.f;
+    int ch = 0;
+    if (i < total) {
+        ch = (int)(i % C);
+        size_t pix = i / C;
+        int i2 = (int)(pix % n2), i1 = (int)((pix / n2) % n1), i0 = (int)(pix / ((size_t)n2 * n1));
+        const int n = axis == 0 ? n0 : (axis == 1 ? n1 : n2);
+        const int pos = axis == 0 ? i0 : (axis == 1 ? i1 : i2);
+        const size_t stride = axis == 0 ? (size_t)n1 * n2 * C : (axis == 1 ? (size_t)n2 * C : (size_t)C);
+        const size_t base = i - (size_t)pos * stride;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 11; ++k) {
+            const size_t j = base + (size_t)reflect_sym(pos + k - 5, n) * stride;
+            const float wk = c_win[k];
+            if (FIRST) {
+                const float x = a[j], y = b[j];
+                acc[0] = fmaf(wk, x, acc[0]);
+                acc[1] = fmaf(wk, y, acc[1]);
+                acc[2] = fmaf(wk, fmaf(x, x, y * y), acc[2]);
+                acc[3] = fmaf(wk, x * y, acc[3]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[q] = fmaf(wk, src[(size_t)q * total + j], acc[q]);
+            }
+        }
+        if (LAST) {
+            const float num0 = acc[0] * acc[1] * 2.0f;
+            const float den0 = acc[0] * acc[0] + acc[1] * acc[1];
+            const float lum = (num0 + c1) / (den0 + c1);
+            const float num1 = acc[3] * 2.0f;
+            const float cs = (num1 - num0 + c2) / (acc[2] - den0 + c2);
+            ssim = lum * cs;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dst[(size_t)q * total + i] = acc[q];
+        }
+    }
+    if (LAST) {
+        // per-channel block sums, fixed order: thread 0 walks the 256 slots
+        __shared__ float s_v[256];
+        __shared__ int s_c[256];
+        s_v[threadIdx.x] = (i < total) ? ssim : 0.f;
+        s_c[threadIdx.x] = ch;
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            double s = 0.0;
+            for (int t = 0; t < 256; ++t)
+                if (s_c[t] == (int)threadIdx.x) s += (double)s_v[t];
+            partial[(size_t)blockIdx.x * 4 + threadIdx.x] = s;
+        }
+    }
+}
+
+__global__ void ssim_final_kernel(const double* __restrict__ partial, int nblocks, int C, double inv_n,
+                                  double* __restrict__ out) {
+    __shared__ double s[256];
+    for (int c = 0; c < C; ++c) {
+        double acc = 0.0;
+        for (int bI = threadIdx.x; bI < nblocks; bI += 256) acc += partial[(size_t)bI * 4 + c];
+        s[threadIdx.x] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int q = 0; q < 256; ++q) t += s[q];
+            out[c] = t * inv_n;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) sqerr_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n,
+                                                    double* __restrict__ partial) {
+    double acc = 0.0;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const float d = a[i] - b[i];
+        acc += (double)d * (double)d;
+    }
+    __shared__ double s[256];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = s[0];
+}
+__global__ void sqerr_final_kernel(const double* __restrict__ partial, int nb, double* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < nb; ++i) t += partial[i];
+        out[0] = t;
+    }
+}
+
+// ---- quantiser --------------------------------------------------------------------------------
+// float32 path: every operation is a separately rounded IEEE op (no FMA contraction), matching
+// NumPy: np.round((p - lb) / (ub - lb + 10e-12) * step)
+template <typename F>
+__global__ void __launch_bounds__(256) quantize_kernel(const float* __restrict__ x, const double* __restrict__ lb,
+                                                       const double* __restrict__ ub, size_t n, int cols, double step,
+                                                       F* __restrict__ codes);
+template <>
+__global__ void __launch_bounds__(256) quantize_kernel<float>(const float* __restrict__ x, const double* __restrict__ lb,
+                                                              const double* __restrict__ ub, size_t n, int cols,
+                                                              double step, float* __restrict__ codes) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int c = (int)(i % cols);
+    const float l = (float)lb[c], u = (float)ub[c];
+    const float den = __fadd_rn(__fsub_rn(u, l), 10e-12f);
+    const float nrm = __fdiv_rn(__fsub_rn(x[i], l), den);
+    codes[i] = rintf(__fmul_rn(nrm, (float)step));
+}
+template <>
+__global__ void __launch_bounds__(256) quantize_kernel<double>(const float* __restrict__ x, const double* __restrict__ lb,
+                                                               const double* __restrict__ ub, size_t n, int cols,
+                                                               double step, double* __restrict__ codes) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int c = (int)(i % cols);
+    const double den = __dadd_rn(__dsub_rn(ub[c], lb[c]), 10e-12);
+    const double nrm = __ddiv_rn(__dsub_rn((double)x[i], lb[c]), den);
+    codes[i] = rint(__dmul_rn(nrm, step));
+}
+// r = q / step * (ub - lb) + lb   (quantizer.py:124-130)
+__global__ void __launch_bounds__(256) rescale_kernel_f32(const float* __restrict__ q, const double* __restrict__ lb,
+                                                          const double* __restrict__ ub, size_t n, int cols, double step,
+                                                          float* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int c = (int)(i % cols);
+    const float l = (float)lb[c], u = (float)ub[c];
+    out[i] = __fadd_rn(__fmul_rn(__fdiv_rn(q[i], (float)step), __fsub_rn(u, l)), l);
+}
+__global__ void __launch_bounds__(256) rescale_kernel_f64(const double* __restrict__ q, const double* __restrict__ lb,
+                                                          const double* __restrict__ ub, size_t n, int cols, double step,
+                                                          double* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int c = (int)(i % cols);
+    out[i] = __dadd_rn(__dmul_rn(__ddiv_rn(q[i], step), __dsub_rn(ub[c], lb[c])), lb[c]);
+}
+__global__ void __launch_bounds__(256) colminmax_kernel(const float* __restrict__ x, int rows, int cols,
+                                                        double* __restrict__ lb, double* __restrict__ ub) {
+    const int c = blockIdx.x;
+    float mn = INFINITY, mx = -INFINITY;
+    for (int r = threadIdx.x; r < rows; r += 256) {
+        const float v = x[(size_t)r * cols + c];
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+    }
+    __shared__ float smn[256], smx[256];
+    smn[threadIdx.x] = mn;
+    smx[threadIdx.x] = mx;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            smn[threadIdx.x] = fminf(smn[threadIdx.x], smn[threadIdx.x + o]);
+            smx[threadIdx.x] = fmaxf(smx[threadIdx.x], smx[threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { lb[c] = (double)smn[0]; ub[c] = (double)smx[0]; }
+}
+
+}  // namespace smoe
+
+using namespace smoe;
+
+extern "C" {
+
+size_t smoe_ssim_workspace_bytes(int d, const int32_t dims[3], int C) {
+    (void)d;
+    size_t total = (size_t)dims[0] * dims[1] * dims[2] * C;
+    size_t nblocks = (total + 255) / 256;
+    return 2 * 4 * total * sizeof(float) + nblocks * 4 * sizeof(double) + 256;
+}
+
+int smoe_ssim(int d, const int32_t dims[3], int C, const float* a, const float* b, double* out, void* workspace,
+              void* stream) {
+    SMOE_REQUIRE(a && b && out && workspace && dims, "null argument");
+    SMOE_REQUIRE((d == 2 || d == 3) && C >= 1 && C <= 4, "unsupported d / C");
+    static bool win_set = false;
+    cudaStream_t st = (cudaStream_t)stream;
+    float w[11];
+    {
+        double s = 0.0, g[11];
+        for (int k = 0; k < 11; ++k) { g[k] = exp(-0.5 * (k - 5.0) * (k - 5.0) / (1.5 * 1.5)); s += g[k]; }
+        for (int k = 0; k < 11; ++k) w[k] = (float)(g[k] / s);
+    }
+    (void)win_set;
+    cudaMemcpyToSymbolAsync(c_win, w, sizeof(w), 0, cudaMemcpyHostToDevice, st);
+    const int n0 = dims[0], n1 = dims[1], n2 = (d == 3) ? dims[2] : 1;
+    const size_t total = (size_t)n0 * n1 * n2 * C;
+    const int nblocks = (int)((total + 255) / 256);
+    float* p0 = (float*)workspace;
+    float* p1 = p0 + 4 * total;
+    size_t off = (2 * 4 * total * sizeof(float) + 255) / 256 * 256;
+    double* partial = (double*)((char*)workspace + off);
+    const float c1 = 0.01f * 0.01f, c2 = 0.03f * 0.03f;
+    if (d == 2) {
+        ssim_pass_kernel<true, false><<<nblocks, 256, 0, st>>>(a, b, nullptr, p0, n0, n1, n2, C, 1, c1, c2, nullptr);
+        ssim_pass_kernel<false, true><<<nblocks, 256, 0, st>>>(a, b, p0, nullptr, n0, n1, n2, C, 0, c1, c2, partial);
+    } else {
+        ssim_pass_kernel<true, false><<<nblocks, 256, 0, st>>>(a, b, nullptr, p0, n0, n1, n2, C, 2, c1, c2, nullptr);
+        ssim_pass_kernel<false, false><<<nblocks, 256, 0, st>>>(a, b, p0, p1, n0, n1, n2, C, 1, c1, c2, nullptr);
+        ssim_pass_kernel<false, true><<<nblocks, 256, 0, st>>>(a, b, p1, nullptr, n0, n1, n2, C, 0, c1, c2, partial);
+    }
+    ssim_final_kernel<<<1, 256, 0, st>>>(partial, nblocks, C, 1.0 / (double)((size_t)n0 * n1 * n2), out);
+    return check_launch("smoe_ssim");
+}
+
+int smoe_sqerr(const float* a, const float* b, size_t n, double* out, void* workspace, void* stream) {
+    SMOE_REQUIRE(a && b && out && workspace && n > 0, "bad argument");
+    int nb = (int)((n + 255) / 256);
+    if (nb > 1024) nb = 1024;
+    cudaStream_t st = (cudaStream_t)stream;
+    sqerr_kernel<<<nb, 256, 0, st>>>(a, b, n, (double*)workspace);
+    sqerr_final_kernel<<<1, 32, 0, st>>>((const double*)workspace, nb, out);
+    return check_launch("smoe_sqerr");
+}
+
+int smoe_quantize(const float* x, const double* lb, const double* ub, int rows, int cols, double step, int f64,
+                  void* codes, void* stream) {
+    SMOE_REQUIRE(x && lb && ub && codes && rows > 0 && cols > 0, "bad argument");
+    size_t n = (size_t)rows * cols;
+    int nb = (int)((n + 255) / 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (f64) quantize_kernel<double><<<nb, 256, 0, st>>>(x, lb, ub, n, cols, step, (double*)codes);
+    else quantize_kernel<float><<<nb, 256, 0, st>>>(x, lb, ub, n, cols, step, (float*)codes);
+    return check_launch("smoe_quantize");
+}
+
+int smoe_rescale(const void* codes, const double* lb, const double* ub, int rows, int cols, double step, int f64,
+                 void* out, void* stream) {
+    SMOE_REQUIRE(codes && lb && ub && out && rows > 0 && cols > 0, "bad argument");
+    size_t n = (size_t)rows * cols;
+    int nb = (int)((n + 255) / 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (f64) rescale_kernel_f64<<<nb, 256, 0, st>>>((const double*)codes, lb, ub, n, cols, step, (double*)out);
+    else rescale_kernel_f32<<<nb, 256, 0, st>>>((const float*)codes, lb, ub, n, cols, step, (float*)out);
+    return check_launch("smoe_rescale");
+}
+
+int smoe_colminmax(const float* x, int rows, int cols, double* lb, double* ub, void* stream) {
+    SMOE_REQUIRE(x && lb && ub && rows > 0 && cols > 0, "bad argument");
+    colminmax_kernel<<<cols, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, lb, ub);
+    return check_launch("smoe_colminmax");
+}
+
+int smoe_suggest_splits(int K_cap, int ntiles) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int slots = 2 * sms;
+    const int kt = (K_cap + kThreads - 1) / kThreads;
+    int best = 1;
+    double best_eff = -1.0;
+    int lo = (2 * slots + kt - 1) / kt;          // at least ~2 waves of CTAs
+    if (lo < 1) lo = 1;
+    for (int ns = lo; ns <= lo + 64 && ns <= ntiles; ++ns) {
+        const double ctas = (double)kt * ns;
+        const double waves = ctas / slots;
+        double eff = waves / ceil(waves);
+        // tiles per split should also divide evenly
+        const double tps = (double)ntiles / ns;
+        eff *= tps / ceil(tps);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = ns; }
+    }
+    if (best > ntiles) best = ntiles;
+    return best < 1 ? 1 : best;
+}
+
+}  // extern "C"

@@ -1,0 +1,302 @@
+// pi-mask stream compaction + parameter staging (smoe_pack, smoe_pack_fed, smoe_update_kernel_list).
+//
+// Replaces smoe.py:474-480 (fake-quant of pis), 732-735 (A assembly), 738-753 (bool_mask,
+// indices, 5x boolean_mask) and 1012 (num_pi).  HBM-bound: reads K_all*(P*4+1) bytes, writes
+// K*(PK*4+4) bytes.  Two launches: (1) per-block flag counts and regulariser partial sums,
+// (2) every block re-derives its exclusive prefix from the <= few-thousand block counts,
+// scans its own flags with warp ballots and scatters records in ascending kernel index
+// (stable, hence bit-exact with numpy boolean masking).  No atomics: sums are fixed-order.
+#include <math.h>
+#include <stdarg.h>
+#include "smoe_common.cuh"
+
+namespace smoe {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+// TF FakeQuantWithMinMaxArgs nudging (float32), see oracle/graph.py:_nudge
+struct Nudged { float nmin, nmax, scale, inv_scale; };
+static Nudged nudge(float mn, float mx, int bits) {
+    float qmin = 0.f, qmax = (float)((1 << bits) - 1);
+    float scale = (mx - mn) / (qmax - qmin);
+    float zp = qmin - mn / scale;
+    float nzp = zp < qmin ? qmin : (zp > qmax ? qmax : floorf(zp + 0.5f));
+    Nudged n;
+    n.nmin = (qmin - nzp) * scale;
+    n.nmax = (qmax - nzp) * scale;
+    n.scale = scale;
+    n.inv_scale = 1.0f / scale;
+    return n;
+}
+
+__device__ __forceinline__ float fake_quant(float x, Nudged n) {
+    float c = fminf(fmaxf(x, n.nmin), n.nmax);
+    float k = floorf(__fadd_rn(__fmul_rn(__fsub_rn(c, n.nmin), n.inv_scale), 0.5f));
+    return __fadd_rn(__fmul_rn(k, n.scale), n.nmin);
+}
+
+struct PackBlk { int32_t count, numpi, nonpos, pad; float sum_pi, sum_diag; };
+
+template <int D, int C>
+__global__ void __launch_bounds__(256) pack_count_kernel(const float* __restrict__ theta,
+                                                         const uint8_t* __restrict__ klist, int K_all,
+                                                         int quantize_pis, Nudged nq, PackBlk* __restrict__ blk) {
+    constexpr int P = nparam(D, C);
+    int i = blockIdx.x * 256 + threadIdx.x;
+    int flag = 0, numpi = 0;
+    float spi = 0.f, sdiag = 0.f;
+    if (i < K_all) {
+        const float* row = theta + (size_t)i * P;
+        float pi = row[off_pi(D, C)];
+        if (quantize_pis) pi = fake_quant(pi, nq);
+        numpi = pi > 0.f;
+        flag = numpi && klist[i];
+        if (flag) {
+            spi = pi;
+#pragma unroll
+            for (int l = 0; l < D; ++l) sdiag += row[off_A(D, C) + lt(l, l)];
+        }
+    }
+    // fixed-order block reduction (shuffle tree, then warp 0 over the 8 warp results)
+    __shared__ int s_c[8], s_n[8];
+    __shared__ float s_p[8], s_d[8];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned bal = __ballot_sync(0xffffffffu, flag);
+    unsigned baln = __ballot_sync(0xffffffffu, numpi);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        spi += __shfl_down_sync(0xffffffffu, spi, o);
+        sdiag += __shfl_down_sync(0xffffffffu, sdiag, o);
+    }
+    if (lane == 0) { s_c[w] = __popc(bal); s_n[w] = __popc(baln); s_p[w] = spi; s_d[w] = sdiag; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        PackBlk b = {0, 0, 0, 0, 0.f, 0.f};
+        for (int j = 0; j < 8; ++j) { b.count += s_c[j]; b.numpi += s_n[j]; b.sum_pi += s_p[j]; b.sum_diag += s_d[j]; }
+        blk[blockIdx.x] = b;
+    }
+}
+
+// Stage one kernel's compute record.  A is given as a full d x d matrix (row-major).
+template <int D, int C>
+__device__ __forceinline__ int stage_record(const smoe_cfg& cfg, const float (&A)[D][D], const float* mu, float pi,
+                                            const float* nu, const float* ga, float* __restrict__ rec) {
+    constexpr int PK = pstride(D, C);
+#pragma unroll
+    for (int l = 0; l < D; ++l) rec[off_mu(D, C) + l] = mu[l];
+#pragma unroll
+    for (int l = 0; l < D; ++l)
+#pragma unroll
+        for (int m = l; m < D; ++m) {
+            float q;
+            if (cfg.train_inverse_cov) {
+                q = 0.5f * (A[l][m] + A[m][l]);          // x^T A x only sees the symmetric part
+            } else {
+                q = 0.f;
+#pragma unroll
+                for (int j = 0; j < D; ++j) q = fmaf(A[l][j], A[m][j], q);   // (A A^T)[l][m]
+            }
+            rec[off_A(D, C) + ut(D, l, m)] = kHalfLog2e * q;
+        }
+    float coef = pi;
+    if (cfg.use_determinant) {
+        float det = 1.f;
+#pragma unroll
+        for (int l = 0; l < D; ++l) det *= A[l][l];
+        coef = coef * (det / sqrtf(powf(6.283185307179586f, (float)D)));
+    }
+    rec[off_pi(D, C)] = log2f(fabsf(coef));            // -inf for coef == 0: the kernel contributes 0
+#pragma unroll
+    for (int c = 0; c < C; ++c) rec[off_nu(D, C) + c] = nu[c];
+#pragma unroll
+    for (int l = 0; l < D; ++l)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float g = ga[l * C + c];
+            if (!cfg.train_gammas) g = 0.f;
+            if (cfg.use_yuv && cfg.train_gammas && cfg.only_y_gamma && c > 0) g = 0.f;
+            rec[off_ga(D, C) + l * C + c] = g;
+        }
+#pragma unroll
+    for (int j = nparam(D, C); j < PK; ++j) rec[j] = 0.f;
+    return coef < 0.f;       // negative weights cannot be carried in the log domain
+}
+
+template <int D, int C>
+__global__ void __launch_bounds__(256) pack_scatter_kernel(smoe_cfg cfg, const float* __restrict__ theta,
+                                                           const uint8_t* __restrict__ klist, int K_all, Nudged nq,
+                                                           const PackBlk* __restrict__ blk, float* __restrict__ packed,
+                                                           int32_t* __restrict__ indices, int32_t* __restrict__ counts,
+                                                           float* __restrict__ regsums, int32_t* __restrict__ nonpos_blk) {
+    constexpr int P = nparam(D, C), PK = pstride(D, C);
+    __shared__ int s_red[8];
+    __shared__ int s_warp[8];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    // exclusive prefix of the block counts before this block
+    int part = 0;
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += 256) part += blk[b].count;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+    if (lane == 0) s_red[w] = part;
+    __syncthreads();
+    int prefix = 0;
+    for (int j = 0; j < 8; ++j) prefix += s_red[j];
+
+    int i = blockIdx.x * 256 + threadIdx.x;
+    int flag = 0;
+    float pi = 0.f;
+    const float* row = theta + (size_t)min(i, K_all - 1) * P;
+    if (i < K_all) {
+        pi = row[off_pi(D, C)];
+        if (cfg.quantize_pis) pi = fake_quant(pi, nq);
+        flag = (pi > 0.f) && klist[i];
+    }
+    unsigned bal = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) s_warp[w] = __popc(bal);
+    __syncthreads();
+    int woff = 0;
+    for (int j = 0; j < w; ++j) woff += s_warp[j];
+    int dst = prefix + woff + __popc(bal & ((1u << lane) - 1u));
+    int neg = 0;
+    if (flag) {
+        indices[dst] = i;
+        float A[D][D];
+#pragma unroll
+        for (int l = 0; l < D; ++l)
+#pragma unroll
+            for (int m = 0; m < D; ++m) A[l][m] = (m <= l) ? row[off_A(D, C) + lt(l, m)] : 0.f;
+        if (cfg.train_inverse_cov) {
+#pragma unroll
+            for (int l = 0; l < D; ++l)
+#pragma unroll
+                for (int m = l + 1; m < D; ++m) A[l][m] = A[m][l];
+        }
+        neg = stage_record<D, C>(cfg, A, row + off_mu(D, C), pi, row + off_nu(D, C), row + off_ga(D, C),
+                                 packed + (size_t)dst * PK);
+    }
+    int negs = __syncthreads_count(neg);
+    if (threadIdx.x == 0) nonpos_blk[blockIdx.x] = negs;
+    // the last block publishes the totals (fixed-order sums over the block records)
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+        int K = 0, np_ = 0;
+        float sp = 0.f, sd = 0.f;
+        for (int b = 0; b < (int)gridDim.x; ++b) { K += blk[b].count; np_ += blk[b].numpi; sp += blk[b].sum_pi; sd += blk[b].sum_diag; }
+        counts[0] = K;
+        counts[1] = np_;
+        counts[3] = 0;
+        regsums[0] = sp;
+        regsums[1] = sd;
+    }
+}
+
+__global__ void nonpos_total_kernel(const int32_t* __restrict__ nonpos_blk, int nb, int32_t* __restrict__ counts) {
+    int s = 0;
+    for (int b = 0; b < nb; ++b) s += nonpos_blk[b];
+    counts[2] = s;
+}
+
+template <int D, int C>
+__global__ void __launch_bounds__(256) pack_fed_kernel(smoe_cfg cfg, const float* __restrict__ A_, const float* __restrict__ mus,
+                                                       const float* __restrict__ nu, const float* __restrict__ ga,
+                                                       const float* __restrict__ pis, int K, float* __restrict__ packed,
+                                                       int32_t* __restrict__ counts) {
+    constexpr int PK = pstride(D, C);
+    int i = blockIdx.x * 256 + threadIdx.x;
+    if (i == 0) { counts[0] = K; counts[1] = K; counts[2] = 0; counts[3] = 0; }
+    if (i >= K) return;
+    float A[D][D];
+#pragma unroll
+    for (int l = 0; l < D; ++l)
+#pragma unroll
+        for (int m = 0; m < D; ++m) A[l][m] = A_[(size_t)i * D * D + l * D + m];
+    stage_record<D, C>(cfg, A, mus + (size_t)i * D, pis[i], nu + (size_t)i * C, ga + (size_t)i * D * C,
+                       packed + (size_t)i * PK);
+}
+
+__global__ void klist_clear_kernel(uint8_t* __restrict__ klist, int K_all) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < K_all) klist[i] = 0;
+}
+__global__ void klist_set_kernel(const int32_t* __restrict__ indices, const int32_t* __restrict__ counts,
+                                 const uint8_t* __restrict__ infl, uint8_t* __restrict__ klist) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < counts[0] && infl[k]) klist[indices[k]] = 1;
+}
+
+}  // namespace smoe
+
+using namespace smoe;
+
+extern "C" {
+
+int smoe_abi_version(void) { return SMOE_ABI_VERSION; }
+const char* smoe_last_error(void) { return smoe::g_err; }
+int smoe_param_count(int d, int C) { return nparam(d, C); }
+int smoe_packed_stride(int d, int C) { return pstride(d, C); }
+int smoe_num_tiles(const smoe_batch* b) {
+    int n = 1;
+    for (int i = 0; i < 3; ++i) n *= (b->extent[i] + b->tile[i] - 1) / b->tile[i];
+    return n;
+}
+size_t smoe_pack_workspace_bytes(int K_all) {
+    size_t nb = (size_t)(K_all + 255) / 256;
+    return nb * sizeof(PackBlk) + nb * sizeof(int32_t) + 256;
+}
+
+int smoe_pack(const smoe_cfg* cfg, const float* theta, const uint8_t* kernel_list, int K_all, float* packed,
+              int32_t* indices, int32_t* counts, float* regsums, void* workspace, void* stream) {
+    SMOE_REQUIRE(cfg && theta && kernel_list && packed && indices && counts && regsums && workspace, "null argument");
+    SMOE_REQUIRE(K_all > 0, "K_all must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    int nb = (K_all + 255) / 256;
+    PackBlk* blk = (PackBlk*)workspace;
+    int32_t* nonpos_blk = (int32_t*)((char*)workspace + (size_t)nb * sizeof(PackBlk));
+    Nudged nq = {0, 0, 1, 1};
+    if (cfg->quantize_pis) nq = nudge(cfg->pis_lb, cfg->pis_ub, cfg->pis_bits);
+#define CALL(D, C)                                                                                              \
+    pack_count_kernel<D, C><<<nb, 256, 0, st>>>(theta, kernel_list, K_all, cfg->quantize_pis, nq, blk);         \
+    pack_scatter_kernel<D, C><<<nb, 256, 0, st>>>(*cfg, theta, kernel_list, K_all, nq, blk, packed, indices,    \
+                                                  counts, regsums, nonpos_blk);
+    SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
+#undef CALL
+    nonpos_total_kernel<<<1, 1, 0, st>>>(nonpos_blk, nb, counts);
+    return check_launch("smoe_pack");
+}
+
+int smoe_pack_fed(const smoe_cfg* cfg, const float* A, const float* musX, const float* nu_e, const float* gamma_e,
+                  const float* pis, int K, float* packed, int32_t* counts, void* stream) {
+    SMOE_REQUIRE(cfg && A && musX && nu_e && gamma_e && pis && packed && counts, "null argument");
+    SMOE_REQUIRE(K > 0, "K must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    int nb = (K + 255) / 256;
+#define CALL(D, C) pack_fed_kernel<D, C><<<nb, 256, 0, st>>>(*cfg, A, musX, nu_e, gamma_e, pis, K, packed, counts);
+    SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
+#undef CALL
+    return check_launch("smoe_pack_fed");
+}
+
+int smoe_update_kernel_list(const int32_t* indices, const int32_t* counts, const uint8_t* infl, uint8_t* kernel_list,
+                            int K_all, void* stream) {
+    SMOE_REQUIRE(indices && counts && infl && kernel_list && K_all > 0, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    int nb = (K_all + 255) / 256;
+    klist_clear_kernel<<<nb, 256, 0, st>>>(kernel_list, K_all);
+    klist_set_kernel<<<nb, 256, 0, st>>>(indices, counts, infl, kernel_list);
+    return check_launch("smoe_update_kernel_list");
+}
+
+}  // extern "C"

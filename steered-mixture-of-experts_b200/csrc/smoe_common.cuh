@@ -1,0 +1,108 @@
+// Shared device/host helpers of libsmoe_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/smoe_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libsmoe_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace smoe {
+
+constexpr int kThreads = 256;                       // threads per CTA of the sweep kernels
+constexpr int kPixPerThread = SMOE_TPIX / kThreads; // 4 pixels per thread in the forward
+constexpr int kChunk = 256;                         // kernels staged per shared-memory chunk
+constexpr float kHalfLog2e = 0.72134752044448170368f;   // log2(e)/2
+constexpr float kSFloor = 10e-12f;                  // the literal of smoe.py:821
+
+__host__ __device__ constexpr int tri(int d) { return d * (d + 1) / 2; }
+__host__ __device__ constexpr int nparam(int d, int C) { return d + tri(d) + 1 + C + d * C; }
+__host__ __device__ constexpr int pstride(int d, int C) { return (nparam(d, C) + 1 + 3) / 4 * 4; }
+// offsets inside a theta / grads row and inside a packed record (same order)
+__host__ __device__ constexpr int off_mu(int, int) { return 0; }
+__host__ __device__ constexpr int off_A(int d, int) { return d; }
+__host__ __device__ constexpr int off_pi(int d, int) { return d + tri(d); }
+__host__ __device__ constexpr int off_nu(int d, int) { return d + tri(d) + 1; }
+__host__ __device__ constexpr int off_ga(int d, int C) { return d + tri(d) + 1 + C; }
+// lower-triangular (l >= m) row-major index; upper-triangular (l <= m) row-major index
+__host__ __device__ constexpr int lt(int l, int m) { return l * (l + 1) / 2 + m; }
+__host__ __device__ constexpr int ut(int d, int l, int m) { return l * d - l * (l - 1) / 2 + (m - l); }
+
+// pixel record written by the forward, streamed by the backward
+//   [0..d) tile-centred coordinates | [3] 1/S (or 1e11 when S is clamped) | [4] gr (0 when clamped)
+//   [5..5+C) g_c = dL/dr_c | [8..8+d) absolute coordinates are NOT stored (fold uses tile centre)
+constexpr int PR_X = 0, PR_INVS = 3, PR_GR = 4, PR_G = 5, PR_XX = 8;
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define SMOE_REQUIRE(cond, msg)                           \
+    do {                                                  \
+        if (!(cond)) {                                    \
+            smoe::set_error("%s: %s", __func__, msg);     \
+            return SMOE_E_BADARG;                         \
+        }                                                 \
+    } while (0)
+
+// dispatch on (d, C): instantiations exist for d in {2,3}, C in {1,3}
+#define SMOE_DISPATCH_DC(d, C, CALL)                                          \
+    if ((d) == 2 && (C) == 1) { CALL(2, 1); }                                 \
+    else if ((d) == 2 && (C) == 3) { CALL(2, 3); }                            \
+    else if ((d) == 3 && (C) == 1) { CALL(3, 1); }                            \
+    else if ((d) == 3 && (C) == 3) { CALL(3, 3); }                            \
+    else { smoe::set_error("%s: unsupported (d,C)=(%d,%d)", __func__, (int)(d), (int)(C)); return SMOE_E_UNSUPPORTED; }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2f(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+// ---- mbarrier + TMA bulk copy (cp.async.bulk, SASS UBLKCP) ---------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+#endif  // __CUDACC__
+
+}  // namespace smoe

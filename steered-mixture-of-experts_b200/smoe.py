@@ -1,0 +1,877 @@
+"""`Smoe`: the reference's model object (smoe.py:37-2578) on top of libsmoe_b200 (sm_100a CUDA).
+
+Same constructor keywords, `set_optimizer` / `train` / `run_batched` / getters, the params dict
+(`pis, musX, A_diagonal, A_corr, gamma_e, nu_e`), `kernel_list_per_batch`, history lists and
+`qparams` / `rparams` as the reference, so `logger.py`, `plotter.py`, `utils.save_model`,
+`quantizer.py` and the `smoe_reconstruction*.py` entry points work against it unchanged.
+What changed is everything below `run_batched`: the TensorFlow graph (`init_model`,
+smoe.py:331-1064) and `session.run` (smoe.py:1702, 1788) are replaced by hand-written CUDA
+kernels called through the C ABI of include/smoe_b200.h.  There is no CPU path.
+
+Deliberate deviations from HEAD (DESIGN.md "Decisions"):
+  D1  single-model path only: affines / train_trafo / train_svs / add_kernel_slots>0 /
+      dim_domain>=4 / ssim_opt / overlap_of_batches>0 / sampling_percentage<100 / loss masks /
+      radial_as / quantization_mode>=2 raise NotImplementedError;
+  D5  `init_params['A_diagonal'] + init_params['A_corr']` is split back into its diagonal
+      (-> A_diagonal) and strictly-lower part (-> A_corr) instead of being stored whole in
+      A_diagonal (where the reference's band_part then drops the steering, smoe.py:256, 436, 732);
+  the TF leaks `smoe.session.run(smoe.re_assign_*_op)` are replaced by `set_params(dict)`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from itertools import product
+
+import numpy as np
+import torch
+
+from . import _ffi
+from ._ffi import Adam, Batch, Cfg, check, lib, ptr, stream_ptr
+from .quantizer import quantize_params, rescaler
+
+PARAM_KEYS = ("pis", "musX", "A_diagonal", "A_corr", "gamma_e", "nu_e")
+
+
+def sliding_window(image, Overlap, BatchSize):
+    """Yields (coord, window) over the domain axes, first axis outermost, last innermost, with a
+    zero halo of `Overlap` (smoe.py:18-35)."""
+    nd = image.ndim - 1
+    if nd not in (2, 3):
+        return
+    pad = np.pad(image, [(Overlap, Overlap)] * nd + [(0, 0)], "constant", constant_values=0)
+    starts = [range(0, pad.shape[a] - 2 * Overlap, BatchSize[a]) for a in range(nd)]
+    for org in product(*starts):
+        sl = tuple(slice(o, o + BatchSize[a] + 2 * Overlap) for a, o in enumerate(org))
+        yield np.array(org) - Overlap, pad[sl + (slice(None),)]
+
+
+class AdamOptimizer:
+    """Stand-in for `tf.train.AdamOptimizer(lr)` as the reference constructs it
+    (smoe_test.py:84-88); `Smoe.set_optimizer` reads `._lr` (smoe.py:1120)."""
+
+    def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-8):
+        self._lr = learning_rate
+        self._beta1, self._beta2, self._epsilon = beta1, beta2, epsilon
+        self._t = 0
+
+    def _step_alpha(self):
+        """Advance the beta powers once (one apply_gradients) and return TF's lr_t in float32."""
+        self._t += 1
+        f = np.float32
+        b1p, b2p = f(self._beta1 ** self._t), f(self._beta2 ** self._t)
+        return float(f(self._lr) * np.sqrt(f(1) - b2p) / (f(1) - b1p))
+
+
+class Smoe:
+    def __init__(self, image, kernels_per_dim=None, train_pis=True, init_params=None, start_batches=1,
+                 batch_size=None, train_gammas=True, train_musx=True, use_diff_center=False, radial_as=False,
+                 use_determinant=False, normalize_pis=True, quantization_mode=0, bit_depths=None,
+                 quantize_pis=False, lower_bounds=None, upper_bounds=None, use_yuv=True, only_y_gamma=False,
+                 ssim_opt=False, precision=8, add_kernel_slots=0, iter_offset=0, margin=0.5,
+                 overlap_of_batches=0, kernel_count_as_norm_l1=False, train_svs=False, affines=None,
+                 train_trafo=False, num_params_model=6, train_inverse_cov=True, init_flag=1,
+                 only_rec_from_checkpoint=False, loss_mask=None, device=None, dense_exec=False,
+                 process_group=None):
+        _ffi.require_cuda()
+        lib()
+        unsupported = {"affines": affines is not None, "train_trafo": train_trafo, "train_svs": train_svs,
+                       "add_kernel_slots": add_kernel_slots > 0, "ssim_opt": ssim_opt, "radial_as": radial_as,
+                       "overlap_of_batches": overlap_of_batches > 0, "loss_mask": loss_mask is not None,
+                       "quantization_mode>=2": quantization_mode >= 2, "use_diff_center": use_diff_center}
+        for k, v in unsupported.items():
+            if v:
+                raise NotImplementedError(f"{k}: outside the single-model hot path (SURVEY.md 8, decision D1)")
+        image = np.ascontiguousarray(np.asarray(image), dtype=np.float32)
+        if image.ndim - 1 not in (2, 3):
+            raise NotImplementedError("dim_domain must be 2 (image) or 3 (video)")
+        if image.shape[-1] not in (1, 3):
+            raise NotImplementedError("1 or 3 channels")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        # --- reference attributes (smoe.py:42-221) ---
+        self.use_yuv, self.only_y_gamma, self.ssim_opt = use_yuv, only_y_gamma, ssim_opt
+        self.use_diff_center, self.precision = use_diff_center, precision
+        self.add_kernel_slots, self.kernel_count_as_norm_l1 = add_kernel_slots, kernel_count_as_norm_l1
+        self.qparams = self.rparams = None
+        self.losses, self.qlosses, self.losses_history = [], [], []
+        self.best_loss = self.best_qloss = None
+        self.mses, self.qmses, self.mses_history = [], [], []
+        self.best_mse, self.best_qmse = [], []
+        self.num_pis, self.num_svs = [], []
+        self.iter = iter_offset
+        self.valid = self.qvalid = False
+        self.reconstruction_image = self.weight_matrix_argmax = None
+        self.qreconstruction_image = self.qweight_matrix_argmax = None
+        self.train_pis, self.train_gammas, self.train_musx = train_pis, train_gammas, train_musx
+        self.radial_as, self.use_determinant = radial_as, use_determinant
+        self.quantization_mode, self.bit_depths, self.quantize_pis = quantization_mode, bit_depths, quantize_pis
+        self.lower_bounds, self.upper_bounds = lower_bounds, upper_bounds
+        self.with_SV, self.train_trafo, self.train_inverse_cov = train_svs, train_trafo, train_inverse_cov
+        self.affines, self.loss_mask = affines, loss_mask
+        self.only_rec_from_checkpoint = only_rec_from_checkpoint
+        self.optimizer1 = self.optimizer2 = self.optimizer3 = None
+        self.grad_clip_value_abs = None
+        if quantize_pis and (lower_bounds is None or upper_bounds is None or bit_depths is None):
+            raise ValueError("quantize_pis needs lower_bounds, upper_bounds and bit_depths")
+
+        self.start_batches = start_batches
+        self.image = image
+        self.dim_domain = image.ndim - 1
+        self.num_pixel = int(np.prod(image.shape[:self.dim_domain]))
+        self.joint_domain_shape = tuple(image.shape[:-1]) + (self.dim_domain + image.shape[-1],)
+        self.batch_shape = self.get_batch_shape(start_batches, self.joint_domain_shape)
+        d = self.dim_domain
+        if batch_size is not None and batch_size[0] is not None:          # smoe.py:231-243
+            if len(batch_size) == d:
+                self.batch_size_valued = tuple(int(b) for b in batch_size)
+            elif len(batch_size) == 1:
+                self.batch_size_valued = (int(batch_size[0]),) * d
+            else:
+                raise ValueError("Required BatchSize doesn't fit to input dimension")
+            for ii in range(d):
+                if image.shape[ii] % self.batch_size_valued[ii] > 0:
+                    raise ValueError("Required BatchSize is not compatible to input dimensions")
+        else:
+            self.batch_size_valued = tuple(self.batch_shape[:-1])
+        self.overlap = overlap_of_batches
+        self.batch_size = tuple(np.array(self.batch_size_valued) + 2 * self.overlap)
+        self.start_batches = int(np.prod(np.ceil(np.array(image.shape[:-1]) / np.array(self.batch_size_valued))))
+
+        assert kernels_per_dim is not None or init_params is not None, \
+            "You need to specify the kernel grid size or give initial parameters."
+        if init_params:
+            self.pis_init = np.asarray(init_params["pis"])
+            self.musX_init = np.asarray(init_params["musX"])
+            self.A_init = np.asarray(init_params["A_diagonal"]) + np.asarray(init_params["A_corr"])
+            self.gamma_e_init = np.asarray(init_params["gamma_e"])
+            self.nu_e_init = np.asarray(init_params["nu_e"])
+        else:
+            self.generate_kernel_grid(kernels_per_dim)
+            self.generate_experts()
+            self.generate_pis(normalize_pis)
+        self.start_pis = int(self.pis_init.size)
+        self.kernel_count = self.start_pis
+        self.margin = margin
+
+        # --- distributed sharding: contiguous bands of the first domain axis ---
+        self._pg = process_group
+        self._world, self._rank = 1, 0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self._world = torch.distributed.get_world_size(process_group)
+            self._rank = torch.distributed.get_rank(process_group)
+        if self._world > 1:
+            if self.start_batches != 1:
+                raise NotImplementedError("pixel sharding over ranks needs start_batches == 1")
+            n0 = image.shape[0]
+            self._band = (n0 * self._rank // self._world, n0 * (self._rank + 1) // self._world)
+        else:
+            self._band = (0, image.shape[0])
+
+        self._init_device(dense_exec)
+
+    # ------------------------------------------------------------------------------------------
+    # initialisers (smoe.py:2146-2242, 2395-2426, 2459-2543)
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def gen_domain(in_, dim_of_input_space=2):
+        if isinstance(in_, np.ndarray):
+            axes = [np.linspace(0, 1, in_.shape[a]) for a in range(dim_of_input_space)]
+            mesh = np.stack(np.meshgrid(*axes, indexing="ij"), axis=-1)
+            return np.append(mesh, in_, axis=-1)
+        per_dim = [int(in_[a] if len(in_) > 1 else in_[0]) for a in range(dim_of_input_space)]
+        axes = [np.linspace((1 / n) / 2, 1 - (1 / n) / 2, n) for n in per_dim]
+        mesh = np.stack(np.meshgrid(*axes, indexing="ij"), axis=-1)
+        return mesh.reshape(int(np.prod(per_dim)), dim_of_input_space)
+
+    def generate_kernel_grid(self, kernels_per_dim):
+        d = self.image.ndim - 1
+        self.musX_init = self.gen_domain(list(kernels_per_dim), d)
+        per_dim = [kernels_per_dim[a] if len(kernels_per_dim) > 1 else kernels_per_dim[0] for a in range(d)]
+        proto = np.diag(np.array([2 * (n + 1) for n in per_dim], dtype=np.float64))
+        self.A_init = np.tile(proto, (self.musX_init.shape[0], 1, 1))
+        if self.train_inverse_cov:
+            self.A_init = self.A_init ** 2
+
+    def generate_experts(self, with_means=True):
+        assert self.musX_init is not None, "need musX to generate experts"
+        d, Cc = self.dim_domain, self.image.shape[-1]
+        K = self.musX_init.shape[0]
+        self.gamma_e_init = np.zeros((K, d, Cc))
+        if not with_means:
+            self.nu_e_init = np.ones((K, Cc)) * 0.5
+            return
+        half = self.musX_init[0]
+        ext = self.image.shape[:d]
+        lo = np.empty((K, d), dtype=np.int64)
+        hi = np.empty((K, d), dtype=np.int64)
+        for a in range(d):          # python round(): half to even, as the reference's int(round(.))
+            lo[:, a] = [int(round(v)) for v in (self.musX_init[:, a] - half[a]) * ext[a]]
+            hi[:, a] = [int(round(v)) for v in (self.musX_init[:, a] + half[a]) * ext[a]]
+        mean = np.empty((K, Cc), dtype=np.float32)
+        red = tuple(range(d))
+        for k in range(K):
+            block = self.image[tuple(slice(lo[k, a], hi[k, a]) for a in range(d))]
+            mean[k] = np.mean(block, axis=red)
+        self.nu_e_init = mean
+
+    def generate_pis(self, normalize_pis):
+        K = self.musX_init.shape[0]
+        self.pis_init = np.ones((K,), dtype=np.float32)
+        if normalize_pis:
+            self.pis_init = self.pis_init / K
+
+    @staticmethod
+    def get_batch_shape(desired_batches, joint_domain_shape):
+        """Divisor tiling with the smallest batch count >= desired_batches, most cube-like
+        (smoe.py:2459-2543; candidate order and tie-breaking as in the reference)."""
+        def divisors(n):
+            fac, nn, i = {}, n, 2
+            while i * i <= nn:
+                while nn % i == 0:
+                    fac[i] = fac.get(i, 0) + 1
+                    nn //= i
+                i += 1
+            if nn > 1:
+                fac[nn] = 1
+            out = [1]
+            for p in reversed(list(fac.keys())):       # innermost prime varies slowest
+                out = [o * p ** e for o in out for e in range(fac[p] + 1)]
+            return out
+        nd = len(joint_domain_shape)
+        factors = [divisors(joint_domain_shape[a]) for a in range(nd - 1)] + [[1]]
+        if nd > 4:
+            factors[0] = factors[1] = [1]
+        shapes = list(product(*factors))
+        counts = np.array([np.prod(s[:-1]) for s in shapes], dtype=np.float64)
+        diff = counts - desired_batches
+        diff[diff < 0] = np.inf
+        aimed = counts[int(np.argmin(diff))]
+        cand = [s for s, c in zip(shapes, counts) if c == aimed]
+        sums = [np.sum(c[2:3]) if len(c) > 4 else np.sum(c) for c in cand]
+        div = cand[int(np.argmin(sums))]
+        return tuple(int(joint_domain_shape[a] / div[a]) for a in range(nd))
+
+    # ------------------------------------------------------------------------------------------
+    # device state
+    # ------------------------------------------------------------------------------------------
+    def _init_device(self, dense_exec):
+        dev, f32 = self.device, torch.float32
+        d, Cc, K = self.dim_domain, self.image.shape[-1], self.start_pis
+        L = lib()
+        self._P = L.smoe_param_count(d, Cc)
+        self._PK = L.smoe_packed_stride(d, Cc)
+        self._T = d * (d + 1) // 2
+        self._off = dict(mu=0, A=d, pi=d + self._T, nu=d + self._T + 1, ga=d + self._T + 1 + Cc)
+        lb3 = float(self.lower_bounds[3]) if self.quantize_pis else 0.0
+        ub3 = float(self.upper_bounds[3]) if self.quantize_pis else 1.0
+        bits3 = int(self.bit_depths[3]) if self.quantize_pis else 8
+        self._cfg = Cfg(d, Cc, int(self.precision), float(self.margin), int(self.use_determinant),
+                        int(self.train_inverse_cov), int(self.use_yuv), int(self.train_gammas),
+                        int(self.only_y_gamma), int(self.quantize_pis), lb3, ub3, bits3, int(dense_exec))
+        # variables
+        A0 = np.asarray(self.A_init, dtype=np.float64)
+        theta = np.zeros((K, self._P), dtype=np.float32)
+        theta[:, 0:d] = self.musX_init
+        for l in range(d):
+            for m in range(l + 1):
+                theta[:, d + l * (l + 1) // 2 + m] = A0[:, l, m]
+        theta[:, self._off["pi"]] = self.pis_init
+        theta[:, self._off["nu"]:self._off["nu"] + Cc] = self.nu_e_init
+        theta[:, self._off["ga"]:] = np.asarray(self.gamma_e_init).reshape(K, d * Cc)
+        self._theta = torch.from_numpy(theta).to(dev)
+        self._theta_best = self._theta.clone()
+        self._grads = torch.zeros_like(self._theta)
+        self._adam_m = torch.zeros_like(self._theta)
+        self._adam_v = torch.zeros_like(self._theta)
+        self._group_owner = [None, None, None]
+        # image band resident on this rank + coordinate axes (np.linspace -> float32 feed, smoe.py:545)
+        b0, b1 = self._band
+        self._local_shape = (b1 - b0,) + tuple(self.image.shape[1:d])
+        self._dims3 = tuple(self._local_shape) + (1,) * (3 - d)
+        self._d_image = torch.from_numpy(np.ascontiguousarray(self.image[b0:b1])).to(dev)
+        axes = [np.linspace(0, 1, self.image.shape[a]).astype(np.float32) for a in range(d)]
+        axes[0] = axes[0][b0:b1]
+        self._d_axes = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in axes]
+        self._h_axes = axes
+        npx = int(np.prod(self._local_shape))
+        self._d_res = torch.zeros((npx, Cc), dtype=f32, device=dev)
+        self._d_res_pre = None
+        self._d_argmax = torch.zeros((npx,), dtype=torch.int32, device=dev)
+        # batches (smoe.py:1643: sliding_window order, first axis outermost)
+        self._tile = self._choose_tile()
+        self._batches = []
+        if self._world > 1:
+            rects = [((0,) * d, self._local_shape)]
+        else:
+            starts = [range(0, self.image.shape[a], self.batch_size_valued[a]) for a in range(d)]
+            rects = [(org, self.batch_size_valued) for org in product(*starts)]
+        max_tiles = 0
+        for org, ext in rects:
+            b = Batch()
+            for a in range(3):
+                b.dims[a] = self._dims3[a]
+                b.origin[a] = org[a] if a < d else 0
+                b.extent[a] = ext[a] if a < d else 1
+                b.tile[a] = self._tile[a]
+            npix = int(np.prod(ext)) if self._world == 1 else self.num_pixel
+            b.inv_count = 1.0 / npix
+            self._batches.append(b)
+            max_tiles = max(max_tiles, L.smoe_num_tiles(C.byref(b)))
+        nb = len(self._batches)
+        self._max_tiles = max_tiles
+        self._klist = torch.ones((nb, K), dtype=torch.uint8, device=dev)
+        self._packed = torch.zeros((K, self._PK), dtype=f32, device=dev)
+        self._indices = torch.zeros((K,), dtype=torch.int32, device=dev)
+        self._counts = torch.zeros((nb, 4), dtype=torch.int32, device=dev)
+        self._regsums = torch.zeros((nb, 2), dtype=f32, device=dev)
+        self._scalars = torch.zeros((nb, _ffi.NSCAL), dtype=f32, device=dev)
+        self._infl = torch.zeros((K,), dtype=torch.uint8, device=dev)
+        self._pix = torch.zeros((max_tiles * _ffi.TPIX * _ffi.PIXREC,), dtype=f32, device=dev)
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        self._partials = torch.zeros((2 * sms * 8,), dtype=f32, device=dev)
+        self._ticket = torch.zeros((4,), dtype=torch.int32, device=dev)
+        self._pack_ws = torch.zeros((L.smoe_pack_workspace_bytes(K) + 15) // 4, dtype=torch.int32, device=dev)
+        self._splits = int(L.smoe_suggest_splits(K, max_tiles))
+        self._raw_part = torch.zeros((self._splits * K * self._P,), dtype=f32, device=dev)
+        # [raw statistics | scalars | influence flags]: the buffer a multi-GPU run all-reduces
+        self._xbuf = torch.zeros((K * self._P + _ffi.NSCAL + K,), dtype=f32, device=dev)
+        self._host_stats = torch.zeros((nb, _ffi.NSCAL + 4 + 2), dtype=f32).pin_memory()
+        self.gpu_launches = 0
+
+    def _enable_res_pre(self):
+        """Keep the mixture output before clip / output quantisation (diagnostics and parity tests;
+        SURVEY.md decision D4 compares reconstructions pre-quantisation)."""
+        if self._d_res_pre is None:
+            self._d_res_pre = torch.zeros_like(self._d_res)
+
+    def get_pre_clip_reconstruction(self):
+        self._enable_res_pre()
+        self.run_batched(train=False, update_reconstruction=True)
+        return self._d_res_pre.reshape(self._local_shape + (self.image.shape[-1],)).cpu().numpy()
+
+    def _choose_tile(self):
+        d = self.dim_domain
+        if d == 2:
+            return (32, 32, 1)
+        T = self._local_shape[2]
+        t2 = 1
+        while t2 * 2 <= min(T, 8):
+            t2 *= 2
+        rest = _ffi.TPIX // t2
+        t1 = 16 if rest // 16 >= 8 else 8
+        return (rest // t1, t1, t2)
+
+    # kernel_list_per_batch is exposed as the reference's list of NumPy bool arrays
+    @property
+    def kernel_list_per_batch(self):
+        return [row.astype(bool) for row in self._klist.cpu().numpy()]
+
+    @kernel_list_per_batch.setter
+    def kernel_list_per_batch(self, value):
+        arr = np.stack([np.asarray(v, dtype=np.uint8) for v in value])
+        self._klist.copy_(torch.from_numpy(arr).to(self.device))
+
+    # ------------------------------------------------------------------------------------------
+    # optimizers (smoe.py:1079-1204)
+    # ------------------------------------------------------------------------------------------
+    def set_optimizer(self, optimizer1, optimizer2=None, optimizer3=None, optimizer4=None, optimizer5=None,
+                      grad_clip_value_abs=None):
+        new = [optimizer1, optimizer2 or optimizer1, optimizer3 or optimizer1]
+        self.optimizer1, self.optimizer2, self.optimizer3 = new
+        self.grad_clip_value_abs = grad_clip_value_abs
+        o = self._off
+        cols = {0: list(range(0, o["A"])) + list(range(o["nu"], self._P)), 1: [o["pi"]], 2: list(range(o["A"], o["pi"]))}
+        for g in range(3):
+            if self._group_owner[g] is not new[g]:          # a new optimizer object gets fresh slots
+                idx = torch.tensor(cols[g], device=self.device)
+                self._adam_m[:, idx] = 0
+                self._adam_v[:, idx] = 0
+                self._group_owner[g] = new[g]
+
+    def _adam_launch(self):
+        hp = Adam()
+        opts = [self.optimizer1, self.optimizer2, self.optimizer3]
+        trainable = [True, self.train_pis, True]
+        for g, (opt, tr) in enumerate(zip(opts, trainable)):
+            on = tr and not opt._lr == 0
+            hp.alpha[g] = opt._step_alpha() if on else 0.0
+            hp.beta1[g], hp.beta2[g], hp.epsilon[g] = opt._beta1, opt._beta2, opt._epsilon
+        hp.grad_clip = float(self.grad_clip_value_abs) if self.grad_clip_value_abs is not None else 0.0
+        hp.train_musx, hp.train_gammas = int(self.train_musx), int(self.train_gammas)
+        check(lib().smoe_adam_step(C.byref(self._cfg), C.byref(hp), ptr(self._theta), ptr(self._grads),
+                                   ptr(self._adam_m), ptr(self._adam_v), self.start_pis, stream_ptr()), "smoe_adam_step")
+        self.gpu_launches += 1
+
+    # ------------------------------------------------------------------------------------------
+    # the batched executor (smoe.py:1606-1793)
+    # ------------------------------------------------------------------------------------------
+    def run_batched(self, pis_l1=0, u_l1=0, sv_l1_sub_l2=0, train=True, update_reconstruction=False,
+                    with_quantized_params=False, sampling_percentage=100, with_inc=False, train_inc=False,
+                    thr_sv=None, use_loss_mask=False, _host_image=None):
+        if sampling_percentage < 100 or with_inc or train_inc or use_loss_mask:
+            raise NotImplementedError("sampling / inc / loss-mask paths are outside the hot path (D1)")
+        if train:
+            assert self.optimizer1 is not None, "no optimizer found, you have to specify one!"
+        L, st = lib(), stream_ptr()
+        self.valid = False
+        if with_quantized_params:
+            self.qvalid = False
+        if _host_image is not None:                      # e2e path: this step's pixels come from pinned host memory
+            self._d_image.copy_(_host_image, non_blocking=True)
+        K, P = self.start_pis, self._P
+        if train:
+            self._grads.zero_()
+        self._scalars.zero_()
+        fed = with_quantized_params and update_reconstruction
+        if fed:
+            rp = {k: torch.as_tensor(np.ascontiguousarray(np.asarray(v, dtype=np.float32)), device=self.device)
+                  for k, v in self.rparams.items()}
+            Kf = int(rp["pis"].shape[0])
+            if Kf > K:
+                raise ValueError("more fed kernels than model kernels")
+        norm = float(self.start_pis)
+        for ii, b in enumerate(self._batches):
+            counts, regs, scal = self._counts[ii], self._regsums[ii], self._scalars[ii]
+            if fed:
+                check(L.smoe_pack_fed(C.byref(self._cfg), ptr(rp["A"]), ptr(rp["musX"]), ptr(rp["nu_e"]),
+                                      ptr(rp["gamma_e"]), ptr(rp["pis"]), Kf, ptr(self._packed), ptr(counts), st),
+                      "smoe_pack_fed")
+                self._indices[:Kf] = torch.arange(Kf, dtype=torch.int32, device=self.device)
+                regs.zero_()
+                self.gpu_launches += 1
+            else:
+                check(L.smoe_pack(C.byref(self._cfg), ptr(self._theta), ptr(self._klist[ii]), K, ptr(self._packed),
+                                  ptr(self._indices), ptr(counts), ptr(regs), ptr(self._pack_ws), st), "smoe_pack")
+                self.gpu_launches += 3
+            self._infl.zero_()
+            check(L.smoe_forward(C.byref(self._cfg), C.byref(b), ptr(self._packed), ptr(self._indices), ptr(counts),
+                                 ptr(self._d_image), ptr(self._d_axes[0]), ptr(self._d_axes[1]),
+                                 ptr(self._d_axes[2]) if self.dim_domain == 3 else ptr(None),
+                                 ptr(self._d_res), ptr(self._d_res_pre),
+                                 ptr(self._d_argmax) if update_reconstruction else ptr(None),
+                                 ptr(self._infl), ptr(self._pix) if train else ptr(None), ptr(scal),
+                                 ptr(self._partials), ptr(self._ticket), st), "smoe_forward")
+            self.gpu_launches += 1
+            if train:
+                check(L.smoe_backward(C.byref(self._cfg), C.byref(b), ptr(self._packed), ptr(counts), K, ptr(self._pix),
+                                      ptr(self._d_axes[0]), ptr(self._d_axes[1]),
+                                      ptr(self._d_axes[2]) if self.dim_domain == 3 else ptr(None),
+                                      self._splits, ptr(self._raw_part), st), "smoe_backward")
+                self.gpu_launches += 1
+            if self._world > 1:
+                self._exchange(train, counts, scal)
+            if train:
+                l1 = float(pis_l1) / norm if not self.kernel_count_as_norm_l1 else None
+                if l1 is None:
+                    raise NotImplementedError("kernel_count_as_norm_l1")
+                raw, ns = (self._xbuf, 1) if self._world > 1 else (self._raw_part, self._splits)
+                check(L.smoe_grad_finalize(C.byref(self._cfg), ptr(raw), ns, K, ptr(self._theta), ptr(self._indices),
+                                           ptr(counts), C.c_float(l1), C.c_float(float(u_l1)), ptr(self._grads), st),
+                      "smoe_grad_finalize")
+                self.gpu_launches += 1
+            if not with_quantized_params:                 # smoe.py:1763-1766
+                check(L.smoe_update_kernel_list(ptr(self._indices), ptr(counts), ptr(self._infl), ptr(self._klist[ii]),
+                                                K, st), "smoe_update_kernel_list")
+                self.gpu_launches += 2
+        if train:
+            self._adam_launch()
+        # one small device->host read per call: scalars, counts, regulariser sums
+        nb = len(self._batches)
+        hs = self._host_stats
+        hs[:, :_ffi.NSCAL].copy_(self._scalars, non_blocking=True)
+        hs[:, _ffi.NSCAL:_ffi.NSCAL + 4].copy_(self._counts.to(torch.float32), non_blocking=True)
+        hs[:, _ffi.NSCAL + 4:].copy_(self._regsums, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        h = hs.numpy().astype(np.float64)
+        Cc = self.image.shape[-1]
+        loss_val = mse_val = 0.0
+        num_pi = -1
+        for ii, b in enumerate(self._batches):
+            inv_n = float(b.inv_count)
+            if self.use_yuv:                               # smoe.py:933-935
+                lp = 6 / 8 * h[ii, 0] * inv_n + 1 / 8 * sum(h[ii, c] * inv_n for c in range(1, Cc))
+            else:
+                lp = sum(h[ii, c] for c in range(Cc)) * inv_n / Cc
+            loss_b = lp + pis_l1 * h[ii, _ffi.NSCAL + 4] / norm + u_l1 * h[ii, _ffi.NSCAL + 5]
+            mse_b = h[ii, 4] * inv_n / Cc * ((2 ** self.precision) ** 2)
+            if h[ii, 5] > 0:
+                loss_b = float("nan")
+            frac = 1.0 if self._world > 1 else np.prod([b.extent[a] for a in range(self.dim_domain)]) / self.num_pixel
+            loss_val += loss_b * frac                       # smoe.py:1758-1759
+            mse_val += mse_b * frac
+            num_pi = int(h[ii, _ffi.NSCAL + 1])
+        self._last_nonpos = int(h[:, _ffi.NSCAL + 2].sum())
+        if update_reconstruction:
+            rec, amax = self._gather_reconstruction()
+            if with_quantized_params:
+                self.qreconstruction_image, self.qweight_matrix_argmax, self.qvalid = rec, amax, True
+            else:
+                self.reconstruction_image, self.weight_matrix_argmax, self.valid = rec, amax, True
+        return loss_val, mse_val, num_pi, 0
+
+    def _exchange(self, train, counts, scal):
+        """The one exchange step of the sharded path: sum over ranks of the
+        per-kernel statistics, the loss scalars and the influence flags."""
+        L, st = lib(), stream_ptr()
+        K, P = self.start_pis, self._P
+        if train:
+            check(L.smoe_reduce_splits(C.byref(self._cfg), ptr(counts), K, self._splits, ptr(self._raw_part),
+                                       ptr(self._xbuf), st), "smoe_reduce_splits")
+            self.gpu_launches += 1
+        else:
+            self._xbuf[:K * P].zero_()
+        self._xbuf[K * P:K * P + _ffi.NSCAL] = scal
+        self._xbuf[K * P + _ffi.NSCAL:] = self._infl.to(torch.float32)
+        torch.distributed.all_reduce(self._xbuf, group=self._pg)
+        scal.copy_(self._xbuf[K * P:K * P + _ffi.NSCAL])
+        self._infl.copy_((self._xbuf[K * P + _ffi.NSCAL:] > 0).to(torch.uint8))
+
+    def _gather_reconstruction(self):
+        Cc = self.image.shape[-1]
+        res = self._d_res.reshape(self._local_shape + (Cc,))
+        amax = self._d_argmax.reshape(self._local_shape)
+        if self._world > 1:
+            # bands can differ by one row: gather through a padded buffer
+            n0 = self.image.shape[0]
+            rows = [n0 * (r + 1) // self._world - n0 * r // self._world for r in range(self._world)]
+            mr = max(rows)
+            pad_res = torch.zeros((mr,) + tuple(res.shape[1:]), dtype=res.dtype, device=self.device)
+            pad_res[:res.shape[0]] = res
+            pad_am = torch.zeros((mr,) + tuple(amax.shape[1:]), dtype=amax.dtype, device=self.device)
+            pad_am[:amax.shape[0]] = amax
+            out_r = [torch.empty_like(pad_res) for _ in range(self._world)]
+            out_a = [torch.empty_like(pad_am) for _ in range(self._world)]
+            torch.distributed.all_gather(out_r, pad_res, group=self._pg)
+            torch.distributed.all_gather(out_a, pad_am, group=self._pg)
+            res = torch.cat([o[:r] for o, r in zip(out_r, rows)], dim=0)
+            amax = torch.cat([o[:r] for o, r in zip(out_a, rows)], dim=0)
+        rec = res.cpu().numpy()
+        am = amax.cpu().numpy().astype(np.float64)
+        if (am < 0).any():
+            # tf.argmax over the influential kernels returns position 0 when every gate is zero:
+            # the lowest-index influential kernel of the batch (smoe.py:833-836, 1716)
+            infl_idx = self._indices[self._infl.to(torch.bool)[:self._indices.shape[0]]]
+            fill = float(infl_idx.min().item()) if infl_idx.numel() else 0.0
+            am[am < 0] = fill
+        return rec, am
+
+    # ------------------------------------------------------------------------------------------
+    # train loop (smoe.py:1485-1603)
+    # ------------------------------------------------------------------------------------------
+    def train(self, num_iter, val_iter=100, ukl_iter=None, optimizer1=None, optimizer2=None, optimizer3=None,
+              grad_clip_value_abs=None, pis_l1=0, u_l1=0, sv_l1_sub_l2=0, sampling_percentage=100, callbacks=(),
+              with_inc=False, train_inc=False, train_orig=True, use_loss_mask=False):
+        if ukl_iter is None:
+            ukl_iter = val_iter
+        if optimizer1:
+            self.set_optimizer(optimizer1, optimizer2, optimizer3, grad_clip_value_abs=grad_clip_value_abs)
+        assert self.optimizer1 is not None, "no optimizer found, you have to specify one!"
+        if self.quantization_mode >= 1:
+            self.qparams = quantize_params(self, self.get_params())
+        if self.quantization_mode == 1:
+            self.rparams = rescaler(self, self.qparams)
+            self.best_qloss, self.best_qmse, _, _ = self.run_batched(
+                pis_l1=pis_l1, u_l1=u_l1, train=False, update_reconstruction=True, with_quantized_params=True)
+            self.qlosses.append((0, self.best_qloss))
+            self.qmses.append((0, self.best_qmse))
+        self.best_loss, self.best_mse, num_pi, num_sv = self.run_batched(
+            pis_l1=pis_l1, u_l1=u_l1, train=False, update_reconstruction=True)
+        self.losses.append((self.iter, self.best_loss))
+        self.mses.append((self.iter, self.best_mse))
+        self.num_pis.append((self.iter, num_pi))
+        self.num_svs.append((self.iter, num_sv))
+        for callback in callbacks:
+            callback(self)
+        loss_val = mse_val = None
+        i = 0
+        for i in range(1, num_iter + 1):
+            self.iter += 1
+            try:
+                validate = i % val_iter == 0
+                update_kl = i % ukl_iter == 0
+                loss_val, mse_val, num_pi, num_sv = self.run_batched(
+                    pis_l1=pis_l1, u_l1=u_l1, train=train_orig, update_reconstruction=False,
+                    sampling_percentage=sampling_percentage)
+                if update_kl:
+                    self.update_kernel_list(self.add_kernel_slots)
+                    if not validate:
+                        loss_val, mse_val, num_pi, num_sv = self.run_batched(
+                            pis_l1=pis_l1, u_l1=u_l1, train=False, update_reconstruction=False)
+                if validate:
+                    if self.quantization_mode >= 1:
+                        self.qparams = quantize_params(self, self.get_params())
+                    if self.quantization_mode == 1:
+                        self.rparams = rescaler(self, self.qparams)
+                        qloss_val, qmse_val, _, _ = self.run_batched(
+                            pis_l1=pis_l1, u_l1=u_l1, train=False, update_reconstruction=True,
+                            with_quantized_params=True)
+                    loss_val, mse_val, num_pi, num_sv = self.run_batched(
+                        pis_l1=pis_l1, u_l1=u_l1, train=False, update_reconstruction=True)
+                if np.isnan(loss_val) or (len(self.losses) > 0 and loss_val + 1 > (self.losses[0][1] + 100) * 10):
+                    print("stop")
+                    break
+                if validate:
+                    if not self.best_loss or loss_val < self.best_loss:
+                        self.best_loss = loss_val
+                        self._theta_best.copy_(self._theta)       # checkpoint_best_op, smoe.py:861-896
+                    self.losses.append((self.iter, loss_val))
+                    if not self.best_mse or mse_val < self.best_mse:
+                        self.best_mse = mse_val
+                    self.mses.append((self.iter, mse_val))
+                    if self.quantization_mode == 1:
+                        self.qmses.append((i, qmse_val))
+                        self.qlosses.append((i, qloss_val))
+                    self.num_pis.append((self.iter, num_pi))
+                    self.num_svs.append((self.iter, num_sv))
+                    for callback in callbacks:
+                        callback(self)
+            except KeyboardInterrupt:
+                break
+        self.losses_history.append(self.losses)
+        self.mses_history.append(self.mses)
+        print("end loss/mse: ", loss_val, "/", mse_val, "@iter: ", i)
+        print("best loss/mse: ", self.best_loss, "/", self.best_mse)
+
+    # ------------------------------------------------------------------------------------------
+    # kernel lists (smoe.py:2287-2365): OR in every pi>0 kernel with maha < 800 at the 3^d
+    # corner / mid points of each batch.  Host-side control, not on the hot path: torch ops.
+    # ------------------------------------------------------------------------------------------
+    def update_kernel_list(self, add_kernel_slots=0):
+        d = self.dim_domain
+        A = self._assembled_A()
+        mu = self._theta[:, 0:d]
+        pis = self._effective_pis()
+        full_axes = [np.linspace(0, 1, self.image.shape[a]) for a in range(d)]
+        rects = self._batch_rects()
+        for ii, (org, ext) in enumerate(rects):
+            pts = []
+            for a in range(d):
+                lo, hi = full_axes[a][org[a]], full_axes[a][org[a] + ext[a] - 1]
+                pts.append([lo, hi, (lo + hi) / 2])
+            probe = torch.tensor(list(product(*pts)), dtype=torch.float32, device=self.device)      # (3^d, d)
+            delta = probe[None, :, :] - mu[:, None, :]
+            if self.train_inverse_cov:
+                maha = torch.einsum("knl,klm,knm->kn", delta, A, delta)
+            else:
+                y = torch.einsum("klm,knl->knm", A, delta)
+                maha = (y * y).sum(-1)
+            near = ((maha < 800).any(dim=1) & (pis > 0)).to(torch.uint8)
+            self._klist[ii] |= near
+
+    def _batch_rects(self):
+        d = self.dim_domain
+        if self._world > 1:
+            return [((self._band[0],) + (0,) * (d - 1), self._local_shape)]
+        starts = [range(0, self.image.shape[a], self.batch_size_valued[a]) for a in range(d)]
+        return [(org, self.batch_size_valued) for org in product(*starts)]
+
+    def _assembled_A(self):
+        d, K = self.dim_domain, self.start_pis
+        A = torch.zeros((K, d, d), dtype=torch.float32, device=self.device)
+        for l in range(d):
+            for m in range(l + 1):
+                A[:, l, m] = self._theta[:, d + l * (l + 1) // 2 + m]
+                if self.train_inverse_cov and m < l:
+                    A[:, m, l] = A[:, l, m]
+        return A
+
+    def _effective_pis(self, theta=None):
+        theta = self._theta if theta is None else theta
+        pis = theta[:, self._off["pi"]]
+        if self.quantize_pis:
+            pis = _fake_quant_torch(pis, self.lower_bounds[3], self.upper_bounds[3], self.bit_depths[3])
+        return pis
+
+    # ------------------------------------------------------------------------------------------
+    # params dict (smoe.py:1795-1849), checkpoints (smoe.py:1066-1077)
+    # ------------------------------------------------------------------------------------------
+    def _params_from(self, theta):
+        d, Cc, K, o = self.dim_domain, self.image.shape[-1], self.start_pis, self._off
+        pis = self._effective_pis(theta).cpu().numpy().copy()
+        th = theta.cpu().numpy()
+        A_diag = np.zeros((K, d, d), dtype=np.float32)
+        A_corr = np.zeros((K, d, d), dtype=np.float32)
+        for l in range(d):
+            for m in range(l + 1):
+                (A_diag if l == m else A_corr)[:, l, m] = th[:, d + l * (l + 1) // 2 + m]
+        return {"pis": pis, "musX": th[:, 0:d].copy(), "A_diagonal": A_diag, "A_corr": A_corr,
+                "gamma_e": th[:, o["ga"]:].reshape(K, d, Cc).copy(), "nu_e": th[:, o["nu"]:o["nu"] + Cc].copy()}
+
+    def get_params(self):
+        return self._params_from(self._theta)
+
+    def get_best_params(self):
+        return self._params_from(self._theta_best)
+
+    def set_params(self, params):
+        """Replacement for the reference's `session.run(re_assign_*_op)` pokes: assign any subset of
+        the K_all-sized variables."""
+        d, Cc, K, o = self.dim_domain, self.image.shape[-1], self.start_pis, self._off
+        th = self._theta.cpu().numpy()
+        if "musX" in params:
+            th[:, 0:d] = params["musX"]
+        for l in range(d):
+            for m in range(l + 1):
+                key = "A_diagonal" if l == m else "A_corr"
+                if key in params:
+                    th[:, d + l * (l + 1) // 2 + m] = np.asarray(params[key])[:, l, m]
+        if "pis" in params:
+            th[:, o["pi"]] = params["pis"]
+        if "nu_e" in params:
+            th[:, o["nu"]:o["nu"] + Cc] = params["nu_e"]
+        if "gamma_e" in params:
+            th[:, o["ga"]:] = np.asarray(params["gamma_e"]).reshape(K, d * Cc)
+        self._theta.copy_(torch.from_numpy(th).to(self.device))
+        self.valid = self.qvalid = False
+
+    def get_gradients(self):
+        """Accumulated gradients of the last training pass, in the params-dict layout.  (The reference
+        leaves this a stub, smoe.py:1812-1813; exposed here because parity is tested on it.)"""
+        d, Cc, K, o = self.dim_domain, self.image.shape[-1], self.start_pis, self._off
+        g = self._grads.cpu().numpy()
+        A_diag = np.zeros((K, d, d), dtype=np.float32)
+        A_corr = np.zeros((K, d, d), dtype=np.float32)
+        for l in range(d):
+            for m in range(l + 1):
+                (A_diag if l == m else A_corr)[:, l, m] = g[:, d + l * (l + 1) // 2 + m]
+        return {"pis": g[:, o["pi"]].copy(), "musX": g[:, 0:d].copy(), "A_diagonal": A_diag, "A_corr": A_corr,
+                "gamma_e": g[:, o["ga"]:].reshape(K, d, Cc).copy(), "nu_e": g[:, o["nu"]:o["nu"] + Cc].copy()}
+
+    def checkpoint(self, path):
+        torch.save({"theta": self._theta.cpu(), "theta_best": self._theta_best.cpu(), "adam_m": self._adam_m.cpu(),
+                    "adam_v": self._adam_v.cpu(), "klist": self._klist.cpu(), "iter": self.iter,
+                    "adam_t": [o._t if o is not None else 0 for o in (self.optimizer1, self.optimizer2, self.optimizer3)]},
+                   path)
+        print("Model saved in file: %s" % path)
+
+    def restore(self, path):
+        cp = torch.load(path, map_location="cpu")
+        for name in ("theta", "theta_best", "adam_m", "adam_v", "klist"):
+            getattr(self, "_" + name).copy_(cp[name].to(self.device))
+        self.iter = cp["iter"]
+        for o, t in zip((self.optimizer1, self.optimizer2, self.optimizer3), cp["adam_t"]):
+            if o is not None:
+                o._t = t
+        self.valid = self.qvalid = False
+        print("Model restored from file: %s" % path)
+
+    # ------------------------------------------------------------------------------------------
+    # getters (smoe.py:1815-1888)
+    # ------------------------------------------------------------------------------------------
+    def get_reconstruction(self):
+        if not self.valid:
+            self.run_batched(train=False, update_reconstruction=True)
+        return self.reconstruction_image
+
+    def get_qreconstruction(self):
+        if not self.qvalid:
+            self.run_batched(train=False, update_reconstruction=True, with_quantized_params=True)
+        return self.qreconstruction_image
+
+    def get_weight_matrix_argmax(self):
+        if not self.valid:
+            self.run_batched(train=False, update_reconstruction=True)
+        return self.weight_matrix_argmax
+
+    def get_weight_matrix(self):
+        """Dense (K_all, *image.shape[:-1]) gate matrix.  The reference allocates it on EVERY
+        run_batched call (smoe.py:1632); here it is materialised only on request, with torch ops
+        (not the hot path), and refuses sizes that cannot fit."""
+        d, K = self.dim_domain, self.start_pis
+        if K * self.num_pixel > 2 ** 31:
+            raise MemoryError("dense weight matrix too large; use get_weight_matrix_argmax()")
+        if self._world > 1:
+            raise NotImplementedError("dense weight matrix on a sharded model")
+        out = torch.zeros((K, self.num_pixel), dtype=torch.float32, device=self.device)
+        A, mu, pis = self._assembled_A(), self._theta[:, 0:d], self._effective_pis()
+        grids = torch.meshgrid(*[torch.linspace(0, 1, n, dtype=torch.float64).to(torch.float32) for n in self.image.shape[:d]],
+                               indexing="ij")
+        dom_full = torch.stack(grids, dim=-1).to(self.device)
+        for ii, (org, ext) in enumerate(self._batch_rects()):
+            sl = tuple(slice(o, o + e) for o, e in zip(org, ext))
+            dom = dom_full[sl].reshape(-1, d)
+            act = (self._klist[ii] > 0) & (pis > 0)
+            idx = torch.nonzero(act).flatten()
+            delta = dom[None] - mu[idx][:, None]
+            if self.train_inverse_cov:
+                maha = torch.einsum("knl,klm,knm->kn", delta, A[idx], delta)
+            else:
+                y = torch.einsum("klm,knl->knm", A[idx], delta)
+                maha = (y * y).sum(-1)
+            n = torch.exp(-0.5 * maha) * pis[idx][:, None]
+            if self.use_determinant:
+                n = n * (torch.diagonal(A[idx], dim1=1, dim2=2).prod(-1) / math.sqrt((2 * math.pi) ** d))[:, None]
+            w = n / torch.clamp_min(n.sum(0), 10e-12)
+            w = w * (w > 0.5 / 2 ** self.precision)
+            lin = torch.arange(self.num_pixel, device=self.device).reshape(self.image.shape[:d])[sl].reshape(-1)
+            out[idx[:, None], lin[None, :]] = w
+        return out.reshape((K,) + tuple(self.image.shape[:d])).cpu().numpy().astype(np.float64)
+
+    def get_best_reconstruction(self):
+        raise NotImplementedError
+
+    def get_best_weight_matrix(self):
+        raise NotImplementedError
+
+    def get_losses(self):
+        return self.losses
+
+    def get_qlosses(self):
+        return self.qlosses
+
+    def get_best_loss(self):
+        return self.best_loss
+
+    def get_losses_history(self):
+        return self.losses_history
+
+    def get_mses(self):
+        return self.mses
+
+    def get_qmses(self):
+        return self.qmses
+
+    def get_best_mse(self):
+        return self.best_mse
+
+    def get_mses_history(self):
+        return self.mses_history
+
+    def get_num_pis(self):
+        return self.num_pis
+
+    def get_num_svs(self):
+        return self.num_svs
+
+    def get_original_image(self):
+        return np.squeeze(self.image)
+
+    def get_iter(self):
+        return self.iter
+
+    # ------------------------------------------------------------------------------------------
+    # GPU metrics (north_star item 4): PSNR from the graph's mse_op, SSIM of ops/image_ops_impl.py
+    # ------------------------------------------------------------------------------------------
+    def psnr(self, quantized=False):
+        from .utils import psnr
+        rec = self.get_qreconstruction() if quantized else self.get_reconstruction()
+        from .ops.image_ops_impl import mse_gpu
+        return psnr(mse_gpu(rec, self.image, device=self.device) * (2 ** self.precision) ** 2, self.precision)
+
+    def ssim(self, quantized=False):
+        from .ops.image_ops_impl import smoe_ssim
+        rec = self.get_qreconstruction() if quantized else self.get_reconstruction()
+        return smoe_ssim(rec, self.image, use_yuv=self.use_yuv, device=self.device)
+
+
+def _fake_quant_torch(x, mn, mx, bits):
+    """TF fake_quant_with_min_max_args values (float32), for get_params (smoe.py:1796-1798)."""
+    f = np.float32
+    qmax = f(2 ** bits - 1)
+    scale = (f(mx) - f(mn)) / qmax
+    zp = f(0) - f(mn) / scale
+    nzp = f(0) if zp < 0 else (qmax if zp > qmax else f(np.floor(zp + f(0.5))))
+    nmin, nmax = float((f(0) - nzp) * scale), float((qmax - nzp) * scale)
+    inv = float(f(1) / scale)
+    c = torch.clamp(x, nmin, nmax)
+    return torch.floor((c - nmin) * inv + 0.5) * float(scale) + nmin

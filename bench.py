@@ -221,10 +221,13 @@ def run_ours(args):
             ms.append(float(t.item()))
         return ms
 
-    timed_steps(max(args.warmup, 3))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    timed_steps(max(args.warmup, 3))
+    if rank == 0:
+        time.sleep(0.3)
+        sampler.rows.clear()          # keep only the samples taken during the timed region
     l0 = m.gpu_launches
     ms = timed_steps(args.steps)
     launches = (m.gpu_launches - l0) // max(args.steps, 1)

@@ -155,7 +155,8 @@ def _maha(x_sub_mu, A, train_inverse_cov, mode):
 
 def graph_forward(params: Dict[str, torch.Tensor], kernel_list, domain, target, cfg: GraphCfg,
                   pis_l1=0.0, u_l1=0.0, loss_weights=None, musX_grid=None,
-                  feed: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+                  feed: Optional[Dict[str, torch.Tensor]] = None,
+                  resq_override: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """One `session.run` of the reference graph on one batch of pixels.
 
     params : K_all-sized variables (pis, musX, A_diagonal, A_corr, gamma_e, nu_e)
@@ -163,6 +164,10 @@ def graph_forward(params: Dict[str, torch.Tensor], kernel_list, domain, target, 
     domain : (N,d) pixel coordinates, target : (N,C) colours
     feed : optional {A, musX, nu_e, gamma_e, pis} fed *over* the compacted tensors
            (with_quantized_params, smoe.py:1688-1689)
+    resq_override : optional (N,C) values to use as the fake-quant OUTPUT (the straight-through
+           gradient path is unchanged).  Lets a test evaluate the gradient conditional on another
+           implementation's rounding decisions, which differ legitimately for pixels that sit
+           within float32 noise of a rounding boundary.
     """
     dt = domain.dtype
     d, C = cfg.dim_domain, cfg.num_channels
@@ -234,6 +239,8 @@ def graph_forward(params: Dict[str, torch.Tensor], kernel_list, domain, target, 
     res = _ClipByValue01.apply(r_pre).t()                                    # smoe.py:857-858 -> (N,C)
 
     resq = fake_quant_args(res, 0.0, 1.0, cfg.precision)                     # smoe.py:899
+    if resq_override is not None:
+        resq = resq + (resq_override.to(dt) - resq).detach()
     diff = resq - target                                                     # smoe.py:905
     sq = diff * diff
     err_map = sq.mean(dim=1)                                                 # smoe.py:906

@@ -203,7 +203,7 @@ def golden_graph():
              "musX": mus + rs.normal(0, 0.01, mus.shape),
              "A_diagonal": np.where(np.eye(d, dtype=bool)[None], A * rs.uniform(0.8, 1.2, A.shape), 0.0),
              "A_corr": np.where(np.tril(np.ones((d, d), bool), -1)[None],
-                                rs.normal(0, 0.15 * A.max(), A.shape) if c["steer"] else 0.0, 0.0),
+                                rs.normal(0, 0.15 * A.max(), A.shape) if c["steer"] else np.zeros(A.shape), 0.0),
              "gamma_e": rs.normal(0, 0.3, ga.shape), "nu_e": nu.astype(np.float64)}
         p["pis"][rs.choice(K, 2, replace=False)] = [0.0, -0.01]          # pruned kernels
         # round to float32 so float32 implementations start from identical values

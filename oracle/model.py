@@ -142,7 +142,7 @@ class OracleSmoe:
 
     # -- the batched executor -----------------------------------------------------------
     def run_batched(self, pis_l1=0, u_l1=0, train=True, update_reconstruction=False,
-                    with_quantized_params=False):
+                    with_quantized_params=False, resq_override=None):
         self.valid = False
         if with_quantized_params:
             self.qvalid = False
@@ -160,8 +160,12 @@ class OracleSmoe:
             feed = None
             if with_quantized_params and update_reconstruction:
                 feed = {k: torch.tensor(np.asarray(v), dtype=self.dtype) for k, v in self.rparams.items()}
+            ovr = None
+            if resq_override is not None:
+                sl = tuple(slice(int(c), int(c) + b) for c, b in zip(coord, self.batch_size_valued))
+                ovr = torch.tensor(np.asarray(resq_override)[sl].reshape(-1, self.image.shape[-1]), dtype=self.dtype)
             out = graph_forward(leaf, self.kernel_list_per_batch[ii], domain, target, self.cfg,
-                                pis_l1, u_l1, musX_grid=self.musX_grid, feed=feed)
+                                pis_l1, u_l1, musX_grid=self.musX_grid, feed=feed, resq_override=ovr)
             if train and trainable:
                 gs = torch.autograd.grad(out["loss"], [leaf[n] for n in trainable], allow_unused=True)
                 for n, g in zip(trainable, gs):

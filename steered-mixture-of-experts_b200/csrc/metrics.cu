@@ -103,8 +103,8 @@ __global__ void __launch_bounds__(256) sqerr_kernel(const float* __restrict__ a,
                                                     double* __restrict__ partial) {
     double acc = 0.0;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
-        const float d = a[i] - b[i];
-        acc += (double)d * (double)d;
+        const double d = (double)a[i] - (double)b[i];
+        acc += d * d;
     }
     __shared__ double s[256];
     s[threadIdx.x] = acc;

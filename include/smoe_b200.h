@@ -45,7 +45,7 @@ extern "C" {
 #endif
 
 #define SMOE_ABI_VERSION 1
-#define SMOE_TPIX 1024     /* pixels per tile (compile-time constant of the kernels) */
+#define SMOE_TPIX 512      /* pixels per tile (compile-time constant of the kernels) */
 #define SMOE_PIXREC 8      /* floats per pixel record */
 #define SMOE_NSCAL 16      /* floats in the scalar block */
 
@@ -134,7 +134,7 @@ int smoe_pack_fed(const smoe_cfg* cfg, const float* A /*[K][d][d]*/, const float
 int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const float* packed, const int32_t* indices,
                  const int32_t* counts, const float* image, const float* ax0, const float* ax1,
                  const float* ax2, float* res, float* res_pre, int32_t* argmax, uint8_t* infl,
-                 float* pix, float* scalars, float* partials /*[num_sms*8][8]*/, int32_t* ticket,
+                 float* pix, float* scalars, float* partials /*[num_sms*4][8]*/, int32_t* ticket,
                  void* stream);
 
 /* Fused backward over one batch: recomputes the gates from the per-pixel state and reduces the

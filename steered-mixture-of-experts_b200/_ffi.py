@@ -13,7 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsmoe_b200.so")
 
-TPIX = 1024
+TPIX = 512
 PIXREC = 8
 NSCAL = 16
 

@@ -3,8 +3,8 @@
 //
 // Kernel-stationary: a thread owns ONE kernel (its record and 2*P accumulators live in
 // registers), a CTA owns 256 consecutive kernels and a 1/num_splits share of the pixel tiles.
-// Pixel state written by the forward ([tile][1024][8] floats: tile-centred x, 1/S, gr, g_c)
-// arrives by TMA bulk copies (32 KB per tile, double buffered) and is broadcast to all threads
+// Pixel state written by the forward ([tile][512][8] floats: tile-centred x, log2(tau*S) | gr, g_c)
+// arrives by TMA bulk copies (16 KB per tile, double buffered) and is broadcast to all threads
 // from shared memory, so the per-kernel reductions over pixels happen in registers with no
 // shuffles and no atomics.  Per (pixel, kernel): recompute the gate (T+d FFMA + ex2), then
 //     t = w (m gE - gr)            [SURVEY 8a-8: dL/dlog(n_w)]
@@ -13,8 +13,10 @@
 // kernel-centred moments (sum t delta, sum t delta delta^T) so that no cancellation against
 // the absolute position builds up.  The chain rule to (mu, A, pi, nu, gamma) is applied once
 // per kernel in smoe_grad_finalize from these P numbers -- for both maha forms.
-// The expert part (gE, sum m w g ...) is skipped for a warp when none of its 32 kernels passes
-// the threshold at that pixel (exact zeros; cfg.dense_exec = 1 executes everything).
+// Exact-zero skipping (bit-identical to cfg.dense_exec = 1): the gate is w = tau * 2^(q - qthr)
+// with qthr = log2(tau*S) from the forward; a group of 4 pixels is skipped after its logits when
+// all 32 kernels of the warp have q - qthr < -126 (ex2.approx.ftz gives exactly +0 there), and
+// the expert part (gE, sum m w g ...) runs only when some kernel of the warp passes the threshold.
 #include "smoe_common.cuh"
 
 namespace smoe {
@@ -168,50 +170,65 @@ __global__ void __launch_bounds__(kThreads, 2) backward_kernel(const BwdArgs a) 
 
         if (buf) { mbar_wait(&bar[1], phase1); phase1 ^= 1; } else { mbar_wait(&bar[0], phase0); phase0 ^= 1; }
         const float4* px = reinterpret_cast<const float4*>(buf ? buf1 : buf0);
-#pragma unroll 4
-        for (int j = 0; j < SMOE_TPIX; ++j) {
-            const float4 p0 = px[2 * j], p1 = px[2 * j + 1];
-            const float xx[3] = {p0.x, p0.y, p0.z};
-            float x[D];
+        constexpr int GRP = 4;          // pixels tested together for the exact-zero skip
+        for (int j0 = 0; j0 < SMOE_TPIX; j0 += GRP) {
+            float xg[GRP][D], dq[GRP];
+            float dmax = -INFINITY;
 #pragma unroll
-            for (int l = 0; l < D; ++l) x[l] = xx[l];
-            const float invS = p0.w, gr = p1.x;
-            const float g[3] = {p1.y, p1.z, p1.w};
-            // gate logit (Horner), gate
-            float q = f[R::OC];
+            for (int u = 0; u < GRP; ++u) {
+                const float4 p0 = px[2 * (j0 + u)];
+                const float xx[3] = {p0.x, p0.y, p0.z};
 #pragma unroll
-            for (int l = 0; l < D; ++l) {
-                float tq = f[R::OL + l];
+                for (int l = 0; l < D; ++l) xg[u][l] = xx[l];
+                // gate logit (Horner) relative to the pixel's threshold: dq = q - log2(tau*S)
+                float q = f[R::OC];
 #pragma unroll
-                for (int m = l; m < D; ++m) tq = fmaf(f[R::OQ + ut(D, l, m)], x[m], tq);
-                q = fmaf(tq, x[l], q);
-            }
-            const float w = ex2f(q) * invS;
-            float t = -w * gr;
-            const bool pass = w > a.tau;
-            if (__any_sync(0xffffffffu, pass) || a.cfg.dense_exec) {
-                const float wm = pass ? w : 0.f;
-                float gE = 0.f;
+                for (int l = 0; l < D; ++l) {
+                    float tq = f[R::OL + l];
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    float E = f[R::ONU + c];
-#pragma unroll
-                    for (int l = 0; l < D; ++l) E = fmaf(f[R::OGA + l * C + c], x[l], E);
-                    gE = fmaf(g[c], E, gE);
-                    const float vc = wm * g[c];
-                    N0[c] += vc;
-#pragma unroll
-                    for (int l = 0; l < D; ++l) N1[l][c] = fmaf(vc, x[l], N1[l][c]);
+                    for (int m = l; m < D; ++m) tq = fmaf(f[R::OQ + ut(D, l, m)], xg[u][m], tq);
+                    q = fmaf(tq, xg[u][l], q);
                 }
-                t = fmaf(wm, gE, t);
+                dq[u] = q - p0.w;
+                dmax = fmaxf(dmax, dq[u]);
             }
-            M0 += t;
+            // w = tau * 2^dq is exactly +0 for dq < -126 (ex2.approx.ftz): nothing to accumulate
+            if (!__any_sync(0xffffffffu, dmax >= -126.0f) && !a.cfg.dense_exec) continue;
 #pragma unroll
-            for (int l = 0; l < D; ++l) {
-                const float u = t * x[l];
-                M1[l] += u;
+            for (int u = 0; u < GRP; ++u) {
+                const float4 p1 = px[2 * (j0 + u) + 1];
+                const float gr = p1.x;
+                const float g[3] = {p1.y, p1.z, p1.w};
+                float x[D];
 #pragma unroll
-                for (int m = l; m < D; ++m) M2[ut(D, l, m)] = fmaf(u, x[m], M2[ut(D, l, m)]);
+                for (int l = 0; l < D; ++l) x[l] = xg[u][l];
+                const float w = a.tau * ex2f(dq[u]);
+                float t = -w * gr;
+                const bool pass = dq[u] > 0.f;
+                if (__any_sync(0xffffffffu, pass) || a.cfg.dense_exec) {
+                    const float wm = pass ? w : 0.f;
+                    float gE = 0.f;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        float E = f[R::ONU + c];
+#pragma unroll
+                        for (int l = 0; l < D; ++l) E = fmaf(f[R::OGA + l * C + c], x[l], E);
+                        gE = fmaf(g[c], E, gE);
+                        const float vc = wm * g[c];
+                        N0[c] += vc;
+#pragma unroll
+                        for (int l = 0; l < D; ++l) N1[l][c] = fmaf(vc, x[l], N1[l][c]);
+                    }
+                    t = fmaf(wm, gE, t);
+                }
+                M0 += t;
+#pragma unroll
+                for (int l = 0; l < D; ++l) {
+                    const float uu = t * x[l];
+                    M1[l] += uu;
+#pragma unroll
+                    for (int m = l; m < D; ++m) M2[ut(D, l, m)] = fmaf(uu, x[m], M2[ut(D, l, m)]);
+                }
             }
         }
         __syncthreads();       // everyone is done with this buffer

@@ -1,7 +1,7 @@
 // Fused SMoE forward (smoe_forward).  Replaces smoe.py:777-858, 899-937, 1053.
 //
-// Pixel-stationary: a CTA owns a spatially compact tile of SMOE_TPIX pixels (4 per thread, in
-// registers) and streams ALL active kernels past it twice:
+// Pixel-stationary: a CTA (128 threads, 4 resident per SM) owns a spatially compact tile of
+// SMOE_TPIX = 512 pixels (4 per thread, in registers) and streams ALL active kernels past it twice:
 //   sweep A  S_n = sum_k 2^{q_k(x_n)}                       (the normaliser of smoe.py:819-821)
 //   sweep B  w = 2^{q}/S, m = w > tau, r_c += m*w*E_kc(x)   (smoe.py:823-848; needs the FINAL S,
 //            and gates are not renormalised after thresholding, so one sweep is not enough)
@@ -13,9 +13,12 @@
 // The N x K gate matrix is never materialised.  FP32 FFMA + MUFU.EX2 bound; no tensor cores
 // (inner dimensions are d = 2..3 and C = 1..3).
 //
-// Sweep B skips the expert part for a warp when none of its 128 (pixel, kernel) gates passes the
-// threshold (>99.8 % of the pairs at the benchmark shapes); the skipped terms are exact zeros,
-// so results are identical to dense execution (cfg.dense_exec = 1 executes everything).
+// Exact-zero skipping (results are bit-identical to dense execution, cfg.dense_exec = 1):
+//   sweep A skips ex2 + add for a thread-iteration whose 4 logits are all < -126, where
+//     ex2.approx.ftz returns exactly +0;
+//   sweep B tests the threshold in the log domain, q > log2(tau*S), so it needs no ex2 at all
+//     unless a gate passes (<0.2 % of the pairs at the benchmark shapes), and skips the expert
+//     part otherwise.
 #include "smoe_common.cuh"
 
 namespace smoe {
@@ -109,7 +112,7 @@ struct FwdArgs {
 };
 
 template <int D, int C>
-__global__ void __launch_bounds__(kThreads, 2) forward_kernel(const FwdArgs a) {
+__global__ void __launch_bounds__(kThreadsF, 4) forward_kernel(const FwdArgs a) {
     using R = Rec<D, C>;
     constexpr int PK = pstride(D, C);
     constexpr int PPT = kPixPerThread;
@@ -118,7 +121,7 @@ __global__ void __launch_bounds__(kThreads, 2) forward_kernel(const FwdArgs a) {
     float* raw1 = raw0 + kChunk * PK;
     float* crec = raw1 + kChunk * PK;
     uint64_t* bar = reinterpret_cast<uint64_t*>(crec + kChunk * R::RC);
-    float* red = reinterpret_cast<float*>(bar + 2);          // [8 warps][8]
+    float* red = reinterpret_cast<float*>(bar + 2);          // [warps][8]
 
     const int tid = threadIdx.x;
     const int K = a.counts[0];
@@ -165,7 +168,7 @@ __global__ void __launch_bounds__(kThreads, 2) forward_kernel(const FwdArgs a) {
         long long gidx[PPT];     // linear pixel index in the image buffer, -1 when outside
 #pragma unroll
         for (int p = 0; p < PPT; ++p) {
-            int j = p * kThreads + tid;
+            int j = p * kThreadsF + tid;
             int i2 = j % e2, i1 = (j / e2) % e1, i0 = j / (e2 * e1);
             int g0 = lo[0] + i0, g1 = lo[1] + i1, g2 = lo[2] + i2;
             bool ok = g0 <= hi[0] && g1 <= hi[1] && g2 <= hi[2];
@@ -187,7 +190,8 @@ __global__ void __launch_bounds__(kThreads, 2) forward_kernel(const FwdArgs a) {
             const int buf = ci & 1;
             const int nk = min(kChunk, K - ci * kChunk);
             if (buf) { mbar_wait(&bar[1], phase1); phase1 ^= 1; } else { mbar_wait(&bar[0], phase0); phase0 ^= 1; }
-            if (tid < nk) transform_record<D, C>((buf ? raw1 : raw0) + tid * PK, ctr, crec + tid * R::RC);
+            for (int kt = tid; kt < nk; kt += kThreadsF)
+                transform_record<D, C>((buf ? raw1 : raw0) + kt * PK, ctr, crec + kt * R::RC);
             __syncthreads();
             if (tid == 0 && ci + 2 < nchunks) issue(ci + 2, buf);
 #pragma unroll 2
@@ -199,19 +203,30 @@ __global__ void __launch_bounds__(kThreads, 2) forward_kernel(const FwdArgs a) {
                     float4 v = r4[j];
                     f[4 * j] = v.x; f[4 * j + 1] = v.y; f[4 * j + 2] = v.z; f[4 * j + 3] = v.w;
                 }
+                float q[PPT];
+                float qmax = -INFINITY;
 #pragma unroll
-                for (int p = 0; p < PPT; ++p) S[p] += ex2f(logit<D, C>(f, x[p]));
+                for (int p = 0; p < PPT; ++p) {
+                    q[p] = logit<D, C>(f, x[p]);
+                    qmax = fmaxf(qmax, q[p]);
+                }
+                // ex2.approx.ftz(q) == +0 exactly for q < -126: adding it would not change S
+                if (__builtin_expect(__any_sync(0xffffffffu, qmax >= -126.0f) || a.cfg.dense_exec, 0)) {
+#pragma unroll
+                    for (int p = 0; p < PPT; ++p) S[p] += ex2f(q[p]);
+                }
             }
             __syncthreads();
         }
 
         // ---- sweep B: thresholded gates, experts ----------------------------------------
-        float invS[PPT], r[PPT][C], bestw[PPT];
+        float qthr[PPT], r[PPT][C], bestw[PPT];
         int bestk[PPT];
 #pragma unroll
         for (int p = 0; p < PPT; ++p) {
             float Sc = fmaxf(S[p], kSFloor);
-            invS[p] = gidx[p] >= 0 ? 1.0f / Sc : 0.f;
+            // w = e/S > tau  <=>  q > log2(tau * S); +inf disables pixels outside the batch
+            qthr[p] = gidx[p] >= 0 ? log2f(a.tau * Sc) : INFINITY;
             bestw[p] = 0.f;
             bestk[p] = -1;
 #pragma unroll
@@ -225,7 +240,8 @@ __global__ void __launch_bounds__(kThreads, 2) forward_kernel(const FwdArgs a) {
             const int buf = ci & 1;
             const int nk = min(kChunk, K - ci * kChunk);
             if (buf) { mbar_wait(&bar[1], phase1); phase1 ^= 1; } else { mbar_wait(&bar[0], phase0); phase0 ^= 1; }
-            if (tid < nk) transform_record<D, C>((buf ? raw1 : raw0) + tid * PK, ctr, crec + tid * R::RC);
+            for (int kt = tid; kt < nk; kt += kThreadsF)
+                transform_record<D, C>((buf ? raw1 : raw0) + kt * PK, ctr, crec + kt * R::RC);
             __syncthreads();
             if (tid == 0 && ci + 2 < nchunks) issue(ci + 2, buf);
 #pragma unroll 2
@@ -237,14 +253,17 @@ __global__ void __launch_bounds__(kThreads, 2) forward_kernel(const FwdArgs a) {
                     float4 v = r4[j];
                     f[4 * j] = v.x; f[4 * j + 1] = v.y; f[4 * j + 2] = v.z; f[4 * j + 3] = v.w;
                 }
-                float w[PPT];
+                float q[PPT];
                 bool any = false;
 #pragma unroll
                 for (int p = 0; p < PPT; ++p) {
-                    w[p] = ex2f(logit<D, C>(f, x[p])) * invS[p];
-                    any |= (w[p] > a.tau);
+                    q[p] = logit<D, C>(f, x[p]);
+                    any |= (q[p] > qthr[p]);
                 }
-                if (any || a.cfg.dense_exec) {
+                if (__builtin_expect(__any_sync(0xffffffffu, any) || a.cfg.dense_exec, 0)) {
+                    float w[PPT];       // w = e/S = tau * 2^(q - log2(tau*S)), the form the backward recomputes
+#pragma unroll
+                    for (int p = 0; p < PPT; ++p) w[p] = a.tau * ex2f(q[p] - qthr[p]);
 #pragma unroll
                     for (int j = R::NG4; j < R::RC / 4; ++j) {
                         float4 v = r4[j];
@@ -253,7 +272,7 @@ __global__ void __launch_bounds__(kThreads, 2) forward_kernel(const FwdArgs a) {
                     const int kglob = ci * kChunk + kk;
 #pragma unroll
                     for (int p = 0; p < PPT; ++p) {
-                        const bool pass = w[p] > a.tau;
+                        const bool pass = q[p] > qthr[p];
                         const float wm = pass ? w[p] : 0.f;
 #pragma unroll
                         for (int c = 0; c < C; ++c) {
@@ -273,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, 2) forward_kernel(const FwdArgs a) {
         // ---- epilogue: clip, output fake-quant, loss, backward state -----------------------
 #pragma unroll
         for (int p = 0; p < PPT; ++p) {
-            const int j = p * kThreads + tid;
+            const int j = p * kThreadsF + tid;
             float g[C], gr = 0.f;
             if (gidx[p] >= 0) {
 #pragma unroll
@@ -305,11 +324,12 @@ __global__ void __launch_bounds__(kThreads, 2) forward_kernel(const FwdArgs a) {
                 float rec[SMOE_PIXREC];
 #pragma unroll
                 for (int q = 0; q < SMOE_PIXREC; ++q) rec[q] = 0.f;
+                rec[PR_QTHR] = INFINITY;          // pixels outside the batch: w = tau * 2^(-inf) = 0
                 if (gidx[p] >= 0) {
 #pragma unroll
                     for (int l = 0; l < D; ++l) rec[PR_X + l] = x[p][l];
                     const bool live = S[p] > kSFloor;                                    // smoe.py:821
-                    rec[PR_INVS] = invS[p];
+                    rec[PR_QTHR] = qthr[p];
                     rec[PR_GR] = live ? gr : 0.f;
 #pragma unroll
                     for (int c = 0; c < C; ++c) rec[PR_G + c] = g[c];
@@ -340,7 +360,7 @@ __global__ void __launch_bounds__(kThreads, 2) forward_kernel(const FwdArgs a) {
     __shared__ int s_last;
     if (tid < 8) {
         float s = 0.f;
-        for (int wv = 0; wv < kThreads / 32; ++wv) s += red[wv * 8 + tid];
+        for (int wv = 0; wv < kThreadsF / 32; ++wv) s += red[wv * 8 + tid];
         a.partials[(size_t)blockIdx.x * 8 + tid] = s;
     }
     __threadfence();
@@ -398,13 +418,13 @@ extern "C" int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const 
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int grid = a.ntiles < 2 * sms ? a.ntiles : 2 * sms;
+    int grid = a.ntiles < 4 * sms ? a.ntiles : 4 * sms;
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL(D, C)                                                                                           \
     {                                                                                                        \
         size_t sm = fwd_smem_bytes<D, C>();                                                                  \
         cudaFuncSetAttribute(forward_kernel<D, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);    \
-        forward_kernel<D, C><<<grid, kThreads, sm, st>>>(a);                                                 \
+        forward_kernel<D, C><<<grid, kThreadsF, sm, st>>>(a);                                                 \
     }
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL

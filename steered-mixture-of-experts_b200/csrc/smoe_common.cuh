@@ -11,9 +11,10 @@
 
 namespace smoe {
 
-constexpr int kThreads = 256;                       // threads per CTA of the sweep kernels
-constexpr int kPixPerThread = SMOE_TPIX / kThreads; // 4 pixels per thread in the forward
-constexpr int kChunk = 256;                         // kernels staged per shared-memory chunk
+constexpr int kThreads = 256;                        // threads per CTA of the backward (one kernel per thread)
+constexpr int kThreadsF = 128;                       // threads per CTA of the forward
+constexpr int kPixPerThread = SMOE_TPIX / kThreadsF; // 4 pixels per thread in the forward
+constexpr int kChunk = 128;                          // kernels staged per shared-memory chunk
 constexpr float kHalfLog2e = 0.72134752044448170368f;   // log2(e)/2
 constexpr float kSFloor = 10e-12f;                  // the literal of smoe.py:821
 
@@ -31,9 +32,9 @@ __host__ __device__ constexpr int lt(int l, int m) { return l * (l + 1) / 2 + m;
 __host__ __device__ constexpr int ut(int d, int l, int m) { return l * d - l * (l - 1) / 2 + (m - l); }
 
 // pixel record written by the forward, streamed by the backward
-//   [0..d) tile-centred coordinates | [3] 1/S (or 1e11 when S is clamped) | [4] gr (0 when clamped)
-//   [5..5+C) g_c = dL/dr_c | [8..8+d) absolute coordinates are NOT stored (fold uses tile centre)
-constexpr int PR_X = 0, PR_INVS = 3, PR_GR = 4, PR_G = 5, PR_XX = 8;
+//   [0..d) tile-centred coordinates | [3] qthr = log2(tau * max(S, 1e-11)), +inf outside the batch |
+//   [4] gr = sum_c g_c r_c (0 where S is clamped, smoe.py:821) | [5..5+C) g_c = dL/dr_c
+constexpr int PR_X = 0, PR_QTHR = 3, PR_GR = 4, PR_G = 5;
 
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);

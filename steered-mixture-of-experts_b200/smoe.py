@@ -328,7 +328,7 @@ class Smoe:
         self._infl = torch.zeros((K,), dtype=torch.uint8, device=dev)
         self._pix = torch.zeros((max_tiles * _ffi.TPIX * _ffi.PIXREC,), dtype=f32, device=dev)
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        self._partials = torch.zeros((2 * sms * 8,), dtype=f32, device=dev)
+        self._partials = torch.zeros((4 * sms * 8,), dtype=f32, device=dev)
         self._ticket = torch.zeros((4,), dtype=torch.int32, device=dev)
         self._pack_ws = torch.zeros((L.smoe_pack_workspace_bytes(K) + 15) // 4, dtype=torch.int32, device=dev)
         self._splits = int(L.smoe_suggest_splits(K, max_tiles))
@@ -352,7 +352,7 @@ class Smoe:
     def _choose_tile(self):
         d = self.dim_domain
         if d == 2:
-            return (32, 32, 1)
+            return (_ffi.TPIX // 32, 32, 1)
         T = self._local_shape[2]
         t2 = 1
         while t2 * 2 <= min(T, 8):

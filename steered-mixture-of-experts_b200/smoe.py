@@ -72,7 +72,7 @@ class Smoe:
                  overlap_of_batches=0, kernel_count_as_norm_l1=False, train_svs=False, affines=None,
                  train_trafo=False, num_params_model=6, train_inverse_cov=True, init_flag=1,
                  only_rec_from_checkpoint=False, loss_mask=None, device=None, dense_exec=False,
-                 process_group=None):
+                 process_group=None, distributed=None, _decoder_only=False):
         _ffi.require_cuda()
         lib()
         unsupported = {"affines": affines is not None, "train_trafo": train_trafo, "train_svs": train_svs,
@@ -147,7 +147,9 @@ class Smoe:
             self.nu_e_init = np.asarray(init_params["nu_e"])
         else:
             self.generate_kernel_grid(kernels_per_dim)
-            self.generate_experts()
+            # the decoder feeds every expert over the graph (smoe_reconstruction_decoded.py:34-45), so the
+            # block-mean initialisation (a Python loop over the full H/4 x W/4 grid) would be dead work
+            self.generate_experts(with_means=not _decoder_only)
             self.generate_pis(normalize_pis)
         self.start_pis = int(self.pis_init.size)
         self.kernel_count = self.start_pis
@@ -156,7 +158,7 @@ class Smoe:
         # --- distributed sharding: contiguous bands of the first domain axis ---
         self._pg = process_group
         self._world, self._rank = 1, 0
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
+        if distributed is not False and torch.distributed.is_available() and torch.distributed.is_initialized():
             self._world = torch.distributed.get_world_size(process_group)
             self._rank = torch.distributed.get_rank(process_group)
         if self._world > 1:
@@ -332,9 +334,9 @@ class Smoe:
         self._ticket = torch.zeros((4,), dtype=torch.int32, device=dev)
         self._pack_ws = torch.zeros((L.smoe_pack_workspace_bytes(K) + 15) // 4, dtype=torch.int32, device=dev)
         self._splits = int(L.smoe_suggest_splits(K, max_tiles))
-        self._raw_part = torch.zeros((self._splits * K * self._P,), dtype=f32, device=dev)
+        self._raw_part = None           # allocated on the first training pass
         # [raw statistics | scalars | influence flags]: the buffer a multi-GPU run all-reduces
-        self._xbuf = torch.zeros((K * self._P + _ffi.NSCAL + K,), dtype=f32, device=dev)
+        self._xbuf = torch.zeros((K * self._P + _ffi.NSCAL + K,), dtype=f32, device=dev) if self._world > 1 else None
         self._host_stats = torch.zeros((nb, _ffi.NSCAL + 4 + 2), dtype=f32).pin_memory()
         self.gpu_launches = 0
 
@@ -421,6 +423,8 @@ class Smoe:
         K, P = self.start_pis, self._P
         if train:
             self._grads.zero_()
+            if self._raw_part is None:
+                self._raw_part = torch.zeros((self._splits * K * P,), dtype=torch.float32, device=self.device)
         self._scalars.zero_()
         fed = with_quantized_params and update_reconstruction
         if fed:

@@ -322,3 +322,67 @@ def test_full_size_properties_config2():
     one.run_batched(train=False, update_reconstruction=True)
     yy, xx = np.meshgrid(np.linspace(0, 1, 64), np.linspace(0, 1, 64), indexing="ij")
     np.testing.assert_allclose(one._d_res_pre.cpu().numpy().reshape(64, 64), 0.4 + 0.3 * yy - 0.2 * xx, atol=2e-6)
+
+
+def _decoded_dict(H, W, C, seed, keep=0.125):
+    """Synthetic decoded-bitstream dict per SURVEY.md 8d (config 5), any size."""
+    rs = np.random.RandomState(seed)
+    gh, gw = H // 4, W // 4
+    used = rs.uniform(size=gh * gw) < keep
+    K = int(used.sum())
+    return {"shape_of_img": [np.array([H, W])], "dim_of_output": [np.array([C])], "used_determinants": 1,
+            "used_kernels": [used.astype(np.float64)], "pis": [rs.uniform(.5, 1.5, K).astype(np.float32)],
+            "musX": (rs.uniform(-.5, .5, (K, 2)) / np.array([gh, gw])).astype(np.float32),
+            "A_diagonal": rs.uniform(0.3 * gw, 1.5 * gw, (K, 2)).astype(np.float32),
+            "A_corr": rs.normal(0, 0.1 * gw, (K, 1)).astype(np.float32),
+            "nu_e": rs.uniform(0, 1, (K, C)).astype(np.float32), "gamma_e": rs.normal(0, 1, (K, 2, C)).astype(np.float32)}
+
+
+def test_decoded_entry_point_matches_oracle():
+    """smoe_reconstruction_decoded.py:16-62 (BASELINE config 5 path) at a size the oracle can hold."""
+    from smoe_b200 import smoe_reconstruction_decoded as dec
+    from oracle.graph import GraphCfg, graph_forward
+    from oracle import init_ref
+    H, W, C = 72, 96, 3
+    cp = _decoded_dict(H, W, C, seed=1005)
+    smoe, rec, loss, mse = dec.main(cp=cp, write=False)
+    assert rec.shape == (H, W, C)
+    mus_grid, _ = init_ref.kernel_grid([H // 4, W // 4], 2, False)
+    rp = dec.decode_params(cp, mus_grid)
+    np.testing.assert_array_equal(rp["A"][:, 0, 1], 0)
+    np.testing.assert_array_equal(rp["A"][:, 1, 0], cp["A_corr"][:, 0])
+    K = rp["pis"].shape[0]
+    cfg = GraphCfg(dim_domain=2, num_channels=C, use_determinant=True, train_inverse_cov=False, use_yuv=True, start_pis=K)
+    jd = init_ref.gen_domain(np.zeros((H, W, C), np.float32), 2).reshape(-1, 2 + C).astype(np.float32).astype(np.float64)
+    feed = {k: torch.tensor(np.asarray(v, np.float64)) for k, v in rp.items()}
+    dummy = {"pis": torch.ones(K, dtype=torch.float64), "musX": feed["musX"], "A_diagonal": feed["A"], "A_corr": feed["A"] * 0,
+             "gamma_e": feed["gamma_e"], "nu_e": feed["nu_e"]}
+    out = graph_forward(dummy, np.ones(K, bool), torch.tensor(jd[:, :2]), torch.tensor(jd[:, 2:]), cfg, feed=feed)
+    ref = out["resq"].numpy().reshape(H, W, C)
+    assert (np.round(rec * 255) != np.round(ref * 255)).mean() < 5e-3
+    assert np.abs(rec - ref).max() <= 1.0 / 255 + 1e-6
+    assert abs(loss - float(out["loss"])) < 2e-5
+
+
+def test_reconstruction_entry_point_round_trip(tmp_path):
+    """train -> save_model -> smoe_reconstruction.main with quantised parameters (smoe_reconstruction.py:15-79)."""
+    from smoe_b200 import save_model, smoe_reconstruction
+    img = np.load(os.path.join(GOLDEN, "init_cases.npz"))["rgb_image"]
+    m = _mk(img, [6, 8], use_determinant=True, train_inverse_cov=False, use_yuv=False)
+    for _ in range(10):
+        m.run_batched(train=True)
+    save_model(m, str(tmp_path / "00000010_params.pkl"), quantize=False)
+    np.save(str(tmp_path / "img.npy"), np.round(img * 255).astype(np.uint8))
+    os.mkdir(str(tmp_path / "out"))
+    s2, loss, mse, path = smoe_reconstruction.main(str(tmp_path / "img.npy"), str(tmp_path / "out"),
+                                                   str(tmp_path / "00000010_params.pkl"))
+    assert os.path.exists(path + ".npy") and path.endswith("_20_18_6_10_10")
+    assert os.path.exists(str(tmp_path / "out" / "00000010_params_20_18_6_10_10.pkl"))
+    # quantisation at these bit depths costs little: PSNR within 1 dB of the unquantised model
+    _, mse_f, _, _ = m.run_batched(train=False)
+    assert abs(10 * np.log10(mse / mse_f)) < 1.0
+    # steering survives the save / load round trip (DESIGN.md D5)
+    p_saved = m.get_params()
+    p_loaded = s2.get_params()
+    np.testing.assert_array_equal(p_saved["A_corr"], p_loaded["A_corr"])
+    np.testing.assert_array_equal(p_saved["A_diagonal"], p_loaded["A_diagonal"])

@@ -376,7 +376,7 @@ def test_reconstruction_entry_point_round_trip(tmp_path):
     os.mkdir(str(tmp_path / "out"))
     s2, loss, mse, path = smoe_reconstruction.main(str(tmp_path / "img.npy"), str(tmp_path / "out"),
                                                    str(tmp_path / "00000010_params.pkl"))
-    assert os.path.exists(path + ".npy") and path.endswith("_20_18_6_10_10")
+    assert os.path.exists(path + ".png") and path.endswith("_20_18_6_10_10")
     assert os.path.exists(str(tmp_path / "out" / "00000010_params_20_18_6_10_10.pkl"))
     # quantisation at these bit depths costs little: PSNR within 1 dB of the unquantised model
     _, mse_f, _, _ = m.run_batched(train=False)

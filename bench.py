@@ -192,7 +192,7 @@ def run_ours(args):
     shape, kgrid, seed, desc = WORKLOADS[args.workload]
     d, C = len(shape) - 1, shape[-1]
     img = synth_image(shape, seed)
-    m = Smoe(img, kernels_per_dim=kgrid, dense_exec=bool(args.dense_exec), **SMOE_KW)
+    m = Smoe(img, kernels_per_dim=kgrid, dense_exec=int(args.dense_exec), **SMOE_KW)
     m.set_optimizer(AdamOptimizer(1e-3), AdamOptimizer(1e-5), AdamOptimizer(1.0))
     N, K = m.num_pixel, m.start_pis
     evals_per_step = float(N) * float(K)
@@ -299,19 +299,21 @@ def kernel_times(m, steps):
     counts, regs, scal = m._counts[0], m._regsums[0], m._scalars[0]
     ax2 = ptr(m._d_axes[2]) if m.dim_domain == 3 else ptr(None)
     check(L.smoe_pack(C.byref(m._cfg), ptr(m._theta), ptr(m._klist[0]), m.start_pis, ptr(m._packed), ptr(m._indices),
-                      ptr(counts), ptr(regs), ptr(m._pack_ws), st), "pack")
+                      ptr(counts), ptr(regs), ptr(m._chunk_bounds), ptr(m._pack_ws), st), "pack")
     fw, bw = [], []
     for _ in range(steps + 1):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         m._infl.zero_()
         scal.zero_()
         e[0].record()
-        check(L.smoe_forward(C.byref(m._cfg), C.byref(b), ptr(m._packed), ptr(m._indices), ptr(counts), ptr(m._d_image),
+        check(L.smoe_forward(C.byref(m._cfg), C.byref(b), ptr(m._packed), ptr(m._indices), ptr(counts),
+                             ptr(m._chunk_bounds), m.start_pis, ptr(m._d_image),
                              ptr(m._d_axes[0]), ptr(m._d_axes[1]), ax2, ptr(m._d_res), ptr(None), ptr(None), ptr(m._infl),
-                             ptr(m._pix), ptr(scal), ptr(m._partials), ptr(m._ticket), st), "forward")
+                             ptr(m._pix), ptr(m._tile_qmin), ptr(scal), ptr(m._partials), ptr(m._ticket), st), "forward")
         e[1].record()
         check(L.smoe_backward(C.byref(m._cfg), C.byref(b), ptr(m._packed), ptr(counts), m.start_pis, ptr(m._pix),
-                              ptr(m._d_axes[0]), ptr(m._d_axes[1]), ax2, m._splits, ptr(m._raw_part), st), "backward")
+                              ptr(m._tile_qmin), ptr(m._d_axes[0]), ptr(m._d_axes[1]), ax2, m._splits, ptr(m._raw_part), st),
+              "backward")
         e[2].record()
         torch.cuda.synchronize()
         fw.append(e[0].elapsed_time(e[1]))
@@ -336,7 +338,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
-    ap.add_argument("--dense-exec", type=int, default=0)
+    ap.add_argument("--dense-exec", type=int, default=0,
+                    help="0: exact culling + exact-zero skipping (default); 1: execute every pair; 2: skipping only")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -66,9 +66,10 @@ typedef struct smoe_cfg {
     int32_t quantize_pis;      /* fake-quantise pis before the >0 mask (smoe.py:474-480)    */
     float   pis_lb, pis_ub;    /* lower_bounds[3], upper_bounds[3]                          */
     int32_t pis_bits;          /* bit_depths[3]                                             */
-    int32_t dense_exec;        /* 1: execute the expert/gradient part for every (pixel,
-                                  kernel) pair instead of skipping warps whose gates are all
-                                  below the threshold (results are identical)               */
+    int32_t dense_exec;        /* 0: exact culling + exact-zero skipping (default);
+                                  1: execute every (pixel, kernel) pair in full;
+                                  2: exact-zero skipping inside the dense sweeps, no tile-level
+                                     culling.  Results of the three modes are bit-identical.  */
 } smoe_cfg;
 
 /* One spatial batch (smoe.py:18-35 sliding_window / one rank's shard) of a resident image. */
@@ -106,16 +107,18 @@ size_t      smoe_backward_workspace_bytes(const smoe_cfg* cfg, int K_cap, int nu
  *   counts[0] = K (active), counts[1] = num_pi, counts[2] = kernels with pi*det <= 0 (unsupported
  *   by the fast path, reported), counts[3] = 0
  *   regsums[0] = sum of active pis, regsums[1] = sum of diag(A) over active kernels (for the
- *   L1 terms of smoe.py:1027, 1044) */
+ *   L1 terms of smoe.py:1027, 1044)
+ *   chunk_bounds: per 128 consecutive active kernels, bounding box of the centres, smallest
+ *   eigenvalue bound and largest c0 -- the coarse level of the exact culling in smoe_forward */
 int smoe_pack(const smoe_cfg* cfg, const float* theta, const uint8_t* kernel_list, int K_all,
               float* packed, int32_t* indices, int32_t* counts, float* regsums,
-              void* workspace, void* stream);
+              float* chunk_bounds /*[ceil(K_all/128)][8]*/, void* workspace, void* stream);
 
 /* Same staging for parameters that are FED over the compacted tensors (with_quantized_params,
  * smoe.py:1688-1689: rparams A, musX, nu_e, gamma_e, pis of K rows each); no mask, K given. */
 int smoe_pack_fed(const smoe_cfg* cfg, const float* A /*[K][d][d]*/, const float* musX, const float* nu_e,
                   const float* gamma_e, const float* pis, int K, float* packed, int32_t* counts,
-                  void* stream);
+                  float* chunk_bounds, void* stream);
 
 /* Fused forward over one batch: Mahalanobis logits, gating with the un-renormalised threshold,
  * experts, clip, output fake-quant, loss partials, per-pixel backward state.  Replaces
@@ -128,14 +131,16 @@ int smoe_pack_fed(const smoe_cfg* cfg, const float* A /*[K][d][d]*/, const float
  *   infl     [K] uint8, optional: 1 where the kernel's gate passed the threshold for some pixel
  *            (kernel_list_batch, smoe.py:829); must be zeroed by the caller
  *   pix      optional: per-pixel state for smoe_backward
+ *   tile_qmin [tiles] (required with pix): min over the tile of log2(tau*S), the culling threshold
+ *            of the backward
  *   scalars  [SMOE_NSCAL]: [0..C) sum_n (|diff|-eps)^2 per channel, [4] sum diff^2,
  *            [5] non-finite flag; accumulated (+=) so that batches/ranks can be summed; the
  *            caller zeroes it */
 int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const float* packed, const int32_t* indices,
-                 const int32_t* counts, const float* image, const float* ax0, const float* ax1,
-                 const float* ax2, float* res, float* res_pre, int32_t* argmax, uint8_t* infl,
-                 float* pix, float* scalars, float* partials /*[num_sms*4][8]*/, int32_t* ticket,
-                 void* stream);
+                 const int32_t* counts, const float* chunk_bounds, int K_cap, const float* image,
+                 const float* ax0, const float* ax1, const float* ax2, float* res, float* res_pre,
+                 int32_t* argmax, uint8_t* infl, float* pix, float* tile_qmin /*[tiles]*/, float* scalars,
+                 float* partials /*[num_sms*4][8]*/, int32_t* ticket, void* stream);
 
 /* Fused backward over one batch: recomputes the gates from the per-pixel state and reduces the
  * per-kernel sufficient statistics (sum t, sum t*delta, sum t*delta*delta^T, sum m*w*g,
@@ -143,8 +148,8 @@ int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const float* pack
  * Replaces tf.gradients(loss_op, variables) at smoe.py:1148 for the data term.
  *   raw_part [num_splits][K_cap][P]  partial statistics, one slab per pixel split */
 int smoe_backward(const smoe_cfg* cfg, const smoe_batch* batch, const float* packed, const int32_t* counts,
-                  int K_cap, const float* pix, const float* ax0, const float* ax1, const float* ax2,
-                  int num_splits, float* raw_part, void* stream);
+                  int K_cap, const float* pix, const float* tile_qmin, const float* ax0, const float* ax1,
+                  const float* ax2, int num_splits, float* raw_part, void* stream);
 /* number of pixel splits that fills the GPU in whole waves for K_cap kernels and ntiles tiles */
 int smoe_suggest_splits(int K_cap, int ntiles);
 

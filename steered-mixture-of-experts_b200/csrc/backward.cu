@@ -36,11 +36,31 @@ struct BwdArgs {
     const float* packed;
     const int32_t* counts;
     const float* pix;
+    const float* tile_qmin;
     const float* ax[3];
     float* raw_part;
-    int K_cap, num_splits, ntiles, nt1, nt2;
+    int K_cap, num_splits, ntiles, nt1, nt2, max_list;
     float tau;
 };
+
+// fixed-order min over the CTA of 8 per-thread values (used once per CTA for its bounding box)
+__device__ __forceinline__ void cta_min8(float (&v)[8], float (*s)[8]) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[q] = fminf(v[q], __shfl_xor_sync(0xffffffffu, v[q], o));
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s[threadIdx.x >> 5][q] = v[q];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        float m = INFINITY;
+        for (int w = 0; w < kThreads / 32; ++w) m = fminf(m, s[w][q]);
+        v[q] = m;
+    }
+    __syncthreads();
+}
 
 template <int D, int C>
 __global__ void __launch_bounds__(kThreads, 2) backward_kernel(const BwdArgs a) {
@@ -52,6 +72,9 @@ __global__ void __launch_bounds__(kThreads, 2) backward_kernel(const BwdArgs a) 
     float* buf0 = reinterpret_cast<float*>(smem_raw);
     float* buf1 = buf0 + SMOE_TPIX * SMOE_PIXREC;
     uint64_t* bar = reinterpret_cast<uint64_t*>(buf1 + SMOE_TPIX * SMOE_PIXREC);
+    float (*sred)[8] = reinterpret_cast<float (*)[8]>(bar + 2);     // [8 warps][8]
+    int* scratch = reinterpret_cast<int*>(sred + 8);                // [16]
+    int* tlist = scratch + 16;                                      // [max_list]
 
     const int tid = threadIdx.x;
     const int K = a.counts[0];
@@ -59,6 +82,8 @@ __global__ void __launch_bounds__(kThreads, 2) backward_kernel(const BwdArgs a) 
     const int k = blockIdx.x * kThreads + tid;
     const bool active = k < K;
     const int split = blockIdx.y;
+    const int mode = a.cfg.dense_exec;                   // 0 cull+skip, 1 dense, 2 skip only
+    const bool cull = mode == 0, skip = mode != 1;
 
     if (tid == 0) {
         mbar_init(&bar[0], 1);
@@ -74,7 +99,7 @@ __global__ void __launch_bounds__(kThreads, 2) backward_kernel(const BwdArgs a) 
     };
 
     // own kernel record (global -> registers)
-    float mu[D], Qm[D][D], c0, nu[C], ga[D][C];
+    float mu[D], Qm[D][D], c0, lam, nu[C], ga[D][C];
     {
         const float* rec = a.packed + (size_t)(active ? k : 0) * PK;
 #pragma unroll
@@ -84,12 +109,83 @@ __global__ void __launch_bounds__(kThreads, 2) backward_kernel(const BwdArgs a) 
 #pragma unroll
             for (int m = l; m < D; ++m) Qm[l][m] = Qm[m][l] = rec[off_A(D, C) + ut(D, l, m)];
         c0 = active ? rec[off_pi(D, C)] : -INFINITY;
+        lam = rec[P];
 #pragma unroll
         for (int c = 0; c < C; ++c) nu[c] = rec[off_nu(D, C) + c];
 #pragma unroll
         for (int l = 0; l < D; ++l)
 #pragma unroll
             for (int c = 0; c < C; ++c) ga[l][c] = rec[off_ga(D, C) + l * C + c];
+    }
+
+    // tile geometry (as the forward derives it)
+    auto tile_box = [&](int tile, float (&ctr)[3], float (&half)[3]) {
+        int tt[3];
+        tt[2] = tile % a.nt2;
+        tt[1] = (tile / a.nt2) % a.nt1;
+        tt[0] = tile / (a.nt2 * a.nt1);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int lo = a.b.origin[i] + tt[i] * a.b.tile[i];
+            const int hi = min(lo + a.b.tile[i], a.b.origin[i] + a.b.extent[i]) - 1;
+            const float x0 = (i < D) ? a.ax[i][lo] : 0.f, x1 = (i < D) ? a.ax[i][hi] : 0.f;
+            ctr[i] = 0.5f * (x0 + x1);
+            half[i] = 0.5f * (x1 - x0) * 1.0001f + 1e-7f;
+        }
+    };
+
+    // ---- CTA-level culling: ordered list of this split's tiles that some kernel of the CTA can
+    //      reach (w = tau*2^(q-qthr) is exactly 0 when q - min qthr < -126) --------------------
+    int nlist = 0;
+    {
+        float v[8];
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            v[l] = (l < D && active) ? mu[l] : INFINITY;
+            v[3 + l] = (l < D && active) ? -mu[l] : INFINITY;
+        }
+        v[6] = active ? lam : INFINITY;
+        v[7] = (c0 == c0) ? -c0 : -INFINITY;
+        cta_min8(v, sred);
+        const float blam = v[6], bc0 = -v[7];
+        const int my_tiles = (a.ntiles - split + a.num_splits - 1) / a.num_splits;
+        for (int base = 0; base < my_tiles; base += kThreads) {
+            const int it = base + tid;
+            bool need = false;
+            int tile = 0;
+            if (it < my_tiles) {
+                tile = split + it * a.num_splits;
+                need = true;
+                if (cull) {
+                    float ctr[3], half[3];
+                    tile_box(tile, ctr, half);
+                    float d2 = 0.f;
+#pragma unroll
+                    for (int l = 0; l < D; ++l) {
+                        const float mn = v[l] - ctr[l], mx = -v[3 + l] - ctr[l];
+                        const float gap = fmaxf(fmaxf(mn - half[l], -half[l] - mx), 0.f);
+                        d2 = fmaf(gap, gap, d2);
+                    }
+                    const float ub = bc0 - blam * d2 - a.tile_qmin[tile];
+                    need = !(blam >= 0.f) || !(ub < -126.5f);
+                }
+            }
+            // ordered compaction over the 8 warps
+            const unsigned bal = __ballot_sync(0xffffffffu, need);
+            const int lane = tid & 31, w = tid >> 5;
+            if (lane == 0) scratch[w] = __popc(bal);
+            __syncthreads();
+            int off = 0, tot = 0;
+#pragma unroll
+            for (int j = 0; j < kThreads / 32; ++j) {
+                const int cnt = scratch[j];
+                off += (j < w) ? cnt : 0;
+                tot += cnt;
+            }
+            if (need) tlist[nlist + off + __popc(bal & ((1u << lane) - 1u))] = tile;
+            nlist += tot;
+            __syncthreads();
+        }
     }
 
     float G0 = 0.f, G1[D], G2[T], GNu[C], GGa[D][C];
@@ -105,155 +201,174 @@ __global__ void __launch_bounds__(kThreads, 2) backward_kernel(const BwdArgs a) 
     }
 
     if (tid == 0) {
-        if (split < a.ntiles) issue(split, 0);
-        if (split + a.num_splits < a.ntiles) issue(split + a.num_splits, 1);
+        if (nlist > 0) issue(tlist[0], 0);
+        if (nlist > 1) issue(tlist[1], 1);
     }
-    int it = 0;
-    for (int tile = split; tile < a.ntiles; tile += a.num_splits, ++it) {
-        const int buf = it & 1;
-        // tile centre, exactly as the forward derives it
-        int tt[3];
-        tt[2] = tile % a.nt2;
-        tt[1] = (tile / a.nt2) % a.nt1;
-        tt[0] = tile / (a.nt2 * a.nt1);
-        float ctr[3];
+    const int RL = a.b.tile[D - 1];          // pixels per row of the tile (run along the last axis)
+    for (int li = 0; li < nlist; ++li) {
+        const int buf = li & 1;
+        const int tile = tlist[li];
+        float ctr[3], half[3];
+        tile_box(tile, ctr, half);
+        float mup[D];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            int lo = a.b.origin[i] + tt[i] * a.b.tile[i];
-            int hi = min(lo + a.b.tile[i], a.b.origin[i] + a.b.extent[i]) - 1;
-            ctr[i] = (i < D) ? 0.5f * (a.ax[i][lo] + a.ax[i][hi]) : 0.f;
-        }
-        // tile-centred record in registers
-        float f[R::RC], mup[D];
-        {
-            float v[D];
-            float qc = c0;
-#pragma unroll
-            for (int l = 0; l < D; ++l) mup[l] = mu[l] - ctr[l];
+        for (int l = 0; l < D; ++l) mup[l] = mu[l] - ctr[l];
+        // own kernel vs this tile, then the warp's 32 kernels together
+        bool need = active;
+        if (cull && need) {
+            float d2 = 0.f;
 #pragma unroll
             for (int l = 0; l < D; ++l) {
-                v[l] = 0.f;
-#pragma unroll
-                for (int m = 0; m < D; ++m) v[l] = fmaf(Qm[l][m], mup[m], v[l]);
+                const float gap = fmaxf(fabsf(mup[l]) - half[l], 0.f);
+                d2 = fmaf(gap, gap, d2);
             }
-#pragma unroll
-            for (int l = 0; l < D; ++l) qc = fmaf(-mup[l], v[l], qc);
-#pragma unroll
-            for (int l = 0; l < D; ++l) {
-                f[R::OL + l] = 2.f * v[l];
-#pragma unroll
-                for (int m = l; m < D; ++m) f[R::OQ + ut(D, l, m)] = (l == m) ? -Qm[l][m] : -2.f * Qm[l][m];
-            }
-            f[R::OC] = qc;
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                float n = nu[c];
-#pragma unroll
-                for (int l = 0; l < D; ++l) {
-                    n = fmaf(ga[l][c], ctr[l], n);
-                    f[R::OGA + l * C + c] = ga[l][c];
-                }
-                f[R::ONU + c] = n;
-            }
+            const float ub = c0 - lam * d2 - a.tile_qmin[tile];
+            need = !(lam >= 0.f) || !(ub < -126.5f);
         }
-        float M0 = 0.f, M1[D], M2[T], N0[C], N1[D][C];
-#pragma unroll
-        for (int l = 0; l < D; ++l) M1[l] = 0.f;
-#pragma unroll
-        for (int q = 0; q < T; ++q) M2[q] = 0.f;
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            N0[c] = 0.f;
-#pragma unroll
-            for (int l = 0; l < D; ++l) N1[l][c] = 0.f;
-        }
+        const bool warp_need = __any_sync(0xffffffffu, need);
 
         if (buf) { mbar_wait(&bar[1], phase1); phase1 ^= 1; } else { mbar_wait(&bar[0], phase0); phase0 ^= 1; }
-        const float4* px = reinterpret_cast<const float4*>(buf ? buf1 : buf0);
-        constexpr int GRP = 4;          // pixels tested together for the exact-zero skip
-        for (int j0 = 0; j0 < SMOE_TPIX; j0 += GRP) {
-            float xg[GRP][D], dq[GRP];
-            float dmax = -INFINITY;
-#pragma unroll
-            for (int u = 0; u < GRP; ++u) {
-                const float4 p0 = px[2 * (j0 + u)];
-                const float xx[3] = {p0.x, p0.y, p0.z};
-#pragma unroll
-                for (int l = 0; l < D; ++l) xg[u][l] = xx[l];
-                // gate logit (Horner) relative to the pixel's threshold: dq = q - log2(tau*S)
-                float q = f[R::OC];
+        if (warp_need) {
+            // tile-centred record in registers
+            float f[R::RC];
+            {
+                float v[D];
+                float qc = c0;
 #pragma unroll
                 for (int l = 0; l < D; ++l) {
-                    float tq = f[R::OL + l];
+                    v[l] = 0.f;
 #pragma unroll
-                    for (int m = l; m < D; ++m) tq = fmaf(f[R::OQ + ut(D, l, m)], xg[u][m], tq);
-                    q = fmaf(tq, xg[u][l], q);
+                    for (int m = 0; m < D; ++m) v[l] = fmaf(Qm[l][m], mup[m], v[l]);
                 }
-                dq[u] = q - p0.w;
-                dmax = fmaxf(dmax, dq[u]);
-            }
-            // w = tau * 2^dq is exactly +0 for dq < -126 (ex2.approx.ftz): nothing to accumulate
-            if (!__any_sync(0xffffffffu, dmax >= -126.0f) && !a.cfg.dense_exec) continue;
 #pragma unroll
-            for (int u = 0; u < GRP; ++u) {
-                const float4 p1 = px[2 * (j0 + u) + 1];
-                const float gr = p1.x;
-                const float g[3] = {p1.y, p1.z, p1.w};
-                float x[D];
+                for (int l = 0; l < D; ++l) qc = fmaf(-mup[l], v[l], qc);
 #pragma unroll
-                for (int l = 0; l < D; ++l) x[l] = xg[u][l];
-                const float w = a.tau * ex2f(dq[u]);
-                float t = -w * gr;
-                const bool pass = dq[u] > 0.f;
-                if (__any_sync(0xffffffffu, pass) || a.cfg.dense_exec) {
-                    const float wm = pass ? w : 0.f;
-                    float gE = 0.f;
+                for (int l = 0; l < D; ++l) {
+                    f[R::OL + l] = 2.f * v[l];
 #pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        float E = f[R::ONU + c];
+                    for (int m = l; m < D; ++m) f[R::OQ + ut(D, l, m)] = (l == m) ? -Qm[l][m] : -2.f * Qm[l][m];
+                }
+                f[R::OC] = qc;
 #pragma unroll
-                        for (int l = 0; l < D; ++l) E = fmaf(f[R::OGA + l * C + c], x[l], E);
-                        gE = fmaf(g[c], E, gE);
-                        const float vc = wm * g[c];
-                        N0[c] += vc;
+                for (int c = 0; c < C; ++c) {
+                    float n = nu[c];
 #pragma unroll
-                        for (int l = 0; l < D; ++l) N1[l][c] = fmaf(vc, x[l], N1[l][c]);
+                    for (int l = 0; l < D; ++l) {
+                        n = fmaf(ga[l][c], ctr[l], n);
+                        f[R::OGA + l * C + c] = ga[l][c];
                     }
-                    t = fmaf(wm, gE, t);
+                    f[R::ONU + c] = n;
                 }
-                M0 += t;
+            }
+            float M0 = 0.f, M1[D], M2[T], N0[C], N1[D][C];
 #pragma unroll
-                for (int l = 0; l < D; ++l) {
-                    const float uu = t * x[l];
-                    M1[l] += uu;
+            for (int l = 0; l < D; ++l) M1[l] = 0.f;
 #pragma unroll
-                    for (int m = l; m < D; ++m) M2[ut(D, l, m)] = fmaf(uu, x[m], M2[ut(D, l, m)]);
+            for (int q = 0; q < T; ++q) M2[q] = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                N0[c] = 0.f;
+#pragma unroll
+                for (int l = 0; l < D; ++l) N1[l][c] = 0.f;
+            }
+
+            const float4* px = reinterpret_cast<const float4*>(buf ? buf1 : buf0);
+            constexpr int GRP = 4;          // pixels tested together for the exact-zero skip
+            for (int r0 = 0; r0 < SMOE_TPIX; r0 += RL) {
+                // the pixels of a row differ only in their LAST coordinate z: q = cr + (br + qq_last z) z
+                float cr, br;
+                {
+                    const float4 pf = px[2 * r0];
+                    const float xr[3] = {pf.x, pf.y, pf.z};
+                    cr = f[R::OC];
+#pragma unroll
+                    for (int l = 0; l < D - 1; ++l) {
+                        float tq = f[R::OL + l];
+#pragma unroll
+                        for (int m = l; m < D - 1; ++m) tq = fmaf(f[R::OQ + ut(D, l, m)], xr[m], tq);
+                        cr = fmaf(tq, xr[l], cr);
+                    }
+                    br = f[R::OL + D - 1];
+#pragma unroll
+                    for (int l = 0; l < D - 1; ++l) br = fmaf(f[R::OQ + ut(D, l, D - 1)], xr[l], br);
                 }
+                const float qz = f[R::OQ + ut(D, D - 1, D - 1)];
+                for (int j0 = r0; j0 < r0 + RL; j0 += GRP) {
+                    float dq[GRP];
+                    float dmax = -INFINITY;
+#pragma unroll
+                    for (int u = 0; u < GRP; ++u) {
+                        const float4 p0 = px[2 * (j0 + u)];
+                        const float z = D == 1 ? p0.x : (D == 2 ? p0.y : p0.z);
+                        // gate logit relative to the pixel's threshold: dq = q - log2(tau*S)
+                        dq[u] = fmaf(fmaf(qz, z, br), z, cr) - p0.w;
+                        dmax = fmaxf(dmax, dq[u]);
+                    }
+                    // w = tau * 2^dq is exactly +0 for dq < -126 (ex2.approx.ftz): nothing to accumulate
+                    if (__builtin_expect(skip && !__any_sync(0xffffffffu, dmax >= -126.0f), 1)) continue;
+#pragma unroll
+                    for (int u = 0; u < GRP; ++u) {
+                        const float4 p0 = px[2 * (j0 + u)];
+                        const float4 p1 = px[2 * (j0 + u) + 1];
+                        const float xx[3] = {p0.x, p0.y, p0.z};
+                        float x[D];
+#pragma unroll
+                        for (int l = 0; l < D; ++l) x[l] = xx[l];
+                        const float gr = p1.x;
+                        const float g[3] = {p1.y, p1.z, p1.w};
+                        const float w = a.tau * ex2f(dq[u]);
+                        float t = -w * gr;
+                        const bool pass = dq[u] > 0.f;
+                        if (!skip || __any_sync(0xffffffffu, pass)) {
+                            const float wm = pass ? w : 0.f;
+                            float gE = 0.f;
+#pragma unroll
+                            for (int c = 0; c < C; ++c) {
+                                float E = f[R::ONU + c];
+#pragma unroll
+                                for (int l = 0; l < D; ++l) E = fmaf(f[R::OGA + l * C + c], x[l], E);
+                                gE = fmaf(g[c], E, gE);
+                                const float vc = wm * g[c];
+                                N0[c] += vc;
+#pragma unroll
+                                for (int l = 0; l < D; ++l) N1[l][c] = fmaf(vc, x[l], N1[l][c]);
+                            }
+                            t = fmaf(wm, gE, t);
+                        }
+                        M0 += t;
+#pragma unroll
+                        for (int l = 0; l < D; ++l) {
+                            const float uu = t * x[l];
+                            M1[l] += uu;
+#pragma unroll
+                            for (int m = l; m < D; ++m) M2[ut(D, l, m)] = fmaf(uu, x[m], M2[ut(D, l, m)]);
+                        }
+                    }
+                }
+            }
+            // fold tile-centred statistics into kernel-centred ones
+            G0 += M0;
+#pragma unroll
+            for (int l = 0; l < D; ++l) G1[l] += fmaf(-mup[l], M0, M1[l]);
+#pragma unroll
+            for (int l = 0; l < D; ++l)
+#pragma unroll
+                for (int m = l; m < D; ++m) {
+                    float dd = M2[ut(D, l, m)];
+                    dd = fmaf(-mup[l], M1[m], dd);
+                    dd = fmaf(-mup[m], M1[l], dd);
+                    dd = fmaf(mup[l] * mup[m], M0, dd);
+                    G2[ut(D, l, m)] += dd;
+                }
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                GNu[c] += N0[c];
+#pragma unroll
+                for (int l = 0; l < D; ++l) GGa[l][c] += fmaf(ctr[l], N0[c], N1[l][c]);
             }
         }
         __syncthreads();       // everyone is done with this buffer
-        if (tid == 0 && tile + 2 * a.num_splits < a.ntiles) issue(tile + 2 * a.num_splits, buf);
-
-        // fold tile-centred statistics into kernel-centred ones
-        G0 += M0;
-#pragma unroll
-        for (int l = 0; l < D; ++l) G1[l] += fmaf(-mup[l], M0, M1[l]);
-#pragma unroll
-        for (int l = 0; l < D; ++l)
-#pragma unroll
-            for (int m = l; m < D; ++m) {
-                float dd = M2[ut(D, l, m)];
-                dd = fmaf(-mup[l], M1[m], dd);
-                dd = fmaf(-mup[m], M1[l], dd);
-                dd = fmaf(mup[l] * mup[m], M0, dd);
-                G2[ut(D, l, m)] += dd;
-            }
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            GNu[c] += N0[c];
-#pragma unroll
-            for (int l = 0; l < D; ++l) GGa[l][c] += fmaf(ctr[l], N0[c], N1[l][c]);
-        }
+        if (tid == 0 && li + 2 < nlist) issue(tlist[li + 2], buf);
     }
 
     if (active) {
@@ -438,14 +553,14 @@ size_t smoe_backward_workspace_bytes(const smoe_cfg* cfg, int K_cap, int num_spl
 }
 
 int smoe_backward(const smoe_cfg* cfg, const smoe_batch* batch, const float* packed, const int32_t* counts, int K_cap,
-                  const float* pix, const float* ax0, const float* ax1, const float* ax2, int num_splits,
-                  float* raw_part, void* stream) {
-    SMOE_REQUIRE(cfg && batch && packed && counts && pix && ax0 && ax1 && raw_part, "null argument");
+                  const float* pix, const float* tile_qmin, const float* ax0, const float* ax1, const float* ax2,
+                  int num_splits, float* raw_part, void* stream) {
+    SMOE_REQUIRE(cfg && batch && packed && counts && pix && tile_qmin && ax0 && ax1 && raw_part, "null argument");
     SMOE_REQUIRE(K_cap > 0 && num_splits > 0 && num_splits <= 65535, "bad K_cap / num_splits");
     BwdArgs a;
     a.cfg = *cfg;
     a.b = *batch;
-    a.packed = packed; a.counts = counts; a.pix = pix; a.raw_part = raw_part;
+    a.packed = packed; a.counts = counts; a.pix = pix; a.tile_qmin = tile_qmin; a.raw_part = raw_part;
     a.ax[0] = ax0; a.ax[1] = ax1; a.ax[2] = ax2 ? ax2 : ax0;
     a.K_cap = K_cap;
     a.num_splits = num_splits;
@@ -453,8 +568,10 @@ int smoe_backward(const smoe_cfg* cfg, const smoe_batch* batch, const float* pac
     a.nt2 = (batch->extent[2] + batch->tile[2] - 1) / batch->tile[2];
     a.ntiles = smoe_num_tiles(batch);
     a.tau = 0.5f / (float)(1 << cfg->precision);
+    a.max_list = (a.ntiles + num_splits - 1) / num_splits;
     dim3 grid((K_cap + kThreads - 1) / kThreads, num_splits);
-    size_t sm = 2 * (size_t)SMOE_TPIX * SMOE_PIXREC * 4 + 64;
+    size_t sm = 2 * (size_t)SMOE_TPIX * SMOE_PIXREC * 4 + 16 + 8 * 8 * 4 + 16 * 4 + (size_t)a.max_list * 4 + 64;
+    SMOE_REQUIRE(sm <= 100 * 1024, "too many tiles per split for the shared-memory tile list: raise num_splits");
     cudaStream_t st = (cudaStream_t)stream;
     // partial slabs of splits that own no tile, and rows k >= K, are never read
 #define CALL(D, C)                                                                                        \

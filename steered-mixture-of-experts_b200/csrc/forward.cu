@@ -1,24 +1,30 @@
 // Fused SMoE forward (smoe_forward).  Replaces smoe.py:777-858, 899-937, 1053.
 //
 // Pixel-stationary: a CTA (128 threads, 4 resident per SM) owns a spatially compact tile of
-// SMOE_TPIX = 512 pixels (4 per thread, in registers) and streams ALL active kernels past it twice:
+// SMOE_TPIX = 512 pixels (4 per thread, in registers) and streams the active kernels past it twice:
 //   sweep A  S_n = sum_k 2^{q_k(x_n)}                       (the normaliser of smoe.py:819-821)
 //   sweep B  w = 2^{q}/S, m = w > tau, r_c += m*w*E_kc(x)   (smoe.py:823-848; needs the FINAL S,
 //            and gates are not renormalised after thresholding, so one sweep is not enough)
 // Kernel records arrive in shared memory by TMA bulk copies (cp.async.bulk + mbarrier, double
 // buffered) and are re-expressed per tile in tile-centred coordinates, where the whole gate
-// logit is one quadratic  q(x') = qc + ql.x' + x'^T qq x'  evaluated by Horner in T+d FFMA
-// (5 for d=2, 9 for d=3) + one ex2.approx: -1/2 maha * log2(e) + log2(pi*det/(2pi)^{d/2}).
+// logit is one quadratic  q(x') = qc + ql.x' + x'^T qq x'.  The 4 pixels of a thread differ only in
+// their first coordinate, so the logit is a parabola  c + (b + qq00 z) z  in z = x'_0 whose
+// coefficients cost T+d-2 FFMA once per (thread, kernel) and 2 FFMA per pixel.
 // The quadratic form covers both ||A^T(x-mu)||^2 and the train_inverse_cov branch x^T A x.
-// The N x K gate matrix is never materialised.  FP32 FFMA + MUFU.EX2 bound; no tensor cores
+// The N x K gate matrix is never materialised.  FP32 FFMA + MUFU.EX2; no tensor cores
 // (inner dimensions are d = 2..3 and C = 1..3).
 //
-// Exact-zero skipping (results are bit-identical to dense execution, cfg.dense_exec = 1):
-//   sweep A skips ex2 + add for a thread-iteration whose 4 logits are all < -126, where
-//     ex2.approx.ftz returns exactly +0;
-//   sweep B tests the threshold in the log domain, q > log2(tau*S), so it needs no ex2 at all
-//     unless a gate passes (<0.2 % of the pairs at the benchmark shapes), and skips the expert
-//     part otherwise.
+// Exact work skipping -- every mode returns bit-identical results (tests assert it):
+//   * ex2.approx.ftz(q) is exactly +0 for q < -126, and a gate below the threshold multiplies its
+//     expert by exactly 0.  Sweep A skips ex2+add for a warp-iteration whose logits are all < -126;
+//     sweep B tests the threshold in the log domain, q > log2(tau*S), so it needs no ex2 at all
+//     unless a gate passes.                                            (dense_exec = 0 and 2)
+//   * Culling: q_k(x) <= c0_k - lam_k * dist(x, mu_k)^2 with lam_k a lower bound of the smallest
+//     eigenvalue of Qm_k.  A chunk of 128 kernels whose bound over the tile's box says "all zero"
+//     (sweep A: < -126.5; sweep B: < min_n qthr - 0.01) is never loaded, and inside a loaded chunk
+//     only the kernels that can matter are re-centred and swept (ordered compaction, so sums keep
+//     the order of the dense sweep).  The 0.5 / 0.01 margins cover the rounding of the evaluated
+//     logit, which is < 1e-4 there.                                          (dense_exec = 0)
 #include "smoe_common.cuh"
 
 namespace smoe {
@@ -28,19 +34,17 @@ struct Rec {
     static constexpr int T = tri(D);
     static constexpr int GN = T + D + 1;          // qq (upper-tri, off-diagonals doubled) | ql | qc
     static constexpr int EN = C + D * C;          // nu' | gamma
-    static constexpr int RC = (GN + EN + 3) / 4 * 4;
+    static constexpr int RC = (GN + EN + 1 + 3) / 4 * 4;   // + the kernel's active index
     static constexpr int NG4 = (GN + 3) / 4;      // float4 loads that cover the geometry part
-    static constexpr int OQ = 0, OL = T, OC = T + D, ONU = GN, OGA = GN + C;
+    static constexpr int OQ = 0, OL = T, OC = T + D, ONU = GN, OGA = GN + C, OK = RC - 1;
 };
 
 // raw packed record + tile centre -> tile-centred compute record
 template <int D, int C>
-__device__ __forceinline__ void transform_record(const float* __restrict__ raw, const float (&ctr)[3],
-                                                 float* __restrict__ out) {
+__device__ __forceinline__ void transform_record(const float* __restrict__ raw, const float (&mu)[D],
+                                                 const float (&ctr)[3], int kglob, float* __restrict__ out) {
     using R = Rec<D, C>;
-    float mu[D], Qm[D][D], v[D];
-#pragma unroll
-    for (int l = 0; l < D; ++l) mu[l] = raw[off_mu(D, C) + l] - ctr[l];
+    float Qm[D][D], v[D];
 #pragma unroll
     for (int l = 0; l < D; ++l)
 #pragma unroll
@@ -73,22 +77,25 @@ __device__ __forceinline__ void transform_record(const float* __restrict__ raw, 
         out[R::ONU + c] = nu;
     }
 #pragma unroll
-    for (int j = R::GN + R::EN; j < R::RC; ++j) out[j] = 0.f;
+    for (int j = R::GN + R::EN; j < R::RC - 1; ++j) out[j] = 0.f;
+    out[R::OK] = __int_as_float(kglob);
 }
 
-// q(x') by Horner: T + D FFMA
+// parabola coefficients of q along x'_0 for fixed x'_1.. : q = c + (b + qq00 z) z
 template <int D, int C>
-__device__ __forceinline__ float logit(const float* __restrict__ f, const float (&x)[D]) {
+__device__ __forceinline__ void parabola(const float* __restrict__ f, const float (&xs)[3], float& c, float& b) {
     using R = Rec<D, C>;
-    float q = f[R::OC];
+    c = f[R::OC];
 #pragma unroll
-    for (int l = 0; l < D; ++l) {
+    for (int l = 1; l < D; ++l) {
         float t = f[R::OL + l];
 #pragma unroll
-        for (int m = l; m < D; ++m) t = fmaf(f[R::OQ + ut(D, l, m)], x[m], t);
-        q = fmaf(t, x[l], q);
+        for (int m = l; m < D; ++m) t = fmaf(f[R::OQ + ut(D, l, m)], xs[m], t);
+        c = fmaf(t, xs[l], c);
     }
-    return q;
+    b = f[R::OL + 0];
+#pragma unroll
+    for (int m = 1; m < D; ++m) b = fmaf(f[R::OQ + ut(D, 0, m)], xs[m], b);
 }
 
 struct FwdArgs {
@@ -97,6 +104,7 @@ struct FwdArgs {
     const float* packed;
     const int32_t* indices;
     const int32_t* counts;
+    const float* chunk_bounds;
     const float* image;
     const float* ax[3];
     float* res;
@@ -104,28 +112,53 @@ struct FwdArgs {
     int32_t* argmax;
     uint8_t* infl;
     float* pix;
+    float* tile_qmin;
     float* scalars;
     float* partials;
     int32_t* ticket;
-    int ntiles, nt1, nt2;
+    int ntiles, nt1, nt2, max_chunks;
     float tau, eps, q_scale, q_inv_scale;
 };
+
+// Ordered compaction helper for a 128-thread CTA: returns this thread's output slot (valid when
+// flag) and the total through *total; `scratch` holds 4 ints.  Contains two __syncthreads.
+__device__ __forceinline__ int cta_compact(bool flag, int* scratch, int* total) {
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) scratch[w] = __popc(bal);
+    __syncthreads();
+    int off = 0, tot = 0;
+#pragma unroll
+    for (int j = 0; j < kThreadsF / 32; ++j) {
+        const int cnt = scratch[j];
+        off += (j < w) ? cnt : 0;
+        tot += cnt;
+    }
+    __syncthreads();
+    *total = tot;
+    return off + __popc(bal & ((1u << lane) - 1u));
+}
 
 template <int D, int C>
 __global__ void __launch_bounds__(kThreadsF, 4) forward_kernel(const FwdArgs a) {
     using R = Rec<D, C>;
     constexpr int PK = pstride(D, C);
     constexpr int PPT = kPixPerThread;
+    static_assert(kChunk == kThreadsF, "one kernel of a chunk per thread");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* raw0 = reinterpret_cast<float*>(smem_raw);
     float* raw1 = raw0 + kChunk * PK;
     float* crec = raw1 + kChunk * PK;
     uint64_t* bar = reinterpret_cast<uint64_t*>(crec + kChunk * R::RC);
-    float* red = reinterpret_cast<float*>(bar + 2);          // [warps][8]
+    float* red = reinterpret_cast<float*>(bar + 2);          // [4 warps][8]
+    int* scratch = reinterpret_cast<int*>(red + 32);         // [8]
+    int* clist = scratch + 8;                                // [max_chunks]
 
     const int tid = threadIdx.x;
     const int K = a.counts[0];
     const int nchunks = (K + kChunk - 1) / kChunk;
+    const int mode = a.cfg.dense_exec;                       // 0 cull+skip, 1 dense, 2 skip only
+    const bool cull = mode == 0, skip = mode != 1;
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
@@ -148,8 +181,7 @@ __global__ void __launch_bounds__(kThreadsF, 4) forward_kernel(const FwdArgs a) 
     float sqsum = 0.f;
     int nonfinite = 0;
 
-    const int e0 = a.b.tile[0], e1 = a.b.tile[1], e2 = a.b.tile[2];
-    (void)e0;
+    const int e1 = a.b.tile[1], e2 = a.b.tile[2];
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         // ---- tile geometry ------------------------------------------------------------
         int tt[3];
@@ -157,136 +189,201 @@ __global__ void __launch_bounds__(kThreadsF, 4) forward_kernel(const FwdArgs a) 
         tt[1] = (tile / a.nt2) % a.nt1;
         tt[0] = tile / (a.nt2 * a.nt1);
         int lo[3], hi[3];
-        float ctr[3];
+        float ctr[3], half[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             lo[i] = a.b.origin[i] + tt[i] * a.b.tile[i];
             hi[i] = min(lo[i] + a.b.tile[i], a.b.origin[i] + a.b.extent[i]) - 1;
-            ctr[i] = (i < D) ? 0.5f * (a.ax[i][lo[i]] + a.ax[i][hi[i]]) : 0.f;
+            const float c0 = (i < D) ? a.ax[i][lo[i]] : 0.f, c1 = (i < D) ? a.ax[i][hi[i]] : 0.f;
+            ctr[i] = 0.5f * (c0 + c1);
+            half[i] = 0.5f * (c1 - c0) * 1.0001f + 1e-7f;     // box half extent, rounded outwards
         }
-        float x[PPT][D];
+        // the thread's PPT pixels: same (i1, i2), rows i0 = p*step + i0_first
+        float x0[PPT], xs[3] = {0.f, 0.f, 0.f};
         long long gidx[PPT];     // linear pixel index in the image buffer, -1 when outside
+        {
+            const int i2 = tid % e2, i1 = (tid / e2) % e1;
+            const int g1 = lo[1] + i1, g2 = lo[2] + i2;
+            if (D > 1) xs[1] = a.ax[1][min(g1, hi[1])] - ctr[1];
+            if (D > 2) xs[2] = a.ax[2][min(g2, hi[2])] - ctr[2];
 #pragma unroll
-        for (int p = 0; p < PPT; ++p) {
-            int j = p * kThreadsF + tid;
-            int i2 = j % e2, i1 = (j / e2) % e1, i0 = j / (e2 * e1);
-            int g0 = lo[0] + i0, g1 = lo[1] + i1, g2 = lo[2] + i2;
-            bool ok = g0 <= hi[0] && g1 <= hi[1] && g2 <= hi[2];
-            gidx[p] = ok ? ((long long)g0 * a.b.dims[1] + g1) * a.b.dims[2] + g2 : -1;
-            int gg[3] = {min(g0, hi[0]), min(g1, hi[1]), min(g2, hi[2])};
-#pragma unroll
-            for (int l = 0; l < D; ++l) x[p][l] = a.ax[l][gg[l]] - ctr[l];
+            for (int p = 0; p < PPT; ++p) {
+                const int j = p * kThreadsF + tid;
+                const int i0 = j / (e2 * e1);
+                const int g0 = lo[0] + i0;
+                const bool ok = g0 <= hi[0] && g1 <= hi[1] && g2 <= hi[2];
+                gidx[p] = ok ? ((long long)g0 * a.b.dims[1] + g1) * a.b.dims[2] + g2 : -1;
+                x0[p] = a.ax[0][min(g0, hi[0])] - ctr[0];
+            }
         }
+
+        // chunk-level culling: ordered list of the chunks whose bound reaches `thr` over this tile
+        auto build_chunk_list = [&](float thr) -> int {
+            int n = 0;
+            for (int base = 0; base < nchunks; base += kThreadsF) {
+                const int ci = base + tid;
+                bool need = false;
+                if (ci < nchunks) {
+                    need = true;
+                    if (cull) {
+                        const float* cb = a.chunk_bounds + (size_t)ci * 8;
+                        float d2 = 0.f;
+#pragma unroll
+                        for (int l = 0; l < D; ++l) {
+                            const float mn = cb[l] - ctr[l], mx = cb[3 + l] - ctr[l];
+                            const float gap = fmaxf(fmaxf(mn - half[l], -half[l] - mx), 0.f);
+                            d2 = fmaf(gap, gap, d2);
+                        }
+                        const float lam = cb[6], ub = cb[7] - lam * d2;
+                        need = !(lam >= 0.f) || !(ub < thr);
+                    }
+                }
+                int tot;
+                const int pos = cta_compact(need, scratch, &tot);
+                if (need) clist[n + pos] = ci;
+                n += tot;
+            }
+            __syncthreads();
+            return n;
+        };
+
+        // one sweep over the needed chunks; `body(rec)` is called for every kernel that can matter
+        auto sweep = [&](int nlist, float thr, auto&& body) {
+            if (tid == 0 && nlist > 0) {
+                issue(clist[0], 0);
+                if (nlist > 1) issue(clist[1], 1);
+            }
+            for (int li = 0; li < nlist; ++li) {
+                const int buf = li & 1;
+                const int ci = clist[li];
+                const int nk = min(kChunk, K - ci * kChunk);
+                if (buf) { mbar_wait(&bar[1], phase1); phase1 ^= 1; } else { mbar_wait(&bar[0], phase0); phase0 ^= 1; }
+                const float* raw = (buf ? raw1 : raw0) + tid * PK;
+                bool need = tid < nk;
+                float mu[D];
+#pragma unroll
+                for (int l = 0; l < D; ++l) mu[l] = need ? raw[off_mu(D, C) + l] - ctr[l] : 0.f;
+                if (need && cull) {
+                    float d2 = 0.f;
+#pragma unroll
+                    for (int l = 0; l < D; ++l) {
+                        const float gap = fmaxf(fabsf(mu[l]) - half[l], 0.f);
+                        d2 = fmaf(gap, gap, d2);
+                    }
+                    const float lam = raw[nparam(D, C)], ub = raw[off_pi(D, C)] - lam * d2;
+                    need = !(lam >= 0.f) || !(ub < thr);
+                }
+                int nneed;
+                const int pos = cta_compact(need, scratch, &nneed);
+                if (need) transform_record<D, C>(raw, mu, ctr, ci * kChunk + tid, crec + pos * R::RC);
+                __syncthreads();
+                if (tid == 0 && li + 2 < nlist) issue(clist[li + 2], buf);
+#pragma unroll 2
+                for (int kk = 0; kk < nneed; ++kk) body(crec + kk * R::RC);
+                __syncthreads();
+            }
+        };
 
         // ---- sweep A: normaliser ------------------------------------------------------
         float S[PPT];
 #pragma unroll
         for (int p = 0; p < PPT; ++p) S[p] = 0.f;
-        if (tid == 0 && nchunks > 0) {
-            issue(0, 0);
-            if (nchunks > 1) issue(1, 1);
-        }
-        for (int ci = 0; ci < nchunks; ++ci) {
-            const int buf = ci & 1;
-            const int nk = min(kChunk, K - ci * kChunk);
-            if (buf) { mbar_wait(&bar[1], phase1); phase1 ^= 1; } else { mbar_wait(&bar[0], phase0); phase0 ^= 1; }
-            for (int kt = tid; kt < nk; kt += kThreadsF)
-                transform_record<D, C>((buf ? raw1 : raw0) + kt * PK, ctr, crec + kt * R::RC);
-            __syncthreads();
-            if (tid == 0 && ci + 2 < nchunks) issue(ci + 2, buf);
-#pragma unroll 2
-            for (int kk = 0; kk < nk; ++kk) {
+        {
+            const int nlist = build_chunk_list(-126.5f);
+            sweep(nlist, -126.5f, [&](const float* rec) {
                 float f[4 * R::NG4];
-                const float4* r4 = reinterpret_cast<const float4*>(crec + kk * R::RC);
+                const float4* r4 = reinterpret_cast<const float4*>(rec);
 #pragma unroll
                 for (int j = 0; j < R::NG4; ++j) {
                     float4 v = r4[j];
                     f[4 * j] = v.x; f[4 * j + 1] = v.y; f[4 * j + 2] = v.z; f[4 * j + 3] = v.w;
                 }
+                float cq, bq;
+                parabola<D, C>(f, xs, cq, bq);
                 float q[PPT];
                 float qmax = -INFINITY;
 #pragma unroll
                 for (int p = 0; p < PPT; ++p) {
-                    q[p] = logit<D, C>(f, x[p]);
+                    q[p] = fmaf(fmaf(f[R::OQ], x0[p], bq), x0[p], cq);
                     qmax = fmaxf(qmax, q[p]);
                 }
                 // ex2.approx.ftz(q) == +0 exactly for q < -126: adding it would not change S
-                if (__builtin_expect(__any_sync(0xffffffffu, qmax >= -126.0f) || a.cfg.dense_exec, 0)) {
+                if (__builtin_expect(!skip || __any_sync(0xffffffffu, qmax >= -126.0f), 0)) {
 #pragma unroll
                     for (int p = 0; p < PPT; ++p) S[p] += ex2f(q[p]);
                 }
-            }
-            __syncthreads();
+            });
         }
 
         // ---- sweep B: thresholded gates, experts ----------------------------------------
         float qthr[PPT], r[PPT][C], bestw[PPT];
         int bestk[PPT];
+        float qmin = INFINITY;
 #pragma unroll
         for (int p = 0; p < PPT; ++p) {
             float Sc = fmaxf(S[p], kSFloor);
             // w = e/S > tau  <=>  q > log2(tau * S); +inf disables pixels outside the batch
             qthr[p] = gidx[p] >= 0 ? log2f(a.tau * Sc) : INFINITY;
+            qmin = fminf(qmin, qthr[p]);
             bestw[p] = 0.f;
             bestk[p] = -1;
 #pragma unroll
             for (int c = 0; c < C; ++c) r[p][c] = 0.f;
         }
-        if (tid == 0 && nchunks > 0) {
-            issue(0, 0);
-            if (nchunks > 1) issue(1, 1);
-        }
-        for (int ci = 0; ci < nchunks; ++ci) {
-            const int buf = ci & 1;
-            const int nk = min(kChunk, K - ci * kChunk);
-            if (buf) { mbar_wait(&bar[1], phase1); phase1 ^= 1; } else { mbar_wait(&bar[0], phase0); phase0 ^= 1; }
-            for (int kt = tid; kt < nk; kt += kThreadsF)
-                transform_record<D, C>((buf ? raw1 : raw0) + kt * PK, ctr, crec + kt * R::RC);
-            __syncthreads();
-            if (tid == 0 && ci + 2 < nchunks) issue(ci + 2, buf);
-#pragma unroll 2
-            for (int kk = 0; kk < nk; ++kk) {
+        // tile minimum of qthr: the sweep-B / backward culling threshold
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) qmin = fminf(qmin, __shfl_xor_sync(0xffffffffu, qmin, o));
+        if ((tid & 31) == 0) red[tid >> 5] = qmin;
+        __syncthreads();
+        qmin = fminf(fminf(red[0], red[1]), fminf(red[2], red[3]));
+        __syncthreads();
+        if (tid == 0 && a.tile_qmin) a.tile_qmin[tile] = qmin;
+        {
+            const float thrB = qmin - 0.01f;
+            const int nlist = build_chunk_list(thrB);
+            sweep(nlist, thrB, [&](const float* rec) {
                 float f[R::RC];
-                const float4* r4 = reinterpret_cast<const float4*>(crec + kk * R::RC);
+                const float4* r4 = reinterpret_cast<const float4*>(rec);
 #pragma unroll
                 for (int j = 0; j < R::NG4; ++j) {
                     float4 v = r4[j];
                     f[4 * j] = v.x; f[4 * j + 1] = v.y; f[4 * j + 2] = v.z; f[4 * j + 3] = v.w;
                 }
+                float cq, bq;
+                parabola<D, C>(f, xs, cq, bq);
                 float q[PPT];
                 bool any = false;
 #pragma unroll
                 for (int p = 0; p < PPT; ++p) {
-                    q[p] = logit<D, C>(f, x[p]);
+                    q[p] = fmaf(fmaf(f[R::OQ], x0[p], bq), x0[p], cq);
                     any |= (q[p] > qthr[p]);
                 }
-                if (__builtin_expect(__any_sync(0xffffffffu, any) || a.cfg.dense_exec, 0)) {
-                    float w[PPT];       // w = e/S = tau * 2^(q - log2(tau*S)), the form the backward recomputes
-#pragma unroll
-                    for (int p = 0; p < PPT; ++p) w[p] = a.tau * ex2f(q[p] - qthr[p]);
+                if (__builtin_expect(!skip || __any_sync(0xffffffffu, any), 0)) {
 #pragma unroll
                     for (int j = R::NG4; j < R::RC / 4; ++j) {
                         float4 v = r4[j];
                         f[4 * j] = v.x; f[4 * j + 1] = v.y; f[4 * j + 2] = v.z; f[4 * j + 3] = v.w;
                     }
-                    const int kglob = ci * kChunk + kk;
+                    const int kglob = __float_as_int(f[R::OK]);
 #pragma unroll
                     for (int p = 0; p < PPT; ++p) {
+                        // w = e/S = tau * 2^(q - log2(tau*S)), the form the backward recomputes
+                        const float w = a.tau * ex2f(q[p] - qthr[p]);
                         const bool pass = q[p] > qthr[p];
-                        const float wm = pass ? w[p] : 0.f;
+                        const float wm = pass ? w : 0.f;
 #pragma unroll
                         for (int c = 0; c < C; ++c) {
                             float E = f[R::ONU + c];
+                            E = fmaf(f[R::OGA + c], x0[p], E);
 #pragma unroll
-                            for (int l = 0; l < D; ++l) E = fmaf(f[R::OGA + l * C + c], x[p][l], E);
+                            for (int l = 1; l < D; ++l) E = fmaf(f[R::OGA + l * C + c], xs[l], E);
                             r[p][c] = fmaf(wm, E, r[p][c]);
                         }
-                        if (pass && w[p] > bestw[p]) { bestw[p] = w[p]; bestk[p] = kglob; }
+                        if (pass && w > bestw[p]) { bestw[p] = w; bestk[p] = kglob; }
                     }
                     if (any && a.infl) a.infl[kglob] = 1;
                 }
-            }
-            __syncthreads();
+            });
         }
 
         // ---- epilogue: clip, output fake-quant, loss, backward state -----------------------
@@ -325,9 +422,11 @@ __global__ void __launch_bounds__(kThreadsF, 4) forward_kernel(const FwdArgs a) 
 #pragma unroll
                 for (int q = 0; q < SMOE_PIXREC; ++q) rec[q] = 0.f;
                 rec[PR_QTHR] = INFINITY;          // pixels outside the batch: w = tau * 2^(-inf) = 0
-                if (gidx[p] >= 0) {
+                // coordinates are stored for every slot: the backward derives row constants from them
+                rec[PR_X] = x0[p];
 #pragma unroll
-                    for (int l = 0; l < D; ++l) rec[PR_X + l] = x[p][l];
+                for (int l = 1; l < D; ++l) rec[PR_X + l] = xs[l];
+                if (gidx[p] >= 0) {
                     const bool live = S[p] > kSFloor;                                    // smoe.py:821
                     rec[PR_QTHR] = qthr[p];
                     rec[PR_GR] = live ? gr : 0.f;
@@ -353,6 +452,7 @@ __global__ void __launch_bounds__(kThreadsF, 4) forward_kernel(const FwdArgs a) 
     for (int q = 0; q < 6; ++q)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) vals[q] += __shfl_down_sync(0xffffffffu, vals[q], o);
+    __syncthreads();
     if ((tid & 31) == 0)
 #pragma unroll
         for (int q = 0; q < 8; ++q) red[(tid >> 5) * 8 + q] = vals[q];
@@ -379,8 +479,9 @@ __global__ void __launch_bounds__(kThreadsF, 4) forward_kernel(const FwdArgs a) 
 }
 
 template <int D, int C>
-static size_t fwd_smem_bytes() {
-    return (size_t)(2 * kChunk * pstride(D, C) + kChunk * Rec<D, C>::RC) * 4 + 2 * 8 + 8 * 8 * 4 + 64;
+static size_t fwd_smem_bytes(int max_chunks) {
+    return (size_t)(2 * kChunk * pstride(D, C) + kChunk * Rec<D, C>::RC) * 4 + 2 * 8 + 32 * 4 + 8 * 4 +
+           (size_t)max_chunks * 4 + 64;
 }
 
 }  // namespace smoe
@@ -388,14 +489,19 @@ static size_t fwd_smem_bytes() {
 using namespace smoe;
 
 extern "C" int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const float* packed, const int32_t* indices,
-                            const int32_t* counts, const float* image, const float* ax0, const float* ax1,
-                            const float* ax2, float* res, float* res_pre, int32_t* argmax, uint8_t* infl, float* pix,
-                            float* scalars, float* partials, int32_t* ticket, void* stream) {
-    SMOE_REQUIRE(cfg && batch && packed && indices && counts && image && ax0 && ax1 && res && scalars && partials &&
-                     ticket,
+                            const int32_t* counts, const float* chunk_bounds, int K_cap, const float* image,
+                            const float* ax0, const float* ax1, const float* ax2, float* res, float* res_pre,
+                            int32_t* argmax, uint8_t* infl, float* pix, float* tile_qmin, float* scalars,
+                            float* partials, int32_t* ticket, void* stream) {
+    SMOE_REQUIRE(cfg && batch && packed && indices && counts && chunk_bounds && image && ax0 && ax1 && res && scalars &&
+                     partials && ticket,
                  "null argument");
+    SMOE_REQUIRE(K_cap > 0, "K_cap must be positive");
     SMOE_REQUIRE(cfg->d == 2 || ax2, "ax2 required for d == 3");
     SMOE_REQUIRE(batch->tile[0] * batch->tile[1] * batch->tile[2] == SMOE_TPIX, "tile product must be SMOE_TPIX");
+    SMOE_REQUIRE(kThreadsF % (batch->tile[1] * batch->tile[2]) == 0 && batch->tile[cfg->d - 1] % 4 == 0,
+                 "tile[1]*tile[2] must divide 128 and the last tile extent must be a multiple of 4");
+    SMOE_REQUIRE(!pix || tile_qmin, "tile_qmin is required with pix");
     for (int i = 0; i < 3; ++i)
         SMOE_REQUIRE(batch->extent[i] > 0 && batch->origin[i] >= 0 && batch->origin[i] + batch->extent[i] <= batch->dims[i],
                      "batch rectangle outside the image");
@@ -403,13 +509,14 @@ extern "C" int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const 
     FwdArgs a;
     a.cfg = *cfg;
     a.b = *batch;
-    a.packed = packed; a.indices = indices; a.counts = counts; a.image = image;
+    a.packed = packed; a.indices = indices; a.counts = counts; a.chunk_bounds = chunk_bounds; a.image = image;
     a.ax[0] = ax0; a.ax[1] = ax1; a.ax[2] = ax2 ? ax2 : ax0;
-    a.res = res; a.res_pre = res_pre; a.argmax = argmax; a.infl = infl; a.pix = pix;
+    a.res = res; a.res_pre = res_pre; a.argmax = argmax; a.infl = infl; a.pix = pix; a.tile_qmin = tile_qmin;
     a.scalars = scalars; a.partials = partials; a.ticket = ticket;
     a.nt1 = (batch->extent[1] + batch->tile[1] - 1) / batch->tile[1];
     a.nt2 = (batch->extent[2] + batch->tile[2] - 1) / batch->tile[2];
     a.ntiles = smoe_num_tiles(batch);
+    a.max_chunks = (K_cap + kChunk - 1) / kChunk;
     const float two_p = (float)(1 << cfg->precision);
     a.tau = 0.5f / two_p;
     a.eps = cfg->margin / two_p;
@@ -422,9 +529,10 @@ extern "C" int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const 
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL(D, C)                                                                                           \
     {                                                                                                        \
-        size_t sm = fwd_smem_bytes<D, C>();                                                                  \
+        size_t sm = fwd_smem_bytes<D, C>(a.max_chunks);                                                      \
+        SMOE_REQUIRE(sm <= 200 * 1024, "too many kernel chunks for the shared-memory chunk list");           \
         cudaFuncSetAttribute(forward_kernel<D, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);    \
-        forward_kernel<D, C><<<grid, kThreadsF, sm, st>>>(a);                                                 \
+        forward_kernel<D, C><<<grid, kThreadsF, sm, st>>>(a);                                                \
     }
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL

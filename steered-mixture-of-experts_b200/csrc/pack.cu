@@ -133,7 +133,83 @@ __device__ __forceinline__ int stage_record(const smoe_cfg& cfg, const float (&A
         }
 #pragma unroll
     for (int j = nparam(D, C); j < PK; ++j) rec[j] = 0.f;
+    // conservative lower bound of the smallest eigenvalue of Qm (slot P of the record): the culling
+    // bound q(x) <= c0 - lam * dist(x, mu)^2.  Negative (indefinite train_inverse_cov forms) = never cull.
+    {
+        double Q[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+        for (int l = 0; l < D; ++l)
+#pragma unroll
+            for (int m = l; m < D; ++m) Q[l][m] = Q[m][l] = (double)rec[off_A(D, C) + ut(D, l, m)];
+        double lam;
+        if (D == 2) {
+            const double hm = 0.5 * (Q[0][0] + Q[1][1]), hd = 0.5 * (Q[0][0] - Q[1][1]);
+            lam = hm - sqrt(hd * hd + Q[0][1] * Q[0][1]);
+        } else {
+            // smallest root of the characteristic polynomial of a symmetric 3x3 (trigonometric form)
+            const double p1 = Q[0][1] * Q[0][1] + Q[0][2] * Q[0][2] + Q[1][2] * Q[1][2];
+            const double tr = (Q[0][0] + Q[1][1] + Q[2][2]) / 3.0;
+            if (p1 == 0.0) {
+                lam = fmin(Q[0][0], fmin(Q[1][1], Q[2][2]));
+            } else {
+                const double a0 = Q[0][0] - tr, a1 = Q[1][1] - tr, a2 = Q[2][2] - tr;
+                const double p2 = a0 * a0 + a1 * a1 + a2 * a2 + 2.0 * p1;
+                const double pp = sqrt(p2 / 6.0);
+                const double b00 = a0 / pp, b11 = a1 / pp, b22 = a2 / pp;
+                const double b01 = Q[0][1] / pp, b02 = Q[0][2] / pp, b12 = Q[1][2] / pp;
+                double r = 0.5 * (b00 * (b11 * b22 - b12 * b12) - b01 * (b01 * b22 - b12 * b02) + b02 * (b01 * b12 - b11 * b02));
+                r = fmin(1.0, fmax(-1.0, r));
+                const double phi = acos(r) / 3.0;
+                lam = tr + 2.0 * pp * cos(phi + 2.0943951023931953);      // + 2pi/3: the smallest eigenvalue
+            }
+        }
+        const double scale = fabs(Q[0][0]) + fabs(Q[1][1]) + fabs(Q[2][2]);
+        lam = lam >= 0.0 ? lam * (1.0 - 1e-3) - 1e-6 * scale : lam;      // keep the bound conservative
+        if (lam < 0.0 && !cfg.train_inverse_cov) lam = 0.0;               // A A^T is PSD: rounding only
+        rec[nparam(D, C)] = (float)lam;
+    }
     return coef < 0.f;       // negative weights cannot be carried in the log domain
+}
+
+// Per chunk of kChunk consecutive active kernels: bounding box of the centres, smallest lam, largest c0
+// (coarse level of the exact culling; layout [mu_min[3] | mu_max[3] | lam_min | c0_max], stride 8).
+template <int D, int C>
+__global__ void __launch_bounds__(kChunk) chunk_bounds_kernel(const float* __restrict__ packed,
+                                                              const int32_t* __restrict__ counts,
+                                                              float* __restrict__ cb) {
+    constexpr int PK = pstride(D, C);
+    const int K = counts[0];
+    const int k = blockIdx.x * kChunk + threadIdx.x;
+    if ((int)blockIdx.x * kChunk >= K) return;
+    float v[8];
+    const bool on = k < K;
+    const float* rec = packed + (size_t)(on ? k : 0) * PK;
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        const float m = (l < D && on) ? rec[off_mu(D, C) + l] : 0.f;
+        v[l] = (l < D && on) ? m : INFINITY;        // min
+        v[3 + l] = (l < D && on) ? -m : INFINITY;   // max as min of the negation
+    }
+    v[6] = on ? rec[nparam(D, C)] : INFINITY;
+    const float c0 = on ? rec[off_pi(D, C)] : -INFINITY;
+    v[7] = -c0;
+    if (!(c0 == c0)) v[7] = -INFINITY;             // NaN c0: never cull
+    __shared__ float s[kChunk / 32][8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[q] = fminf(v[q], __shfl_xor_sync(0xffffffffu, v[q], o));
+    }
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s[threadIdx.x >> 5][q] = v[q];
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float m = INFINITY;
+        for (int w = 0; w < kChunk / 32; ++w) m = fminf(m, s[w][threadIdx.x]);
+        const int q = threadIdx.x;
+        cb[(size_t)blockIdx.x * 8 + q] = (q >= 3 && q != 6) ? -m : m;
+    }
 }
 
 template <int D, int C>
@@ -258,8 +334,9 @@ size_t smoe_pack_workspace_bytes(int K_all) {
 }
 
 int smoe_pack(const smoe_cfg* cfg, const float* theta, const uint8_t* kernel_list, int K_all, float* packed,
-              int32_t* indices, int32_t* counts, float* regsums, void* workspace, void* stream) {
-    SMOE_REQUIRE(cfg && theta && kernel_list && packed && indices && counts && regsums && workspace, "null argument");
+              int32_t* indices, int32_t* counts, float* regsums, float* chunk_bounds, void* workspace, void* stream) {
+    SMOE_REQUIRE(cfg && theta && kernel_list && packed && indices && counts && regsums && chunk_bounds && workspace,
+                 "null argument");
     SMOE_REQUIRE(K_all > 0, "K_all must be positive");
     cudaStream_t st = (cudaStream_t)stream;
     int nb = (K_all + 255) / 256;
@@ -274,16 +351,24 @@ int smoe_pack(const smoe_cfg* cfg, const float* theta, const uint8_t* kernel_lis
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL
     nonpos_total_kernel<<<1, 1, 0, st>>>(nonpos_blk, nb, counts);
+    const int nchunks = (K_all + kChunk - 1) / kChunk;
+#define CALL(D, C) chunk_bounds_kernel<D, C><<<nchunks, kChunk, 0, st>>>(packed, counts, chunk_bounds);
+    SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
+#undef CALL
     return check_launch("smoe_pack");
 }
 
 int smoe_pack_fed(const smoe_cfg* cfg, const float* A, const float* musX, const float* nu_e, const float* gamma_e,
-                  const float* pis, int K, float* packed, int32_t* counts, void* stream) {
-    SMOE_REQUIRE(cfg && A && musX && nu_e && gamma_e && pis && packed && counts, "null argument");
+                  const float* pis, int K, float* packed, int32_t* counts, float* chunk_bounds, void* stream) {
+    SMOE_REQUIRE(cfg && A && musX && nu_e && gamma_e && pis && packed && counts && chunk_bounds, "null argument");
     SMOE_REQUIRE(K > 0, "K must be positive");
     cudaStream_t st = (cudaStream_t)stream;
     int nb = (K + 255) / 256;
 #define CALL(D, C) pack_fed_kernel<D, C><<<nb, 256, 0, st>>>(*cfg, A, musX, nu_e, gamma_e, pis, K, packed, counts);
+    SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
+#undef CALL
+    const int nchunks = (K + kChunk - 1) / kChunk;
+#define CALL(D, C) chunk_bounds_kernel<D, C><<<nchunks, kChunk, 0, st>>>(packed, counts, chunk_bounds);
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL
     return check_launch("smoe_pack_fed");

@@ -269,7 +269,7 @@ class Smoe:
         bits3 = int(self.bit_depths[3]) if self.quantize_pis else 8
         self._cfg = Cfg(d, Cc, int(self.precision), float(self.margin), int(self.use_determinant),
                         int(self.train_inverse_cov), int(self.use_yuv), int(self.train_gammas),
-                        int(self.only_y_gamma), int(self.quantize_pis), lb3, ub3, bits3, int(dense_exec))
+                        int(self.only_y_gamma), int(self.quantize_pis), lb3, ub3, bits3, int(dense_exec))   # dense_exec: 0 cull+skip, 1 dense, 2 skip only
         # variables
         A0 = np.asarray(self.A_init, dtype=np.float64)
         theta = np.zeros((K, self._P), dtype=np.float32)
@@ -329,6 +329,8 @@ class Smoe:
         self._scalars = torch.zeros((nb, _ffi.NSCAL), dtype=f32, device=dev)
         self._infl = torch.zeros((K,), dtype=torch.uint8, device=dev)
         self._pix = torch.zeros((max_tiles * _ffi.TPIX * _ffi.PIXREC,), dtype=f32, device=dev)
+        self._tile_qmin = torch.zeros((max_tiles,), dtype=f32, device=dev)
+        self._chunk_bounds = torch.zeros(((K + 127) // 128, 8), dtype=f32, device=dev)
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         self._partials = torch.zeros((4 * sms * 8,), dtype=f32, device=dev)
         self._ticket = torch.zeros((4,), dtype=torch.int32, device=dev)
@@ -355,13 +357,11 @@ class Smoe:
         d = self.dim_domain
         if d == 2:
             return (_ffi.TPIX // 32, 32, 1)
+        # tile[1]*tile[2] must divide 128 and tile[2] must be a multiple of 4 (include/smoe_b200.h)
         T = self._local_shape[2]
-        t2 = 1
-        while t2 * 2 <= min(T, 8):
-            t2 *= 2
-        rest = _ffi.TPIX // t2
-        t1 = 16 if rest // 16 >= 8 else 8
-        return (rest // t1, t1, t2)
+        t2 = 8 if T > 4 else 4
+        t1 = 64 // t2
+        return (_ffi.TPIX // (t1 * t2), t1, t2)
 
     # kernel_list_per_batch is exposed as the reference's list of NumPy bool arrays
     @property
@@ -438,27 +438,29 @@ class Smoe:
             counts, regs, scal = self._counts[ii], self._regsums[ii], self._scalars[ii]
             if fed:
                 check(L.smoe_pack_fed(C.byref(self._cfg), ptr(rp["A"]), ptr(rp["musX"]), ptr(rp["nu_e"]),
-                                      ptr(rp["gamma_e"]), ptr(rp["pis"]), Kf, ptr(self._packed), ptr(counts), st),
-                      "smoe_pack_fed")
+                                      ptr(rp["gamma_e"]), ptr(rp["pis"]), Kf, ptr(self._packed), ptr(counts),
+                                      ptr(self._chunk_bounds), st), "smoe_pack_fed")
                 self._indices[:Kf] = torch.arange(Kf, dtype=torch.int32, device=self.device)
                 regs.zero_()
                 self.gpu_launches += 1
             else:
                 check(L.smoe_pack(C.byref(self._cfg), ptr(self._theta), ptr(self._klist[ii]), K, ptr(self._packed),
-                                  ptr(self._indices), ptr(counts), ptr(regs), ptr(self._pack_ws), st), "smoe_pack")
+                                  ptr(self._indices), ptr(counts), ptr(regs), ptr(self._chunk_bounds),
+                                  ptr(self._pack_ws), st), "smoe_pack")
                 self.gpu_launches += 3
             self._infl.zero_()
             check(L.smoe_forward(C.byref(self._cfg), C.byref(b), ptr(self._packed), ptr(self._indices), ptr(counts),
+                                 ptr(self._chunk_bounds), K,
                                  ptr(self._d_image), ptr(self._d_axes[0]), ptr(self._d_axes[1]),
                                  ptr(self._d_axes[2]) if self.dim_domain == 3 else ptr(None),
                                  ptr(self._d_res), ptr(self._d_res_pre),
                                  ptr(self._d_argmax) if update_reconstruction else ptr(None),
-                                 ptr(self._infl), ptr(self._pix) if train else ptr(None), ptr(scal),
-                                 ptr(self._partials), ptr(self._ticket), st), "smoe_forward")
+                                 ptr(self._infl), ptr(self._pix) if train else ptr(None), ptr(self._tile_qmin),
+                                 ptr(scal), ptr(self._partials), ptr(self._ticket), st), "smoe_forward")
             self.gpu_launches += 1
             if train:
                 check(L.smoe_backward(C.byref(self._cfg), C.byref(b), ptr(self._packed), ptr(counts), K, ptr(self._pix),
-                                      ptr(self._d_axes[0]), ptr(self._d_axes[1]),
+                                      ptr(self._tile_qmin), ptr(self._d_axes[0]), ptr(self._d_axes[1]),
                                       ptr(self._d_axes[2]) if self.dim_domain == 3 else ptr(None),
                                       self._splits, ptr(self._raw_part), st), "smoe_backward")
                 self.gpu_launches += 1

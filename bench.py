@@ -299,7 +299,7 @@ def kernel_times(m, steps):
     counts, regs, scal = m._counts[0], m._regsums[0], m._scalars[0]
     ax2 = ptr(m._d_axes[2]) if m.dim_domain == 3 else ptr(None)
     check(L.smoe_pack(C.byref(m._cfg), ptr(m._theta), ptr(m._klist[0]), m.start_pis, ptr(m._packed), ptr(m._indices),
-                      ptr(counts), ptr(regs), ptr(m._chunk_bounds), ptr(m._pack_ws), st), "pack")
+                      ptr(m._pos), ptr(counts), ptr(regs), ptr(m._chunk_bounds), ptr(m._pack_ws), st), "pack")
     fw, bw = [], []
     for _ in range(steps + 1):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -311,8 +311,8 @@ def kernel_times(m, steps):
                              ptr(m._d_axes[0]), ptr(m._d_axes[1]), ax2, ptr(m._d_res), ptr(None), ptr(None), ptr(m._infl),
                              ptr(m._pix), ptr(m._tile_qmin), ptr(scal), ptr(m._partials), ptr(m._ticket), st), "forward")
         e[1].record()
-        check(L.smoe_backward(C.byref(m._cfg), C.byref(b), ptr(m._packed), ptr(counts), m.start_pis, ptr(m._pix),
-                              ptr(m._tile_qmin), ptr(m._d_axes[0]), ptr(m._d_axes[1]), ax2, m._splits, ptr(m._raw_part), st),
+        check(L.smoe_backward(C.byref(m._cfg), C.byref(b), ptr(m._packed), ptr(counts), m.start_pis,
+                              ptr(m._perm), ptr(m._pos), ptr(m._pix), ptr(m._tile_qmin), ptr(m._d_axes[0]), ptr(m._d_axes[1]), ax2, m._splits, ptr(m._raw_part), st),
               "backward")
         e[2].record()
         torch.cuda.synchronize()

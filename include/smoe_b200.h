@@ -111,7 +111,8 @@ size_t      smoe_backward_workspace_bytes(const smoe_cfg* cfg, int K_cap, int nu
  *   chunk_bounds: per 128 consecutive active kernels, bounding box of the centres, smallest
  *   eigenvalue bound and largest c0 -- the coarse level of the exact culling in smoe_forward */
 int smoe_pack(const smoe_cfg* cfg, const float* theta, const uint8_t* kernel_list, int K_all,
-              float* packed, int32_t* indices, int32_t* counts, float* regsums,
+              float* packed, int32_t* indices, int32_t* pos /*[K_all]: packed row of each kernel or -1*/,
+              int32_t* counts, float* regsums,
               float* chunk_bounds /*[ceil(K_all/128)][8]*/, void* workspace, void* stream);
 
 /* Same staging for parameters that are FED over the compacted tensors (with_quantized_params,
@@ -148,8 +149,13 @@ int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const float* pack
  * Replaces tf.gradients(loss_op, variables) at smoe.py:1148 for the data term.
  *   raw_part [num_splits][K_cap][P]  partial statistics, one slab per pixel split */
 int smoe_backward(const smoe_cfg* cfg, const smoe_batch* batch, const float* packed, const int32_t* counts,
-                  int K_cap, const float* pix, const float* tile_qmin, const float* ax0, const float* ax1,
-                  const float* ax2, int num_splits, float* raw_part, void* stream);
+                  int K_cap, const int32_t* perm, const int32_t* pos, const float* pix, const float* tile_qmin,
+                  const float* ax0, const float* ax1, const float* ax2, int num_splits, float* raw_part,
+                  void* stream);
+/*   perm, pos (both NULL, or both given): thread slot s of the backward works on the kernel with
+ *   ORIGINAL index perm[s] (s in [0,K_cap)), whose packed row is pos[perm[s]] (-1 = inactive).  Any
+ *   permutation gives the same results; a spatially coherent one (e.g. Morton order of the centres)
+ *   makes the kernels of a warp / CTA neighbours, which is what the tile culling exploits. */
 /* number of pixel splits that fills the GPU in whole waves for K_cap kernels and ntiles tiles */
 int smoe_suggest_splits(int K_cap, int ntiles);
 

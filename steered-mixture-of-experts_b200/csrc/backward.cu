@@ -35,6 +35,8 @@ struct BwdArgs {
     smoe_batch b;
     const float* packed;
     const int32_t* counts;
+    const int32_t* perm;
+    const int32_t* pos;
     const float* pix;
     const float* tile_qmin;
     const float* ax[3];
@@ -63,7 +65,7 @@ __device__ __forceinline__ void cta_min8(float (&v)[8], float (*s)[8]) {
 }
 
 template <int D, int C>
-__global__ void __launch_bounds__(kThreads, 2) backward_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(kThreads, 4) backward_kernel(const BwdArgs a) {
     using R = BRec<D, C>;
     constexpr int T = tri(D);
     constexpr int P = nparam(D, C), PK = pstride(D, C);
@@ -78,9 +80,14 @@ __global__ void __launch_bounds__(kThreads, 2) backward_kernel(const BwdArgs a) 
 
     const int tid = threadIdx.x;
     const int K = a.counts[0];
-    if ((int)blockIdx.x * kThreads >= K) return;
-    const int k = blockIdx.x * kThreads + tid;
-    const bool active = k < K;
+    int k = blockIdx.x * kThreads + tid;                 // slot -> packed row
+    if (a.perm) {
+        k = k < a.K_cap ? a.pos[a.perm[k]] : -1;
+    } else if ((int)blockIdx.x * kThreads >= K) {
+        return;
+    }
+    const bool active = k >= 0 && k < K;
+    if (a.perm && !__syncthreads_or(active)) return;
     const int split = blockIdx.y;
     const int mode = a.cfg.dense_exec;                   // 0 cull+skip, 1 dense, 2 skip only
     const bool cull = mode == 0, skip = mode != 1;
@@ -553,14 +560,16 @@ size_t smoe_backward_workspace_bytes(const smoe_cfg* cfg, int K_cap, int num_spl
 }
 
 int smoe_backward(const smoe_cfg* cfg, const smoe_batch* batch, const float* packed, const int32_t* counts, int K_cap,
-                  const float* pix, const float* tile_qmin, const float* ax0, const float* ax1, const float* ax2,
-                  int num_splits, float* raw_part, void* stream) {
+                  const int32_t* perm, const int32_t* pos, const float* pix, const float* tile_qmin, const float* ax0,
+                  const float* ax1, const float* ax2, int num_splits, float* raw_part, void* stream) {
     SMOE_REQUIRE(cfg && batch && packed && counts && pix && tile_qmin && ax0 && ax1 && raw_part, "null argument");
+    SMOE_REQUIRE((perm == nullptr) == (pos == nullptr), "perm and pos go together");
     SMOE_REQUIRE(K_cap > 0 && num_splits > 0 && num_splits <= 65535, "bad K_cap / num_splits");
     BwdArgs a;
     a.cfg = *cfg;
     a.b = *batch;
-    a.packed = packed; a.counts = counts; a.pix = pix; a.tile_qmin = tile_qmin; a.raw_part = raw_part;
+    a.packed = packed; a.counts = counts; a.perm = perm; a.pos = pos; a.pix = pix; a.tile_qmin = tile_qmin;
+    a.raw_part = raw_part;
     a.ax[0] = ax0; a.ax[1] = ax1; a.ax[2] = ax2 ? ax2 : ax0;
     a.K_cap = K_cap;
     a.num_splits = num_splits;

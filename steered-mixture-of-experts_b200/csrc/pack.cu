@@ -216,7 +216,8 @@ template <int D, int C>
 __global__ void __launch_bounds__(256) pack_scatter_kernel(smoe_cfg cfg, const float* __restrict__ theta,
                                                            const uint8_t* __restrict__ klist, int K_all, Nudged nq,
                                                            const PackBlk* __restrict__ blk, float* __restrict__ packed,
-                                                           int32_t* __restrict__ indices, int32_t* __restrict__ counts,
+                                                           int32_t* __restrict__ indices, int32_t* __restrict__ pos,
+                                                           int32_t* __restrict__ counts,
                                                            float* __restrict__ regsums, int32_t* __restrict__ nonpos_blk) {
     constexpr int P = nparam(D, C), PK = pstride(D, C);
     __shared__ int s_red[8];
@@ -248,6 +249,7 @@ __global__ void __launch_bounds__(256) pack_scatter_kernel(smoe_cfg cfg, const f
     for (int j = 0; j < w; ++j) woff += s_warp[j];
     int dst = prefix + woff + __popc(bal & ((1u << lane) - 1u));
     int neg = 0;
+    if (i < K_all) pos[i] = flag ? dst : -1;          // original index -> packed row (the inverse of `indices`)
     if (flag) {
         indices[dst] = i;
         float A[D][D];
@@ -334,8 +336,9 @@ size_t smoe_pack_workspace_bytes(int K_all) {
 }
 
 int smoe_pack(const smoe_cfg* cfg, const float* theta, const uint8_t* kernel_list, int K_all, float* packed,
-              int32_t* indices, int32_t* counts, float* regsums, float* chunk_bounds, void* workspace, void* stream) {
-    SMOE_REQUIRE(cfg && theta && kernel_list && packed && indices && counts && regsums && chunk_bounds && workspace,
+              int32_t* indices, int32_t* pos, int32_t* counts, float* regsums, float* chunk_bounds, void* workspace,
+              void* stream) {
+    SMOE_REQUIRE(cfg && theta && kernel_list && packed && indices && pos && counts && regsums && chunk_bounds && workspace,
                  "null argument");
     SMOE_REQUIRE(K_all > 0, "K_all must be positive");
     cudaStream_t st = (cudaStream_t)stream;
@@ -347,7 +350,7 @@ int smoe_pack(const smoe_cfg* cfg, const float* theta, const uint8_t* kernel_lis
 #define CALL(D, C)                                                                                              \
     pack_count_kernel<D, C><<<nb, 256, 0, st>>>(theta, kernel_list, K_all, cfg->quantize_pis, nq, blk);         \
     pack_scatter_kernel<D, C><<<nb, 256, 0, st>>>(*cfg, theta, kernel_list, K_all, nq, blk, packed, indices,    \
-                                                  counts, regsums, nonpos_blk);
+                                                  pos, counts, regsums, nonpos_blk);
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL
     nonpos_total_kernel<<<1, 1, 0, st>>>(nonpos_blk, nb, counts);

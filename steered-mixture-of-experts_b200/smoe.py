@@ -324,6 +324,9 @@ class Smoe:
         self._klist = torch.ones((nb, K), dtype=torch.uint8, device=dev)
         self._packed = torch.zeros((K, self._PK), dtype=f32, device=dev)
         self._indices = torch.zeros((K,), dtype=torch.int32, device=dev)
+        self._pos = torch.zeros((K,), dtype=torch.int32, device=dev)
+        self._perm = None
+        self._refresh_perm()
         self._counts = torch.zeros((nb, 4), dtype=torch.int32, device=dev)
         self._regsums = torch.zeros((nb, 2), dtype=f32, device=dev)
         self._scalars = torch.zeros((nb, _ffi.NSCAL), dtype=f32, device=dev)
@@ -341,6 +344,21 @@ class Smoe:
         self._xbuf = torch.zeros((K * self._P + _ffi.NSCAL + K,), dtype=f32, device=dev) if self._world > 1 else None
         self._host_stats = torch.zeros((nb, _ffi.NSCAL + 4 + 2), dtype=f32).pin_memory()
         self.gpu_launches = 0
+
+    def _refresh_perm(self):
+        """Spatially coherent kernel -> thread-slot assignment for the backward (Morton order of the current
+        centres).  Purely a work-assignment heuristic: any permutation gives bit-identical results, a coherent
+        one makes the kernels of a warp / CTA neighbours so that the tile culling bites."""
+        d = self.dim_domain
+        mu = self._theta[:, 0:d].detach().cpu().numpy()
+        bits = 10
+        cell = np.clip((mu * (1 << bits)).astype(np.int64), 0, (1 << bits) - 1)
+        key = np.zeros(mu.shape[0], dtype=np.int64)
+        for b in range(bits):
+            for a in range(d):
+                key |= ((cell[:, a] >> b) & 1) << (b * d + (d - 1 - a))
+        perm = np.argsort(key, kind="stable").astype(np.int32)
+        self._perm = torch.from_numpy(perm).to(self.device)
 
     def _enable_res_pre(self):
         """Keep the mixture output before clip / output quantisation (diagnostics and parity tests;
@@ -445,7 +463,7 @@ class Smoe:
                 self.gpu_launches += 1
             else:
                 check(L.smoe_pack(C.byref(self._cfg), ptr(self._theta), ptr(self._klist[ii]), K, ptr(self._packed),
-                                  ptr(self._indices), ptr(counts), ptr(regs), ptr(self._chunk_bounds),
+                                  ptr(self._indices), ptr(self._pos), ptr(counts), ptr(regs), ptr(self._chunk_bounds),
                                   ptr(self._pack_ws), st), "smoe_pack")
                 self.gpu_launches += 3
             self._infl.zero_()
@@ -459,7 +477,8 @@ class Smoe:
                                  ptr(scal), ptr(self._partials), ptr(self._ticket), st), "smoe_forward")
             self.gpu_launches += 1
             if train:
-                check(L.smoe_backward(C.byref(self._cfg), C.byref(b), ptr(self._packed), ptr(counts), K, ptr(self._pix),
+                check(L.smoe_backward(C.byref(self._cfg), C.byref(b), ptr(self._packed), ptr(counts), K,
+                                      ptr(self._perm), ptr(self._pos), ptr(self._pix),
                                       ptr(self._tile_qmin), ptr(self._d_axes[0]), ptr(self._d_axes[1]),
                                       ptr(self._d_axes[2]) if self.dim_domain == 3 else ptr(None),
                                       self._splits, ptr(self._raw_part), st), "smoe_backward")
@@ -663,6 +682,7 @@ class Smoe:
                 maha = (y * y).sum(-1)
             near = ((maha < 800).any(dim=1) & (pis > 0)).to(torch.uint8)
             self._klist[ii] |= near
+        self._refresh_perm()
 
     def _batch_rects(self):
         d = self.dim_domain
@@ -728,6 +748,8 @@ class Smoe:
         if "gamma_e" in params:
             th[:, o["ga"]:] = np.asarray(params["gamma_e"]).reshape(K, d * Cc)
         self._theta.copy_(torch.from_numpy(th).to(self.device))
+        if "musX" in params:
+            self._refresh_perm()
         self.valid = self.qvalid = False
 
     def get_gradients(self):

@@ -178,8 +178,9 @@ int smoe_update_kernel_list(const int32_t* indices, const int32_t* counts, const
 
 /* TF1 ApplyAdam on every K_all row (dense, pruned rows included), three groups.  Replaces
  * session.run(train_op) at smoe.py:1788 (apply_gradients at smoe.py:1173-1193). */
-int smoe_adam_step(const smoe_cfg* cfg, const smoe_adam* hp, float* theta, const float* grads,
-                   float* adam_m, float* adam_v, int K_all, void* stream);
+int smoe_adam_step(const smoe_cfg* cfg, const smoe_adam* hp, const float* alpha_dev /* optional device [3]:
+                   overrides hp->alpha, so that a captured CUDA graph carries no step count */,
+                   float* theta, const float* grads, float* adam_m, float* adam_v, int K_all, void* stream);
 
 /* custom_ssim (ops/image_ops_impl.py:235-293) as evaluated by the loss graph (smoe.py:993-1010):
  * SYMMETRIC pad 5, 11-tap sigma-1.5 Gaussian window, VALID; out[c] = mean SSIM of channel c.

@@ -65,7 +65,7 @@ __device__ __forceinline__ void cta_min8(float (&v)[8], float (*s)[8]) {
 }
 
 template <int D, int C>
-__global__ void __launch_bounds__(kThreads, 4) backward_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(kThreads, 7) backward_kernel(const BwdArgs a) {
     using R = BRec<D, C>;
     constexpr int T = tri(D);
     constexpr int P = nparam(D, C), PK = pstride(D, C);
@@ -524,7 +524,8 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(smoe_cfg cfg, const 
 
 // TF1 ApplyAdam: m += (g-m)(1-b1); v += (g^2-v)(1-b2); var -= alpha*m/(sqrt(v)+eps)
 template <int D, int C>
-__global__ void __launch_bounds__(256) adam_kernel(smoe_adam hp, float* __restrict__ theta, const float* __restrict__ grads,
+__global__ void __launch_bounds__(256) adam_kernel(smoe_adam hp, const float* __restrict__ alpha_dev,
+                                                   float* __restrict__ theta, const float* __restrict__ grads,
                                                    float* __restrict__ am, float* __restrict__ av, size_t n) {
     constexpr int P = nparam(D, C);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -536,7 +537,7 @@ __global__ void __launch_bounds__(256) adam_kernel(smoe_adam hp, float* __restri
         else if (j == off_pi(D, C)) grp = 1;
         else if (j < off_ga(D, C)) grp = 0;
         else { grp = 0; on = hp.train_gammas != 0; }
-        const float alpha = hp.alpha[grp];
+        const float alpha = alpha_dev ? alpha_dev[grp] : hp.alpha[grp];
         if (!on || alpha == 0.f) continue;
         float g = grads[i];
         if (hp.grad_clip > 0.f) g = fminf(fmaxf(g, -hp.grad_clip), hp.grad_clip);
@@ -629,14 +630,14 @@ int smoe_grad_finalize(const smoe_cfg* cfg, const float* raw, int num_splits, in
     return check_launch("smoe_grad_finalize");
 }
 
-int smoe_adam_step(const smoe_cfg* cfg, const smoe_adam* hp, float* theta, const float* grads, float* adam_m,
-                   float* adam_v, int K_all, void* stream) {
+int smoe_adam_step(const smoe_cfg* cfg, const smoe_adam* hp, const float* alpha_dev, float* theta, const float* grads,
+                   float* adam_m, float* adam_v, int K_all, void* stream) {
     SMOE_REQUIRE(cfg && hp && theta && grads && adam_m && adam_v && K_all > 0, "bad argument");
     size_t n = (size_t)K_all * nparam(cfg->d, cfg->C);
     int nb = (int)((n + 255) / 256);
     if (nb > 148 * 8) nb = 148 * 8;
     cudaStream_t st = (cudaStream_t)stream;
-#define CALL(D, C) adam_kernel<D, C><<<nb, 256, 0, st>>>(*hp, theta, grads, adam_m, adam_v, n);
+#define CALL(D, C) adam_kernel<D, C><<<nb, 256, 0, st>>>(*hp, alpha_dev, theta, grads, adam_m, adam_v, n);
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL
     return check_launch("smoe_adam_step");

@@ -282,7 +282,7 @@ int smoe_colminmax(const float* x, int rows, int cols, double* lb, double* ub, v
 int smoe_suggest_splits(int K_cap, int ntiles) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int slots = 4 * sms;
+    const int slots = 7 * sms;
     const int kt = (K_cap + kThreads - 1) / kThreads;
     int best = 1;
     double best_eff = -1.0;

@@ -11,7 +11,7 @@
 
 namespace smoe {
 
-constexpr int kThreads = 128;                        // threads per CTA of the backward (one kernel per thread)
+constexpr int kThreads = 64;                        // threads per CTA of the backward (one kernel per thread)
 constexpr int kThreadsF = 128;                       // threads per CTA of the forward
 constexpr int kPixPerThread = SMOE_TPIX / kThreadsF; // 4 pixels per thread in the forward
 constexpr int kChunk = 128;                          // kernels staged per shared-memory chunk

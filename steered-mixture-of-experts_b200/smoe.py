@@ -343,6 +343,12 @@ class Smoe:
         # [raw statistics | scalars | influence flags]: the buffer a multi-GPU run all-reduces
         self._xbuf = torch.zeros((K * self._P + _ffi.NSCAL + K,), dtype=f32, device=dev) if self._world > 1 else None
         self._host_stats = torch.zeros((nb, _ffi.NSCAL + 4 + 2), dtype=f32).pin_memory()
+        self._alpha_host = torch.zeros((4,), dtype=f32).pin_memory()
+        self._alpha_dev = torch.zeros((4,), dtype=f32, device=dev)
+        self._graphs = {}
+        # graph replay is used on one GPU; with several ranks the step stays eager (capturing the NCCL
+        # all-reduce next to the watchdog thread hung on this stack)
+        self.use_cuda_graphs = self._world == 1
         self.gpu_launches = 0
 
     def _refresh_perm(self):
@@ -408,18 +414,27 @@ class Smoe:
                 self._adam_v[:, idx] = 0
                 self._group_owner[g] = new[g]
 
-    def _adam_launch(self):
-        hp = Adam()
+    def _adam_prepare(self):
+        """Advance the optimizers' beta powers (one apply_gradients each) and stage TF's bias-corrected
+        step sizes in pinned host memory; the launch (eager or a replayed CUDA graph) copies them to the
+        device, so a captured step never bakes a step count into its kernel arguments."""
         opts = [self.optimizer1, self.optimizer2, self.optimizer3]
         trainable = [True, self.train_pis, True]
         for g, (opt, tr) in enumerate(zip(opts, trainable)):
             on = tr and not opt._lr == 0
-            hp.alpha[g] = opt._step_alpha() if on else 0.0
+            self._alpha_host[g] = opt._step_alpha() if on else 0.0
+
+    def _adam_launch(self):
+        hp = Adam()
+        for g, opt in enumerate([self.optimizer1, self.optimizer2, self.optimizer3]):
+            hp.alpha[g] = 0.0
             hp.beta1[g], hp.beta2[g], hp.epsilon[g] = opt._beta1, opt._beta2, opt._epsilon
         hp.grad_clip = float(self.grad_clip_value_abs) if self.grad_clip_value_abs is not None else 0.0
         hp.train_musx, hp.train_gammas = int(self.train_musx), int(self.train_gammas)
-        check(lib().smoe_adam_step(C.byref(self._cfg), C.byref(hp), ptr(self._theta), ptr(self._grads),
-                                   ptr(self._adam_m), ptr(self._adam_v), self.start_pis, stream_ptr()), "smoe_adam_step")
+        self._alpha_dev.copy_(self._alpha_host, non_blocking=True)
+        check(lib().smoe_adam_step(C.byref(self._cfg), C.byref(hp), ptr(self._alpha_dev), ptr(self._theta),
+                                   ptr(self._grads), ptr(self._adam_m), ptr(self._adam_v), self.start_pis,
+                                   stream_ptr()), "smoe_adam_step")
         self.gpu_launches += 1
 
     # ------------------------------------------------------------------------------------------
@@ -430,84 +445,54 @@ class Smoe:
                     thr_sv=None, use_loss_mask=False, _host_image=None):
         if sampling_percentage < 100 or with_inc or train_inc or use_loss_mask:
             raise NotImplementedError("sampling / inc / loss-mask paths are outside the hot path (D1)")
+        if self.kernel_count_as_norm_l1:
+            raise NotImplementedError("kernel_count_as_norm_l1")
         if train:
             assert self.optimizer1 is not None, "no optimizer found, you have to specify one!"
-        L, st = lib(), stream_ptr()
         self.valid = False
         if with_quantized_params:
             self.qvalid = False
-        if _host_image is not None:                      # e2e path: this step's pixels come from pinned host memory
-            self._d_image.copy_(_host_image, non_blocking=True)
         K, P = self.start_pis, self._P
+        if train and self._raw_part is None:
+            self._raw_part = torch.zeros((self._splits * K * P,), dtype=torch.float32, device=self.device)
         if train:
-            self._grads.zero_()
-            if self._raw_part is None:
-                self._raw_part = torch.zeros((self._splits * K * P,), dtype=torch.float32, device=self.device)
-        self._scalars.zero_()
-        fed = with_quantized_params and update_reconstruction
-        if fed:
-            rp = {k: torch.as_tensor(np.ascontiguousarray(np.asarray(v, dtype=np.float32)), device=self.device)
-                  for k, v in self.rparams.items()}
-            Kf = int(rp["pis"].shape[0])
-            if Kf > K:
-                raise ValueError("more fed kernels than model kernels")
-        norm = float(self.start_pis)
-        for ii, b in enumerate(self._batches):
-            counts, regs, scal = self._counts[ii], self._regsums[ii], self._scalars[ii]
-            if fed:
-                check(L.smoe_pack_fed(C.byref(self._cfg), ptr(rp["A"]), ptr(rp["musX"]), ptr(rp["nu_e"]),
-                                      ptr(rp["gamma_e"]), ptr(rp["pis"]), Kf, ptr(self._packed), ptr(counts),
-                                      ptr(self._chunk_bounds), st), "smoe_pack_fed")
-                self._indices[:Kf] = torch.arange(Kf, dtype=torch.int32, device=self.device)
-                regs.zero_()
-                self.gpu_launches += 1
+            self._adam_prepare()
+        # A plain training step (the hot loop of Smoe.train, smoe.py:1527) is captured once into a CUDA
+        # graph and replayed: one graph launch + one stream sync per iteration instead of ~25 launches.
+        graphable = self.use_cuda_graphs and train and not update_reconstruction and not with_quantized_params
+        replayed = False
+        if graphable:
+            key = (float(pis_l1), float(u_l1), self.grad_clip_value_abs, id(self.optimizer1), id(self.optimizer2),
+                   id(self.optimizer3), self.optimizer1._lr, self.optimizer2._lr, self.optimizer3._lr,
+                   None if _host_image is None else _host_image.data_ptr())
+            state = self._graphs.get(key)
+            if state is None:
+                self._graphs[key] = "warm"              # first step with this signature runs eagerly
             else:
-                check(L.smoe_pack(C.byref(self._cfg), ptr(self._theta), ptr(self._klist[ii]), K, ptr(self._packed),
-                                  ptr(self._indices), ptr(self._pos), ptr(counts), ptr(regs), ptr(self._chunk_bounds),
-                                  ptr(self._pack_ws), st), "smoe_pack")
-                self.gpu_launches += 3
-            self._infl.zero_()
-            check(L.smoe_forward(C.byref(self._cfg), C.byref(b), ptr(self._packed), ptr(self._indices), ptr(counts),
-                                 ptr(self._chunk_bounds), K,
-                                 ptr(self._d_image), ptr(self._d_axes[0]), ptr(self._d_axes[1]),
-                                 ptr(self._d_axes[2]) if self.dim_domain == 3 else ptr(None),
-                                 ptr(self._d_res), ptr(self._d_res_pre),
-                                 ptr(self._d_argmax) if update_reconstruction else ptr(None),
-                                 ptr(self._infl), ptr(self._pix) if train else ptr(None), ptr(self._tile_qmin),
-                                 ptr(scal), ptr(self._partials), ptr(self._ticket), st), "smoe_forward")
-            self.gpu_launches += 1
-            if train:
-                check(L.smoe_backward(C.byref(self._cfg), C.byref(b), ptr(self._packed), ptr(counts), K,
-                                      ptr(self._perm), ptr(self._pos), ptr(self._pix),
-                                      ptr(self._tile_qmin), ptr(self._d_axes[0]), ptr(self._d_axes[1]),
-                                      ptr(self._d_axes[2]) if self.dim_domain == 3 else ptr(None),
-                                      self._splits, ptr(self._raw_part), st), "smoe_backward")
-                self.gpu_launches += 1
-            if self._world > 1:
-                self._exchange(train, counts, scal)
-            if train:
-                l1 = float(pis_l1) / norm if not self.kernel_count_as_norm_l1 else None
-                if l1 is None:
-                    raise NotImplementedError("kernel_count_as_norm_l1")
-                raw, ns = (self._xbuf, 1) if self._world > 1 else (self._raw_part, self._splits)
-                check(L.smoe_grad_finalize(C.byref(self._cfg), ptr(raw), ns, K, ptr(self._theta), ptr(self._indices),
-                                           ptr(counts), C.c_float(l1), C.c_float(float(u_l1)), ptr(self._grads), st),
-                      "smoe_grad_finalize")
-                self.gpu_launches += 1
-            if not with_quantized_params:                 # smoe.py:1763-1766
-                check(L.smoe_update_kernel_list(ptr(self._indices), ptr(counts), ptr(self._infl), ptr(self._klist[ii]),
-                                                K, st), "smoe_update_kernel_list")
-                self.gpu_launches += 2
-        if train:
-            self._adam_launch()
-        # one small device->host read per call: scalars, counts, regulariser sums
-        nb = len(self._batches)
-        hs = self._host_stats
-        hs[:, :_ffi.NSCAL].copy_(self._scalars, non_blocking=True)
-        hs[:, _ffi.NSCAL:_ffi.NSCAL + 4].copy_(self._counts.to(torch.float32), non_blocking=True)
-        hs[:, _ffi.NSCAL + 4:].copy_(self._regsums, non_blocking=True)
+                if state == "warm":
+                    try:
+                        g = torch.cuda.CUDAGraph()
+                        l0 = self.gpu_launches
+                        torch.cuda.synchronize()
+                        with torch.cuda.graph(g):
+                            self._enqueue(pis_l1, u_l1, True, False, False, _host_image)
+                        state = (g, self.gpu_launches - l0)
+                        self.gpu_launches = l0
+                        self._graphs[key] = state
+                    except Exception as exc:             # capture unsupported here: stay eager, loudly
+                        print(f"smoe_b200: CUDA graph capture disabled ({exc})")
+                        self.use_cuda_graphs = False
+                        torch.cuda.synchronize()
+                        state = None
+                if state is not None:
+                    state[0].replay()
+                    self.gpu_launches += state[1]
+                    replayed = True
+        if not replayed:
+            self._enqueue(pis_l1, u_l1, train, update_reconstruction, with_quantized_params, _host_image)
         torch.cuda.current_stream().synchronize()
-        h = hs.numpy().astype(np.float64)
+        h = self._host_stats.numpy().astype(np.float64)
+        norm = float(self.start_pis)
         Cc = self.image.shape[-1]
         loss_val = mse_val = 0.0
         num_pi = -1
@@ -533,6 +518,75 @@ class Smoe:
             else:
                 self.reconstruction_image, self.weight_matrix_argmax, self.valid = rec, amax, True
         return loss_val, mse_val, num_pi, 0
+
+    def _enqueue(self, pis_l1, u_l1, train, update_reconstruction, with_quantized_params, _host_image):
+        """Every launch of one run_batched call, asynchronous on the current stream (capturable)."""
+        L, st = lib(), stream_ptr()
+        K = self.start_pis
+        if _host_image is not None:                      # e2e path: this step's pixels come from pinned host memory
+            self._d_image.copy_(_host_image, non_blocking=True)
+        if train:
+            self._grads.zero_()
+        self._scalars.zero_()
+        fed = with_quantized_params and update_reconstruction
+        if fed:
+            rp = {k: torch.as_tensor(np.ascontiguousarray(np.asarray(v, dtype=np.float32)), device=self.device)
+                  for k, v in self.rparams.items()}
+            Kf = int(rp["pis"].shape[0])
+            if Kf > K:
+                raise ValueError("more fed kernels than model kernels")
+        norm = float(self.start_pis)
+        for ii, b in enumerate(self._batches):
+            counts, regs, scal = self._counts[ii], self._regsums[ii], self._scalars[ii]
+            if fed:
+                check(L.smoe_pack_fed(C.byref(self._cfg), ptr(rp["A"]), ptr(rp["musX"]), ptr(rp["nu_e"]),
+                                      ptr(rp["gamma_e"]), ptr(rp["pis"]), Kf, ptr(self._packed), ptr(counts),
+                                      ptr(self._chunk_bounds), st), "smoe_pack_fed")
+                self._indices[:Kf] = torch.arange(Kf, dtype=torch.int32, device=self.device)
+                regs.zero_()
+                self.gpu_launches += 2
+            else:
+                check(L.smoe_pack(C.byref(self._cfg), ptr(self._theta), ptr(self._klist[ii]), K, ptr(self._packed),
+                                  ptr(self._indices), ptr(self._pos), ptr(counts), ptr(regs), ptr(self._chunk_bounds),
+                                  ptr(self._pack_ws), st), "smoe_pack")
+                self.gpu_launches += 4
+            self._infl.zero_()
+            check(L.smoe_forward(C.byref(self._cfg), C.byref(b), ptr(self._packed), ptr(self._indices), ptr(counts),
+                                 ptr(self._chunk_bounds), K,
+                                 ptr(self._d_image), ptr(self._d_axes[0]), ptr(self._d_axes[1]),
+                                 ptr(self._d_axes[2]) if self.dim_domain == 3 else ptr(None),
+                                 ptr(self._d_res), ptr(self._d_res_pre),
+                                 ptr(self._d_argmax) if update_reconstruction else ptr(None),
+                                 ptr(self._infl), ptr(self._pix) if train else ptr(None), ptr(self._tile_qmin),
+                                 ptr(scal), ptr(self._partials), ptr(self._ticket), st), "smoe_forward")
+            self.gpu_launches += 1
+            if train:
+                check(L.smoe_backward(C.byref(self._cfg), C.byref(b), ptr(self._packed), ptr(counts), K,
+                                      ptr(self._perm), ptr(self._pos), ptr(self._pix),
+                                      ptr(self._tile_qmin), ptr(self._d_axes[0]), ptr(self._d_axes[1]),
+                                      ptr(self._d_axes[2]) if self.dim_domain == 3 else ptr(None),
+                                      self._splits, ptr(self._raw_part), st), "smoe_backward")
+                self.gpu_launches += 1
+            if self._world > 1:
+                self._exchange(train, counts, scal)
+            if train:
+                l1 = float(pis_l1) / norm
+                raw, ns = (self._xbuf, 1) if self._world > 1 else (self._raw_part, self._splits)
+                check(L.smoe_grad_finalize(C.byref(self._cfg), ptr(raw), ns, K, ptr(self._theta), ptr(self._indices),
+                                           ptr(counts), C.c_float(l1), C.c_float(float(u_l1)), ptr(self._grads), st),
+                      "smoe_grad_finalize")
+                self.gpu_launches += 1
+            if not with_quantized_params:                 # smoe.py:1763-1766
+                check(L.smoe_update_kernel_list(ptr(self._indices), ptr(counts), ptr(self._infl), ptr(self._klist[ii]),
+                                                K, st), "smoe_update_kernel_list")
+                self.gpu_launches += 2
+        if train:
+            self._adam_launch()
+        # one small device->host read per call: scalars, counts, regulariser sums
+        hs = self._host_stats
+        hs[:, :_ffi.NSCAL].copy_(self._scalars, non_blocking=True)
+        hs[:, _ffi.NSCAL:_ffi.NSCAL + 4].copy_(self._counts.to(torch.float32), non_blocking=True)
+        hs[:, _ffi.NSCAL + 4:].copy_(self._regsums, non_blocking=True)
 
     def _exchange(self, train, counts, scal):
         """The one exchange step of the sharded path: sum over ranks of the

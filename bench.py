@@ -260,11 +260,32 @@ def run_ours(args):
                 "algorithmic_lane_instr_per_eval": {"fwd": f_fwd, "bwd": f_bwd},
                 "forward_ms": ker["forward_ms"], "backward_ms": ker["backward_ms"], "other_ms": ker["other_ms"],
                 "step_frac_fwd_bwd": (local_evals * (f_fwd + f_bwd) * 2 / (np.mean(ms) / 1e3) / 1e12) / peak_tflops,
-                "note": "achieved counts the ALGORITHMIC lane-instructions of SURVEY 8d; with dense_exec=0 the kernels skip "
-                        "warps whose gates are all below the threshold (exact zeros), so frac can exceed what the FP32 "
-                        "pipe executed; run with --dense-exec 1 for the dense-executed figure"}
+                "note": "achieved = ALGORITHMIC lane-instructions of SURVEY 8d (N*K*F) / launch time.  In the default mode "
+                        "the kernels cull and skip (pixel,kernel) pairs whose contribution is exactly 0 (bit-identical "
+                        "results, asserted by tests), so frac >> 1 means work provably not needed, not work not done; "
+                        "'dense_exec' holds the same kernels executing every pair"}
     if clocks and clocks.get("sm_mhz"):
         roofline["frac_at_observed_clock"] = roofline["frac"] * peaks["sm_max_mhz"] / clocks["sm_mhz"]
+    roofline["mode"] = {0: "exact culling + exact-zero skipping", 1: "every (pixel,kernel) pair executed",
+                        2: "exact-zero skipping only"}[int(args.dense_exec)]
+    tr = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tr):
+        with open(tr) as fd:
+            roofline["traffic"] = json.load(fd).get(f"{dom}_kernel<{d},{C}>@{args.workload}@mode{int(args.dense_exec)}")
+    # the same two kernels with every (pixel, kernel) pair executed (dense_exec=1): the figure that compares
+    # like with like against the algorithmic instruction count
+    if world == 1 and int(args.dense_exec) == 0 and not args.no_dense:
+        md = Smoe(img, kernels_per_dim=kgrid, dense_exec=1, **SMOE_KW)
+        md.set_optimizer(AdamOptimizer(1e-3), AdamOptimizer(1e-5), AdamOptimizer(1.0))
+        md.run_batched(train=True)
+        kd = kernel_times(md, steps=2, with_step=False)
+        domd = "backward" if kd["backward_ms"] >= kd["forward_ms"] else "forward"
+        ach = evals_per_step * (f_bwd if domd == "backward" else f_fwd) * 2 / (kd[domd + "_ms"] / 1e3) / 1e12
+        roofline["dense_exec"] = {"kernel": f"smoe::{domd}_kernel<{d},{C}>", "forward_ms": kd["forward_ms"],
+                                  "backward_ms": kd["backward_ms"], "achieved": ach, "frac": ach / peak_tflops,
+                                  "fwd_bwd_frac": (evals_per_step * (f_fwd + f_bwd) * 2 /
+                                                   ((kd["forward_ms"] + kd["backward_ms"]) / 1e3) / 1e12) / peak_tflops}
+        del md
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -288,7 +309,7 @@ def run_ours(args):
         torch.distributed.destroy_process_group()
 
 
-def kernel_times(m, steps):
+def kernel_times(m, steps, with_step=True):
     """Average launch duration of the forward and backward sweep kernels, CUDA events on the
     launching stream around the C-ABI calls (parameters frozen: no Adam between launches)."""
     import ctypes as C
@@ -319,6 +340,8 @@ def kernel_times(m, steps):
         fw.append(e[0].elapsed_time(e[1]))
         bw.append(e[1].elapsed_time(e[2]))
     fw, bw = fw[1:], bw[1:]
+    if not with_step:
+        return {"forward_ms": float(np.mean(fw)), "backward_ms": float(np.mean(bw)), "other_ms": 0.0}
     # everything else in a step: pack, finalize, list upkeep, Adam, memsets
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -341,6 +364,7 @@ def main():
     ap.add_argument("--dense-exec", type=int, default=0,
                     help="0: exact culling + exact-zero skipping (default); 1: execute every pair; 2: skipping only")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense_exec=1 roofline leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

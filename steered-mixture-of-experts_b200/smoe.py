@@ -346,9 +346,9 @@ class Smoe:
         self._alpha_host = torch.zeros((4,), dtype=f32).pin_memory()
         self._alpha_dev = torch.zeros((4,), dtype=f32, device=dev)
         self._graphs = {}
-        # graph replay is used on one GPU; with several ranks the step stays eager (capturing the NCCL
-        # all-reduce next to the watchdog thread hung on this stack)
-        self.use_cuda_graphs = self._world == 1
+        # with several ranks the step is two graphs around an eager NCCL all-reduce (capturing the
+        # collective itself hung on this stack)
+        self.use_cuda_graphs = True
         self.gpu_launches = 0
 
     def _refresh_perm(self):
@@ -471,12 +471,16 @@ class Smoe:
             else:
                 if state == "warm":
                     try:
-                        g = torch.cuda.CUDAGraph()
                         l0 = self.gpu_launches
                         torch.cuda.synchronize()
-                        with torch.cuda.graph(g):
-                            self._enqueue(pis_l1, u_l1, True, False, False, _host_image)
-                        state = (g, self.gpu_launches - l0)
+                        graphs = []
+                        # with several ranks the NCCL all-reduce stays outside: [pre] -> all_reduce -> [post]
+                        for phase in (("all",) if self._world == 1 else ("pre", "post")):
+                            g = torch.cuda.CUDAGraph()
+                            with torch.cuda.graph(g):
+                                self._enqueue(pis_l1, u_l1, True, False, False, _host_image, phase=phase)
+                            graphs.append(g)
+                        state = (graphs, self.gpu_launches - l0)
                         self.gpu_launches = l0
                         self._graphs[key] = state
                     except Exception as exc:             # capture unsupported here: stay eager, loudly
@@ -485,7 +489,10 @@ class Smoe:
                         torch.cuda.synchronize()
                         state = None
                 if state is not None:
-                    state[0].replay()
+                    state[0][0].replay()
+                    if self._world > 1:
+                        torch.distributed.all_reduce(self._xbuf, group=self._pg)
+                        state[0][1].replay()
                     self.gpu_launches += state[1]
                     replayed = True
         if not replayed:
@@ -519,15 +526,18 @@ class Smoe:
                 self.reconstruction_image, self.weight_matrix_argmax, self.valid = rec, amax, True
         return loss_val, mse_val, num_pi, 0
 
-    def _enqueue(self, pis_l1, u_l1, train, update_reconstruction, with_quantized_params, _host_image):
-        """Every launch of one run_batched call, asynchronous on the current stream (capturable)."""
+    def _enqueue(self, pis_l1, u_l1, train, update_reconstruction, with_quantized_params, _host_image, phase="all"):
+        """Every launch of one run_batched call, asynchronous on the current stream (capturable).
+        phase "pre" / "post" enqueue only the part before / after the all-reduce of a sharded step."""
         L, st = lib(), stream_ptr()
         K = self.start_pis
-        if _host_image is not None:                      # e2e path: this step's pixels come from pinned host memory
-            self._d_image.copy_(_host_image, non_blocking=True)
-        if train:
-            self._grads.zero_()
-        self._scalars.zero_()
+        pre, post = phase in ("all", "pre"), phase in ("all", "post")
+        if pre:
+            if _host_image is not None:                  # e2e path: this step's pixels come from pinned host memory
+                self._d_image.copy_(_host_image, non_blocking=True)
+            if train:
+                self._grads.zero_()
+            self._scalars.zero_()
         fed = with_quantized_params and update_reconstruction
         if fed:
             rp = {k: torch.as_tensor(np.ascontiguousarray(np.asarray(v, dtype=np.float32)), device=self.device)
@@ -538,7 +548,9 @@ class Smoe:
         norm = float(self.start_pis)
         for ii, b in enumerate(self._batches):
             counts, regs, scal = self._counts[ii], self._regsums[ii], self._scalars[ii]
-            if fed:
+            if not pre:
+                pass
+            elif fed:
                 check(L.smoe_pack_fed(C.byref(self._cfg), ptr(rp["A"]), ptr(rp["musX"]), ptr(rp["nu_e"]),
                                       ptr(rp["gamma_e"]), ptr(rp["pis"]), Kf, ptr(self._packed), ptr(counts),
                                       ptr(self._chunk_bounds), st), "smoe_pack_fed")
@@ -550,17 +562,18 @@ class Smoe:
                                   ptr(self._indices), ptr(self._pos), ptr(counts), ptr(regs), ptr(self._chunk_bounds),
                                   ptr(self._pack_ws), st), "smoe_pack")
                 self.gpu_launches += 4
-            self._infl.zero_()
-            check(L.smoe_forward(C.byref(self._cfg), C.byref(b), ptr(self._packed), ptr(self._indices), ptr(counts),
-                                 ptr(self._chunk_bounds), K,
-                                 ptr(self._d_image), ptr(self._d_axes[0]), ptr(self._d_axes[1]),
-                                 ptr(self._d_axes[2]) if self.dim_domain == 3 else ptr(None),
-                                 ptr(self._d_res), ptr(self._d_res_pre),
-                                 ptr(self._d_argmax) if update_reconstruction else ptr(None),
-                                 ptr(self._infl), ptr(self._pix) if train else ptr(None), ptr(self._tile_qmin),
-                                 ptr(scal), ptr(self._partials), ptr(self._ticket), st), "smoe_forward")
-            self.gpu_launches += 1
-            if train:
+            if pre:
+                self._infl.zero_()
+                check(L.smoe_forward(C.byref(self._cfg), C.byref(b), ptr(self._packed), ptr(self._indices), ptr(counts),
+                                     ptr(self._chunk_bounds), K,
+                                     ptr(self._d_image), ptr(self._d_axes[0]), ptr(self._d_axes[1]),
+                                     ptr(self._d_axes[2]) if self.dim_domain == 3 else ptr(None),
+                                     ptr(self._d_res), ptr(self._d_res_pre),
+                                     ptr(self._d_argmax) if update_reconstruction else ptr(None),
+                                     ptr(self._infl), ptr(self._pix) if train else ptr(None), ptr(self._tile_qmin),
+                                     ptr(scal), ptr(self._partials), ptr(self._ticket), st), "smoe_forward")
+                self.gpu_launches += 1
+            if train and pre:
                 check(L.smoe_backward(C.byref(self._cfg), C.byref(b), ptr(self._packed), ptr(counts), K,
                                       ptr(self._perm), ptr(self._pos), ptr(self._pix),
                                       ptr(self._tile_qmin), ptr(self._d_axes[0]), ptr(self._d_axes[1]),
@@ -568,7 +581,9 @@ class Smoe:
                                       self._splits, ptr(self._raw_part), st), "smoe_backward")
                 self.gpu_launches += 1
             if self._world > 1:
-                self._exchange(train, counts, scal)
+                self._exchange(train, counts, scal, phase)
+            if not post:
+                continue
             if train:
                 l1 = float(pis_l1) / norm
                 raw, ns = (self._xbuf, 1) if self._world > 1 else (self._raw_part, self._splits)
@@ -580,6 +595,8 @@ class Smoe:
                 check(L.smoe_update_kernel_list(ptr(self._indices), ptr(counts), ptr(self._infl), ptr(self._klist[ii]),
                                                 K, st), "smoe_update_kernel_list")
                 self.gpu_launches += 2
+        if not post:
+            return
         if train:
             self._adam_launch()
         # one small device->host read per call: scalars, counts, regulariser sums
@@ -588,22 +605,25 @@ class Smoe:
         hs[:, _ffi.NSCAL:_ffi.NSCAL + 4].copy_(self._counts.to(torch.float32), non_blocking=True)
         hs[:, _ffi.NSCAL + 4:].copy_(self._regsums, non_blocking=True)
 
-    def _exchange(self, train, counts, scal):
+    def _exchange(self, train, counts, scal, phase="all"):
         """The one exchange step of the sharded path: sum over ranks of the
         per-kernel statistics, the loss scalars and the influence flags."""
         L, st = lib(), stream_ptr()
         K, P = self.start_pis, self._P
-        if train:
-            check(L.smoe_reduce_splits(C.byref(self._cfg), ptr(counts), K, self._splits, ptr(self._raw_part),
-                                       ptr(self._xbuf), st), "smoe_reduce_splits")
-            self.gpu_launches += 1
-        else:
-            self._xbuf[:K * P].zero_()
-        self._xbuf[K * P:K * P + _ffi.NSCAL] = scal
-        self._xbuf[K * P + _ffi.NSCAL:] = self._infl.to(torch.float32)
-        torch.distributed.all_reduce(self._xbuf, group=self._pg)
-        scal.copy_(self._xbuf[K * P:K * P + _ffi.NSCAL])
-        self._infl.copy_((self._xbuf[K * P + _ffi.NSCAL:] > 0).to(torch.uint8))
+        if phase in ("all", "pre"):
+            if train:
+                check(L.smoe_reduce_splits(C.byref(self._cfg), ptr(counts), K, self._splits, ptr(self._raw_part),
+                                           ptr(self._xbuf), st), "smoe_reduce_splits")
+                self.gpu_launches += 1
+            else:
+                self._xbuf[:K * P].zero_()
+            self._xbuf[K * P:K * P + _ffi.NSCAL] = scal
+            self._xbuf[K * P + _ffi.NSCAL:] = self._infl.to(torch.float32)
+        if phase == "all":
+            torch.distributed.all_reduce(self._xbuf, group=self._pg)
+        if phase in ("all", "post"):
+            scal.copy_(self._xbuf[K * P:K * P + _ffi.NSCAL])
+            self._infl.copy_((self._xbuf[K * P + _ffi.NSCAL:] > 0).to(torch.uint8))
 
     def _gather_reconstruction(self):
         Cc = self.image.shape[-1]

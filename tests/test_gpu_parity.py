@@ -409,3 +409,89 @@ def test_reconstruction_entry_point_round_trip(tmp_path):
     p_loaded = s2.get_params()
     np.testing.assert_array_equal(p_saved["A_corr"], p_loaded["A_corr"])
     np.testing.assert_array_equal(p_saved["A_diagonal"], p_loaded["A_diagonal"])
+
+
+def _oracle_at_pixels(img, params, flat_idx, cfgkw, feed=None):
+    """float64 oracle forward at a sample of pixels (each pixel's output depends on no other pixel)."""
+    from oracle.graph import GraphCfg, graph_forward
+    d, C = img.ndim - 1, img.shape[-1]
+    K = params["pis"].shape[0]
+    axes = [np.linspace(0, 1, n).astype(np.float32).astype(np.float64) for n in img.shape[:d]]
+    sub = np.unravel_index(flat_idx, img.shape[:d])
+    dom = np.stack([axes[a][sub[a]] for a in range(d)], axis=1)
+    tgt = img.reshape(-1, C)[flat_idx].astype(np.float64)
+    cfg = GraphCfg(dim_domain=d, num_channels=C, start_pis=K, **cfgkw)
+    tp = {k: torch.tensor(np.asarray(v, np.float64)) for k, v in params.items()}
+    fd = None if feed is None else {k: torch.tensor(np.asarray(v, np.float64)) for k, v in feed.items()}
+    return graph_forward(tp, np.ones(K, bool), torch.tensor(dom), torch.tensor(tgt), cfg, feed=fd)
+
+
+def _check_sampled_forward(pre_gpu, out, tol_frac=0.97):
+    thr = (out["w_full"] / TAU - 1).abs().min(dim=0).values.numpy()
+    ok = thr > 1e-3
+    assert ok.mean() > tol_frac
+    ref = out["r_pre"].detach().numpy()
+    assert np.abs(pre_gpu[ok] - ref[ok]).max() <= 1e-5
+    assert np.abs(pre_gpu - ref).max() <= 2 * TAU
+
+
+@pytest.mark.parametrize("workload", ["c3", "c4s"])
+def test_full_size_culling_is_exact_and_forward_matches_oracle(workload):
+    """BASELINE config 3 (1080p RGB, 32,768 kernels) and config 4 at 1/8 scale (video, 3x3 A): one training
+    step with exact culling vs exact-zero skipping only -- gradients, updated parameters, kernel lists and the
+    reconstruction must agree BITWISE; the reconstruction is checked against the float64 oracle at a random
+    sample of pixels (a pixel's output depends on no other pixel)."""
+    import bench
+    shape, kgrid, seed, _ = bench.WORKLOADS[workload]
+    img = bench.synth_image(shape, seed)
+    res = []
+    for mode in (0, 2):
+        m = _mk(img, kgrid, dense_exec=mode, **bench.SMOE_KW)
+        m._enable_res_pre()
+        p0 = m.get_params() if mode == 0 else None
+        loss = m.run_batched(pis_l1=0.1, train=True, update_reconstruction=True)
+        res.append((m._grads.cpu().numpy(), m._theta.cpu().numpy(), m._klist.cpu().numpy(), m._d_res_pre.cpu().numpy(),
+                    m._d_argmax.cpu().numpy(), loss))
+        if mode == 0:
+            params0 = p0
+        del m
+        torch.cuda.empty_cache()
+    for q in range(5):
+        np.testing.assert_array_equal(res[0][q], res[1][q])
+    assert res[0][5] == res[1][5]
+    assert np.isfinite(res[0][0]).all() and np.abs(res[0][0]).max() > 0
+    rs = np.random.RandomState(1)
+    idx = rs.choice(int(np.prod(shape[:-1])), 160, replace=False)
+    out = _oracle_at_pixels(img, params0, idx, dict(use_determinant=True, train_inverse_cov=False, use_yuv=False))
+    _check_sampled_forward(res[0][3][idx], out)
+
+
+def test_full_size_decoder_config5():
+    """BASELINE config 5: 3840x2160 RGB decoded reconstruction (smoe_reconstruction_decoded.py), forward only,
+    ~64.8k surviving kernels of a 540x960 grid, with GPU PSNR / SSIM against a synthetic 4K target."""
+    from smoe_b200 import smoe_reconstruction_decoded as dec
+    from smoe_b200.ops.image_ops_impl import mse_gpu, smoe_ssim
+    import bench
+    H, W, C = 2160, 3840, 3
+    cp = _decoded_dict(H, W, C, seed=1005)
+    smoe, rec, loss, mse = dec.main(cp=cp, write=False)
+    assert rec.shape == (H, W, C) and rec.min() >= 0 and rec.max() <= 1
+    assert np.abs(rec * 255 - np.round(rec * 255)).max() < 1e-3
+    smoe._enable_res_pre()
+    smoe.run_batched(train=False, update_reconstruction=True, with_quantized_params=True)
+    pre = smoe._d_res_pre.cpu().numpy()
+    rs = np.random.RandomState(2)
+    idx = rs.choice(H * W, 120, replace=False)
+    rp = smoe.rparams
+    K = rp["pis"].shape[0]
+    dummy = {"pis": np.ones(K), "musX": rp["musX"], "A_diagonal": rp["A"], "A_corr": rp["A"] * 0, "gamma_e": rp["gamma_e"],
+             "nu_e": rp["nu_e"]}
+    out = _oracle_at_pixels(np.zeros((H, W, C), np.float32), dummy, idx,
+                            dict(use_determinant=True, train_inverse_cov=False, use_yuv=True), feed=rp)
+    _check_sampled_forward(pre[idx], out, tol_frac=0.9)
+    # GPU metrics of north_star item 4 against a synthetic 4K frame
+    target = bench.synth_image((H, W, C), 1005)
+    m = mse_gpu(rec, target)
+    assert abs(m - float(((rec.astype(np.float64) - target) ** 2).mean())) < 1e-9
+    s, per = smoe_ssim(rec, target, use_yuv=True)
+    assert -1 <= s <= 1 and per.shape == (3,)

@@ -314,7 +314,7 @@ def test_ssim_and_psnr_kernels():
     vid_b = np.clip(vid_a + 0.1 * rs.standard_normal(vid_a.shape), 0, 1).astype(np.float32)
     np.testing.assert_allclose(smoe_ssim(vid_a, vid_b, use_yuv=False)[1],
                                ossim.smoe_ssim(vid_a, vid_b, use_yuv=False, dtype=np.float64)[1], atol=2e-5)
-    assert abs(mse_gpu(a, b) - float(((a.astype(np.float64) - b) ** 2).mean())) < 1e-12
+    assert abs(mse_gpu(a, b) - float(((a.astype(np.float64) - b) ** 2).mean())) < 1e-9
 
 
 def test_full_size_properties_config2():
@@ -497,6 +497,6 @@ def test_full_size_decoder_config5():
     # GPU metrics of north_star item 4 against a synthetic 4K frame
     target = bench.synth_image((H, W, C), 1005)
     m = mse_gpu(rec, target)
-    assert abs(m - float(((rec.astype(np.float64) - target) ** 2).mean())) < 1e-9
+    assert abs(m / float(((rec.astype(np.float64) - target) ** 2).mean()) - 1) < 1e-7
     s, per = smoe_ssim(rec, target, use_yuv=True)
     assert -1 <= s <= 1 and per.shape == (3,)

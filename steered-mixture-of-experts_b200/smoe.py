@@ -291,6 +291,7 @@ class Smoe:
         self._local_shape = (b1 - b0,) + tuple(self.image.shape[1:d])
         self._dims3 = tuple(self._local_shape) + (1,) * (3 - d)
         self._d_image = torch.from_numpy(np.ascontiguousarray(self.image[b0:b1])).to(dev)
+        self._d_image_u8 = None
         axes = [np.linspace(0, 1, self.image.shape[a]).astype(np.float32) for a in range(d)]
         axes[0] = axes[0][b0:b1]
         self._d_axes = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in axes]
@@ -534,7 +535,13 @@ class Smoe:
         pre, post = phase in ("all", "pre"), phase in ("all", "post")
         if pre:
             if _host_image is not None:                  # e2e path: this step's pixels come from pinned host memory
-                self._d_image.copy_(_host_image, non_blocking=True)
+                if _host_image.dtype == torch.uint8:     # 8-bit pixels as read from disk; /255 as utils.py:126-128
+                    if self._d_image_u8 is None:
+                        self._d_image_u8 = torch.empty(self._d_image.shape, dtype=torch.uint8, device=self.device)
+                    self._d_image_u8.copy_(_host_image, non_blocking=True)
+                    torch.div(self._d_image_u8.to(torch.float32), 255.0, out=self._d_image)
+                else:
+                    self._d_image.copy_(_host_image, non_blocking=True)
             if train:
                 self._grads.zero_()
             self._scalars.zero_()

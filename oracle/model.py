@@ -200,6 +200,29 @@ class OracleSmoe:
                 opt.apply(gv)
         return loss_val, mse_val, num_pi, 0
 
+    def update_kernel_list(self):
+        """smoe.py:2287-2365 (single-model part): OR into every batch's list the pi>0 kernels whose Mahalanobis
+        distance is < 800 at one of the 3^d corner / mid points of the batch."""
+        from itertools import product as _product
+        from .graph import assemble_A
+        d = self.dim_domain
+        A = assemble_A(self.vars["A_diagonal"], self.vars["A_corr"], self.cfg.train_inverse_cov).double()
+        mu = self.vars["musX"].double()
+        pis = torch.tensor(self.get_params()["pis"], dtype=torch.float64)
+        for k, (coord, batch) in enumerate(init_ref.sliding_window(self.joint_domain, 0, self.batch_size_valued)):
+            flat = batch.reshape(-1, batch.shape[-1])[:, :d]
+            mn, mx = flat.min(axis=0), flat.max(axis=0)
+            pts = np.array(list(_product(*[[mn[a], mx[a], (mn[a] + mx[a]) / 2] for a in range(d)])))
+            probe = torch.tensor(pts.astype(np.float32).astype(np.float64))
+            delta = probe[None] - mu[:, None]
+            if self.cfg.train_inverse_cov:
+                maha = torch.einsum("knl,klm,knm->kn", delta, A, delta)
+            else:
+                y = torch.einsum("klm,knl->knm", A, delta)
+                maha = (y * y).sum(-1)
+            near = ((maha < 800).any(dim=1) & (pis > 0)).numpy()
+            self.kernel_list_per_batch[k] = np.logical_or(self.kernel_list_per_batch[k], near)
+
     def _unique_optimizers(self):
         # one apply_gradients per group (smoe.py:1173-1184); a shared optimizer object advances
         # its beta powers once per apply_gradients call, as in TF
@@ -207,7 +230,9 @@ class OracleSmoe:
 
     # -- train loop -----------------------------------------------------------------
     def train(self, num_iter, val_iter=100, optimizer1=None, optimizer2=None, optimizer3=None,
-              grad_clip_value_abs=None, pis_l1=0, u_l1=0, callbacks=()):
+              grad_clip_value_abs=None, pis_l1=0, u_l1=0, callbacks=(), ukl_iter=None):
+        if ukl_iter is None:
+            ukl_iter = val_iter
         if optimizer1:
             self.set_optimizer(optimizer1, optimizer2, optimizer3, grad_clip_value_abs)
         assert self.optimizers is not None, "no optimizer found, you have to specify one!"
@@ -224,6 +249,10 @@ class OracleSmoe:
             self.iter += 1
             validate = i % val_iter == 0
             loss_val, mse_val, num_pi, _ = self.run_batched(pis_l1, u_l1, train=True)
+            if i % ukl_iter == 0:                                        # smoe.py:1531-1536
+                self.update_kernel_list()
+                if not validate:
+                    loss_val, mse_val, num_pi, _ = self.run_batched(pis_l1, u_l1, train=False)
             if validate:
                 if self.quantization_mode >= 1:
                     self.qparams = quantize_params(self, self.get_params())

@@ -500,3 +500,86 @@ def test_full_size_decoder_config5():
     assert abs(m / float(((rec.astype(np.float64) - target) ** 2).mean()) - 1) < 1e-7
     s, per = smoe_ssim(rec, target, use_yuv=True)
     assert -1 <= s <= 1 and per.shape == (3,)
+
+
+def test_train_loop_cadence_histories_and_best_params_match_oracle():
+    """Smoe.train (smoe.py:1485-1603): initial evaluation, validation / kernel-list cadence, quantisation
+    mode 1 side path, best-parameter shadow copy, history lists."""
+    from oracle.model import OracleAdam, OracleSmoe
+    from smoe_b200 import AdamOptimizer
+    img = np.load(os.path.join(GOLDEN, "init_cases.npz"))["rgb_image"][:40, :48]
+    kw = dict(use_determinant=True, train_inverse_cov=False, use_yuv=True, quantization_mode=1,
+              bit_depths=[20, 18, 6, 10, 10])
+    m = _mk(img, [5, 6], **kw)
+    o = OracleSmoe(img, kernels_per_dim=[5, 6], dtype=torch.float64, **kw)
+    seen = []
+    m.train(12, val_iter=4, ukl_iter=3, pis_l1=0.05, callbacks=[lambda s: seen.append(s.iter)])
+    o.train(12, val_iter=4, ukl_iter=3, optimizer1=OracleAdam(1e-3), optimizer2=OracleAdam(1e-5), optimizer3=OracleAdam(1.0),
+            pis_l1=0.05)
+    assert seen == [0, 4, 8, 12] and m.iter == 12
+    assert [i for i, _ in m.get_losses()] == [i for i, _ in o.losses] == [0, 4, 8, 12]
+    for (_, a), (_, b) in zip(m.get_losses(), o.losses):
+        assert abs(a - b) < 5e-5 * max(1.0, abs(b))
+    for (_, a), (_, b) in zip(m.get_mses(), o.mses):
+        assert abs(10 * np.log10(a / b)) < 0.05            # PSNR within 0.05 dB at every validation
+    assert [n for _, n in m.get_num_pis()] == [n for _, n in o.num_pis]
+    assert abs(m.get_best_loss() - o.best_loss) < 5e-5 and len(m.get_qlosses()) == 4
+    bp, ob = m.get_best_params(), {k: v.numpy() for k, v in o.best.items()}
+    for k in ("musX", "nu_e", "pis"):
+        assert np.abs(bp[k] - ob[k]).max() < 2e-4 * max(1.0, np.abs(ob[k]).max()), k
+    assert m.qparams is not None and m.rparams is not None and m.get_qreconstruction().shape == img.shape
+
+
+@pytest.mark.parametrize("flags", [dict(train_pis=False), dict(train_musx=False), dict(train_gammas=False),
+                                   dict(grad_clip=1e-4), dict(precision=10), dict(only_y_gamma=True)])
+def test_trainable_flags_clip_and_precision(flags):
+    """One Adam step under the constructor's trainability flags (smoe.py:389-396, 1112-1117), gradient clipping
+    (smoe.py:1152-1153), a 10-bit output precision and only_y_gamma (smoe.py:725-729), against the oracle."""
+    from oracle.model import OracleAdam, OracleSmoe
+    img = np.load(os.path.join(GOLDEN, "init_cases.npz"))["rgb_image"][:34, :38]      # ragged vs the 16x32 tiles
+    clip = flags.pop("grad_clip", None)
+    kw = dict(use_determinant=True, train_inverse_cov=False, use_yuv=True, **flags)
+    m = _mk(img, [4, 5], **kw)
+    o = OracleSmoe(img, kernels_per_dim=[4, 5], dtype=torch.float64, **kw)
+    m.set_optimizer(m.optimizer1, m.optimizer2, m.optimizer3, grad_clip_value_abs=clip)
+    o.set_optimizer(OracleAdam(1e-3), OracleAdam(1e-5), OracleAdam(1.0), grad_clip_value_abs=clip)
+    rs = np.random.RandomState(8)
+    p = m.get_params()
+    p["gamma_e"] = rs.normal(0, 0.2, p["gamma_e"].shape).astype(np.float32)
+    m.set_params({"gamma_e": p["gamma_e"]})
+    o.vars["gamma_e"] = torch.tensor(p["gamma_e"].astype(np.float64))
+    p0 = m.get_params()
+    a, b = _train_pass_both(m, o)
+    assert abs(a[0] - b[0]) < 1e-6
+    pg, po = m.get_params(), o.get_params()
+    for k in PARAM_KEYS:
+        assert np.abs(pg[k] - po[k]).max() <= 3e-6 * max(1.0, np.abs(po[k]).max()) + 2e-3 * (k in ("A_diagonal", "A_corr")), k
+    if flags.get("train_pis") is False:
+        np.testing.assert_array_equal(pg["pis"], p0["pis"])
+    if flags.get("train_musx") is False:
+        np.testing.assert_array_equal(pg["musX"], p0["musX"])
+    if flags.get("train_gammas") is False:
+        np.testing.assert_array_equal(pg["gamma_e"], p0["gamma_e"])
+
+
+def test_degenerate_inputs():
+    """No active kernel at all, a single-row image, kernels that influence nothing."""
+    img = np.load(os.path.join(GOLDEN, "init_cases.npz"))["c1_image"][:20, :24]
+    m = _mk(img, [3, 3], use_determinant=False, train_inverse_cov=False, use_yuv=False)
+    m.set_params({"pis": -np.ones(9, np.float32)})
+    loss, mse, num_pi, _ = m.run_batched(train=True, update_reconstruction=True)
+    assert num_pi == 0 and np.isfinite(loss) and np.all(m.get_reconstruction() == 0)
+    assert not np.any(m.kernel_list_per_batch[0]) and np.all(m._grads.cpu().numpy() == 0)
+    expect = float(np.mean((np.abs(img.astype(np.float64)) - 0.5 / 256) ** 2))
+    assert abs(loss - expect) < 1e-7
+    row = np.load(os.path.join(GOLDEN, "init_cases.npz"))["c1_image"][:1, :50]
+    one = _mk(row, [1, 5], use_determinant=True, train_inverse_cov=False, use_yuv=False)
+    l1, _, n1, _ = one.run_batched(train=True, update_reconstruction=True)
+    assert n1 == 5 and np.isfinite(l1) and one.get_reconstruction().shape == (1, 50, 1)
+    far = _mk(img, [3, 3], use_determinant=False, train_inverse_cov=False, use_yuv=False)
+    p = far.get_params()
+    p["musX"][4] = (7.0, -3.0)                       # a kernel far outside the image influences no pixel
+    far.set_params({"musX": p["musX"]})
+    far.run_batched(train=True)
+    kl = far.kernel_list_per_batch[0]
+    assert not kl[4] and kl.sum() == 8

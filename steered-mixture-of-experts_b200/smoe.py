@@ -364,8 +364,11 @@ class Smoe:
         for b in range(bits):
             for a in range(d):
                 key |= ((cell[:, a] >> b) & 1) << (b * d + (d - 1 - a))
-        perm = np.argsort(key, kind="stable").astype(np.int32)
-        self._perm = torch.from_numpy(perm).to(self.device)
+        perm = torch.from_numpy(np.argsort(key, kind="stable").astype(np.int32)).to(self.device)
+        if self._perm is None:
+            self._perm = perm
+        else:
+            self._perm.copy_(perm)      # in place: captured CUDA graphs hold this buffer's address
 
     def _enable_res_pre(self):
         """Keep the mixture output before clip / output quantisation (diagnostics and parity tests;

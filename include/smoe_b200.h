@@ -31,7 +31,7 @@
  *   image  [H][W]([T])[C]  target colours, the numpy layout of the reference's `image`
  *   axes   ax0[H], ax1[W], ax2[T]  pixel coordinates per axis (np.linspace(0,1,n) cast to f32,
  *                      smoe.py:2412 / the float32 feed at smoe.py:545)
- *   pix    [tiles][SMOE_TPIX][SMOE_PIXREC]  per-pixel state written by the forward and streamed
+ *   pix    [tiles][SMOE_PIXREC][SMOE_TPIX]  per-pixel state (plane-major per tile) written by the forward and streamed
  *                      by the backward
  */
 #ifndef SMOE_B200_H

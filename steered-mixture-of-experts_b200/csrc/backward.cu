@@ -3,7 +3,7 @@
 //
 // Kernel-stationary: a thread owns ONE kernel (its record and 2*P accumulators live in
 // registers), a CTA owns 256 consecutive kernels and a 1/num_splits share of the pixel tiles.
-// Pixel state written by the forward ([tile][512][8] floats: tile-centred x, log2(tau*S) | gr, g_c)
+// Pixel state written by the forward ([tile][8 planes][512] floats: tile-centred x, log2(tau*S), gr, g_c)
 // arrives by TMA bulk copies (16 KB per tile, double buffered) and is broadcast to all threads
 // from shared memory, so the per-kernel reductions over pixels happen in registers with no
 // shuffles and no atomics.  Per (pixel, kernel): recompute the gate (T+d FFMA + ex2), then
@@ -279,52 +279,57 @@ __global__ void __launch_bounds__(kThreads, 7) backward_kernel(const BwdArgs a) 
                 for (int l = 0; l < D; ++l) N1[l][c] = 0.f;
             }
 
-            const float4* px = reinterpret_cast<const float4*>(buf ? buf1 : buf0);
+            // pixel state is plane-major inside a tile: [x0 | x1 | x2 | qthr | gr | g0 | g1 | g2][512]
+            const float* pl = buf ? buf1 : buf0;
             constexpr int GRP = 4;          // pixels tested together for the exact-zero skip
             for (int r0 = 0; r0 < SMOE_TPIX; r0 += RL) {
                 // the pixels of a row differ only in their LAST coordinate z: q = cr + (br + qq_last z) z
-                float cr, br;
-                {
-                    const float4 pf = px[2 * r0];
-                    const float xr[3] = {pf.x, pf.y, pf.z};
-                    cr = f[R::OC];
+                float xr[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-                    for (int l = 0; l < D - 1; ++l) {
-                        float tq = f[R::OL + l];
+                for (int l = 0; l < D - 1; ++l) xr[l] = pl[(PR_X + l) * SMOE_TPIX + r0];
+                float cr = f[R::OC];
 #pragma unroll
-                        for (int m = l; m < D - 1; ++m) tq = fmaf(f[R::OQ + ut(D, l, m)], xr[m], tq);
-                        cr = fmaf(tq, xr[l], cr);
-                    }
-                    br = f[R::OL + D - 1];
+                for (int l = 0; l < D - 1; ++l) {
+                    float tq = f[R::OL + l];
 #pragma unroll
-                    for (int l = 0; l < D - 1; ++l) br = fmaf(f[R::OQ + ut(D, l, D - 1)], xr[l], br);
+                    for (int m = l; m < D - 1; ++m) tq = fmaf(f[R::OQ + ut(D, l, m)], xr[m], tq);
+                    cr = fmaf(tq, xr[l], cr);
                 }
+                float br = f[R::OL + D - 1];
+#pragma unroll
+                for (int l = 0; l < D - 1; ++l) br = fmaf(f[R::OQ + ut(D, l, D - 1)], xr[l], br);
                 const float qz = f[R::OQ + ut(D, D - 1, D - 1)];
                 for (int j0 = r0; j0 < r0 + RL; j0 += GRP) {
+                    const float4 zv = *reinterpret_cast<const float4*>(pl + (PR_X + D - 1) * SMOE_TPIX + j0);
+                    const float4 tv = *reinterpret_cast<const float4*>(pl + PR_QTHR * SMOE_TPIX + j0);
+                    const float z4[GRP] = {zv.x, zv.y, zv.z, zv.w};
+                    const float t4[GRP] = {tv.x, tv.y, tv.z, tv.w};
                     float dq[GRP];
                     float dmax = -INFINITY;
 #pragma unroll
                     for (int u = 0; u < GRP; ++u) {
-                        const float4 p0 = px[2 * (j0 + u)];
-                        const float z = D == 1 ? p0.x : (D == 2 ? p0.y : p0.z);
                         // gate logit relative to the pixel's threshold: dq = q - log2(tau*S)
-                        dq[u] = fmaf(fmaf(qz, z, br), z, cr) - p0.w;
+                        dq[u] = fmaf(fmaf(qz, z4[u], br), z4[u], cr) - t4[u];
                         dmax = fmaxf(dmax, dq[u]);
                     }
                     // w = tau * 2^dq is exactly +0 for dq < -126 (ex2.approx.ftz): nothing to accumulate
                     if (__builtin_expect(skip && !__any_sync(0xffffffffu, dmax >= -126.0f), 1)) continue;
+                    const float4 grv = *reinterpret_cast<const float4*>(pl + PR_GR * SMOE_TPIX + j0);
+                    const float gr4[GRP] = {grv.x, grv.y, grv.z, grv.w};
+                    float g4[C][GRP];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const float4 gv = *reinterpret_cast<const float4*>(pl + (PR_G + c) * SMOE_TPIX + j0);
+                        g4[c][0] = gv.x; g4[c][1] = gv.y; g4[c][2] = gv.z; g4[c][3] = gv.w;
+                    }
 #pragma unroll
                     for (int u = 0; u < GRP; ++u) {
-                        const float4 p0 = px[2 * (j0 + u)];
-                        const float4 p1 = px[2 * (j0 + u) + 1];
-                        const float xx[3] = {p0.x, p0.y, p0.z};
                         float x[D];
 #pragma unroll
-                        for (int l = 0; l < D; ++l) x[l] = xx[l];
-                        const float gr = p1.x;
-                        const float g[3] = {p1.y, p1.z, p1.w};
+                        for (int l = 0; l < D - 1; ++l) x[l] = xr[l];
+                        x[D - 1] = z4[u];
                         const float w = a.tau * ex2f(dq[u]);
-                        float t = -w * gr;
+                        float t = -w * gr4[u];
                         const bool pass = dq[u] > 0.f;
                         if (!skip || __any_sync(0xffffffffu, pass)) {
                             const float wm = pass ? w : 0.f;
@@ -334,8 +339,8 @@ __global__ void __launch_bounds__(kThreads, 7) backward_kernel(const BwdArgs a) 
                                 float E = f[R::ONU + c];
 #pragma unroll
                                 for (int l = 0; l < D; ++l) E = fmaf(f[R::OGA + l * C + c], x[l], E);
-                                gE = fmaf(g[c], E, gE);
-                                const float vc = wm * g[c];
+                                gE = fmaf(g4[c][u], E, gE);
+                                const float vc = wm * g4[c][u];
                                 N0[c] += vc;
 #pragma unroll
                                 for (int l = 0; l < D; ++l) N1[l][c] = fmaf(vc, x[l], N1[l][c]);

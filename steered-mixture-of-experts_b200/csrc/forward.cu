@@ -433,9 +433,10 @@ __global__ void __launch_bounds__(kThreadsF, 4) forward_kernel(const FwdArgs a) 
 #pragma unroll
                     for (int c = 0; c < C; ++c) rec[PR_G + c] = g[c];
                 }
-                float4* dst = reinterpret_cast<float4*>(a.pix + ((size_t)tile * SMOE_TPIX + j) * SMOE_PIXREC);
-                dst[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
-                dst[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
+                // plane-major inside the tile ([8][512]): coalesced here, float4-per-4-pixels in the backward
+                float* dst = a.pix + (size_t)tile * SMOE_TPIX * SMOE_PIXREC + j;
+#pragma unroll
+                for (int q = 0; q < SMOE_PIXREC; ++q) dst[q * SMOE_TPIX] = rec[q];
             }
         }
     }

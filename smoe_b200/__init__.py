@@ -13,4 +13,4 @@ __path__.insert(0, _pkg_dir)
 from .smoe import Smoe, AdamOptimizer, sliding_window  # noqa: E402,F401
 from .quantizer import quantize_params, rescaler        # noqa: E402,F401
 from .utils import reduce_params, save_model, load_params, read_image, write_image, psnr  # noqa: E402,F401
-from . import smoe_reconstruction, smoe_reconstruction_decoded  # noqa: E402,F401
+from . import smoe_reconstruction, smoe_reconstruction_decoded, smoe_test  # noqa: E402,F401

@@ -31,7 +31,7 @@ __host__ __device__ constexpr int off_ga(int d, int C) { return d + tri(d) + 1 +
 __host__ __device__ constexpr int lt(int l, int m) { return l * (l + 1) / 2 + m; }
 __host__ __device__ constexpr int ut(int d, int l, int m) { return l * d - l * (l - 1) / 2 + (m - l); }
 
-// pixel record written by the forward, streamed by the backward
+// pixel state written by the forward (plane-major per tile: [SMOE_PIXREC][SMOE_TPIX]), streamed by the backward; planes:
 //   [0..d) tile-centred coordinates | [3] qthr = log2(tau * max(S, 1e-11)), +inf outside the batch |
 //   [4] gr = sum_c g_c r_c (0 where S is clamped, smoe.py:821) | [5..5+C) g_c = dL/dr_c
 constexpr int PR_X = 0, PR_QTHR = 3, PR_GR = 4, PR_G = 5;
@@ -59,11 +59,6 @@ int check_launch(const char* what);
 __device__ __forceinline__ float ex2f(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float lg2f(float x) {
-    float y;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -583,3 +583,18 @@ def test_degenerate_inputs():
     far.run_batched(train=True)
     kl = far.kernel_list_per_batch[0]
     assert not kl[4] and kl.sum() == 8
+
+
+def test_training_cli_driver(tmp_path):
+    """The minimal `smoe_test.py` driver: grid model, three Adam optimizers, pi-sparsification, pickles."""
+    from smoe_b200 import smoe_test, load_params
+    img = np.load(os.path.join(GOLDEN, "init_cases.npz"))["c1_image"][:64, :64]
+    np.save(str(tmp_path / "img.npy"), np.round(img * 255).astype(np.uint8))
+    m = smoe_test.main(str(tmp_path / "img.npy"), str(tmp_path / "out"), 30, 10, [8, 8], None, 1.0, 1e-3, 1, 100.0, 1000.0,
+                       True, True, 0, [20, 18, 6, 10, 10], False, [-2500, -.3, -5, 0, -32], [2500, 1.3, 5, 2, 32], False,
+                       False, None)
+    assert [i for i, _ in m.get_losses()] == [0, 10, 20, 30]
+    assert m.get_losses()[-1][1] < m.get_losses()[0][1]
+    p = load_params(str(tmp_path / "out" / "params_last.pkl"))
+    assert p["pis"].shape[0] == m.get_num_pis()[-1][1] and (p["pis"] > 0).all()
+    assert os.path.exists(str(tmp_path / "out" / "reconstruction.png"))

@@ -407,6 +407,7 @@ int smoe_suggest_splits(int K_cap, int ntiles) {
     double best_eff = -1.0;
     int lo = (2 * slots + kt - 1) / kt;          // at least ~2 waves of CTAs
     if (lo < 1) lo = 1;
+    if (lo >= ntiles) return ntiles < 1 ? 1 : ntiles;      // small problems: one tile per CTA
     for (int ns = lo; ns <= lo + 64 && ns <= ntiles; ++ns) {
         const double ctas = (double)kt * ns;
         const double waves = ctas / slots;

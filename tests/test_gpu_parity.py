@@ -598,3 +598,29 @@ def test_training_cli_driver(tmp_path):
     p = load_params(str(tmp_path / "out" / "params_last.pkl"))
     assert p["pis"].shape[0] == m.get_num_pis()[-1][1] and (p["pis"] > 0).all()
     assert os.path.exists(str(tmp_path / "out" / "reconstruction.png"))
+
+
+def test_pi_sparsification_prunes_and_index_sets_follow_pis():
+    """BASELINE config 2 path at reduced size: training with an L1 penalty on pi (smoe.py:1027) drives pis
+    through 0 and the kernels drop out of the compaction (smoe.py:480, 738-753).  After every step the active
+    index set must equal `kernel_list & (pis > 0)` evaluated on the parameters the step started from, and the
+    pruning trajectory must track the float64 oracle."""
+    from oracle.model import OracleAdam, OracleSmoe
+    img = np.load(os.path.join(GOLDEN, "init_cases.npz"))["c1_image"][:64, :64]
+    kw = dict(use_determinant=True, train_inverse_cov=False, use_yuv=False, normalize_pis=True)
+    m = _mk(img, [16, 16], **kw)
+    o = OracleSmoe(img, kernels_per_dim=[16, 16], dtype=torch.float64, **kw)
+    o.set_optimizer(OracleAdam(1e-3), OracleAdam(1e-5), OracleAdam(1.0))
+    counts_g, counts_o = [], []
+    for it in range(450):
+        pis_before = m.get_params()["pis"] if it % 50 == 0 else None
+        kl_before = m.kernel_list_per_batch[0] if it % 50 == 0 else None
+        counts_g.append(m.run_batched(pis_l1=10.0, train=True)[2])
+        if pis_before is not None:
+            K = int(m._counts[0, 0].item())
+            np.testing.assert_array_equal(m._indices[:K].cpu().numpy(), np.nonzero(kl_before & (pis_before > 0))[0])
+            assert counts_g[-1] == int((pis_before > 0).sum())
+        counts_o.append(o.run_batched(pis_l1=10.0, train=True)[2])
+    assert counts_g[0] == 256 and counts_g[-1] <= 0.7 * 256          # >= 30 % pruned
+    assert np.abs(np.array(counts_g) - np.array(counts_o)).max() <= 8  # same trajectory (pi crossings within noise)
+    assert np.isfinite(m.run_batched(train=False)[0])

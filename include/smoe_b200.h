@@ -19,7 +19,7 @@
  *     never needs a device->host copy to size a launch.
  *
  * Layouts (float32 unless noted; d = dim_domain in {2,3}, C = channels in {1,3},
- * T = d(d+1)/2, P = d + T + 1 + C + d*C, PK = smoe_packed_stride(d,C)):
+ * T = d(d+1)/2, P = d + T + 1 + C + d*C, PK = smoe_packed_stride(d,C) = roundup4(P+1+d)):
  *   theta  [K_all][P]  the K_all-sized variables, one row per kernel:
  *                      musX[d] | A lower-tri row-major (l,m), l>=m: diagonal entries are
  *                      A_diagonal_var[l,l], strictly-lower entries are A_corr_var[l,m] | pis |
@@ -27,7 +27,8 @@
  *   grads, adam_m, adam_v : same shape as theta
  *   packed [K][PK]     compacted compute records (smoe_pack): musX[d] | Qm (upper-tri row-major
  *                      of s*A*A^T, or s*A_sym when train_inverse_cov; s = log2(e)/2) |
- *                      c0 = log2(pi * prod(diag A)/(2pi)^(d/2)) | nu_e[C] | gamma_e[d][C] | pad
+ *                      c0 = log2(pi * prod(diag A)/(2pi)^(d/2)) | nu_e[C] | gamma_e[d][C] |
+ *                      lam, kap[d] (culling bounds) | pad
  *   image  [H][W]([T])[C]  target colours, the numpy layout of the reference's `image`
  *   axes   ax0[H], ax1[W], ax2[T]  pixel coordinates per axis (np.linspace(0,1,n) cast to f32,
  *                      smoe.py:2412 / the float32 feed at smoe.py:545)
@@ -113,7 +114,7 @@ size_t      smoe_backward_workspace_bytes(const smoe_cfg* cfg, int K_cap, int nu
 int smoe_pack(const smoe_cfg* cfg, const float* theta, const uint8_t* kernel_list, int K_all,
               float* packed, int32_t* indices, int32_t* pos /*[K_all]: packed row of each kernel or -1*/,
               int32_t* counts, float* regsums,
-              float* chunk_bounds /*[ceil(K_all/128)][8]*/, void* workspace, void* stream);
+              float* chunk_bounds /*[ceil(K_all/128)][12]*/, void* workspace, void* stream);
 
 /* Same staging for parameters that are FED over the compacted tensors (with_quantized_params,
  * smoe.py:1688-1689: rparams A, musX, nu_e, gamma_e, pis of K rows each); no mask, K given. */

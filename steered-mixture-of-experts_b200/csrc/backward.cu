@@ -45,18 +45,18 @@ struct BwdArgs {
     float tau;
 };
 
-// fixed-order min over the CTA of 8 per-thread values (used once per CTA for its bounding box)
-__device__ __forceinline__ void cta_min8(float (&v)[8], float (*s)[8]) {
+// fixed-order min over the CTA of kCB per-thread values (used once per CTA for its bounding box)
+__device__ __forceinline__ void cta_min8(float (&v)[kCB], float (*s)[kCB]) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
+    for (int q = 0; q < kCB; ++q)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v[q] = fminf(v[q], __shfl_xor_sync(0xffffffffu, v[q], o));
     if ((threadIdx.x & 31) == 0)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) s[threadIdx.x >> 5][q] = v[q];
+        for (int q = 0; q < kCB; ++q) s[threadIdx.x >> 5][q] = v[q];
     __syncthreads();
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < kCB; ++q) {
         float m = INFINITY;
         for (int w = 0; w < kThreads / 32; ++w) m = fminf(m, s[w][q]);
         v[q] = m;
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kThreads, 7) backward_kernel(const BwdArgs a) 
     float* buf0 = reinterpret_cast<float*>(smem_raw);
     float* buf1 = buf0 + SMOE_TPIX * SMOE_PIXREC;
     uint64_t* bar = reinterpret_cast<uint64_t*>(buf1 + SMOE_TPIX * SMOE_PIXREC);
-    float (*sred)[8] = reinterpret_cast<float (*)[8]>(bar + 2);     // [8 warps][8]
+    float (*sred)[kCB] = reinterpret_cast<float (*)[kCB]>(bar + 2);     // [8 warps][kCB]
     int* scratch = reinterpret_cast<int*>(sred + 8);                // [16]
     int* tlist = scratch + 16;                                      // [max_list]
 
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kThreads, 7) backward_kernel(const BwdArgs a) 
     };
 
     // own kernel record (global -> registers)
-    float mu[D], Qm[D][D], c0, lam, nu[C], ga[D][C];
+    float mu[D], Qm[D][D], c0, lam, kap[D], nu[C], ga[D][C];
     {
         const float* rec = a.packed + (size_t)(active ? k : 0) * PK;
 #pragma unroll
@@ -117,6 +117,8 @@ __global__ void __launch_bounds__(kThreads, 7) backward_kernel(const BwdArgs a) 
             for (int m = l; m < D; ++m) Qm[l][m] = Qm[m][l] = rec[off_A(D, C) + ut(D, l, m)];
         c0 = active ? rec[off_pi(D, C)] : -INFINITY;
         lam = rec[P];
+#pragma unroll
+        for (int l = 0; l < D; ++l) kap[l] = rec[P + 1 + l];
 #pragma unroll
         for (int c = 0; c < C; ++c) nu[c] = rec[off_nu(D, C) + c];
 #pragma unroll
@@ -145,14 +147,18 @@ __global__ void __launch_bounds__(kThreads, 7) backward_kernel(const BwdArgs a) 
     //      reach (w = tau*2^(q-qthr) is exactly 0 when q - min qthr < -126) --------------------
     int nlist = 0;
     {
-        float v[8];
+        float v[kCB];
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
             v[l] = (l < D && active) ? mu[l] : INFINITY;
             v[3 + l] = (l < D && active) ? -mu[l] : INFINITY;
+            v[8 + l] = INFINITY;
         }
+#pragma unroll
+        for (int l = 0; l < D; ++l) v[8 + l] = active ? kap[l] : INFINITY;
         v[6] = active ? lam : INFINITY;
         v[7] = (c0 == c0) ? -c0 : -INFINITY;
+        v[11] = 0.f;
         cta_min8(v, sred);
         const float blam = v[6], bc0 = -v[7];
         const int my_tiles = (a.ntiles - split + a.num_splits - 1) / a.num_splits;
@@ -166,14 +172,15 @@ __global__ void __launch_bounds__(kThreads, 7) backward_kernel(const BwdArgs a) 
                 if (cull) {
                     float ctr[3], half[3];
                     tile_box(tile, ctr, half);
-                    float d2 = 0.f;
+                    float d2 = 0.f, kd = 0.f;
 #pragma unroll
                     for (int l = 0; l < D; ++l) {
                         const float mn = v[l] - ctr[l], mx = -v[3 + l] - ctr[l];
                         const float gap = fmaxf(fmaxf(mn - half[l], -half[l] - mx), 0.f);
                         d2 = fmaf(gap, gap, d2);
+                        kd = fmaxf(kd, v[8 + l] * gap * gap);
                     }
-                    const float ub = bc0 - blam * d2 - a.tile_qmin[tile];
+                    const float ub = bc0 - fmaxf(blam * d2, kd) - a.tile_qmin[tile];
                     need = !(blam >= 0.f) || !(ub < -126.5f);
                 }
             }
@@ -223,13 +230,14 @@ __global__ void __launch_bounds__(kThreads, 7) backward_kernel(const BwdArgs a) 
         // own kernel vs this tile, then the warp's 32 kernels together
         bool need = active;
         if (cull && need) {
-            float d2 = 0.f;
+            float d2 = 0.f, kd = 0.f;
 #pragma unroll
             for (int l = 0; l < D; ++l) {
                 const float gap = fmaxf(fabsf(mup[l]) - half[l], 0.f);
                 d2 = fmaf(gap, gap, d2);
+                kd = fmaxf(kd, kap[l] * gap * gap);
             }
-            const float ub = c0 - lam * d2 - a.tile_qmin[tile];
+            const float ub = c0 - fmaxf(lam * d2, kd) - a.tile_qmin[tile];
             need = !(lam >= 0.f) || !(ub < -126.5f);
         }
         const bool warp_need = __any_sync(0xffffffffu, need);
@@ -282,6 +290,9 @@ __global__ void __launch_bounds__(kThreads, 7) backward_kernel(const BwdArgs a) 
             // pixel state is plane-major inside a tile: [x0 | x1 | x2 | qthr | gr | g0 | g1 | g2][512]
             const float* pl = buf ? buf1 : buf0;
             constexpr int GRP = 4;          // pixels tested together for the exact-zero skip
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, nv[C], nz[C];      // row sums, reset after every folded row
+#pragma unroll
+            for (int c = 0; c < C; ++c) nv[c] = nz[c] = 0.f;
             for (int r0 = 0; r0 < SMOE_TPIX; r0 += RL) {
                 // the pixels of a row differ only in their LAST coordinate z: q = cr + (br + qq_last z) z
                 float xr[3] = {0.f, 0.f, 0.f};
@@ -299,6 +310,9 @@ __global__ void __launch_bounds__(kThreads, 7) backward_kernel(const BwdArgs a) 
 #pragma unroll
                 for (int l = 0; l < D - 1; ++l) br = fmaf(f[R::OQ + ut(D, l, D - 1)], xr[l], br);
                 const float qz = f[R::OQ + ut(D, D - 1, D - 1)];
+                // row sums: along a row only z varies, so sum t, sum t z, sum t z^2 (and sum v_c, sum v_c z)
+                // carry every moment of the row; they are folded once per row
+                bool row_active = false;
                 for (int j0 = r0; j0 < r0 + RL; j0 += GRP) {
                     const float4 zv = *reinterpret_cast<const float4*>(pl + (PR_X + D - 1) * SMOE_TPIX + j0);
                     const float4 tv = *reinterpret_cast<const float4*>(pl + PR_QTHR * SMOE_TPIX + j0);
@@ -314,6 +328,7 @@ __global__ void __launch_bounds__(kThreads, 7) backward_kernel(const BwdArgs a) 
                     }
                     // w = tau * 2^dq is exactly +0 for dq < -126 (ex2.approx.ftz): nothing to accumulate
                     if (__builtin_expect(skip && !__any_sync(0xffffffffu, dmax >= -126.0f), 1)) continue;
+                    row_active = true;
                     const float4 grv = *reinterpret_cast<const float4*>(pl + PR_GR * SMOE_TPIX + j0);
                     const float gr4[GRP] = {grv.x, grv.y, grv.z, grv.w};
                     float g4[C][GRP];
@@ -341,21 +356,39 @@ __global__ void __launch_bounds__(kThreads, 7) backward_kernel(const BwdArgs a) 
                                 for (int l = 0; l < D; ++l) E = fmaf(f[R::OGA + l * C + c], x[l], E);
                                 gE = fmaf(g4[c][u], E, gE);
                                 const float vc = wm * g4[c][u];
-                                N0[c] += vc;
-#pragma unroll
-                                for (int l = 0; l < D; ++l) N1[l][c] = fmaf(vc, x[l], N1[l][c]);
+                                nv[c] += vc;
+                                nz[c] = fmaf(vc, z4[u], nz[c]);
                             }
                             t = fmaf(wm, gE, t);
                         }
-                        M0 += t;
-#pragma unroll
-                        for (int l = 0; l < D; ++l) {
-                            const float uu = t * x[l];
-                            M1[l] += uu;
-#pragma unroll
-                            for (int m = l; m < D; ++m) M2[ut(D, l, m)] = fmaf(uu, x[m], M2[ut(D, l, m)]);
-                        }
+                        const float uz = t * z4[u];
+                        s0 += t;
+                        s1 += uz;
+                        s2 = fmaf(uz, z4[u], s2);
                     }
+                }
+                if (row_active) {
+                    // fold the row: x_l = xr[l] for l < D-1, x_{D-1} = z
+                    M0 += s0;
+#pragma unroll
+                    for (int l = 0; l < D - 1; ++l) {
+                        const float a0 = xr[l] * s0;
+                        M1[l] += a0;
+#pragma unroll
+                        for (int m = l; m < D - 1; ++m) M2[ut(D, l, m)] = fmaf(a0, xr[m], M2[ut(D, l, m)]);
+                        M2[ut(D, l, D - 1)] = fmaf(xr[l], s1, M2[ut(D, l, D - 1)]);
+                    }
+                    M1[D - 1] += s1;
+                    M2[ut(D, D - 1, D - 1)] += s2;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        N0[c] += nv[c];
+#pragma unroll
+                        for (int l = 0; l < D - 1; ++l) N1[l][c] = fmaf(xr[l], nv[c], N1[l][c]);
+                        N1[D - 1][c] += nz[c];
+                        nv[c] = nz[c] = 0.f;
+                    }
+                    s0 = s1 = s2 = 0.f;
                 }
             }
             // fold tile-centred statistics into kernel-centred ones
@@ -585,7 +618,7 @@ int smoe_backward(const smoe_cfg* cfg, const smoe_batch* batch, const float* pac
     a.tau = 0.5f / (float)(1 << cfg->precision);
     a.max_list = (a.ntiles + num_splits - 1) / num_splits;
     dim3 grid((K_cap + kThreads - 1) / kThreads, num_splits);
-    size_t sm = 2 * (size_t)SMOE_TPIX * SMOE_PIXREC * 4 + 16 + 8 * 8 * 4 + 16 * 4 + (size_t)a.max_list * 4 + 64;
+    size_t sm = 2 * (size_t)SMOE_TPIX * SMOE_PIXREC * 4 + 16 + 8 * kCB * 4 + 16 * 4 + (size_t)a.max_list * 4 + 64;
     SMOE_REQUIRE(sm <= 100 * 1024, "too many tiles per split for the shared-memory tile list: raise num_splits");
     cudaStream_t st = (cudaStream_t)stream;
     // partial slabs of splits that own no tile, and rows k >= K, are never read

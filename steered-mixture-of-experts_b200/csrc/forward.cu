@@ -19,8 +19,8 @@
 //     expert by exactly 0.  Sweep A skips ex2+add for a warp-iteration whose logits are all < -126;
 //     sweep B tests the threshold in the log domain, q > log2(tau*S), so it needs no ex2 at all
 //     unless a gate passes.                                            (dense_exec = 0 and 2)
-//   * Culling: q_k(x) <= c0_k - lam_k * dist(x, mu_k)^2 with lam_k a lower bound of the smallest
-//     eigenvalue of Qm_k.  A chunk of 128 kernels whose bound over the tile's box says "all zero"
+//   * Culling: q_k(x) <= c0_k - max(lam_k * dist(x, mu_k)^2, max_l kap_kl * gap_l^2) with lam_k a lower
+//     bound of the smallest eigenvalue of Qm_k and kap_kl = 1/(Qm_k^-1)_ll the per-axis bounds.  A chunk of 128 kernels whose bound over the tile's box says "all zero"
 //     (sweep A: < -126.5; sweep B: < min_n qthr - 0.01) is never loaded, and inside a loaded chunk
 //     only the kernels that can matter are re-centred and swept (ordered compaction, so sums keep
 //     the order of the dense sweep).  The 0.5 / 0.01 margins cover the rounding of the evaluated
@@ -226,15 +226,16 @@ __global__ void __launch_bounds__(kThreadsF, 4) forward_kernel(const FwdArgs a) 
                 if (ci < nchunks) {
                     need = true;
                     if (cull) {
-                        const float* cb = a.chunk_bounds + (size_t)ci * 8;
-                        float d2 = 0.f;
+                        const float* cb = a.chunk_bounds + (size_t)ci * kCB;
+                        float d2 = 0.f, kd = 0.f;
 #pragma unroll
                         for (int l = 0; l < D; ++l) {
                             const float mn = cb[l] - ctr[l], mx = cb[3 + l] - ctr[l];
                             const float gap = fmaxf(fmaxf(mn - half[l], -half[l] - mx), 0.f);
                             d2 = fmaf(gap, gap, d2);
+                            kd = fmaxf(kd, cb[8 + l] * gap * gap);
                         }
-                        const float lam = cb[6], ub = cb[7] - lam * d2;
+                        const float lam = cb[6], ub = cb[7] - fmaxf(lam * d2, kd);
                         need = !(lam >= 0.f) || !(ub < thr);
                     }
                 }
@@ -264,13 +265,14 @@ __global__ void __launch_bounds__(kThreadsF, 4) forward_kernel(const FwdArgs a) 
 #pragma unroll
                 for (int l = 0; l < D; ++l) mu[l] = need ? raw[off_mu(D, C) + l] - ctr[l] : 0.f;
                 if (need && cull) {
-                    float d2 = 0.f;
+                    float d2 = 0.f, kd = 0.f;
 #pragma unroll
                     for (int l = 0; l < D; ++l) {
                         const float gap = fmaxf(fabsf(mu[l]) - half[l], 0.f);
                         d2 = fmaf(gap, gap, d2);
+                        kd = fmaxf(kd, raw[nparam(D, C) + 1 + l] * gap * gap);
                     }
-                    const float lam = raw[nparam(D, C)], ub = raw[off_pi(D, C)] - lam * d2;
+                    const float lam = raw[nparam(D, C)], ub = raw[off_pi(D, C)] - fmaxf(lam * d2, kd);
                     need = !(lam >= 0.f) || !(ub < thr);
                 }
                 int nneed;

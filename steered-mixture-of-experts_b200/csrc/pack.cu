@@ -167,12 +167,32 @@ __device__ __forceinline__ int stage_record(const smoe_cfg& cfg, const float (&A
         lam = lam >= 0.0 ? lam * (1.0 - 1e-3) - 1e-6 * scale : lam;      // keep the bound conservative
         if (lam < 0.0 && !cfg.train_inverse_cov) lam = 0.0;               // A A^T is PSD: rounding only
         rec[nparam(D, C)] = (float)lam;
+        // per-axis bounds: d^T Qm d >= kap_l * d_l^2 with kap_l = 1 / (Qm^-1)_ll = det(Qm) / cofactor_ll (the
+        // minimum of the form over the other coordinates); much tighter than lam for anisotropic kernels
+        double det, cof[3] = {1.0, 1.0, 1.0};
+        if (D == 2) {
+            det = Q[0][0] * Q[1][1] - Q[0][1] * Q[0][1];
+            cof[0] = Q[1][1];
+            cof[1] = Q[0][0];
+        } else {
+            cof[0] = Q[1][1] * Q[2][2] - Q[1][2] * Q[1][2];
+            cof[1] = Q[0][0] * Q[2][2] - Q[0][2] * Q[0][2];
+            cof[2] = Q[0][0] * Q[1][1] - Q[0][1] * Q[0][1];
+            det = Q[0][0] * cof[0] - Q[0][1] * (Q[0][1] * Q[2][2] - Q[1][2] * Q[0][2]) +
+                  Q[0][2] * (Q[0][1] * Q[1][2] - Q[1][1] * Q[0][2]);
+        }
+#pragma unroll
+        for (int l = 0; l < D; ++l) {
+            double kap = 0.0;
+            if (lam > 0.0 && det > 0.0 && cof[l] > 0.0) kap = det / cof[l] * (1.0 - 1e-3) - 1e-6 * scale;
+            rec[nparam(D, C) + 1 + l] = (float)fmax(kap, 0.0);
+        }
     }
     return coef < 0.f;       // negative weights cannot be carried in the log domain
 }
 
 // Per chunk of kChunk consecutive active kernels: bounding box of the centres, smallest lam, largest c0
-// (coarse level of the exact culling; layout [mu_min[3] | mu_max[3] | lam_min | c0_max], stride 8).
+// (coarse level of the exact culling; layout [mu_min[3] | mu_max[3] | lam_min | c0_max | kap_min[3] | -], stride kCB).
 template <int D, int C>
 __global__ void __launch_bounds__(kChunk) chunk_bounds_kernel(const float* __restrict__ packed,
                                                               const int32_t* __restrict__ counts,
@@ -181,7 +201,7 @@ __global__ void __launch_bounds__(kChunk) chunk_bounds_kernel(const float* __res
     const int K = counts[0];
     const int k = blockIdx.x * kChunk + threadIdx.x;
     if ((int)blockIdx.x * kChunk >= K) return;
-    float v[8];
+    float v[kCB];
     const bool on = k < K;
     const float* rec = packed + (size_t)(on ? k : 0) * PK;
 #pragma unroll
@@ -189,26 +209,28 @@ __global__ void __launch_bounds__(kChunk) chunk_bounds_kernel(const float* __res
         const float m = (l < D && on) ? rec[off_mu(D, C) + l] : 0.f;
         v[l] = (l < D && on) ? m : INFINITY;        // min
         v[3 + l] = (l < D && on) ? -m : INFINITY;   // max as min of the negation
+        v[8 + l] = (l < D && on) ? rec[nparam(D, C) + 1 + l] : INFINITY;
     }
     v[6] = on ? rec[nparam(D, C)] : INFINITY;
     const float c0 = on ? rec[off_pi(D, C)] : -INFINITY;
     v[7] = -c0;
     if (!(c0 == c0)) v[7] = -INFINITY;             // NaN c0: never cull
-    __shared__ float s[kChunk / 32][8];
+    v[11] = 0.f;
+    __shared__ float s[kChunk / 32][kCB];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < kCB; ++q) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v[q] = fminf(v[q], __shfl_xor_sync(0xffffffffu, v[q], o));
     }
     if ((threadIdx.x & 31) == 0)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) s[threadIdx.x >> 5][q] = v[q];
+        for (int q = 0; q < kCB; ++q) s[threadIdx.x >> 5][q] = v[q];
     __syncthreads();
-    if (threadIdx.x < 8) {
+    if (threadIdx.x < kCB) {
         float m = INFINITY;
         for (int w = 0; w < kChunk / 32; ++w) m = fminf(m, s[w][threadIdx.x]);
         const int q = threadIdx.x;
-        cb[(size_t)blockIdx.x * 8 + q] = (q >= 3 && q != 6) ? -m : m;
+        cb[(size_t)blockIdx.x * kCB + q] = ((q >= 3 && q <= 5) || q == 7) ? -m : m;
     }
 }
 

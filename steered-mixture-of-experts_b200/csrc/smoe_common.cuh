@@ -20,7 +20,9 @@ constexpr float kSFloor = 10e-12f;                  // the literal of smoe.py:82
 
 __host__ __device__ constexpr int tri(int d) { return d * (d + 1) / 2; }
 __host__ __device__ constexpr int nparam(int d, int C) { return d + tri(d) + 1 + C + d * C; }
-__host__ __device__ constexpr int pstride(int d, int C) { return (nparam(d, C) + 1 + 3) / 4 * 4; }
+// packed record = P parameters | lam (eigenvalue bound) | kap[d] (per-axis bounds) | pad to a multiple of 4
+__host__ __device__ constexpr int pstride(int d, int C) { return (nparam(d, C) + 1 + d + 3) / 4 * 4; }
+constexpr int kCB = 12;                              // floats per chunk-bounds entry
 // offsets inside a theta / grads row and inside a packed record (same order)
 __host__ __device__ constexpr int off_mu(int, int) { return 0; }
 __host__ __device__ constexpr int off_A(int d, int) { return d; }

@@ -334,7 +334,7 @@ class Smoe:
         self._infl = torch.zeros((K,), dtype=torch.uint8, device=dev)
         self._pix = torch.zeros((max_tiles * _ffi.TPIX * _ffi.PIXREC,), dtype=f32, device=dev)
         self._tile_qmin = torch.zeros((max_tiles,), dtype=f32, device=dev)
-        self._chunk_bounds = torch.zeros(((K + 127) // 128, 8), dtype=f32, device=dev)
+        self._chunk_bounds = torch.zeros(((K + 127) // 128, 12), dtype=f32, device=dev)
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         self._partials = torch.zeros((4 * sms * 8,), dtype=f32, device=dev)
         self._ticket = torch.zeros((4,), dtype=torch.int32, device=dev)

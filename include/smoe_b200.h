@@ -32,8 +32,8 @@
  *   image  [H][W]([T])[C]  target colours, the numpy layout of the reference's `image`
  *   axes   ax0[H], ax1[W], ax2[T]  pixel coordinates per axis (np.linspace(0,1,n) cast to f32,
  *                      smoe.py:2412 / the float32 feed at smoe.py:545)
- *   pix    [tiles][SMOE_PIXREC][SMOE_TPIX]  per-pixel state (plane-major per tile) written by the forward and streamed
- *                      by the backward
+ *   pix    [tiles][smoe_pix_stride]  per-pixel backward state written by the forward and streamed by the
+ *                      backward: planes z, qthr, gr, g_c of SMOE_TPIX floats + the row-constant coordinates
  */
 #ifndef SMOE_B200_H
 #define SMOE_B200_H
@@ -47,7 +47,6 @@ extern "C" {
 
 #define SMOE_ABI_VERSION 1
 #define SMOE_TPIX 512      /* pixels per tile (compile-time constant of the kernels) */
-#define SMOE_PIXREC 8      /* floats per pixel record */
 #define SMOE_NSCAL 16      /* floats in the scalar block */
 
 #define SMOE_E_BADARG (-1)
@@ -99,6 +98,7 @@ const char* smoe_last_error(void);
 int         smoe_param_count(int d, int C);      /* P  */
 int         smoe_packed_stride(int d, int C);    /* PK */
 int         smoe_num_tiles(const smoe_batch* b);
+int         smoe_pix_stride(int d, int C, const smoe_batch* b);   /* floats of `pix` per tile */
 size_t      smoe_pack_workspace_bytes(int K_all);
 size_t      smoe_backward_workspace_bytes(const smoe_cfg* cfg, int K_cap, int num_splits);
 
@@ -157,8 +157,9 @@ int smoe_backward(const smoe_cfg* cfg, const smoe_batch* batch, const float* pac
  *   ORIGINAL index perm[s] (s in [0,K_cap)), whose packed row is pos[perm[s]] (-1 = inactive).  Any
  *   permutation gives the same results; a spatially coherent one (e.g. Morton order of the centres)
  *   makes the kernels of a warp / CTA neighbours, which is what the tile culling exploits. */
-/* number of pixel splits that fills the GPU in whole waves for K_cap kernels and ntiles tiles */
-int smoe_suggest_splits(int K_cap, int ntiles);
+/* number of pixel splits for smoe_backward on this batch (split s owns tiles s, s+NS, ...): a prime that keeps
+ * the grid a few waves deep and does not divide the tile-grid extents */
+int smoe_suggest_splits(int K_cap, const smoe_batch* batch);
 
 /* Fixed-order reduction of the pixel splits: raw[k][j] = sum_s raw_part[s][k][j].  (The buffer a
  * multi-GPU run all-reduces with NCCL.) */

@@ -14,11 +14,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsmoe_b200.so")
 
 TPIX = 512
-PIXREC = 8
 NSCAL = 16
 
 EXPORTS = [
-    "smoe_abi_version", "smoe_last_error", "smoe_param_count", "smoe_packed_stride", "smoe_num_tiles",
+    "smoe_abi_version", "smoe_last_error", "smoe_param_count", "smoe_packed_stride", "smoe_num_tiles", "smoe_pix_stride",
     "smoe_pack_workspace_bytes", "smoe_backward_workspace_bytes", "smoe_pack", "smoe_pack_fed", "smoe_forward",
     "smoe_backward", "smoe_suggest_splits", "smoe_reduce_splits", "smoe_grad_finalize", "smoe_update_kernel_list",
     "smoe_adam_step", "smoe_ssim_workspace_bytes", "smoe_ssim", "smoe_sqerr", "smoe_quantize", "smoe_rescale",

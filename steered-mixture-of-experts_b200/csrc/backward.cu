@@ -3,8 +3,8 @@
 //
 // Kernel-stationary: a thread owns ONE kernel (its record and 2*P accumulators live in
 // registers), a CTA owns 256 consecutive kernels and a 1/num_splits share of the pixel tiles.
-// Pixel state written by the forward ([tile][8 planes][512] floats: tile-centred x, log2(tau*S), gr, g_c)
-// arrives by TMA bulk copies (16 KB per tile, double buffered) and is broadcast to all threads
+// Pixel state written by the forward (per tile: planes z, log2(tau*S), gr, g_c of 512 floats + row constants)
+// arrives by TMA bulk copies (12 KB per tile for d=2, C=3; double buffered) and is broadcast to all threads
 // from shared memory, so the per-kernel reductions over pixels happen in registers with no
 // shuffles and no atomics.  Per (pixel, kernel): recompute the gate (T+d FFMA + ex2), then
 //     t = w (m gE - gr)            [SURVEY 8a-8: dL/dlog(n_w)]
@@ -65,15 +65,17 @@ __device__ __forceinline__ void cta_min8(float (&v)[kCB], float (*s)[kCB]) {
 }
 
 template <int D, int C>
-__global__ void __launch_bounds__(kThreads, 7) backward_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) {
     using R = BRec<D, C>;
     constexpr int T = tri(D);
     constexpr int P = nparam(D, C), PK = pstride(D, C);
-    constexpr uint32_t kTileBytes = SMOE_TPIX * SMOE_PIXREC * 4;
+    const int RL = a.b.tile[D - 1];          // pixels per row of the tile (run along the last axis)
+    const int tstride = pix_stride(D, C, RL);
+    const uint32_t kTileBytes = (uint32_t)tstride * 4u;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* buf0 = reinterpret_cast<float*>(smem_raw);
-    float* buf1 = buf0 + SMOE_TPIX * SMOE_PIXREC;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(buf1 + SMOE_TPIX * SMOE_PIXREC);
+    float* buf1 = buf0 + tstride;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(buf1 + tstride);
     float (*sred)[kCB] = reinterpret_cast<float (*)[kCB]>(bar + 2);     // [8 warps][kCB]
     int* scratch = reinterpret_cast<int*>(sred + 8);                // [16]
     int* tlist = scratch + 16;                                      // [max_list]
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(kThreads, 7) backward_kernel(const BwdArgs a) 
     auto issue = [&](int tile, int buf) {
         fence_proxy_async();
         mbar_expect_tx(&bar[buf], kTileBytes);
-        tma_load_1d(buf ? buf1 : buf0, a.pix + (size_t)tile * SMOE_TPIX * SMOE_PIXREC, kTileBytes, &bar[buf]);
+        tma_load_1d(buf ? buf1 : buf0, a.pix + (size_t)tile * tstride, kTileBytes, &bar[buf]);
     };
 
     // own kernel record (global -> registers)
@@ -218,7 +220,6 @@ __global__ void __launch_bounds__(kThreads, 7) backward_kernel(const BwdArgs a) 
         if (nlist > 0) issue(tlist[0], 0);
         if (nlist > 1) issue(tlist[1], 1);
     }
-    const int RL = a.b.tile[D - 1];          // pixels per row of the tile (run along the last axis)
     for (int li = 0; li < nlist; ++li) {
         const int buf = li & 1;
         const int tile = tlist[li];
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, 7) backward_kernel(const BwdArgs a) 
                 for (int l = 0; l < D; ++l) N1[l][c] = 0.f;
             }
 
-            // pixel state is plane-major inside a tile: [x0 | x1 | x2 | qthr | gr | g0 | g1 | g2][512]
+            // pixel state: planes [z | qthr | gr | g_c][512] + the row-constant coordinates (smoe_common.cuh)
             const float* pl = buf ? buf1 : buf0;
             constexpr int GRP = 4;          // pixels tested together for the exact-zero skip
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, nv[C], nz[C];      // row sums, reset after every folded row
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(kThreads, 7) backward_kernel(const BwdArgs a) 
                 // the pixels of a row differ only in their LAST coordinate z: q = cr + (br + qq_last z) z
                 float xr[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-                for (int l = 0; l < D - 1; ++l) xr[l] = pl[(PR_X + l) * SMOE_TPIX + r0];
+                for (int l = 0; l < D - 1; ++l) xr[l] = pl[pix_rowc_offset(C) + l * (SMOE_TPIX / RL) + r0 / RL];
                 float cr = f[R::OC];
 #pragma unroll
                 for (int l = 0; l < D - 1; ++l) {
@@ -314,8 +315,8 @@ __global__ void __launch_bounds__(kThreads, 7) backward_kernel(const BwdArgs a) 
                 // carry every moment of the row; they are folded once per row
                 bool row_active = false;
                 for (int j0 = r0; j0 < r0 + RL; j0 += GRP) {
-                    const float4 zv = *reinterpret_cast<const float4*>(pl + (PR_X + D - 1) * SMOE_TPIX + j0);
-                    const float4 tv = *reinterpret_cast<const float4*>(pl + PR_QTHR * SMOE_TPIX + j0);
+                    const float4 zv = *reinterpret_cast<const float4*>(pl + PL_Z * SMOE_TPIX + j0);
+                    const float4 tv = *reinterpret_cast<const float4*>(pl + PL_QTHR * SMOE_TPIX + j0);
                     const float z4[GRP] = {zv.x, zv.y, zv.z, zv.w};
                     const float t4[GRP] = {tv.x, tv.y, tv.z, tv.w};
                     float dq[GRP];
@@ -329,12 +330,12 @@ __global__ void __launch_bounds__(kThreads, 7) backward_kernel(const BwdArgs a) 
                     // w = tau * 2^dq is exactly +0 for dq < -126 (ex2.approx.ftz): nothing to accumulate
                     if (__builtin_expect(skip && !__any_sync(0xffffffffu, dmax >= -126.0f), 1)) continue;
                     row_active = true;
-                    const float4 grv = *reinterpret_cast<const float4*>(pl + PR_GR * SMOE_TPIX + j0);
+                    const float4 grv = *reinterpret_cast<const float4*>(pl + PL_GR * SMOE_TPIX + j0);
                     const float gr4[GRP] = {grv.x, grv.y, grv.z, grv.w};
                     float g4[C][GRP];
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
-                        const float4 gv = *reinterpret_cast<const float4*>(pl + (PR_G + c) * SMOE_TPIX + j0);
+                        const float4 gv = *reinterpret_cast<const float4*>(pl + (PL_G + c) * SMOE_TPIX + j0);
                         g4[c][0] = gv.x; g4[c][1] = gv.y; g4[c][2] = gv.z; g4[c][3] = gv.w;
                     }
 #pragma unroll
@@ -618,7 +619,8 @@ int smoe_backward(const smoe_cfg* cfg, const smoe_batch* batch, const float* pac
     a.tau = 0.5f / (float)(1 << cfg->precision);
     a.max_list = (a.ntiles + num_splits - 1) / num_splits;
     dim3 grid((K_cap + kThreads - 1) / kThreads, num_splits);
-    size_t sm = 2 * (size_t)SMOE_TPIX * SMOE_PIXREC * 4 + 16 + 8 * kCB * 4 + 16 * 4 + (size_t)a.max_list * 4 + 64;
+    size_t sm = 2 * (size_t)pix_stride(cfg->d, cfg->C, batch->tile[cfg->d - 1]) * 4 + 16 + 8 * kCB * 4 + 16 * 4 +
+                (size_t)a.max_list * 4 + 64;
     SMOE_REQUIRE(sm <= 100 * 1024, "too many tiles per split for the shared-memory tile list: raise num_splits");
     cudaStream_t st = (cudaStream_t)stream;
     // partial slabs of splits that own no tile, and rows k >= K, are never read

@@ -420,25 +420,22 @@ __global__ void __launch_bounds__(kThreadsF, 4) forward_kernel(const FwdArgs a) 
                 for (int c = 0; c < C; ++c) g[c] = 0.f;
             }
             if (a.pix) {
-                float rec[SMOE_PIXREC];
+                // planes [z | qthr | gr | g_c][512] + row constants; coordinates are stored for every slot
+                const int RLf = a.b.tile[D - 1];
+                float* tp = a.pix + (size_t)tile * pix_stride(D, C, RLf);
+                const bool in = gidx[p] >= 0;
+                const bool live = S[p] > kSFloor;                                        // smoe.py:821
+                tp[PL_Z * SMOE_TPIX + j] = D == 1 ? x0[p] : xs[D - 1];
+                tp[PL_QTHR * SMOE_TPIX + j] = in ? qthr[p] : INFINITY;   // outside the batch: w = tau * 2^(-inf) = 0
+                tp[PL_GR * SMOE_TPIX + j] = (in && live) ? gr : 0.f;
 #pragma unroll
-                for (int q = 0; q < SMOE_PIXREC; ++q) rec[q] = 0.f;
-                rec[PR_QTHR] = INFINITY;          // pixels outside the batch: w = tau * 2^(-inf) = 0
-                // coordinates are stored for every slot: the backward derives row constants from them
-                rec[PR_X] = x0[p];
+                for (int c = 0; c < C; ++c) tp[(PL_G + c) * SMOE_TPIX + j] = in ? g[c] : 0.f;
+                if (D > 1 && j % RLf == 0) {
+                    const int row = j / RLf, nrows = SMOE_TPIX / RLf;
+                    tp[pix_rowc_offset(C) + row] = x0[p];
 #pragma unroll
-                for (int l = 1; l < D; ++l) rec[PR_X + l] = xs[l];
-                if (gidx[p] >= 0) {
-                    const bool live = S[p] > kSFloor;                                    // smoe.py:821
-                    rec[PR_QTHR] = qthr[p];
-                    rec[PR_GR] = live ? gr : 0.f;
-#pragma unroll
-                    for (int c = 0; c < C; ++c) rec[PR_G + c] = g[c];
+                    for (int l = 1; l < D - 1; ++l) tp[pix_rowc_offset(C) + l * nrows + row] = xs[l];
                 }
-                // plane-major inside the tile ([8][512]): coalesced here, float4-per-4-pixels in the backward
-                float* dst = a.pix + (size_t)tile * SMOE_TPIX * SMOE_PIXREC + j;
-#pragma unroll
-                for (int q = 0; q < SMOE_PIXREC; ++q) dst[q * SMOE_TPIX] = rec[q];
             }
         }
     }

@@ -398,27 +398,28 @@ int smoe_colminmax(const float* x, int rows, int cols, double* lb, double* ub, v
     return check_launch("smoe_colminmax");
 }
 
-int smoe_suggest_splits(int K_cap, int ntiles) {
+int smoe_suggest_splits(int K_cap, const smoe_batch* b) {
+    // Pixel splits of the backward: split s owns tiles s, s+NS, s+2NS, ...  Enough splits that the grid has a
+    // few waves of CTAs and a CTA's list stays short (~180 tiles of the whole batch per split measured best on
+    // c3), and NS coprime to the tile-grid extents: the kernels of a CTA are spatial neighbours, so a split
+    // whose tiles share columns (NS dividing the tiles per row) would give some CTAs all the work and others none.
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int slots = 7 * sms;
+    int nt[3], ntiles = 1;
+    for (int i = 0; i < 3; ++i) { nt[i] = (b->extent[i] + b->tile[i] - 1) / b->tile[i]; ntiles *= nt[i]; }
     const int kt = (K_cap + kThreads - 1) / kThreads;
-    int best = 1;
-    double best_eff = -1.0;
-    int lo = (2 * slots + kt - 1) / kt;          // at least ~2 waves of CTAs
-    if (lo < 1) lo = 1;
-    if (lo >= ntiles) return ntiles < 1 ? 1 : ntiles;      // small problems: one tile per CTA
-    for (int ns = lo; ns <= lo + 64 && ns <= ntiles; ++ns) {
-        const double ctas = (double)kt * ns;
-        const double waves = ctas / slots;
-        double eff = waves / ceil(waves);
-        // tiles per split should also divide evenly
-        const double tps = (double)ntiles / ns;
-        eff *= tps / ceil(tps);
-        if (eff > best_eff + 1e-9) { best_eff = eff; best = ns; }
+    int want = (2 * 8 * sms + kt - 1) / kt;          // >= ~2 waves of 8 CTAs per SM
+    if (want < ntiles / 180) want = ntiles / 180;
+    if (want < 8) want = 8;
+    if (want >= ntiles) return ntiles < 1 ? 1 : ntiles;      // small problems: one tile per CTA
+    for (int ns = want; ns < ntiles; ++ns) {
+        bool prime = true;
+        for (int q = 2; q * q <= ns; ++q) if (ns % q == 0) { prime = false; break; }
+        if (!prime) continue;
+        if ((nt[1] > 1 && nt[1] % ns == 0) || (nt[2] > 1 && nt[2] % ns == 0) || (nt[1] * nt[2] > 1 && (nt[1] * nt[2]) % ns == 0)) continue;
+        return ns;
     }
-    if (best > ntiles) best = ntiles;
-    return best < 1 ? 1 : best;
+    return ntiles;
 }
 
 }  // extern "C"

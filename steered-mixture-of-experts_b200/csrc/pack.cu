@@ -347,6 +347,7 @@ int smoe_abi_version(void) { return SMOE_ABI_VERSION; }
 const char* smoe_last_error(void) { return smoe::g_err; }
 int smoe_param_count(int d, int C) { return nparam(d, C); }
 int smoe_packed_stride(int d, int C) { return pstride(d, C); }
+int smoe_pix_stride(int d, int C, const smoe_batch* b) { return pix_stride(d, C, b->tile[d - 1]); }
 int smoe_num_tiles(const smoe_batch* b) {
     int n = 1;
     for (int i = 0; i < 3; ++i) n *= (b->extent[i] + b->tile[i] - 1) / b->tile[i];

@@ -33,10 +33,15 @@ __host__ __device__ constexpr int off_ga(int d, int C) { return d + tri(d) + 1 +
 __host__ __device__ constexpr int lt(int l, int m) { return l * (l + 1) / 2 + m; }
 __host__ __device__ constexpr int ut(int d, int l, int m) { return l * d - l * (l - 1) / 2 + (m - l); }
 
-// pixel state written by the forward (plane-major per tile: [SMOE_PIXREC][SMOE_TPIX]), streamed by the backward; planes:
-//   [0..d) tile-centred coordinates | [3] qthr = log2(tau * max(S, 1e-11)), +inf outside the batch |
-//   [4] gr = sum_c g_c r_c (0 where S is clamped, smoe.py:821) | [5..5+C) g_c = dL/dr_c
-constexpr int PR_X = 0, PR_QTHR = 3, PR_GR = 4, PR_G = 5;
+// Pixel state written by the forward and streamed by the backward, per tile:
+//   planes [3 + C][SMOE_TPIX]: z = tile-centred LAST coordinate | qthr = log2(tau * max(S, 1e-11)), +inf
+//   outside the batch | gr = sum_c g_c r_c (0 where S is clamped, smoe.py:821) | g_c = dL/dr_c
+//   then rowc [d-1][SMOE_TPIX / RL]: the other tile-centred coordinates, constant along a row of RL pixels
+constexpr int PL_Z = 0, PL_QTHR = 1, PL_GR = 2, PL_G = 3;
+__host__ __device__ constexpr int pix_rowc_offset(int C) { return (3 + C) * SMOE_TPIX; }
+__host__ __device__ inline int pix_stride(int d, int C, int RL) {
+    return pix_rowc_offset(C) + ((d - 1) * (SMOE_TPIX / RL) + 3) / 4 * 4;
+}
 
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);

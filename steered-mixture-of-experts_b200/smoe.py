@@ -332,14 +332,16 @@ class Smoe:
         self._regsums = torch.zeros((nb, 2), dtype=f32, device=dev)
         self._scalars = torch.zeros((nb, _ffi.NSCAL), dtype=f32, device=dev)
         self._infl = torch.zeros((K,), dtype=torch.uint8, device=dev)
-        self._pix = torch.zeros((max_tiles * _ffi.TPIX * _ffi.PIXREC,), dtype=f32, device=dev)
+        self._pix = torch.zeros((max_tiles * L.smoe_pix_stride(d, Cc, C.byref(self._batches[0])),), dtype=f32, device=dev)
         self._tile_qmin = torch.zeros((max_tiles,), dtype=f32, device=dev)
         self._chunk_bounds = torch.zeros(((K + 127) // 128, 12), dtype=f32, device=dev)
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         self._partials = torch.zeros((4 * sms * 8,), dtype=f32, device=dev)
         self._ticket = torch.zeros((4,), dtype=torch.int32, device=dev)
         self._pack_ws = torch.zeros((L.smoe_pack_workspace_bytes(K) + 15) // 4, dtype=torch.int32, device=dev)
-        self._splits = int(L.smoe_suggest_splits(K, max_tiles))
+        import os as _os
+        self._splits = int(_os.environ.get("SMOE_SPLITS", 0)) or max(int(L.smoe_suggest_splits(K, C.byref(b)))
+                                                                     for b in self._batches)
         self._raw_part = None           # allocated on the first training pass
         # [raw statistics | scalars | influence flags]: the buffer a multi-GPU run all-reduces
         self._xbuf = torch.zeros((K * self._P + _ffi.NSCAL + K,), dtype=f32, device=dev) if self._world > 1 else None

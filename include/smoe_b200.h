@@ -142,7 +142,7 @@ int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const float* pack
                  const int32_t* counts, const float* chunk_bounds, int K_cap, const float* image,
                  const float* ax0, const float* ax1, const float* ax2, float* res, float* res_pre,
                  int32_t* argmax, uint8_t* infl, float* pix, float* tile_qmin /*[tiles]*/, float* scalars,
-                 float* partials /*[num_sms*4][8]*/, int32_t* ticket, void* stream);
+                 float* partials /*[num_sms*8][8]*/, int32_t* ticket, void* stream);
 
 /* Fused backward over one batch: recomputes the gates from the per-pixel state and reduces the
  * per-kernel sufficient statistics (sum t, sum t*delta, sum t*delta*delta^T, sum m*w*g,

@@ -1,6 +1,6 @@
 // Fused SMoE forward (smoe_forward).  Replaces smoe.py:777-858, 899-937, 1053.
 //
-// Pixel-stationary: a CTA (128 threads, 4 resident per SM) owns a spatially compact tile of
+// Pixel-stationary: a CTA (128 threads, 6 resident per SM for images, 4 for video) owns a spatially compact tile of
 // SMOE_TPIX = 512 pixels (4 per thread, in registers) and streams the active kernels past it twice:
 //   sweep A  S_n = sum_k 2^{q_k(x_n)}                       (the normaliser of smoe.py:819-821)
 //   sweep B  w = 2^{q}/S, m = w > tau, r_c += m*w*E_kc(x)   (smoe.py:823-848; needs the FINAL S,
@@ -140,7 +140,7 @@ __device__ __forceinline__ int cta_compact(bool flag, int* scratch, int* total) 
 }
 
 template <int D, int C>
-__global__ void __launch_bounds__(kThreadsF, 4) forward_kernel(const FwdArgs a) {
+__global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(const FwdArgs a) {
     using R = Rec<D, C>;
     constexpr int PK = pstride(D, C);
     constexpr int PPT = kPixPerThread;
@@ -525,7 +525,8 @@ extern "C" int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const 
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int grid = a.ntiles < 4 * sms ? a.ntiles : 4 * sms;
+    const int per_sm = cfg->d == 2 ? 6 : 4;          // resident CTAs per SM (matches __launch_bounds__)
+    int grid = a.ntiles < per_sm * sms ? a.ntiles : per_sm * sms;
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL(D, C)                                                                                           \
     {                                                                                                        \

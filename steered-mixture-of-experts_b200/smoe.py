@@ -336,7 +336,7 @@ class Smoe:
         self._tile_qmin = torch.zeros((max_tiles,), dtype=f32, device=dev)
         self._chunk_bounds = torch.zeros(((K + 127) // 128, 12), dtype=f32, device=dev)
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        self._partials = torch.zeros((4 * sms * 8,), dtype=f32, device=dev)
+        self._partials = torch.zeros((8 * sms * 8,), dtype=f32, device=dev)
         self._ticket = torch.zeros((4,), dtype=torch.int32, device=dev)
         self._pack_ws = torch.zeros((L.smoe_pack_workspace_bytes(K) + 15) // 4, dtype=torch.int32, device=dev)
         import os as _os

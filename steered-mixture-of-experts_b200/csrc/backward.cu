@@ -216,10 +216,13 @@ __global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) 
         for (int l = 0; l < D; ++l) GGa[l][c] = 0.f;
     }
 
+    int* done = scratch + 8;                 // per-buffer count of warps that finished the current tile
     if (tid == 0) {
+        done[0] = done[1] = 0;
         if (nlist > 0) issue(tlist[0], 0);
         if (nlist > 1) issue(tlist[1], 1);
     }
+    __syncthreads();
     for (int li = 0; li < nlist; ++li) {
         const int buf = li & 1;
         const int tile = tlist[li];
@@ -413,8 +416,18 @@ __global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) 
                 for (int l = 0; l < D; ++l) GGa[l][c] += fmaf(ctr[l], N0[c], N1[l][c]);
             }
         }
-        __syncthreads();       // everyone is done with this buffer
-        if (tid == 0 && li + 2 < nlist) issue(tlist[li + 2], buf);
+        // Release the buffer without a CTA barrier: the warp that finishes this tile LAST refills the buffer
+        // with tile li+2, so a warp never waits for a slower sibling (only for the TMA of its next tile).
+        __syncwarp();
+        if ((tid & 31) == 0) {
+            __threadfence_block();
+            const int old = atomicAdd(&done[buf], 1);
+            if (old == kThreads / 32 - 1) {
+                done[buf] = 0;
+                __threadfence_block();
+                if (li + 2 < nlist) issue(tlist[li + 2], buf);
+            }
+        }
     }
 
     if (active) {

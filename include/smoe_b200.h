@@ -66,6 +66,14 @@ typedef struct smoe_cfg {
     int32_t quantize_pis;      /* fake-quantise pis before the >0 mask (smoe.py:474-480)    */
     float   pis_lb, pis_ub;    /* lower_bounds[3], upper_bounds[3]                          */
     int32_t pis_bits;          /* bit_depths[3]                                             */
+    int32_t quantization_mode; /* 2: every parameter is fake-quantised with the fixed bounds below before use,
+                                  gradients pass straight through inside the bounds (smoe.py:482-496);
+                                  0/1: parameters are used as they are (mode 1 quantises on the host only) */
+    float   q_lb[5], q_ub[5];  /* lower_bounds / upper_bounds in the reference's order: A, musX, nu_e, pis,
+                                  gamma_e (smoe_test.py:306-309)                                        */
+    int32_t q_bits[5];         /* bit_depths, same order (smoe_test.py:302)                            */
+    int32_t use_diff_center;   /* the musX variable holds offsets from a fixed grid (smoe.py:390-394, 746-747) */
+    int32_t kernel_count_as_norm_l1; /* L1 on pis normalised by the live kernel count (smoe.py:1022-1025) */
     int32_t dense_exec;        /* 0: exact culling + exact-zero skipping (default);
                                   1: execute every (pixel, kernel) pair in full;
                                   2: exact-zero skipping inside the dense sweeps, no tile-level
@@ -111,7 +119,8 @@ size_t      smoe_backward_workspace_bytes(const smoe_cfg* cfg, int K_cap, int nu
  *   L1 terms of smoe.py:1027, 1044)
  *   chunk_bounds: per 128 consecutive active kernels, bounding box of the centres, smallest
  *   eigenvalue bound and largest c0 -- the coarse level of the exact culling in smoe_forward */
-int smoe_pack(const smoe_cfg* cfg, const float* theta, const uint8_t* kernel_list, int K_all,
+int smoe_pack(const smoe_cfg* cfg, const float* theta, const float* mus_grid /*[K_all][d], use_diff_center only*/,
+              const uint8_t* kernel_list, int K_all,
               float* packed, int32_t* indices, int32_t* pos /*[K_all]: packed row of each kernel or -1*/,
               int32_t* counts, float* regsums,
               float* chunk_bounds /*[ceil(K_all/128)][12]*/, void* workspace, void* stream);
@@ -171,8 +180,8 @@ int smoe_reduce_splits(const smoe_cfg* cfg, const int32_t* counts, int K_cap, in
  * (assign_add, smoe.py:1150).  Also rewrites kernel_list[indices[k]] = infl[k] when infl != NULL
  * (smoe.py:1763-1766). */
 int smoe_grad_finalize(const smoe_cfg* cfg, const float* raw, int num_splits, int K_cap, const float* theta,
-                       const int32_t* indices, const int32_t* counts, float pis_l1_over_norm, float u_l1,
-                       float* grads, void* stream);
+                       const int32_t* indices, const int32_t* counts, float pis_l1, float l1_norm /* start_pis */,
+                       float u_l1, float* grads, void* stream);
 
 /* kernel_list[i] = 0 for all i, then kernel_list[indices[k]] = infl[k] (smoe.py:1763-1766). */
 int smoe_update_kernel_list(const int32_t* indices, const int32_t* counts, const uint8_t* infl,

@@ -111,6 +111,32 @@ def fake_quant_args(x, mn, mx, bits):
     return _FakeQuantArgs.apply(x, nmin, nmax, scale)
 
 
+def fake_quant_var(x, mn, mx, bits):
+    """fake_quant_with_min_max_args on a VARIABLE (smoe.py:482-496).  TF variables are float32, so the
+    code is decided on the float32 value whatever dtype the oracle computes in."""
+    nmin, nmax, scale = _nudge(mn, mx, bits)
+    x32 = x.detach().to(torch.float32)
+    q = fq_values(x32, nmin, nmax, scale).to(x.dtype)
+    mask = ((x32 >= nmin) & (x32 <= nmax)).to(x.dtype)
+    return x * mask + (q - x * mask).detach()                   # value q, gradient = straight-through mask
+
+
+def effective_params(params, cfg):
+    """The q* tensors of smoe.py:482-496, 534-538: mode 2 fake-quantises every variable with the fixed
+    bounds (order A, musX, nu_e, pis, gamma_e: smoe_test.py:302-309); modes 0/1 use them as they are.
+    `pis` is handled by the caller (smoe.py:474-478)."""
+    if cfg.quantization_mode != 2:
+        return params
+    lb, ub, bd = cfg.lower_bounds, cfg.upper_bounds, cfg.bit_depths
+    out = dict(params)
+    out["A_diagonal"] = fake_quant_var(params["A_diagonal"], lb[0], ub[0], bd[0])
+    out["A_corr"] = fake_quant_var(params["A_corr"], lb[0], ub[0], bd[0])
+    out["musX"] = fake_quant_var(params["musX"], lb[1], ub[1], bd[1])
+    out["nu_e"] = fake_quant_var(params["nu_e"], lb[2], ub[2], bd[2])
+    out["gamma_e"] = fake_quant_var(params["gamma_e"], lb[4], ub[4], bd[4])
+    return out
+
+
 class _ClipByValue01(torch.autograd.Function):
     """tf.clip_by_value(x, 0, 1) (smoe.py:857): gradient passes iff 0 <= x <= 1."""
 
@@ -171,12 +197,12 @@ def graph_forward(params: Dict[str, torch.Tensor], kernel_list, domain, target, 
     """
     dt = domain.dtype
     d, C = cfg.dim_domain, cfg.num_channels
-    if cfg.quantization_mode >= 2:
-        raise NotImplementedError("fake-quant training modes 2/3 are a 'next' row (SURVEY 8f-3)")
+    if cfg.quantization_mode >= 3:
+        raise NotImplementedError("fake-quant training mode 3 is a 'next' row (SURVEY 8f-3)")
 
     pis_var = params["pis"]
     # smoe.py:474-480
-    if cfg.quantize_pis:
+    if cfg.quantize_pis or cfg.quantization_mode >= 2:
         qpis = fake_quant_args(pis_var, cfg.lower_bounds[3], cfg.upper_bounds[3], cfg.bit_depths[3])
     else:
         qpis = pis_var
@@ -184,6 +210,7 @@ def graph_forward(params: Dict[str, torch.Tensor], kernel_list, domain, target, 
     bool_mask = torch.as_tensor(kernel_list, dtype=torch.bool) & pis_mask.detach()
     indices = torch.nonzero(bool_mask).flatten()
 
+    params = effective_params(params, cfg)                          # smoe.py:482-496 (mode 2), else identity
     gamma_all = params["gamma_e"]
     if cfg.use_yuv and cfg.train_gammas and cfg.only_y_gamma:       # smoe.py:725-729
         gmask = torch.zeros(d, C, dtype=dt)
@@ -291,6 +318,8 @@ def closed_form_grads(params_np: Dict[str, np.ndarray], kernel_list, domain, tar
     """
     f8 = np.float64
     d, C = cfg.dim_domain, cfg.num_channels
+    if cfg.quantization_mode >= 2 or cfg.use_diff_center:
+        raise NotImplementedError("closed form covers quantization_mode 0/1 without use_diff_center")
     pis_all = params_np["pis"].astype(f8)
     if cfg.quantize_pis:
         nmin, nmax, scale = _nudge(cfg.lower_bounds[3], cfg.upper_bounds[3], cfg.bit_depths[3])

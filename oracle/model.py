@@ -204,10 +204,13 @@ class OracleSmoe:
         """smoe.py:2287-2365 (single-model part): OR into every batch's list the pi>0 kernels whose Mahalanobis
         distance is < 800 at one of the 3^d corner / mid points of the batch."""
         from itertools import product as _product
-        from .graph import assemble_A
+        from .graph import assemble_A, effective_params
         d = self.dim_domain
-        A = assemble_A(self.vars["A_diagonal"], self.vars["A_corr"], self.cfg.train_inverse_cov).double()
-        mu = self.vars["musX"].double()
+        eff = effective_params({k: v.detach() for k, v in self.vars.items()}, self.cfg)
+        A = assemble_A(eff["A_diagonal"], eff["A_corr"], self.cfg.train_inverse_cov).double()
+        mu = eff["musX"].double()
+        if self.use_diff_center:
+            mu = mu + self.musX_grid.double()
         pis = torch.tensor(self.get_params()["pis"], dtype=torch.float64)
         for k, (coord, batch) in enumerate(init_ref.sliding_window(self.joint_domain, 0, self.batch_size_valued)):
             flat = batch.reshape(-1, batch.shape[-1])[:, :d]
@@ -279,8 +282,10 @@ class OracleSmoe:
 
     # -- getters --------------------------------------------------------------------
     def get_params(self):
-        out = {k: v.detach().numpy().astype(np.float32).copy() for k, v in self.vars.items()}
-        if self.quantize_pis:
+        from .graph import effective_params
+        eff = effective_params({k: v.detach() for k, v in self.vars.items()}, self.cfg)   # smoe.py:1796-1798
+        out = {k: v.numpy().astype(np.float32).copy() for k, v in eff.items()}
+        if self.quantize_pis or self.quantization_mode >= 2:
             from .graph import fake_quant_args
             out["pis"] = fake_quant_args(self.vars["pis"].detach(), self.lower_bounds[3], self.upper_bounds[3],
                                          self.bit_depths[3]).numpy().astype(np.float32)

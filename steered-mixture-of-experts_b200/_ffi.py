@@ -29,7 +29,10 @@ class Cfg(C.Structure):
     _fields_ = [("d", C.c_int32), ("C", C.c_int32), ("precision", C.c_int32), ("margin", C.c_float),
                 ("use_determinant", C.c_int32), ("train_inverse_cov", C.c_int32), ("use_yuv", C.c_int32),
                 ("train_gammas", C.c_int32), ("only_y_gamma", C.c_int32), ("quantize_pis", C.c_int32),
-                ("pis_lb", C.c_float), ("pis_ub", C.c_float), ("pis_bits", C.c_int32), ("dense_exec", C.c_int32)]
+                ("pis_lb", C.c_float), ("pis_ub", C.c_float), ("pis_bits", C.c_int32),
+                ("quantization_mode", C.c_int32), ("q_lb", C.c_float * 5), ("q_ub", C.c_float * 5),
+                ("q_bits", C.c_int32 * 5), ("use_diff_center", C.c_int32), ("kernel_count_as_norm_l1", C.c_int32),
+                ("dense_exec", C.c_int32)]
 
 
 class Batch(C.Structure):

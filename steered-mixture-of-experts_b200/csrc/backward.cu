@@ -459,15 +459,15 @@ __global__ void __launch_bounds__(256) reduce_splits_kernel(const int32_t* __res
     }
 }
 
-struct Nudged { float nmin, nmax, scale, inv_scale; };
 
 // statistics -> variable gradients, one thread per active kernel
 template <int D, int C>
 __global__ void __launch_bounds__(256) grad_finalize_kernel(smoe_cfg cfg, const float* __restrict__ raw, int num_splits,
                                                             int K_cap, const float* __restrict__ theta,
                                                             const int32_t* __restrict__ indices,
-                                                            const int32_t* __restrict__ counts, float l1, float u_l1,
-                                                            Nudged nq, float* __restrict__ grads) {
+                                                            const int32_t* __restrict__ counts, float pis_l1,
+                                                            float l1_norm, float u_l1, QuantSet qs,
+                                                            float* __restrict__ grads) {
     constexpr int T = tri(D);
     constexpr int P = nparam(D, C);
     const int k = blockIdx.x * 256 + threadIdx.x;
@@ -483,11 +483,18 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(smoe_cfg cfg, const 
     const int row = indices[k];
     const float* th = theta + (size_t)row * P;
     float* gr = grads + (size_t)row * P;
-    float A[D][D];
+    const bool fq = qs.mode == 2;
+    const float l1 = pis_l1 / (cfg.kernel_count_as_norm_l1 ? (float)counts[1] : l1_norm);     // smoe.py:1022-1027
+    float A[D][D], steA[D][D];
 #pragma unroll
     for (int l = 0; l < D; ++l)
 #pragma unroll
-        for (int m = 0; m < D; ++m) A[l][m] = (m <= l) ? th[off_A(D, C) + lt(l, m)] : 0.f;
+        for (int m = 0; m < D; ++m) {
+            float v = (m <= l) ? th[off_A(D, C) + lt(l, m)] : 0.f;
+            steA[l][m] = (fq && m <= l) ? ste_mask(v, qs.g[0]) : 1.f;
+            if (fq && m <= l) v = fake_quant(v, qs.g[0]);
+            A[l][m] = v;
+        }
     float V[D], Dm[D][D];
 #pragma unroll
     for (int l = 0; l < D; ++l) V[l] = s[off_mu(D, C) + l];
@@ -500,10 +507,8 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(smoe_cfg cfg, const 
     float pi = th[off_pi(D, C)];
     float ste = 1.f;
     if (cfg.quantize_pis) {
-        ste = (pi >= nq.nmin && pi <= nq.nmax) ? 1.f : 0.f;
-        float cq = fminf(fmaxf(pi, nq.nmin), nq.nmax);
-        float kq = floorf(__fadd_rn(__fmul_rn(__fsub_rn(cq, nq.nmin), nq.inv_scale), 0.5f));
-        pi = __fadd_rn(__fmul_rn(kq, nq.scale), nq.nmin);
+        ste = ste_mask(pi, qs.g[3]);
+        pi = fake_quant(pi, qs.g[3]);
     }
     gr[off_pi(D, C)] += (M0 / pi + l1) * ste;
     // mu and A
@@ -550,7 +555,7 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(smoe_cfg cfg, const 
     }
 #pragma unroll
     for (int l = 0; l < D; ++l) {
-        gr[off_mu(D, C) + l] += gmu[l];
+        gr[off_mu(D, C) + l] += fq ? gmu[l] * ste_mask(th[off_mu(D, C) + l], qs.g[1]) : gmu[l];
 #pragma unroll
         for (int m = 0; m <= l; ++m) {
             float gv = gA[l][m];
@@ -558,17 +563,18 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(smoe_cfg cfg, const 
                 gv += u_l1;                                             // smoe.py:1044
                 if (cfg.use_determinant) gv += M0 / A[l][l];            // smoe.py:810
             }
-            gr[off_A(D, C) + lt(l, m)] += gv;
+            gr[off_A(D, C) + lt(l, m)] += gv * steA[l][m];
         }
     }
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        gr[off_nu(D, C) + c] += s[off_nu(D, C) + c];
+        gr[off_nu(D, C) + c] += fq ? s[off_nu(D, C) + c] * ste_mask(th[off_nu(D, C) + c], qs.g[2]) : s[off_nu(D, C) + c];
 #pragma unroll
         for (int l = 0; l < D; ++l) {
             float gv = s[off_ga(D, C) + l * C + c];
             if (!cfg.train_gammas) gv = 0.f;
             if (cfg.use_yuv && cfg.only_y_gamma && c > 0) gv = 0.f;
+            if (fq) gv *= ste_mask(th[off_ga(D, C) + l * C + c], qs.g[4]);
             gr[off_ga(D, C) + l * C + c] += gv;
         }
     }
@@ -659,25 +665,16 @@ int smoe_reduce_splits(const smoe_cfg* cfg, const int32_t* counts, int K_cap, in
 }
 
 int smoe_grad_finalize(const smoe_cfg* cfg, const float* raw, int num_splits, int K_cap, const float* theta,
-                       const int32_t* indices, const int32_t* counts, float pis_l1_over_norm, float u_l1, float* grads,
-                       void* stream) {
+                       const int32_t* indices, const int32_t* counts, float pis_l1, float l1_norm, float u_l1,
+                       float* grads, void* stream) {
     SMOE_REQUIRE(cfg && raw && theta && indices && counts && grads && K_cap > 0 && num_splits > 0, "bad argument");
-    Nudged nq = {0, 0, 1, 1};
-    if (cfg->quantize_pis) {
-        float qmax = (float)((1 << cfg->pis_bits) - 1);
-        float scale = (cfg->pis_ub - cfg->pis_lb) / qmax;
-        float zp = 0.f - cfg->pis_lb / scale;
-        float nzp = zp < 0.f ? 0.f : (zp > qmax ? qmax : floorf(zp + 0.5f));
-        nq.nmin = (0.f - nzp) * scale;
-        nq.nmax = (qmax - nzp) * scale;
-        nq.scale = scale;
-        nq.inv_scale = 1.0f / scale;
-    }
+    SMOE_REQUIRE(cfg->kernel_count_as_norm_l1 || l1_norm > 0.f, "l1_norm must be positive");
+    const QuantSet qs = make_quantset(cfg);
     int nb = (K_cap + 255) / 256;
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL(D, C)                                                                                              \
-    grad_finalize_kernel<D, C><<<nb, 256, 0, st>>>(*cfg, raw, num_splits, K_cap, theta, indices, counts,        \
-                                                   pis_l1_over_norm, u_l1, nq, grads);
+    grad_finalize_kernel<D, C><<<nb, 256, 0, st>>>(*cfg, raw, num_splits, K_cap, theta, indices, counts, pis_l1, \
+                                                   l1_norm, u_l1, qs, grads);
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL
     return check_launch("smoe_grad_finalize");

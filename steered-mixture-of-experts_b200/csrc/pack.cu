@@ -28,33 +28,12 @@ int check_launch(const char* what) {
     return 0;
 }
 
-// TF FakeQuantWithMinMaxArgs nudging (float32), see oracle/graph.py:_nudge
-struct Nudged { float nmin, nmax, scale, inv_scale; };
-static Nudged nudge(float mn, float mx, int bits) {
-    float qmin = 0.f, qmax = (float)((1 << bits) - 1);
-    float scale = (mx - mn) / (qmax - qmin);
-    float zp = qmin - mn / scale;
-    float nzp = zp < qmin ? qmin : (zp > qmax ? qmax : floorf(zp + 0.5f));
-    Nudged n;
-    n.nmin = (qmin - nzp) * scale;
-    n.nmax = (qmax - nzp) * scale;
-    n.scale = scale;
-    n.inv_scale = 1.0f / scale;
-    return n;
-}
-
-__device__ __forceinline__ float fake_quant(float x, Nudged n) {
-    float c = fminf(fmaxf(x, n.nmin), n.nmax);
-    float k = floorf(__fadd_rn(__fmul_rn(__fsub_rn(c, n.nmin), n.inv_scale), 0.5f));
-    return __fadd_rn(__fmul_rn(k, n.scale), n.nmin);
-}
-
 struct PackBlk { int32_t count, numpi, nonpos, pad; float sum_pi, sum_diag; };
 
 template <int D, int C>
 __global__ void __launch_bounds__(256) pack_count_kernel(const float* __restrict__ theta,
                                                          const uint8_t* __restrict__ klist, int K_all,
-                                                         int quantize_pis, Nudged nq, PackBlk* __restrict__ blk) {
+                                                         int quantize_pis, QuantSet qs, PackBlk* __restrict__ blk) {
     constexpr int P = nparam(D, C);
     int i = blockIdx.x * 256 + threadIdx.x;
     int flag = 0, numpi = 0;
@@ -62,13 +41,17 @@ __global__ void __launch_bounds__(256) pack_count_kernel(const float* __restrict
     if (i < K_all) {
         const float* row = theta + (size_t)i * P;
         float pi = row[off_pi(D, C)];
-        if (quantize_pis) pi = fake_quant(pi, nq);
+        if (quantize_pis) pi = fake_quant(pi, qs.g[3]);
         numpi = pi > 0.f;
         flag = numpi && klist[i];
         if (flag) {
             spi = pi;
 #pragma unroll
-            for (int l = 0; l < D; ++l) sdiag += row[off_A(D, C) + lt(l, l)];
+            for (int l = 0; l < D; ++l) {
+                float a = row[off_A(D, C) + lt(l, l)];
+                if (qs.mode == 2) a = fake_quant(a, qs.g[0]);
+                sdiag += a;
+            }
         }
     }
     // fixed-order block reduction (shuffle tree, then warp 0 over the 8 warp results)
@@ -236,7 +219,8 @@ __global__ void __launch_bounds__(kChunk) chunk_bounds_kernel(const float* __res
 
 template <int D, int C>
 __global__ void __launch_bounds__(256) pack_scatter_kernel(smoe_cfg cfg, const float* __restrict__ theta,
-                                                           const uint8_t* __restrict__ klist, int K_all, Nudged nq,
+                                                           const float* __restrict__ mus_grid,
+                                                           const uint8_t* __restrict__ klist, int K_all, QuantSet qs,
                                                            const PackBlk* __restrict__ blk, float* __restrict__ packed,
                                                            int32_t* __restrict__ indices, int32_t* __restrict__ pos,
                                                            int32_t* __restrict__ counts,
@@ -261,7 +245,7 @@ __global__ void __launch_bounds__(256) pack_scatter_kernel(smoe_cfg cfg, const f
     const float* row = theta + (size_t)min(i, K_all - 1) * P;
     if (i < K_all) {
         pi = row[off_pi(D, C)];
-        if (cfg.quantize_pis) pi = fake_quant(pi, nq);
+        if (cfg.quantize_pis) pi = fake_quant(pi, qs.g[3]);
         flag = (pi > 0.f) && klist[i];
     }
     unsigned bal = __ballot_sync(0xffffffffu, flag);
@@ -274,19 +258,35 @@ __global__ void __launch_bounds__(256) pack_scatter_kernel(smoe_cfg cfg, const f
     if (i < K_all) pos[i] = flag ? dst : -1;          // original index -> packed row (the inverse of `indices`)
     if (flag) {
         indices[dst] = i;
-        float A[D][D];
+        // the variables, fake-quantised when quantization_mode == 2 (smoe.py:482-496)
+        float A[D][D], mu[D], nu[C], ga[D * C];
+        const bool fq = qs.mode == 2;
 #pragma unroll
         for (int l = 0; l < D; ++l)
 #pragma unroll
-            for (int m = 0; m < D; ++m) A[l][m] = (m <= l) ? row[off_A(D, C) + lt(l, m)] : 0.f;
+            for (int m = 0; m < D; ++m) {
+                float v = (m <= l) ? row[off_A(D, C) + lt(l, m)] : 0.f;
+                if (fq && m <= l) v = fake_quant(v, qs.g[0]);
+                A[l][m] = v;
+            }
         if (cfg.train_inverse_cov) {
 #pragma unroll
             for (int l = 0; l < D; ++l)
 #pragma unroll
                 for (int m = l + 1; m < D; ++m) A[l][m] = A[m][l];
         }
-        neg = stage_record<D, C>(cfg, A, row + off_mu(D, C), pi, row + off_nu(D, C), row + off_ga(D, C),
-                                 packed + (size_t)dst * PK);
+#pragma unroll
+        for (int l = 0; l < D; ++l) {
+            float v = row[off_mu(D, C) + l];
+            if (fq) v = fake_quant(v, qs.g[1]);
+            if (cfg.use_diff_center) v += mus_grid[(size_t)i * D + l];       // smoe.py:746-747
+            mu[l] = v;
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) nu[c] = fq ? fake_quant(row[off_nu(D, C) + c], qs.g[2]) : row[off_nu(D, C) + c];
+#pragma unroll
+        for (int j = 0; j < D * C; ++j) ga[j] = fq ? fake_quant(row[off_ga(D, C) + j], qs.g[4]) : row[off_ga(D, C) + j];
+        neg = stage_record<D, C>(cfg, A, mu, pi, nu, ga, packed + (size_t)dst * PK);
     }
     int negs = __syncthreads_count(neg);
     if (threadIdx.x == 0) nonpos_blk[blockIdx.x] = negs;
@@ -358,9 +358,11 @@ size_t smoe_pack_workspace_bytes(int K_all) {
     return nb * sizeof(PackBlk) + nb * sizeof(int32_t) + 256;
 }
 
-int smoe_pack(const smoe_cfg* cfg, const float* theta, const uint8_t* kernel_list, int K_all, float* packed,
-              int32_t* indices, int32_t* pos, int32_t* counts, float* regsums, float* chunk_bounds, void* workspace,
-              void* stream) {
+int smoe_pack(const smoe_cfg* cfg, const float* theta, const float* mus_grid, const uint8_t* kernel_list, int K_all,
+              float* packed, int32_t* indices, int32_t* pos, int32_t* counts, float* regsums, float* chunk_bounds,
+              void* workspace, void* stream) {
+    SMOE_REQUIRE(!cfg || !cfg->use_diff_center || mus_grid, "use_diff_center needs mus_grid");
+    SMOE_REQUIRE(!cfg || cfg->quantization_mode <= 2, "quantization_mode 3 is not implemented");
     SMOE_REQUIRE(cfg && theta && kernel_list && packed && indices && pos && counts && regsums && chunk_bounds && workspace,
                  "null argument");
     SMOE_REQUIRE(K_all > 0, "K_all must be positive");
@@ -368,12 +370,11 @@ int smoe_pack(const smoe_cfg* cfg, const float* theta, const uint8_t* kernel_lis
     int nb = (K_all + 255) / 256;
     PackBlk* blk = (PackBlk*)workspace;
     int32_t* nonpos_blk = (int32_t*)((char*)workspace + (size_t)nb * sizeof(PackBlk));
-    Nudged nq = {0, 0, 1, 1};
-    if (cfg->quantize_pis) nq = nudge(cfg->pis_lb, cfg->pis_ub, cfg->pis_bits);
+    const QuantSet qs = make_quantset(cfg);
 #define CALL(D, C)                                                                                              \
-    pack_count_kernel<D, C><<<nb, 256, 0, st>>>(theta, kernel_list, K_all, cfg->quantize_pis, nq, blk);         \
-    pack_scatter_kernel<D, C><<<nb, 256, 0, st>>>(*cfg, theta, kernel_list, K_all, nq, blk, packed, indices,    \
-                                                  pos, counts, regsums, nonpos_blk);
+    pack_count_kernel<D, C><<<nb, 256, 0, st>>>(theta, kernel_list, K_all, cfg->quantize_pis, qs, blk);         \
+    pack_scatter_kernel<D, C><<<nb, 256, 0, st>>>(*cfg, theta, mus_grid, kernel_list, K_all, qs, blk, packed,   \
+                                                  indices, pos, counts, regsums, nonpos_blk);
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL
     nonpos_total_kernel<<<1, 1, 0, st>>>(nonpos_blk, nb, counts);

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <math.h>
 #include "../../include/smoe_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -43,6 +44,32 @@ __host__ __device__ inline int pix_stride(int d, int C, int RL) {
     return pix_rowc_offset(C) + ((d - 1) * (SMOE_TPIX / RL) + 3) / 4 * 4;
 }
 
+// TF FakeQuantWithMinMaxArgs (float32): nudged range and scale, see oracle/graph.py:_nudge
+struct Nudged { float nmin, nmax, scale, inv_scale; };
+struct QuantSet { Nudged g[5]; int mode; };        // groups: A, musX, nu_e, pis, gamma_e
+static inline Nudged nudge(float mn, float mx, int bits) {
+    float qmin = 0.f, qmax = (float)((1 << bits) - 1);
+    float scale = (mx - mn) / (qmax - qmin);
+    float zp = qmin - mn / scale;
+    float nzp = zp < qmin ? qmin : (zp > qmax ? qmax : floorf(zp + 0.5f));
+    Nudged n;
+    n.nmin = (qmin - nzp) * scale;
+    n.nmax = (qmax - nzp) * scale;
+    n.scale = scale;
+    n.inv_scale = 1.0f / scale;
+    return n;
+}
+static inline QuantSet make_quantset(const smoe_cfg* cfg) {
+    QuantSet q;
+    q.mode = cfg->quantization_mode;
+    for (int i = 0; i < 5; ++i) {
+        q.g[i].nmin = 0.f; q.g[i].nmax = 0.f; q.g[i].scale = 1.f; q.g[i].inv_scale = 1.f;
+        if (cfg->quantization_mode == 2) q.g[i] = nudge(cfg->q_lb[i], cfg->q_ub[i], cfg->q_bits[i]);
+    }
+    if (cfg->quantization_mode != 2 && cfg->quantize_pis) q.g[3] = nudge(cfg->pis_lb, cfg->pis_ub, cfg->pis_bits);
+    return q;
+}
+
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 
@@ -63,6 +90,12 @@ int check_launch(const char* what);
     else { smoe::set_error("%s: unsupported (d,C)=(%d,%d)", __func__, (int)(d), (int)(C)); return SMOE_E_UNSUPPORTED; }
 
 #ifdef __CUDACC__
+__device__ __forceinline__ float fake_quant(float x, Nudged n) {
+    float c = fminf(fmaxf(x, n.nmin), n.nmax);
+    float k = floorf(__fadd_rn(__fmul_rn(__fsub_rn(c, n.nmin), n.inv_scale), 0.5f));
+    return __fadd_rn(__fmul_rn(k, n.scale), n.nmin);
+}
+__device__ __forceinline__ float ste_mask(float x, Nudged n) { return (x >= n.nmin && x <= n.nmax) ? 1.f : 0.f; }
 __device__ __forceinline__ float ex2f(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

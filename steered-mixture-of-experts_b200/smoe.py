@@ -11,7 +11,7 @@ kernels called through the C ABI of include/smoe_b200.h.  There is no CPU path.
 Deliberate deviations from HEAD (DESIGN.md "Decisions"):
   D1  single-model path only: affines / train_trafo / train_svs / add_kernel_slots>0 /
       dim_domain>=4 / ssim_opt / overlap_of_batches>0 / sampling_percentage<100 / loss masks /
-      radial_as / quantization_mode>=2 raise NotImplementedError;
+      radial_as / quantization_mode 3 raise NotImplementedError;
   D5  `init_params['A_diagonal'] + init_params['A_corr']` is split back into its diagonal
       (-> A_diagonal) and strictly-lower part (-> A_corr) instead of being stored whole in
       A_diagonal (where the reference's band_part then drops the steering, smoe.py:256, 436, 732);
@@ -78,7 +78,7 @@ class Smoe:
         unsupported = {"affines": affines is not None, "train_trafo": train_trafo, "train_svs": train_svs,
                        "add_kernel_slots": add_kernel_slots > 0, "ssim_opt": ssim_opt, "radial_as": radial_as,
                        "overlap_of_batches": overlap_of_batches > 0, "loss_mask": loss_mask is not None,
-                       "quantization_mode>=2": quantization_mode >= 2, "use_diff_center": use_diff_center}
+                       "quantization_mode 3": quantization_mode >= 3}
         for k, v in unsupported.items():
             if v:
                 raise NotImplementedError(f"{k}: outside the single-model hot path (SURVEY.md 8, decision D1)")
@@ -111,8 +111,10 @@ class Smoe:
         self.only_rec_from_checkpoint = only_rec_from_checkpoint
         self.optimizer1 = self.optimizer2 = self.optimizer3 = None
         self.grad_clip_value_abs = None
+        if quantization_mode >= 2:
+            self.quantize_pis = quantize_pis = True          # smoe.py:474 (and smoe_test.py:36-37)
         if quantize_pis and (lower_bounds is None or upper_bounds is None or bit_depths is None):
-            raise ValueError("quantize_pis needs lower_bounds, upper_bounds and bit_depths")
+            raise ValueError("quantize_pis / quantization_mode 2 need lower_bounds, upper_bounds and bit_depths")
 
         self.start_batches = start_batches
         self.image = image
@@ -267,13 +269,21 @@ class Smoe:
         lb3 = float(self.lower_bounds[3]) if self.quantize_pis else 0.0
         ub3 = float(self.upper_bounds[3]) if self.quantize_pis else 1.0
         bits3 = int(self.bit_depths[3]) if self.quantize_pis else 8
+        qm2 = self.quantization_mode == 2
+        q_lb = (C.c_float * 5)(*([float(v) for v in self.lower_bounds] if qm2 else [0.0] * 5))
+        q_ub = (C.c_float * 5)(*([float(v) for v in self.upper_bounds] if qm2 else [1.0] * 5))
+        q_bits = (C.c_int32 * 5)(*([int(v) for v in self.bit_depths] if qm2 else [8] * 5))
         self._cfg = Cfg(d, Cc, int(self.precision), float(self.margin), int(self.use_determinant),
                         int(self.train_inverse_cov), int(self.use_yuv), int(self.train_gammas),
-                        int(self.only_y_gamma), int(self.quantize_pis), lb3, ub3, bits3, int(dense_exec))   # dense_exec: 0 cull+skip, 1 dense, 2 skip only
+                        int(self.only_y_gamma), int(self.quantize_pis), lb3, ub3, bits3,
+                        2 if qm2 else 0, q_lb, q_ub, q_bits, int(self.use_diff_center),
+                        int(self.kernel_count_as_norm_l1), int(dense_exec))   # dense_exec: 0 cull+skip, 1 dense, 2 skip only
         # variables
         A0 = np.asarray(self.A_init, dtype=np.float64)
         theta = np.zeros((K, self._P), dtype=np.float32)
-        theta[:, 0:d] = self.musX_init
+        theta[:, 0:d] = 0.0 if self.use_diff_center else self.musX_init      # smoe.py:390-394
+        self._mus_grid = (torch.from_numpy(np.ascontiguousarray(self.musX_init, dtype=np.float32)).to(dev)
+                          if self.use_diff_center else None)
         for l in range(d):
             for m in range(l + 1):
                 theta[:, d + l * (l + 1) // 2 + m] = A0[:, l, m]
@@ -359,7 +369,7 @@ class Smoe:
         centres).  Purely a work-assignment heuristic: any permutation gives bit-identical results, a coherent
         one makes the kernels of a warp / CTA neighbours so that the tile culling bites."""
         d = self.dim_domain
-        mu = self._theta[:, 0:d].detach().cpu().numpy()
+        mu = self._centres().detach().cpu().numpy()
         bits = 10
         cell = np.clip((mu * (1 << bits)).astype(np.int64), 0, (1 << bits) - 1)
         key = np.zeros(mu.shape[0], dtype=np.int64)
@@ -451,8 +461,6 @@ class Smoe:
                     thr_sv=None, use_loss_mask=False, _host_image=None):
         if sampling_percentage < 100 or with_inc or train_inc or use_loss_mask:
             raise NotImplementedError("sampling / inc / loss-mask paths are outside the hot path (D1)")
-        if self.kernel_count_as_norm_l1:
-            raise NotImplementedError("kernel_count_as_norm_l1")
         if train:
             assert self.optimizer1 is not None, "no optimizer found, you have to specify one!"
         self.valid = False
@@ -515,7 +523,8 @@ class Smoe:
                 lp = 6 / 8 * h[ii, 0] * inv_n + 1 / 8 * sum(h[ii, c] * inv_n for c in range(1, Cc))
             else:
                 lp = sum(h[ii, c] for c in range(Cc)) * inv_n / Cc
-            loss_b = lp + pis_l1 * h[ii, _ffi.NSCAL + 4] / norm + u_l1 * h[ii, _ffi.NSCAL + 5]
+            l1n = max(h[ii, _ffi.NSCAL + 1], 1.0) if self.kernel_count_as_norm_l1 else norm      # smoe.py:1022-1025
+            loss_b = lp + pis_l1 * h[ii, _ffi.NSCAL + 4] / l1n + u_l1 * h[ii, _ffi.NSCAL + 5]
             mse_b = h[ii, 4] * inv_n / Cc * ((2 ** self.precision) ** 2)
             if h[ii, 5] > 0:
                 loss_b = float("nan")
@@ -570,7 +579,8 @@ class Smoe:
                 regs.zero_()
                 self.gpu_launches += 2
             else:
-                check(L.smoe_pack(C.byref(self._cfg), ptr(self._theta), ptr(self._klist[ii]), K, ptr(self._packed),
+                check(L.smoe_pack(C.byref(self._cfg), ptr(self._theta), ptr(self._mus_grid), ptr(self._klist[ii]), K,
+                                  ptr(self._packed),
                                   ptr(self._indices), ptr(self._pos), ptr(counts), ptr(regs), ptr(self._chunk_bounds),
                                   ptr(self._pack_ws), st), "smoe_pack")
                 self.gpu_launches += 4
@@ -597,11 +607,10 @@ class Smoe:
             if not post:
                 continue
             if train:
-                l1 = float(pis_l1) / norm
                 raw, ns = (self._xbuf, 1) if self._world > 1 else (self._raw_part, self._splits)
                 check(L.smoe_grad_finalize(C.byref(self._cfg), ptr(raw), ns, K, ptr(self._theta), ptr(self._indices),
-                                           ptr(counts), C.c_float(l1), C.c_float(float(u_l1)), ptr(self._grads), st),
-                      "smoe_grad_finalize")
+                                           ptr(counts), C.c_float(float(pis_l1)), C.c_float(norm),
+                                           C.c_float(float(u_l1)), ptr(self._grads), st), "smoe_grad_finalize")
                 self.gpu_launches += 1
             if not with_quantized_params:                 # smoe.py:1763-1766
                 check(L.smoe_update_kernel_list(ptr(self._indices), ptr(counts), ptr(self._infl), ptr(self._klist[ii]),
@@ -750,7 +759,7 @@ class Smoe:
     def update_kernel_list(self, add_kernel_slots=0):
         d = self.dim_domain
         A = self._assembled_A()
-        mu = self._theta[:, 0:d]
+        mu = self._centres()
         pis = self._effective_pis()
         full_axes = [np.linspace(0, 1, self.image.shape[a]) for a in range(d)]
         rects = self._batch_rects()
@@ -780,9 +789,10 @@ class Smoe:
     def _assembled_A(self):
         d, K = self.dim_domain, self.start_pis
         A = torch.zeros((K, d, d), dtype=torch.float32, device=self.device)
+        th = self._effective_theta()
         for l in range(d):
             for m in range(l + 1):
-                A[:, l, m] = self._theta[:, d + l * (l + 1) // 2 + m]
+                A[:, l, m] = th[:, d + l * (l + 1) // 2 + m]
                 if self.train_inverse_cov and m < l:
                     A[:, m, l] = A[:, l, m]
         return A
@@ -794,15 +804,40 @@ class Smoe:
             pis = _fake_quant_torch(pis, self.lower_bounds[3], self.upper_bounds[3], self.bit_depths[3])
         return pis
 
+    def _effective_theta(self, theta=None):
+        """The variables as the graph uses them: fake-quantised per group when quantization_mode == 2
+        (smoe.py:482-496); pis also under quantize_pis."""
+        theta = self._theta if theta is None else theta
+        if self.quantization_mode != 2 and not self.quantize_pis:
+            return theta
+        out = theta.clone()
+        o = self._off
+        out[:, o["pi"]] = self._effective_pis(theta)
+        if self.quantization_mode == 2:
+            lb, ub, bd = self.lower_bounds, self.upper_bounds, self.bit_depths
+            out[:, 0:o["A"]] = _fake_quant_torch(theta[:, 0:o["A"]], lb[1], ub[1], bd[1])
+            out[:, o["A"]:o["pi"]] = _fake_quant_torch(theta[:, o["A"]:o["pi"]], lb[0], ub[0], bd[0])
+            out[:, o["nu"]:o["ga"]] = _fake_quant_torch(theta[:, o["nu"]:o["ga"]], lb[2], ub[2], bd[2])
+            out[:, o["ga"]:] = _fake_quant_torch(theta[:, o["ga"]:], lb[4], ub[4], bd[4])
+        return out
+
+    def _centres(self):
+        """Kernel centres as the graph uses them (offsets + grid under use_diff_center, smoe.py:746-747)."""
+        mu = self._effective_theta()[:, 0:self.dim_domain]
+        return mu + self._mus_grid if self.use_diff_center else mu
+
     # ------------------------------------------------------------------------------------------
     # params dict (smoe.py:1795-1849), checkpoints (smoe.py:1066-1077)
     # ------------------------------------------------------------------------------------------
     def _params_from(self, theta):
         d, Cc, K, o = self.dim_domain, self.image.shape[-1], self.start_pis, self._off
         pis = self._effective_pis(theta).cpu().numpy().copy()
-        th = theta.cpu().numpy()
+        th = self._effective_theta(theta).cpu().numpy()        # get_params returns the q* tensors (smoe.py:1796-1798)
         A_diag = np.zeros((K, d, d), dtype=np.float32)
         A_corr = np.zeros((K, d, d), dtype=np.float32)
+        if self.quantization_mode == 2:      # the reference fake-quantises the whole (K,d,d) variables (smoe.py:483-486)
+            A_diag[:] = A_corr[:] = float(_fake_quant_torch(torch.zeros(1), self.lower_bounds[0], self.upper_bounds[0],
+                                                            self.bit_depths[0]))
         for l in range(d):
             for m in range(l + 1):
                 (A_diag if l == m else A_corr)[:, l, m] = th[:, d + l * (l + 1) // 2 + m]
@@ -897,7 +932,7 @@ class Smoe:
         if self._world > 1:
             raise NotImplementedError("dense weight matrix on a sharded model")
         out = torch.zeros((K, self.num_pixel), dtype=torch.float32, device=self.device)
-        A, mu, pis = self._assembled_A(), self._theta[:, 0:d], self._effective_pis()
+        A, mu, pis = self._assembled_A(), self._centres(), self._effective_pis()
         grids = torch.meshgrid(*[torch.linspace(0, 1, n, dtype=torch.float64).to(torch.float32) for n in self.image.shape[:d]],
                                indexing="ij")
         dom_full = torch.stack(grids, dim=-1).to(self.device)

@@ -625,3 +625,64 @@ def test_pi_sparsification_prunes_and_index_sets_follow_pis():
     # same trajectory: a pi crosses 0 a few iterations earlier or later in float32 than in float64
     assert np.abs(np.array(counts_g) - np.array(counts_o)).max() <= 16 and abs(counts_g[-1] - counts_o[-1]) <= 8
     assert np.isfinite(m.run_batched(train=False)[0])
+
+
+@pytest.mark.parametrize("case", ["img_yuv", "video"])
+def test_fake_quant_training_mode2_diff_center_and_kernel_count_norm(case):
+    """quantization_mode 2 (smoe.py:482-496): every variable is fake-quantised with fixed bounds before use,
+    gradients pass straight through inside the bounds; use_diff_center (smoe.py:390-394, 746-747): the musX
+    variable holds offsets from the fixed grid; kernel_count_as_norm_l1 (smoe.py:1022-1025)."""
+    from oracle.model import OracleAdam, OracleSmoe
+    from oracle.graph import _nudge
+    z = np.load(os.path.join(GOLDEN, "init_cases.npz"))
+    img, k = (z["rgb_image"], [6, 8]) if case == "img_yuv" else (z["vid_image"], [3, 4, 2])
+    lb, ub, bd = [-40.0, -0.3, 0.1, 0.0, -2.0], [40.0, 1.3, 0.9, 2.0, 2.0], [12, 12, 7, 10, 8]
+    kw = dict(use_determinant=True, train_inverse_cov=False, use_yuv=(case == "img_yuv"), normalize_pis=False,
+              quantization_mode=2, lower_bounds=lb, upper_bounds=ub, bit_depths=bd, use_diff_center=True,
+              kernel_count_as_norm_l1=True)
+    m = _mk(img, k, **kw)
+    o = OracleSmoe(img, kernels_per_dim=k, dtype=torch.float64, **kw)
+    o.set_optimizer(OracleAdam(1e-3), OracleAdam(1e-5), OracleAdam(1.0))
+    K, d, C = m.start_pis, m.dim_domain, img.shape[-1]
+    rs = np.random.RandomState(11)
+    pert = {"musX": rs.uniform(-0.02, 0.02, (K, d)), "pis": rs.uniform(0.3, 1.7, K),
+            "gamma_e": rs.normal(0, 0.3, (K, d, C)), "nu_e": o.vars["nu_e"].numpy() + rs.normal(0, 0.05, (K, C)),
+            "A_corr": np.tril(rs.normal(0, 2.0, (K, d, d)), -1)}
+    pert["pis"][[2, 9]] = -0.2                                  # pruned: fake-quant clamps to 0, mask is qpis > 0
+    pert = {kk: v.astype(np.float32) for kk, v in pert.items()}
+    m.set_params(pert)
+    for kk, v in pert.items():
+        o.vars[kk] = torch.tensor(v.astype(np.float64))
+    # get_params returns the fake-quantised tensors (smoe.py:1796-1798), bit for bit
+    pg, po = m.get_params(), o.get_params()
+    for kk in PARAM_KEYS:
+        np.testing.assert_array_equal(pg[kk], po[kk], err_msg=kk)
+    nmin, nmax, _ = _nudge(lb[2], ub[2], bd[2])
+    outside = (pert["nu_e"] < nmin) | (pert["nu_e"] > nmax)
+    assert outside.any()
+    (lg, mg, npg, _), (lo, mo, npo, _) = _train_pass_both(m, o, pis_l1=0.3, u_l1=1e-5)
+    assert npg == npo == K - 2
+    assert abs(lg - lo) < 2e-6 * max(1.0, abs(lo)) and abs(mg - mo) < 2e-3 * mo + 1e-3
+    g = m.get_gradients()
+    for kk, ref in o.last_grads.items():
+        assert _rel(g[kk], ref.numpy()) < 1e-4, kk
+    assert np.abs(g["nu_e"][outside]).max() == 0               # straight-through mask outside the bounds
+    assert np.abs(g["pis"][[2, 9]]).max() == 0
+    # 8 more iterations: the quantised parameters follow the oracle up to a few code flips.  (Not more: with
+    # the reference's lr of 1.0 on A the quantised trajectory is chaotic -- one flipped code or one kernel
+    # dropping off the influence list at the gate threshold and float32 / float64 runs part ways; on this
+    # case they stay together for 13 iterations.)
+    for _ in range(8):
+        m.run_batched(train=True, pis_l1=0.3, u_l1=1e-5)
+        o.run_batched(train=True, pis_l1=0.3, u_l1=1e-5)
+    pg, po = m.get_params(), o.get_params()
+    for kk, grp in (("pis", 3), ("musX", 1), ("A_diagonal", 0), ("A_corr", 0), ("gamma_e", 4), ("nu_e", 2)):
+        step = (ub[grp] - lb[grp]) / (2 ** bd[grp] - 1)
+        dcode = np.abs(pg[kk] - po[kk]) / step
+        assert dcode.max() < 4 and (dcode > 0.5).mean() < 0.05, (kk, dcode.max(), (dcode > 0.5).mean())
+    assert abs(m.psnr() - o_psnr(o)) < 0.05
+
+
+def o_psnr(o):
+    _, mse, _, _ = o.run_batched(train=False, update_reconstruction=True)
+    return 10 * np.log10((2 ** o.precision) ** 2 / mse)

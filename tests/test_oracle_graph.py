@@ -122,3 +122,61 @@ def test_mirrored_kernels_gate_half_on_bisector_and_pruned_absent():
     np.testing.assert_allclose(out["w"].numpy(), 0.5, atol=1e-12)
     assert out["indices"].tolist() == [0, 1] and out["num_pi"] == 2
     assert out["w_e_max"].tolist() == [0, 0]          # argmax tie -> lowest index
+
+
+# ----------------------------------------------------------------------------------------------------
+# quantization_mode 2 (fake-quant-aware training with fixed bounds, smoe.py:482-496)
+# ----------------------------------------------------------------------------------------------------
+LB, UB = [-40.0, -0.3, 0.1, 0.0, -2.0], [40.0, 1.3, 0.9, 2.0, 2.0]       # order: A, musX, nu_e, pis, gamma_e
+
+
+def test_mode2_values_lie_on_the_code_grid_and_gradients_pass_inside_the_bounds_only():
+    p, x, t, kl, cfg = _rand_case(2, 3, False, True, True, 5)
+    cfg.quantization_mode, cfg.lower_bounds, cfg.upper_bounds, cfg.bit_depths = 2, LB, UB, [10, 12, 6, 10, 8]
+    p = {k: v.astype(np.float32).astype(np.float64) for k, v in p.items()}      # TF variables are float32
+    tp = {k: torch.tensor(v) for k, v in p.items()}
+    out, g = graph_grads(tp, kl, torch.tensor(x), torch.tensor(t), cfg, pis_l1=0.2, u_l1=1e-3)
+    # the graph sees values on the nudged code grid
+    from oracle.graph import _nudge
+    for key, grp in (("nu_e", 2), ("musX", 1), ("gamma_e", 4)):
+        nmin, nmax, scale = _nudge(LB[grp], UB[grp], cfg.bit_depths[grp])
+        code = (out[key].detach().numpy() - nmin) / scale
+        assert np.abs(code - np.round(code)).max() < 1e-3
+    nmin, nmax, _ = _nudge(LB[2], UB[2], 6)
+    outside = (p["nu_e"] < nmin) | (p["nu_e"] > nmax)
+    assert outside.any() and (~outside).any()
+    assert float(g["nu_e"][torch.tensor(outside)].abs().max()) == 0          # straight-through mask
+    live = out["indices"].numpy()
+    assert float(g["nu_e"][live][torch.tensor(~outside[live])].abs().max()) > 0
+    # pis are fake-quantised in mode 2 even without quantize_pis (smoe.py:474)
+    code = out["pis"].detach().numpy() / (2.0 / 1023)
+    assert np.abs(code - np.round(code)).max() < 1e-3
+
+
+def test_mode2_with_wide_bounds_and_16_bits_approaches_mode0():
+    p, x, t, kl, cfg = _rand_case(2, 1, False, False, False, 6)
+    p = {k: v.astype(np.float32).astype(np.float64) for k, v in p.items()}
+    tp = {k: torch.tensor(v) for k, v in p.items()}
+    out0, g0 = graph_grads(tp, kl, torch.tensor(x), torch.tensor(t), cfg)
+    cfg.quantization_mode, cfg.bit_depths = 2, [16] * 5
+    cfg.lower_bounds, cfg.upper_bounds = [-8.0, -0.5, -0.5, -1.0, -2.0], [8.0, 1.5, 1.5, 1.0, 2.0]
+    out2, g2 = graph_grads(tp, kl, torch.tensor(x), torch.tensor(t), cfg)
+    assert np.abs(out0["r_pre"].detach().numpy() - out2["r_pre"].detach().numpy()).max() < 2e-3
+    assert out0["num_pi"] == out2["num_pi"]
+
+
+def test_diff_center_and_kernel_count_norm():
+    p, x, t, kl, cfg = _rand_case(2, 1, False, True, False, 7)
+    tp = {k: torch.tensor(v) for k, v in p.items()}
+    out, g = graph_grads(tp, kl, torch.tensor(x), torch.tensor(t), cfg, pis_l1=0.5)
+    grid = torch.tensor(np.random.RandomState(1).uniform(0, 1, p["musX"].shape))
+    tp2 = dict(tp, musX=tp["musX"] - grid)
+    cfg.use_diff_center = True
+    out2, g2 = graph_grads(tp2, kl, torch.tensor(x), torch.tensor(t), cfg, pis_l1=0.5, musX_grid=grid)
+    assert abs(float(out["loss"].detach()) - float(out2["loss"].detach())) < 1e-12
+    np.testing.assert_allclose(g["musX"], g2["musX"], atol=1e-12)
+    cfg.kernel_count_as_norm_l1 = True                                        # smoe.py:1022-1025
+    out3, g3 = graph_grads(tp2, kl, torch.tensor(x), torch.tensor(t), cfg, pis_l1=0.5, musX_grid=grid)
+    live = out3["indices"].numpy()
+    num_pi = int((p["pis"] > 0).sum())
+    np.testing.assert_allclose((g3["pis"] - g2["pis"])[live], 0.5 / num_pi - 0.5 / cfg.start_pis, atol=1e-12)

@@ -352,7 +352,7 @@ def kernel_times(m, steps, with_step=True):
         scal.zero_()
         e[0].record()
         check(L.smoe_forward(C.byref(m._cfg), C.byref(b), ptr(m._packed), ptr(m._indices), ptr(counts),
-                             ptr(m._chunk_bounds), m.start_pis, ptr(m._d_image),
+                             ptr(m._chunk_bounds), m.start_pis, ptr(m._d_image), ptr(None),
                              ptr(m._d_axes[0]), ptr(m._d_axes[1]), ax2, ptr(m._d_res), ptr(None), ptr(None), ptr(m._infl),
                              ptr(m._pix), ptr(m._tile_qmin), ptr(scal), ptr(m._partials), ptr(m._ticket), st), "forward")
         e[1].record()

@@ -49,6 +49,10 @@ extern "C" {
 #define SMOE_TPIX 512      /* pixels per tile (compile-time constant of the kernels) */
 #define SMOE_NSCAL 16      /* floats in the scalar block */
 
+/* sentinels of the optional per-pixel `loss_weights` of smoe_forward */
+#define SMOE_PIXEL_ABSENT (-1.0f)   /* pixel is not part of this run's feed (sampling_percentage < 100)        */
+#define SMOE_PIXEL_HALO   (-2.0f)   /* pixel of the overlap halo: forwarded, outside the loss (overlap_of_batches) */
+
 #define SMOE_E_BADARG (-1)
 #define SMOE_E_UNSUPPORTED (-2)
 
@@ -144,12 +148,16 @@ int smoe_pack_fed(const smoe_cfg* cfg, const float* A /*[K][d][d]*/, const float
  *   pix      optional: per-pixel state for smoe_backward
  *   tile_qmin [tiles] (required with pix): min over the tile of log2(tau*S), the culling threshold
  *            of the backward
+ *   loss_weights [dims..] optional (NULL = every pixel of the rectangle, weight 1): per-pixel weight of the
+ *            loss term (the `loss_weights` feed of smoe.py:550, 932, 1674-1677), or one of the sentinels
+ *            SMOE_PIXEL_ABSENT (the pixel is not fed at all: random sub-sampling, smoe.py:1664-1667) and
+ *            SMOE_PIXEL_HALO (fed, but cropped away before the loss: overlap_of_batches, smoe.py:909-923)
  *   scalars  [SMOE_NSCAL]: [0..C) sum_n (|diff|-eps)^2 per channel, [4] sum diff^2,
  *            [5] non-finite flag; accumulated (+=) so that batches/ranks can be summed; the
  *            caller zeroes it */
 int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const float* packed, const int32_t* indices,
                  const int32_t* counts, const float* chunk_bounds, int K_cap, const float* image,
-                 const float* ax0, const float* ax1, const float* ax2, float* res, float* res_pre,
+                 const float* loss_weights, const float* ax0, const float* ax1, const float* ax2, float* res, float* res_pre,
                  int32_t* argmax, uint8_t* infl, float* pix, float* tile_qmin /*[tiles]*/, float* scalars,
                  float* partials /*[num_sms*8][8]*/, int32_t* ticket, void* stream);
 

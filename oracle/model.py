@@ -58,7 +58,7 @@ class OracleSmoe:
                  quantize_pis=False, lower_bounds=None, upper_bounds=None, use_yuv=True,
                  only_y_gamma=False, precision=8, iter_offset=0, margin=0.5,
                  kernel_count_as_norm_l1=False, train_inverse_cov=True, dtype=torch.float32,
-                 einsum_mode="einsum"):
+                 einsum_mode="einsum", loss_mask=None):
         self.image = np.asarray(image)
         self.dtype = dtype
         self.dim_domain = self.image.ndim - 1
@@ -72,6 +72,7 @@ class OracleSmoe:
         self.bit_depths, self.lower_bounds, self.upper_bounds = bit_depths, lower_bounds, upper_bounds
         self.train_pis, self.train_gammas, self.train_musx = train_pis, train_gammas, train_musx
         self.iter = iter_offset
+        self.loss_mask = loss_mask
         self.joint_domain = init_ref.gen_domain(self.image, self.dim_domain)      # float64
         self.batch_shape = init_ref.get_batch_shape(start_batches, self.joint_domain.shape)
         if batch_size is not None and batch_size[0] is not None:
@@ -118,6 +119,8 @@ class OracleSmoe:
                             kernel_count_as_norm_l1=kernel_count_as_norm_l1, start_pis=K,
                             einsum_mode=einsum_mode)
         self.kernel_list_per_batch = [np.ones((K,), dtype=bool) for _ in range(self.start_batches)]
+        nb = int(np.prod(self.batch_size_valued))                                   # smoe.py:271-273
+        self.random_sampling_per_batch = [np.ones((nb,), dtype=np.float32) / nb] * self.start_batches
         self.optimizers = None
         self.grad_clip = None
         self.losses, self.mses, self.num_pis = [], [], []
@@ -142,7 +145,8 @@ class OracleSmoe:
 
     # -- the batched executor -----------------------------------------------------------
     def run_batched(self, pis_l1=0, u_l1=0, train=True, update_reconstruction=False,
-                    with_quantized_params=False, resq_override=None):
+                    with_quantized_params=False, resq_override=None, sampling_percentage=100,
+                    use_loss_mask=False):
         self.valid = False
         if with_quantized_params:
             self.qvalid = False
@@ -154,8 +158,20 @@ class OracleSmoe:
         amax = np.zeros(self.image.shape[:-1])
         d = self.dim_domain
         for ii, (coord, batch) in enumerate(init_ref.sliding_window(self.joint_domain, 0, self.batch_size_valued)):
-            patch = torch.tensor(batch.reshape(-1, batch.shape[-1]), dtype=self.dtype)   # f64 -> f32 feed
+            img_patch = batch.reshape(-1, batch.shape[-1])
+            samples = None
+            if train and sampling_percentage < 100:                     # smoe.py:1664-1667
+                num_samples = np.uint32(np.round(img_patch.shape[0] * sampling_percentage / 100))
+                samples = np.random.choice(img_patch.shape[0], (num_samples,), replace=False,
+                                           p=self.random_sampling_per_batch[ii])
+                img_patch = img_patch[samples, :]
+            self.last_samples = samples
+            patch = torch.tensor(img_patch, dtype=self.dtype)   # f64 -> f32 feed
             domain, target = patch[:, :d], patch[:, d:]
+            lw = None
+            if use_loss_mask:                                           # smoe.py:1674-1677 (2-D: evident intent)
+                sl = tuple(slice(int(c), int(c) + b) for c, b in zip(coord, self.batch_size_valued))
+                lw = torch.tensor(np.asarray(self.loss_mask)[sl].reshape(-1, 1), dtype=self.dtype)
             leaf = {k: v.detach().clone().requires_grad_(k in trainable) for k, v in self.vars.items()}
             feed = None
             if with_quantized_params and update_reconstruction:
@@ -164,8 +180,11 @@ class OracleSmoe:
             if resq_override is not None:
                 sl = tuple(slice(int(c), int(c) + b) for c, b in zip(coord, self.batch_size_valued))
                 ovr = torch.tensor(np.asarray(resq_override)[sl].reshape(-1, self.image.shape[-1]), dtype=self.dtype)
+                if samples is not None:
+                    ovr = ovr[torch.as_tensor(samples)]
             out = graph_forward(leaf, self.kernel_list_per_batch[ii], domain, target, self.cfg,
-                                pis_l1, u_l1, musX_grid=self.musX_grid, feed=feed, resq_override=ovr)
+                                pis_l1, u_l1, musX_grid=self.musX_grid, feed=feed, resq_override=ovr,
+                                loss_weights=lw)
             if train and trainable:
                 gs = torch.autograd.grad(out["loss"], [leaf[n] for n in trainable], allow_unused=True)
                 for n, g in zip(trainable, gs):
@@ -175,6 +194,7 @@ class OracleSmoe:
                 sl = tuple(slice(int(c), int(c) + b) for c, b in zip(coord, self.batch_size_valued))
                 rec[sl] = out["resq"].detach().numpy().reshape(tuple(self.batch_size_valued) + (-1,))
                 amax[sl] = out["w_e_max"].numpy().reshape(tuple(self.batch_size_valued))
+                self.random_sampling_per_batch[ii] = out["sampl_prob"].detach().numpy().astype(np.float32)  # smoe.py:1768-1769
             frac = np.prod(self.batch_size_valued) / self.num_pixel
             loss_val += float(out["loss"].detach()) * frac
             mse_val += float(out["mse_op"].detach()) * frac

@@ -35,6 +35,9 @@ class Cfg(C.Structure):
                 ("dense_exec", C.c_int32)]
 
 
+PIXEL_ABSENT, PIXEL_HALO = -1.0, -2.0          # SMOE_PIXEL_ABSENT / SMOE_PIXEL_HALO
+
+
 class Batch(C.Structure):
     _fields_ = [("dims", C.c_int32 * 3), ("origin", C.c_int32 * 3), ("extent", C.c_int32 * 3),
                 ("tile", C.c_int32 * 3), ("inv_count", C.c_float)]

@@ -106,6 +106,7 @@ struct FwdArgs {
     const int32_t* counts;
     const float* chunk_bounds;
     const float* image;
+    const float* lossw;
     const float* ax[3];
     float* res;
     float* res_pre;
@@ -213,6 +214,8 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
                 const int g0 = lo[0] + i0;
                 const bool ok = g0 <= hi[0] && g1 <= hi[1] && g2 <= hi[2];
                 gidx[p] = ok ? ((long long)g0 * a.b.dims[1] + g1) * a.b.dims[2] + g2 : -1;
+                // a pixel that is not part of this run's feed (random sub-sampling, smoe.py:1664-1667)
+                if (a.lossw && ok && a.lossw[gidx[p]] == SMOE_PIXEL_ABSENT) gidx[p] = -1;
                 x0[p] = a.ax[0][min(g0, hi[0])] - ctr[0];
             }
         }
@@ -393,6 +396,10 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
         for (int p = 0; p < PPT; ++p) {
             const int j = p * kThreadsF + tid;
             float g[C], gr = 0.f;
+            // per-pixel loss weight (loss_mask, smoe.py:932, 1674-1677); SMOE_PIXEL_HALO marks a pixel of the
+            // overlap halo: forwarded (gates, influence list) but outside the loss crop (smoe.py:909-923)
+            const float lwv = (a.lossw && gidx[p] >= 0) ? a.lossw[gidx[p]] : 1.f;
+            const bool halo = lwv == SMOE_PIXEL_HALO;
             if (gidx[p] >= 0) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
@@ -403,13 +410,19 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
                     const float rq = __fmul_rn(kq, a.q_scale);                          // smoe.py:899
                     const float tgt = a.image[gidx[p] * C + c];
                     const float diff = __fsub_rn(rq, tgt);                              // smoe.py:905
-                    sqsum = fmaf(diff, diff, sqsum);
                     const float ad = fabsf(diff) - a.eps;                               // smoe.py:932
-                    lsum[c] = fmaf(ad, ad, lsum[c]);
+                    if (!a.lossw) {
+                        sqsum = fmaf(diff, diff, sqsum);
+                        lsum[c] = fmaf(ad, ad, lsum[c]);
+                    } else if (!halo) {
+                        sqsum = fmaf(diff, diff, sqsum);
+                        lsum[c] = fmaf(ad * ad, lwv, lsum[c]);
+                    }
                     const float cw = a.cfg.use_yuv ? (c == 0 ? 0.75f : 0.125f) : (1.0f / C);
                     const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
-                    const bool ste = (rv >= 0.f) && (rv <= 1.f);                        // clip + fake-quant STE
+                    const bool ste = (rv >= 0.f) && (rv <= 1.f) && !halo;               // clip + fake-quant STE
                     g[c] = ste ? 2.f * ad * sgn * cw * a.b.inv_count : 0.f;
+                    if (a.lossw) g[c] *= lwv;
                     gr = fmaf(g[c], rv, gr);
                     a.res[gidx[p] * C + c] = rq;
                     if (a.res_pre) a.res_pre[gidx[p] * C + c] = rv;
@@ -490,9 +503,9 @@ using namespace smoe;
 
 extern "C" int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const float* packed, const int32_t* indices,
                             const int32_t* counts, const float* chunk_bounds, int K_cap, const float* image,
-                            const float* ax0, const float* ax1, const float* ax2, float* res, float* res_pre,
-                            int32_t* argmax, uint8_t* infl, float* pix, float* tile_qmin, float* scalars,
-                            float* partials, int32_t* ticket, void* stream) {
+                            const float* loss_weights, const float* ax0, const float* ax1, const float* ax2,
+                            float* res, float* res_pre, int32_t* argmax, uint8_t* infl, float* pix,
+                            float* tile_qmin, float* scalars, float* partials, int32_t* ticket, void* stream) {
     SMOE_REQUIRE(cfg && batch && packed && indices && counts && chunk_bounds && image && ax0 && ax1 && res && scalars &&
                      partials && ticket,
                  "null argument");
@@ -510,6 +523,7 @@ extern "C" int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const 
     a.cfg = *cfg;
     a.b = *batch;
     a.packed = packed; a.indices = indices; a.counts = counts; a.chunk_bounds = chunk_bounds; a.image = image;
+    a.lossw = loss_weights;
     a.ax[0] = ax0; a.ax[1] = ax1; a.ax[2] = ax2 ? ax2 : ax0;
     a.res = res; a.res_pre = res_pre; a.argmax = argmax; a.infl = infl; a.pix = pix; a.tile_qmin = tile_qmin;
     a.scalars = scalars; a.partials = partials; a.ticket = ticket;

@@ -77,7 +77,7 @@ class Smoe:
         lib()
         unsupported = {"affines": affines is not None, "train_trafo": train_trafo, "train_svs": train_svs,
                        "add_kernel_slots": add_kernel_slots > 0, "ssim_opt": ssim_opt, "radial_as": radial_as,
-                       "overlap_of_batches": overlap_of_batches > 0, "loss_mask": loss_mask is not None,
+                       "overlap_of_batches": overlap_of_batches > 0,
                        "quantization_mode 3": quantization_mode >= 3}
         for k, v in unsupported.items():
             if v:
@@ -302,6 +302,14 @@ class Smoe:
         self._dims3 = tuple(self._local_shape) + (1,) * (3 - d)
         self._d_image = torch.from_numpy(np.ascontiguousarray(self.image[b0:b1])).to(dev)
         self._d_image_u8 = None
+        self._d_loss_mask = None
+        if self.loss_mask is not None:                       # per-pixel loss weights (smoe.py:550, 932, 1674-1677)
+            lm = np.asarray(self.loss_mask, dtype=np.float32).reshape(self.image.shape[:-1])
+            if (lm < 0).any():
+                raise ValueError("loss_mask weights must be >= 0")
+            self._d_loss_mask = torch.from_numpy(np.ascontiguousarray(lm[b0:b1])).to(dev)
+        self._d_sample_w = None                              # per-call pixel selection of sampling_percentage < 100
+        self.random_sampling_per_batch = None                # None = uniform (smoe.py:271-273)
         axes = [np.linspace(0, 1, self.image.shape[a]).astype(np.float32) for a in range(d)]
         axes[0] = axes[0][b0:b1]
         self._d_axes = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in axes]
@@ -459,10 +467,21 @@ class Smoe:
     def run_batched(self, pis_l1=0, u_l1=0, sv_l1_sub_l2=0, train=True, update_reconstruction=False,
                     with_quantized_params=False, sampling_percentage=100, with_inc=False, train_inc=False,
                     thr_sv=None, use_loss_mask=False, _host_image=None):
-        if sampling_percentage < 100 or with_inc or train_inc or use_loss_mask:
-            raise NotImplementedError("sampling / inc / loss-mask paths are outside the hot path (D1)")
+        if with_inc or train_inc:
+            raise NotImplementedError("inc paths are outside the hot path (D1)")
         if train:
             assert self.optimizer1 is not None, "no optimizer found, you have to specify one!"
+        sampling = train and not self.ssim_opt and sampling_percentage < 100          # smoe.py:1664
+        if use_loss_mask and self._d_loss_mask is None:
+            raise ValueError("use_loss_mask needs the loss_mask constructor argument")
+        if sampling and use_loss_mask:
+            raise ValueError("loss_mask and sampling_percentage < 100 cannot be combined (the reference feeds a "
+                             "full-batch mask against the sampled pixels, smoe.py:1666-1677)")
+        if sampling and self._world > 1:
+            raise NotImplementedError("sampling_percentage < 100 on a sharded model")
+        lossw, batches = (self._d_loss_mask if use_loss_mask else None), self._batches
+        if sampling:
+            lossw, batches = self._draw_samples(sampling_percentage)
         self.valid = False
         if with_quantized_params:
             self.qvalid = False
@@ -473,12 +492,13 @@ class Smoe:
             self._adam_prepare()
         # A plain training step (the hot loop of Smoe.train, smoe.py:1527) is captured once into a CUDA
         # graph and replayed: one graph launch + one stream sync per iteration instead of ~25 launches.
-        graphable = self.use_cuda_graphs and train and not update_reconstruction and not with_quantized_params
+        graphable = (self.use_cuda_graphs and train and not update_reconstruction and not with_quantized_params
+                     and not sampling)
         replayed = False
         if graphable:
             key = (float(pis_l1), float(u_l1), self.grad_clip_value_abs, id(self.optimizer1), id(self.optimizer2),
                    id(self.optimizer3), self.optimizer1._lr, self.optimizer2._lr, self.optimizer3._lr,
-                   None if _host_image is None else _host_image.data_ptr())
+                   None if _host_image is None else _host_image.data_ptr(), bool(use_loss_mask))
             state = self._graphs.get(key)
             if state is None:
                 self._graphs[key] = "warm"              # first step with this signature runs eagerly
@@ -492,7 +512,7 @@ class Smoe:
                         for phase in (("all",) if self._world == 1 else ("pre", "post")):
                             g = torch.cuda.CUDAGraph()
                             with torch.cuda.graph(g):
-                                self._enqueue(pis_l1, u_l1, True, False, False, _host_image, phase=phase)
+                                self._enqueue(pis_l1, u_l1, True, False, False, _host_image, phase=phase, lossw=lossw)
                             graphs.append(g)
                         state = (graphs, self.gpu_launches - l0)
                         self.gpu_launches = l0
@@ -510,14 +530,15 @@ class Smoe:
                     self.gpu_launches += state[1]
                     replayed = True
         if not replayed:
-            self._enqueue(pis_l1, u_l1, train, update_reconstruction, with_quantized_params, _host_image)
+            self._enqueue(pis_l1, u_l1, train, update_reconstruction, with_quantized_params, _host_image,
+                          lossw=lossw, batches=batches)
         torch.cuda.current_stream().synchronize()
         h = self._host_stats.numpy().astype(np.float64)
         norm = float(self.start_pis)
         Cc = self.image.shape[-1]
         loss_val = mse_val = 0.0
         num_pi = -1
-        for ii, b in enumerate(self._batches):
+        for ii, b in enumerate(batches):
             inv_n = float(b.inv_count)
             if self.use_yuv:                               # smoe.py:933-935
                 lp = 6 / 8 * h[ii, 0] * inv_n + 1 / 8 * sum(h[ii, c] * inv_n for c in range(1, Cc))
@@ -534,6 +555,7 @@ class Smoe:
             num_pi = int(h[ii, _ffi.NSCAL + 1])
         self._last_nonpos = int(h[:, _ffi.NSCAL + 2].sum())
         if update_reconstruction:
+            self._update_sampling_probabilities()
             rec, amax = self._gather_reconstruction()
             if with_quantized_params:
                 self.qreconstruction_image, self.qweight_matrix_argmax, self.qvalid = rec, amax, True
@@ -541,11 +563,55 @@ class Smoe:
                 self.reconstruction_image, self.weight_matrix_argmax, self.valid = rec, amax, True
         return loss_val, mse_val, num_pi, 0
 
-    def _enqueue(self, pis_l1, u_l1, train, update_reconstruction, with_quantized_params, _host_image, phase="all"):
+    def _draw_samples(self, sampling_percentage):
+        """Random pixel sub-sampling of a training pass (smoe.py:1664-1667): per batch, round(N_b * pct / 100)
+        pixels drawn without replacement by np.random.choice (the global NumPy generator, as the reference) with
+        the error-proportional probabilities of the last reconstruction pass (smoe.py:906-907, 1768-1769).
+        Returns the per-pixel selection (1 = fed, SMOE_PIXEL_ABSENT = not fed) and batches whose loss means run
+        over the drawn pixels."""
+        d = self.dim_domain
+        if self._d_sample_w is None:
+            self._d_sample_w = torch.empty(self._local_shape, dtype=torch.float32, device=self.device)
+        w = np.full(self._local_shape, _ffi.PIXEL_ABSENT, dtype=np.float32)
+        batches = []
+        self.last_samples = []
+        for ii, ((org, ext), b) in enumerate(zip(self._batch_rects(), self._batches)):
+            n = int(np.prod(ext))
+            num_samples = int(np.uint32(np.round(n * sampling_percentage / 100)))
+            p = None if self.random_sampling_per_batch is None else self.random_sampling_per_batch[ii].cpu().numpy()
+            if p is None:
+                p = np.ones((n,), dtype=np.float32) / n
+            samples = np.random.choice(n, (num_samples,), replace=False, p=p)
+            self.last_samples.append(samples)
+            sel = np.full((n,), _ffi.PIXEL_ABSENT, dtype=np.float32)
+            sel[samples] = 1.0
+            w[tuple(slice(o, o + e) for o, e in zip(org, ext))] = sel.reshape(ext)
+            nb = Batch.from_buffer_copy(b)
+            nb.inv_count = 1.0 / max(num_samples, 1)
+            batches.append(nb)
+        self._d_sample_w.copy_(torch.from_numpy(w))
+        return self._d_sample_w, batches
+
+    def _update_sampling_probabilities(self):
+        """sampl_prob = err_map / sum(err_map) per batch, err_map = mean_c (resq - target)^2 (smoe.py:906-907),
+        kept on the device; replaces `random_sampling_per_batch[ii] = results[-1]` (smoe.py:1768-1769)."""
+        if self._world > 1:
+            return
+        d, Cc = self.dim_domain, self.image.shape[-1]
+        err = ((self._d_res.reshape(self._local_shape + (Cc,)) - self._d_image) ** 2).mean(dim=-1)
+        probs = []
+        for org, ext in self._batch_rects():
+            e = err[tuple(slice(o, o + x) for o, x in zip(org, ext))].reshape(-1)
+            probs.append(e / e.sum())
+        self.random_sampling_per_batch = probs
+
+    def _enqueue(self, pis_l1, u_l1, train, update_reconstruction, with_quantized_params, _host_image, phase="all",
+                 lossw=None, batches=None):
         """Every launch of one run_batched call, asynchronous on the current stream (capturable).
         phase "pre" / "post" enqueue only the part before / after the all-reduce of a sharded step."""
         L, st = lib(), stream_ptr()
         K = self.start_pis
+        batches = self._batches if batches is None else batches
         pre, post = phase in ("all", "pre"), phase in ("all", "post")
         if pre:
             if _host_image is not None:                  # e2e path: this step's pixels come from pinned host memory
@@ -567,7 +633,7 @@ class Smoe:
             if Kf > K:
                 raise ValueError("more fed kernels than model kernels")
         norm = float(self.start_pis)
-        for ii, b in enumerate(self._batches):
+        for ii, b in enumerate(batches):
             counts, regs, scal = self._counts[ii], self._regsums[ii], self._scalars[ii]
             if not pre:
                 pass
@@ -588,7 +654,7 @@ class Smoe:
                 self._infl.zero_()
                 check(L.smoe_forward(C.byref(self._cfg), C.byref(b), ptr(self._packed), ptr(self._indices), ptr(counts),
                                      ptr(self._chunk_bounds), K,
-                                     ptr(self._d_image), ptr(self._d_axes[0]), ptr(self._d_axes[1]),
+                                     ptr(self._d_image), ptr(lossw), ptr(self._d_axes[0]), ptr(self._d_axes[1]),
                                      ptr(self._d_axes[2]) if self.dim_domain == 3 else ptr(None),
                                      ptr(self._d_res), ptr(self._d_res_pre),
                                      ptr(self._d_argmax) if update_reconstruction else ptr(None),
@@ -695,7 +761,7 @@ class Smoe:
             self.qlosses.append((0, self.best_qloss))
             self.qmses.append((0, self.best_qmse))
         self.best_loss, self.best_mse, num_pi, num_sv = self.run_batched(
-            pis_l1=pis_l1, u_l1=u_l1, train=False, update_reconstruction=True)
+            pis_l1=pis_l1, u_l1=u_l1, train=False, update_reconstruction=True, use_loss_mask=use_loss_mask)
         self.losses.append((self.iter, self.best_loss))
         self.mses.append((self.iter, self.best_mse))
         self.num_pis.append((self.iter, num_pi))
@@ -711,7 +777,7 @@ class Smoe:
                 update_kl = i % ukl_iter == 0
                 loss_val, mse_val, num_pi, num_sv = self.run_batched(
                     pis_l1=pis_l1, u_l1=u_l1, train=train_orig, update_reconstruction=False,
-                    sampling_percentage=sampling_percentage)
+                    sampling_percentage=sampling_percentage, use_loss_mask=use_loss_mask)
                 if update_kl:
                     self.update_kernel_list(self.add_kernel_slots)
                     if not validate:
@@ -724,9 +790,10 @@ class Smoe:
                         self.rparams = rescaler(self, self.qparams)
                         qloss_val, qmse_val, _, _ = self.run_batched(
                             pis_l1=pis_l1, u_l1=u_l1, train=False, update_reconstruction=True,
-                            with_quantized_params=True)
+                            with_quantized_params=True, use_loss_mask=use_loss_mask)
                     loss_val, mse_val, num_pi, num_sv = self.run_batched(
-                        pis_l1=pis_l1, u_l1=u_l1, train=False, update_reconstruction=True)
+                        pis_l1=pis_l1, u_l1=u_l1, train=False, update_reconstruction=True,
+                        use_loss_mask=use_loss_mask)
                 if np.isnan(loss_val) or (len(self.losses) > 0 and loss_val + 1 > (self.losses[0][1] + 100) * 10):
                     print("stop")
                     break

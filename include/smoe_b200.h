@@ -92,6 +92,9 @@ typedef struct smoe_batch {
     int32_t tile[3];     /* tile extents, tile[0]*tile[1]*tile[2] == SMOE_TPIX                 */
     float   inv_count;   /* 1 / number of pixels the loss means run over (smoe.py:927-937);
                             N_batch on one GPU, N_total when pixels are sharded over ranks     */
+    int32_t halo;        /* overlap_of_batches: the rectangle is the window PLUS this many halo pixels on every
+                            side that is not the image border; halo pixels are forwarded (gates, influence
+                            list) and cropped away before the loss (smoe.py:909-923, 985-991)                 */
 } smoe_batch;
 
 /* Adam hyper-parameters of the three optimizer groups (smoe.py:1102-1104, smoe_test.py:84-88):
@@ -207,6 +210,17 @@ int smoe_adam_step(const smoe_cfg* cfg, const smoe_adam* hp, const float* alpha_
 size_t smoe_ssim_workspace_bytes(int d, const int32_t dims[3], int C);
 int    smoe_ssim(int d, const int32_t dims[3], int C, const float* a, const float* b, double* out /*[C]*/,
                  void* workspace, void* stream);
+
+/* SSIM as the training loss (`ssim_opt`, smoe.py:981-1010) on one batch, after smoe_forward and before
+ * smoe_backward: per-channel sum over the loss rectangle (the batch minus its halo) of the SSIM map of
+ * (res, image), SYMMETRIC-padded by 5 at the rectangle's borders, ACCUMULATED into scalars[8 + c] (the caller
+ * divides by the number of positions and forms 1 - sum_c w_c ssim_c); and, when pix != NULL, d loss / d res
+ * pushed through the output fake-quant and the clip (straight-through where 0 <= res_pre <= 1) and written
+ * over the g_c / gr planes of the backward state that smoe_forward filled for the squared-error loss.
+ *   res, image, res_pre: [dims..][C] as in smoe_forward (res_pre is required) */
+size_t smoe_ssim_loss_workspace_bytes(const smoe_cfg* cfg, const smoe_batch* batch);
+int    smoe_ssim_loss(const smoe_cfg* cfg, const smoe_batch* batch, const float* res, const float* image,
+                      const float* res_pre, float* pix, float* scalars, void* workspace, void* stream);
 
 /* sum over all elements of (a-b)^2 -> out[0] (double accumulation in fixed order);
  * PSNR = 10 log10((2^p)^2 / (mean * (2^p)^2)) on the host (plotter.py:14-15, smoe.py:1053). */

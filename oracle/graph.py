@@ -48,6 +48,7 @@ class GraphCfg:
     upper_bounds: Optional[list] = None
     bit_depths: Optional[list] = None
     kernel_count_as_norm_l1: bool = False
+    ssim_opt: bool = False      # SSIM instead of the squared-error loss (smoe.py:981-1010)
     start_pis: int = 0          # smoe.py:264 (K at construction)
     einsum_mode: str = "einsum"  # "einsum" | "broadcast" (TF materialisation strategy)
 
@@ -151,6 +152,42 @@ class _ClipByValue01(torch.autograd.Function):
         return g * mask.to(g.dtype)
 
 
+def _gauss_window_torch(ndim, dtype, size=11, sigma=1.5):
+    """ops/image_ops_impl.py:131-151: softmax of -x^2/(2 sigma^2) over the full size^ndim window."""
+    c = torch.arange(size, dtype=dtype) - (size - 1) / 2.0
+    g = -(c * c) / (2.0 * sigma * sigma)
+    full = g[:, None] + g[None, :] if ndim == 2 else g[:, None, None] + g[None, :, None] + g[None, None, :]
+    return torch.softmax(full.reshape(-1), dim=0).reshape(full.shape)
+
+
+def _symmetric_pad(x, ndim, pad=5):
+    """tf.pad(..., "SYMMETRIC") on the first ndim axes (smoe.py:994-1003); differentiable gather."""
+    for ax in range(ndim):
+        idx = np.pad(np.arange(x.shape[ax]), pad, mode="symmetric")
+        x = x.index_select(ax, torch.as_tensor(idx, dtype=torch.long))
+    return x
+
+
+def custom_ssim_torch(img1, img2, ndim, max_val=1.0):
+    """ops/image_ops_impl.py:235-293 (helpers :77-233) on already padded (spatial..., C) tensors: depthwise
+    VALID correlation with the Gaussian window, luminance * contrast-structure, mean over positions -> (C,)."""
+    import torch.nn.functional as F
+    win = _gauss_window_torch(ndim, img1.dtype)[None, None]
+    conv = F.conv2d if ndim == 2 else F.conv3d
+
+    def reducer(x):                                            # channels -> batch (image_ops_impl.py:206-222)
+        return conv(x.movedim(-1, 0)[:, None], win)[:, 0]
+    c1, c2 = (0.01 * max_val) ** 2, (0.03 * max_val) ** 2
+    mean0, mean1 = reducer(img1), reducer(img2)
+    num0 = mean0 * mean1 * 2.0
+    den0 = mean0 * mean0 + mean1 * mean1
+    lum = (num0 + c1) / (den0 + c1)
+    num1 = reducer(img1 * img2) * 2.0
+    den1 = reducer(img1 * img1 + img2 * img2)
+    cs = (num1 - num0 + c2) / (den1 - den0 + c2)
+    return (lum * cs).reshape(lum.shape[0], -1).mean(dim=1)
+
+
 def assemble_A(A_diagonal, A_corr, train_inverse_cov):
     """smoe.py:732-735: band_part(A_diag,0,0) + strict-lower(A_corr) (+ its transpose)."""
     diag = torch.diag_embed(torch.diagonal(A_diagonal, dim1=-2, dim2=-1))
@@ -182,7 +219,7 @@ def _maha(x_sub_mu, A, train_inverse_cov, mode):
 def graph_forward(params: Dict[str, torch.Tensor], kernel_list, domain, target, cfg: GraphCfg,
                   pis_l1=0.0, u_l1=0.0, loss_weights=None, musX_grid=None,
                   feed: Optional[Dict[str, torch.Tensor]] = None,
-                  resq_override: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                  resq_override: Optional[torch.Tensor] = None, crop=None) -> Dict[str, torch.Tensor]:
     """One `session.run` of the reference graph on one batch of pixels.
 
     params : K_all-sized variables (pis, musX, A_diagonal, A_corr, gamma_e, nu_e)
@@ -190,6 +227,8 @@ def graph_forward(params: Dict[str, torch.Tensor], kernel_list, domain, target, 
     domain : (N,d) pixel coordinates, target : (N,C) colours
     feed : optional {A, musX, nu_e, gamma_e, pis} fed *over* the compacted tensors
            (with_quantized_params, smoe.py:1688-1689)
+    crop : optional (window shape incl. halo, overlap): the fed pixels are a window padded by `overlap` on every
+           side (smoe.py:18-35); the halo is cropped before the loss (smoe.py:909-923, 985-991)
     resq_override : optional (N,C) values to use as the fake-quant OUTPUT (the straight-through
            gradient path is unchanged).  Lets a test evaluate the gradient conditional on another
            implementation's rounding decisions, which differ legitimately for pixels that sit
@@ -272,14 +311,35 @@ def graph_forward(params: Dict[str, torch.Tensor], kernel_list, domain, target, 
     sq = diff * diff
     err_map = sq.mean(dim=1)                                                 # smoe.py:906
     sampl_prob = err_map / err_map.sum()
+    inner = None
+    if crop is not None and crop[1] > 0:                                     # smoe.py:909-923
+        shp, ov = tuple(crop[0]), int(crop[1])
+        inner = (slice(ov, -ov),) * d
+        diff = diff.reshape(shp + (C,))[inner].reshape(-1, C)
+        sq = diff * diff
     mse = sq.mean()                                                          # smoe.py:927
-    eps = cfg.margin * 1 / (2 ** cfg.precision)                              # smoe.py:931
-    lw = torch.ones(domain.shape[0], 1, dtype=dt) if loss_weights is None else loss_weights
-    loss_px = torch.clamp_min((diff.abs() - eps) ** 2, 0.0) * lw             # smoe.py:932
-    if cfg.use_yuv:                                                          # smoe.py:933-935
-        loss_pixel = 6 / 8 * loss_px[:, 0].mean() + 1 / 8 * loss_px[:, 1:].mean(dim=0).sum()
-    else:
-        loss_pixel = loss_px.mean()                                          # smoe.py:937
+    if not cfg.ssim_opt:
+        eps = cfg.margin * 1 / (2 ** cfg.precision)                          # smoe.py:931
+        # (with a halo HEAD multiplies the cropped loss by un-cropped weights and fails; intent: weights of ones)
+        lw = torch.ones(diff.shape[0], 1, dtype=dt) if loss_weights is None else loss_weights
+        loss_px = torch.clamp_min((diff.abs() - eps) ** 2, 0.0) * lw         # smoe.py:932
+        if cfg.use_yuv:                                                      # smoe.py:933-935
+            loss_pixel = 6 / 8 * loss_px[:, 0].mean() + 1 / 8 * loss_px[:, 1:].mean(dim=0).sum()
+        else:
+            loss_pixel = loss_px.mean()                                      # smoe.py:937
+    else:                                                                    # smoe.py:981-1010
+        assert crop is not None, "ssim_opt needs the window shape"
+        shp = tuple(crop[0])
+        res_img, tgt_img = resq.reshape(shp + (C,)), target.reshape(shp + (C,))
+        if inner is not None:
+            res_img, tgt_img = res_img[inner], tgt_img[inner]
+        ssim_c = custom_ssim_torch(_symmetric_pad(res_img, d), _symmetric_pad(tgt_img, d), d)
+        if cfg.use_yuv:
+            ssim = (ssim_c * torch.tensor([6.0, 1.0, 1.0], dtype=dt)[:max(C, 1)]).sum() / 8 if C == 3 \
+                else (ssim_c * torch.tensor([6.0, 1.0, 1.0], dtype=dt)).sum() / 8
+        else:
+            ssim = ssim_c.mean()
+        loss_pixel = 1 - ssim
 
     num_pi = int(pis_mask.sum())                                             # smoe.py:1012
     norm = float(num_pi) if cfg.kernel_count_as_norm_l1 else float(cfg.start_pis)   # smoe.py:1022-1025

@@ -58,7 +58,7 @@ class OracleSmoe:
                  quantize_pis=False, lower_bounds=None, upper_bounds=None, use_yuv=True,
                  only_y_gamma=False, precision=8, iter_offset=0, margin=0.5,
                  kernel_count_as_norm_l1=False, train_inverse_cov=True, dtype=torch.float32,
-                 einsum_mode="einsum", loss_mask=None):
+                 einsum_mode="einsum", loss_mask=None, ssim_opt=False, overlap_of_batches=0):
         self.image = np.asarray(image)
         self.dtype = dtype
         self.dim_domain = self.image.ndim - 1
@@ -73,6 +73,7 @@ class OracleSmoe:
         self.train_pis, self.train_gammas, self.train_musx = train_pis, train_gammas, train_musx
         self.iter = iter_offset
         self.loss_mask = loss_mask
+        self.ssim_opt, self.overlap = ssim_opt, int(overlap_of_batches)
         self.joint_domain = init_ref.gen_domain(self.image, self.dim_domain)      # float64
         self.batch_shape = init_ref.get_batch_shape(start_batches, self.joint_domain.shape)
         if batch_size is not None and batch_size[0] is not None:
@@ -116,7 +117,7 @@ class OracleSmoe:
                             use_diff_center=use_diff_center, quantize_pis=quantize_pis,
                             quantization_mode=quantization_mode, lower_bounds=lower_bounds,
                             upper_bounds=upper_bounds, bit_depths=bit_depths,
-                            kernel_count_as_norm_l1=kernel_count_as_norm_l1, start_pis=K,
+                            kernel_count_as_norm_l1=kernel_count_as_norm_l1, start_pis=K, ssim_opt=ssim_opt,
                             einsum_mode=einsum_mode)
         self.kernel_list_per_batch = [np.ones((K,), dtype=bool) for _ in range(self.start_batches)]
         nb = int(np.prod(self.batch_size_valued))                                   # smoe.py:271-273
@@ -157,7 +158,9 @@ class OracleSmoe:
         rec = np.zeros_like(self.image)
         amax = np.zeros(self.image.shape[:-1])
         d = self.dim_domain
-        for ii, (coord, batch) in enumerate(init_ref.sliding_window(self.joint_domain, 0, self.batch_size_valued)):
+        ov = self.overlap
+        for ii, (coord, batch) in enumerate(init_ref.sliding_window(self.joint_domain, ov, self.batch_size_valued)):
+            coord = coord + ov                                          # smoe.py:1719-1720
             img_patch = batch.reshape(-1, batch.shape[-1])
             samples = None
             if train and sampling_percentage < 100:                     # smoe.py:1664-1667
@@ -178,13 +181,16 @@ class OracleSmoe:
                 feed = {k: torch.tensor(np.asarray(v), dtype=self.dtype) for k, v in self.rparams.items()}
             ovr = None
             if resq_override is not None:
-                sl = tuple(slice(int(c), int(c) + b) for c, b in zip(coord, self.batch_size_valued))
-                ovr = torch.tensor(np.asarray(resq_override)[sl].reshape(-1, self.image.shape[-1]), dtype=self.dtype)
+                # the window with its halo, out of the zero-padded override image (halo values are cropped
+                # before the loss, so only the interior ones matter)
+                arr = np.pad(np.asarray(resq_override), ((ov, ov),) * d + ((0, 0),))
+                sl = tuple(slice(int(c), int(c) + b + 2 * ov) for c, b in zip(coord, self.batch_size_valued))
+                ovr = torch.tensor(arr[sl].reshape(-1, self.image.shape[-1]), dtype=self.dtype)
                 if samples is not None:
                     ovr = ovr[torch.as_tensor(samples)]
             out = graph_forward(leaf, self.kernel_list_per_batch[ii], domain, target, self.cfg,
                                 pis_l1, u_l1, musX_grid=self.musX_grid, feed=feed, resq_override=ovr,
-                                loss_weights=lw)
+                                loss_weights=lw, crop=(batch.shape[:-1], ov))
             if train and trainable:
                 gs = torch.autograd.grad(out["loss"], [leaf[n] for n in trainable], allow_unused=True)
                 for n, g in zip(trainable, gs):
@@ -192,8 +198,9 @@ class OracleSmoe:
                         accum[n] += g                                   # assign_add, smoe.py:1150
             if update_reconstruction:
                 sl = tuple(slice(int(c), int(c) + b) for c, b in zip(coord, self.batch_size_valued))
-                rec[sl] = out["resq"].detach().numpy().reshape(tuple(self.batch_size_valued) + (-1,))
-                amax[sl] = out["w_e_max"].numpy().reshape(tuple(self.batch_size_valued))
+                inner = tuple(slice(ov, ov + b) for b in self.batch_size_valued)      # smoe.py:1725-1744
+                rec[sl] = out["resq"].detach().numpy().reshape(tuple(batch.shape[:-1]) + (-1,))[inner]
+                amax[sl] = out["w_e_max"].numpy().reshape(tuple(batch.shape[:-1]))[inner]
                 self.random_sampling_per_batch[ii] = out["sampl_prob"].detach().numpy().astype(np.float32)  # smoe.py:1768-1769
             frac = np.prod(self.batch_size_valued) / self.num_pixel
             loss_val += float(out["loss"].detach()) * frac
@@ -232,7 +239,8 @@ class OracleSmoe:
         if self.use_diff_center:
             mu = mu + self.musX_grid.double()
         pis = torch.tensor(self.get_params()["pis"], dtype=torch.float64)
-        for k, (coord, batch) in enumerate(init_ref.sliding_window(self.joint_domain, 0, self.batch_size_valued)):
+        for k, (coord, batch) in enumerate(init_ref.sliding_window(self.joint_domain, self.overlap,
+                                                                    self.batch_size_valued)):
             flat = batch.reshape(-1, batch.shape[-1])[:, :d]
             mn, mx = flat.min(axis=0), flat.max(axis=0)
             pts = np.array(list(_product(*[[mn[a], mx[a], (mn[a] + mx[a]) / 2] for a in range(d)])))

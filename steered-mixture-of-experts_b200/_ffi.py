@@ -18,7 +18,7 @@ NSCAL = 16
 
 EXPORTS = [
     "smoe_abi_version", "smoe_last_error", "smoe_param_count", "smoe_packed_stride", "smoe_num_tiles", "smoe_pix_stride",
-    "smoe_pack_workspace_bytes", "smoe_backward_workspace_bytes", "smoe_pack", "smoe_pack_fed", "smoe_forward",
+    "smoe_pack_workspace_bytes", "smoe_backward_workspace_bytes", "smoe_pack", "smoe_pack_fed", "smoe_forward", "smoe_ssim_loss_workspace_bytes", "smoe_ssim_loss",
     "smoe_backward", "smoe_suggest_splits", "smoe_reduce_splits", "smoe_grad_finalize", "smoe_update_kernel_list",
     "smoe_adam_step", "smoe_ssim_workspace_bytes", "smoe_ssim", "smoe_sqerr", "smoe_quantize", "smoe_rescale",
     "smoe_colminmax",
@@ -40,7 +40,7 @@ PIXEL_ABSENT, PIXEL_HALO = -1.0, -2.0          # SMOE_PIXEL_ABSENT / SMOE_PIXEL_
 
 class Batch(C.Structure):
     _fields_ = [("dims", C.c_int32 * 3), ("origin", C.c_int32 * 3), ("extent", C.c_int32 * 3),
-                ("tile", C.c_int32 * 3), ("inv_count", C.c_float)]
+                ("tile", C.c_int32 * 3), ("inv_count", C.c_float), ("halo", C.c_int32)]
 
 
 class Adam(C.Structure):
@@ -61,7 +61,8 @@ def lib():
                 "smoe_b200 has no CPU or PyTorch fallback.")
         _lib = C.CDLL(LIB_PATH)
         _lib.smoe_last_error.restype = C.c_char_p
-        for name in ("smoe_pack_workspace_bytes", "smoe_backward_workspace_bytes", "smoe_ssim_workspace_bytes"):
+        for name in ("smoe_pack_workspace_bytes", "smoe_backward_workspace_bytes", "smoe_ssim_workspace_bytes",
+                     "smoe_ssim_loss_workspace_bytes"):
             getattr(_lib, name).restype = C.c_size_t
         if _lib.smoe_abi_version() != 1:
             raise RuntimeError("libsmoe_b200.so ABI version mismatch")

@@ -202,9 +202,16 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
         // the thread's PPT pixels: same (i1, i2), rows i0 = p*step + i0_first
         float x0[PPT], xs[3] = {0.f, 0.f, 0.f};
         long long gidx[PPT];     // linear pixel index in the image buffer, -1 when outside
+        unsigned hmask = 0;      // bit p: pixel p lies in the overlap halo (forwarded, outside the loss crop)
         {
             const int i2 = tid % e2, i1 = (tid / e2) % e1;
             const int g1 = lo[1] + i1, g2 = lo[2] + i2;
+            // the halo of overlap_of_batches (smoe.py:909-923) is cropped on every side that is not the image border
+            auto in_halo = [&](int ax, int g) {
+                const int o = a.b.origin[ax], e = o + a.b.extent[ax];
+                return ax < D && ((o > 0 && g < o + a.b.halo) || (e < a.b.dims[ax] && g >= e - a.b.halo));
+            };
+            const bool h12 = a.b.halo > 0 && (in_halo(1, g1) || in_halo(2, g2));
             if (D > 1) xs[1] = a.ax[1][min(g1, hi[1])] - ctr[1];
             if (D > 2) xs[2] = a.ax[2][min(g2, hi[2])] - ctr[2];
 #pragma unroll
@@ -216,6 +223,7 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
                 gidx[p] = ok ? ((long long)g0 * a.b.dims[1] + g1) * a.b.dims[2] + g2 : -1;
                 // a pixel that is not part of this run's feed (random sub-sampling, smoe.py:1664-1667)
                 if (a.lossw && ok && a.lossw[gidx[p]] == SMOE_PIXEL_ABSENT) gidx[p] = -1;
+                if (a.b.halo > 0 && (h12 || in_halo(0, g0))) hmask |= 1u << p;
                 x0[p] = a.ax[0][min(g0, hi[0])] - ctr[0];
             }
         }
@@ -399,7 +407,7 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
             // per-pixel loss weight (loss_mask, smoe.py:932, 1674-1677); SMOE_PIXEL_HALO marks a pixel of the
             // overlap halo: forwarded (gates, influence list) but outside the loss crop (smoe.py:909-923)
             const float lwv = (a.lossw && gidx[p] >= 0) ? a.lossw[gidx[p]] : 1.f;
-            const bool halo = lwv == SMOE_PIXEL_HALO;
+            const bool halo = ((hmask >> p) & 1u) || lwv == SMOE_PIXEL_HALO;
             if (gidx[p] >= 0) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
@@ -411,12 +419,9 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
                     const float tgt = a.image[gidx[p] * C + c];
                     const float diff = __fsub_rn(rq, tgt);                              // smoe.py:905
                     const float ad = fabsf(diff) - a.eps;                               // smoe.py:932
-                    if (!a.lossw) {
+                    if (!halo) {
                         sqsum = fmaf(diff, diff, sqsum);
-                        lsum[c] = fmaf(ad, ad, lsum[c]);
-                    } else if (!halo) {
-                        sqsum = fmaf(diff, diff, sqsum);
-                        lsum[c] = fmaf(ad * ad, lwv, lsum[c]);
+                        lsum[c] = a.lossw ? fmaf(ad * ad, lwv, lsum[c]) : fmaf(ad, ad, lsum[c]);
                     }
                     const float cw = a.cfg.use_yuv ? (c == 0 ? 0.75f : 0.125f) : (1.0f / C);
                     const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
@@ -424,10 +429,12 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
                     g[c] = ste ? 2.f * ad * sgn * cw * a.b.inv_count : 0.f;
                     if (a.lossw) g[c] *= lwv;
                     gr = fmaf(g[c], rv, gr);
-                    a.res[gidx[p] * C + c] = rq;
-                    if (a.res_pre) a.res_pre[gidx[p] * C + c] = rv;
+                    if (!halo) {                 // a halo pixel is the interior of another window, which writes it
+                        a.res[gidx[p] * C + c] = rq;
+                        if (a.res_pre) a.res_pre[gidx[p] * C + c] = rv;
+                    }
                 }
-                if (a.argmax) a.argmax[gidx[p]] = bestk[p] >= 0 ? a.indices[bestk[p]] : -1;
+                if (a.argmax && !halo) a.argmax[gidx[p]] = bestk[p] >= 0 ? a.indices[bestk[p]] : -1;
             } else {
 #pragma unroll
                 for (int c = 0; c < C; ++c) g[c] = 0.f;
@@ -515,6 +522,7 @@ extern "C" int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const 
     SMOE_REQUIRE(kThreadsF % (batch->tile[1] * batch->tile[2]) == 0 && batch->tile[cfg->d - 1] % 4 == 0,
                  "tile[1]*tile[2] must divide 128 and the last tile extent must be a multiple of 4");
     SMOE_REQUIRE(!pix || tile_qmin, "tile_qmin is required with pix");
+    SMOE_REQUIRE(batch->halo >= 0, "negative halo");
     for (int i = 0; i < 3; ++i)
         SMOE_REQUIRE(batch->extent[i] > 0 && batch->origin[i] >= 0 && batch->origin[i] + batch->extent[i] <= batch->dims[i],
                      "batch rectangle outside the image");

@@ -1,0 +1,268 @@
+// SSIM as the training loss (smoe_ssim_loss).  Replaces the `ssim_opt` branch of the loss graph, smoe.py:981-1010:
+//     res, target -> crop the overlap halo -> SYMMETRIC pad 5 -> custom_ssim (ops/image_ops_impl.py:235-293)
+//     -> ssim = sum(ssim_c * [6,1,1]) / 8  or  mean_c ;  loss_pixel = 1 - ssim
+// and the part of tf.gradients (smoe.py:1148) that runs through it: d loss / d res, through the output
+// fake-quant and the clip (straight-through inside [0,1]), written as the per-pixel backward state g_c, gr
+// that smoe_backward consumes (the planes smoe_forward fills for the squared-error loss).
+//
+// With x = res, y = target, the Gaussian window W (11 taps per axis, sigma 1.5) and per output position
+//     mx = W*x, my = W*y, e2 = W*(x^2+y^2), exy = W*(xy),
+//     lum = (2 mx my + c1) / (mx^2 + my^2 + c1),  cs = (2 exy - 2 mx my + c2) / (e2 - mx^2 - my^2 + c2),
+// the derivative of mean(lum * cs) with respect to a pixel is  (P^T a + 2 x P^T b + y P^T c) / Np  with
+//     a = d/d mx = 2 cs (my - lum mx) / Dl + 2 lum (cs mx - my) / Dc,   b = d/d e2 = -lum cs / Dc,
+//     c = d/d exy = 2 lum / Dc,   Dl = mx^2+my^2+c1,  Dc = e2-mx^2-my^2+c2,
+// where P is "symmetric pad, then VALID correlation" and P^T its adjoint.  P is separable, so both P and
+// P^T run as one 11-tap pass per axis over planes local to the batch's loss rectangle.  HBM-bound
+// elementwise / stencil work; no atomics, fixed-order reductions.
+#include <math.h>
+#include "smoe_common.cuh"
+
+namespace smoe {
+
+// exp(-(k-5)^2 / (2 * 1.5^2)) / sum, rounded to float32 (ops/image_ops_impl.py:131-151); a compile-time
+// initialiser, so that the launches below can be captured into a CUDA graph
+__constant__ float c_lwin[11] = {1.028380124e-03f, 7.598758209e-03f, 3.600077331e-02f, 1.093606874e-01f, 2.130055428e-01f, 2.660117149e-01f, 2.130055428e-01f, 1.093606874e-01f, 3.600077331e-02f, 7.598758209e-03f, 1.028380124e-03f};
+
+__device__ __forceinline__ int refl(int i, int n) {
+    while (i < 0 || i >= n) i = i < 0 ? -i - 1 : 2 * n - 1 - i;
+    return i;
+}
+
+struct LRect {
+    int dims[3];      // resident image extents
+    int lo[3];        // loss rectangle inside the image
+    int n[3];         // its extents
+    int C;
+};
+
+__device__ __forceinline__ size_t rect_global(const LRect& r, int i0, int i1, int i2, int c) {
+    return (((size_t)(r.lo[0] + i0) * r.dims[1] + (r.lo[1] + i1)) * r.dims[2] + (r.lo[2] + i2)) * r.C + c;
+}
+
+// forward passes of P over planes 0: W*x, 1: W*y, 2: W*(x^2+y^2), 3: W*(xy); the last one turns them into
+// the maps a, b, c and reduces the SSIM values per channel
+template <bool FIRST, bool LAST>
+__global__ void __launch_bounds__(256) sl_fwd_pass(LRect r, const float* __restrict__ x, const float* __restrict__ y,
+                                                   const float* __restrict__ src, float* __restrict__ dst, int axis,
+                                                   float c1, float c2, double* __restrict__ partial) {
+    const size_t total = (size_t)r.n[0] * r.n[1] * r.n[2] * r.C;
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    float ssim = 0.f;
+    int ch = 0;
+    if (i < total) {
+        ch = (int)(i % r.C);
+        const size_t pix = i / r.C;
+        int id[3] = {(int)(pix / ((size_t)r.n[2] * r.n[1])), (int)((pix / r.n[2]) % r.n[1]), (int)(pix % r.n[2])};
+        const int n = r.n[axis], pos = id[axis];
+        const size_t stride = axis == 0 ? (size_t)r.n[1] * r.n[2] * r.C : (axis == 1 ? (size_t)r.n[2] * r.C : (size_t)r.C);
+        const size_t base = i - (size_t)pos * stride;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 11; ++k) {
+            const int q = refl(pos + k - 5, n);
+            const float wk = c_lwin[k];
+            if (FIRST) {
+                id[axis] = q;
+                const size_t g = rect_global(r, id[0], id[1], id[2], ch);
+                const float xv = x[g], yv = y[g];
+                acc[0] = fmaf(wk, xv, acc[0]);
+                acc[1] = fmaf(wk, yv, acc[1]);
+                acc[2] = fmaf(wk, fmaf(xv, xv, yv * yv), acc[2]);
+                acc[3] = fmaf(wk, xv * yv, acc[3]);
+            } else {
+                const size_t j = base + (size_t)q * stride;
+#pragma unroll
+                for (int p = 0; p < 4; ++p) acc[p] = fmaf(wk, src[(size_t)p * total + j], acc[p]);
+            }
+        }
+        if (LAST) {
+            const float mx = acc[0], my = acc[1];
+            const float num0 = mx * my * 2.0f;
+            const float den0 = mx * mx + my * my;
+            const float Dl = den0 + c1, Dc = acc[2] - den0 + c2;
+            const float lum = (num0 + c1) / Dl;
+            const float cs = (acc[3] * 2.0f - num0 + c2) / Dc;
+            ssim = lum * cs;
+            dst[i] = 2.f * cs * (my - lum * mx) / Dl + 2.f * lum * (cs * mx - my) / Dc;
+            dst[total + i] = -ssim / Dc;
+            dst[2 * total + i] = 2.f * lum / Dc;
+        } else {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) dst[(size_t)p * total + i] = acc[p];
+        }
+    }
+    if (LAST) {
+        __shared__ float s_v[256];
+        __shared__ int s_c[256];
+        s_v[threadIdx.x] = (i < total) ? ssim : 0.f;
+        s_c[threadIdx.x] = ch;
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            double s = 0.0;
+            for (int t = 0; t < 256; ++t)
+                if (s_c[t] == (int)threadIdx.x) s += (double)s_v[t];
+            partial[(size_t)blockIdx.x * 4 + threadIdx.x] = s;
+        }
+    }
+}
+
+// one axis of P^T over the 3 planes a, b, c:  out[i] = sum over padded positions j' that reflect onto i of
+// sum_t w[t] in[j' + t - 5]  (in = 0 outside the rectangle)
+__global__ void __launch_bounds__(256) sl_adj_pass(LRect r, const float* __restrict__ src, float* __restrict__ dst,
+                                                   int axis) {
+    const size_t total = (size_t)r.n[0] * r.n[1] * r.n[2] * r.C;
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= total) return;
+    const size_t pix = i / r.C;
+    const int id[3] = {(int)(pix / ((size_t)r.n[2] * r.n[1])), (int)((pix / r.n[2]) % r.n[1]), (int)(pix % r.n[2])};
+    const int n = r.n[axis], pos = id[axis];
+    const size_t stride = axis == 0 ? (size_t)r.n[1] * r.n[2] * r.C : (axis == 1 ? (size_t)r.n[2] * r.C : (size_t)r.C);
+    const size_t base = i - (size_t)pos * stride;
+    float acc[3] = {0.f, 0.f, 0.f};
+    auto tap = [&](int jp) {
+#pragma unroll
+        for (int k = 0; k < 11; ++k) {
+            const int q = jp + k - 5;
+            if (q >= 0 && q < n) {
+                const float wk = c_lwin[k];
+                const size_t j = base + (size_t)q * stride;
+#pragma unroll
+                for (int p = 0; p < 3; ++p) acc[p] = fmaf(wk, src[(size_t)p * total + j], acc[p]);
+            }
+        }
+    };
+    tap(pos);
+    if (pos < 5 || pos >= n - 5) {       // mirror images of this pixel in the symmetric padding
+        for (int jp = -5; jp < 0; ++jp)
+            if (refl(jp, n) == pos) tap(jp);
+        for (int jp = n; jp < n + 5; ++jp)
+            if (refl(jp, n) == pos) tap(jp);
+    }
+#pragma unroll
+    for (int p = 0; p < 3; ++p) dst[(size_t)p * total + i] = acc[p];
+}
+
+__global__ void sl_final(const double* __restrict__ partial, int nblocks, int C, float* __restrict__ scalars) {
+    __shared__ double s[256];
+    for (int c = 0; c < C; ++c) {
+        double acc = 0.0;
+        for (int bI = threadIdx.x; bI < nblocks; bI += 256) acc += partial[(size_t)bI * 4 + c];
+        s[threadIdx.x] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int q = 0; q < 256; ++q) t += s[q];
+            scalars[8 + c] += (float)t;
+        }
+        __syncthreads();
+    }
+}
+
+// d loss / d res -> the g_c and gr planes of the backward state (layout of smoe_forward's epilogue)
+template <int D, int C>
+__global__ void __launch_bounds__(256) sl_apply(smoe_cfg cfg, smoe_batch b, LRect r, const float* __restrict__ adj,
+                                                const float* __restrict__ res, const float* __restrict__ image,
+                                                const float* __restrict__ res_pre, float* __restrict__ pix,
+                                                int nt1, int nt2, float tau) {
+    const size_t total = (size_t)r.n[0] * r.n[1] * r.n[2];
+    const size_t ip = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (ip >= total) return;
+    const int i2 = (int)(ip % r.n[2]), i1 = (int)((ip / r.n[2]) % r.n[1]), i0 = (int)(ip / ((size_t)r.n[2] * r.n[1]));
+    // position inside the batch (forward) rectangle -> tile and slot
+    const int f[3] = {r.lo[0] + i0 - b.origin[0], r.lo[1] + i1 - b.origin[1], r.lo[2] + i2 - b.origin[2]};
+    const int t0 = f[0] / b.tile[0], t1 = f[1] / b.tile[1], t2 = f[2] / b.tile[2];
+    const int tile = (t0 * nt1 + t1) * nt2 + t2;
+    const int j = ((f[0] % b.tile[0]) * b.tile[1] + (f[1] % b.tile[1])) * b.tile[2] + (f[2] % b.tile[2]);
+    float* tp = pix + (size_t)tile * pix_stride(D, C, b.tile[D - 1]);
+    const size_t nC = total * C;
+    const float inv_np = 1.0f / (float)total;
+    float gr = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const size_t g = rect_global(r, i0, i1, i2, c);
+        const size_t l = ip * C + c;
+        const float x = res[g], y = image[g], rv = res_pre[g];
+        const float cw = cfg.use_yuv ? (C == 3 ? (c == 0 ? 0.75f : 0.125f) : 1.0f) : (1.0f / C);   // smoe.py:1006-1009
+        const float dS = fmaf(y, adj[2 * nC + l], fmaf(2.f * x, adj[nC + l], adj[l])) * inv_np;
+        const bool ste = (rv >= 0.f) && (rv <= 1.f);
+        const float gc = ste ? -cw * dS : 0.f;                    // loss_pixel = 1 - ssim
+        gr = fmaf(gc, rv, gr);
+        tp[(PL_G + c) * SMOE_TPIX + j] = gc;
+    }
+    // S > 1e-11 (smoe.py:821): the forward stored qthr = log2f(tau * max(S, floor)), same device log2f here
+    const bool live = tp[PL_QTHR * SMOE_TPIX + j] > log2f(tau * kSFloor);
+    tp[PL_GR * SMOE_TPIX + j] = live ? gr : 0.f;
+}
+
+static LRect loss_rect(const smoe_cfg* cfg, const smoe_batch* b) {
+    LRect r;
+    for (int a = 0; a < 3; ++a) {
+        r.dims[a] = b->dims[a];
+        int lo = b->origin[a], hi = b->origin[a] + b->extent[a];
+        if (a < cfg->d && b->halo > 0) {          // the halo is cropped on every side that is not the image border
+            if (lo > 0) lo += b->halo;
+            if (hi < b->dims[a]) hi -= b->halo;
+        }
+        r.lo[a] = lo;
+        r.n[a] = hi - lo;
+    }
+    r.C = cfg->C;
+    return r;
+}
+
+}  // namespace smoe
+
+using namespace smoe;
+
+extern "C" size_t smoe_ssim_loss_workspace_bytes(const smoe_cfg* cfg, const smoe_batch* batch) {
+    if (!cfg || !batch) return 0;
+    const size_t total = (size_t)batch->extent[0] * batch->extent[1] * batch->extent[2] * cfg->C;
+    const size_t nblocks = (total + 255) / 256;
+    return 2 * 4 * total * sizeof(float) + 256 + nblocks * 4 * sizeof(double) + 256;
+}
+
+extern "C" int smoe_ssim_loss(const smoe_cfg* cfg, const smoe_batch* batch, const float* res, const float* image,
+                              const float* res_pre, float* pix, float* scalars, void* workspace, void* stream) {
+    SMOE_REQUIRE(cfg && batch && res && image && res_pre && scalars && workspace, "null argument");
+    SMOE_REQUIRE(cfg->d == 2 || cfg->d == 3, "unsupported d");
+    const LRect r = loss_rect(cfg, batch);
+    for (int a = 0; a < 3; ++a) SMOE_REQUIRE(r.n[a] > 0, "overlap halo swallows the batch");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t npos = (size_t)r.n[0] * r.n[1] * r.n[2];
+    const size_t total = npos * r.C;
+    const size_t cap = (size_t)batch->extent[0] * batch->extent[1] * batch->extent[2] * cfg->C;
+    const int nblocks = (int)((total + 255) / 256);
+    float* p0 = (float*)workspace;
+    float* p1 = p0 + 4 * cap;
+    double* partial = (double*)((char*)workspace + (2 * 4 * cap * sizeof(float) + 255) / 256 * 256);
+    const float c1 = 0.01f * 0.01f, c2 = 0.03f * 0.03f;
+    float* src = nullptr;
+    float* dst = p0;
+    for (int axis = cfg->d - 1; axis >= 0; --axis) {
+        const bool first = axis == cfg->d - 1, last = axis == 0;
+        if (first)
+            sl_fwd_pass<true, false><<<nblocks, 256, 0, st>>>(r, res, image, nullptr, dst, axis, c1, c2, nullptr);
+        else if (!last)
+            sl_fwd_pass<false, false><<<nblocks, 256, 0, st>>>(r, res, image, src, dst, axis, c1, c2, nullptr);
+        else
+            sl_fwd_pass<false, true><<<nblocks, 256, 0, st>>>(r, res, image, src, dst, axis, c1, c2, partial);
+        src = dst;
+        dst = (dst == p0) ? p1 : p0;
+    }
+    sl_final<<<1, 256, 0, st>>>(partial, nblocks, r.C, scalars);
+    if (pix) {
+        for (int axis = 0; axis < cfg->d; ++axis) {
+            sl_adj_pass<<<nblocks, 256, 0, st>>>(r, src, dst, axis);
+            src = dst;
+            dst = (dst == p0) ? p1 : p0;
+        }
+        const int nt1 = (batch->extent[1] + batch->tile[1] - 1) / batch->tile[1];
+        const int nt2 = (batch->extent[2] + batch->tile[2] - 1) / batch->tile[2];
+        const float tau = 0.5f / (float)(1 << cfg->precision);
+        const int nb = (int)((npos + 255) / 256);
+#define CALL(D, C) sl_apply<D, C><<<nb, 256, 0, st>>>(*cfg, *batch, r, src, res, image, res_pre, pix, nt1, nt2, tau);
+        SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
+#undef CALL
+    }
+    return check_launch("smoe_ssim_loss");
+}

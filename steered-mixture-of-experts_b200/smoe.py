@@ -76,8 +76,7 @@ class Smoe:
         _ffi.require_cuda()
         lib()
         unsupported = {"affines": affines is not None, "train_trafo": train_trafo, "train_svs": train_svs,
-                       "add_kernel_slots": add_kernel_slots > 0, "ssim_opt": ssim_opt, "radial_as": radial_as,
-                       "overlap_of_batches": overlap_of_batches > 0,
+                       "add_kernel_slots": add_kernel_slots > 0, "radial_as": radial_as,
                        "quantization_mode 3": quantization_mode >= 3}
         for k, v in unsupported.items():
             if v:
@@ -117,6 +116,9 @@ class Smoe:
             raise ValueError("quantize_pis / quantization_mode 2 need lower_bounds, upper_bounds and bit_depths")
 
         self.start_batches = start_batches
+        self.overlap = int(overlap_of_batches)                # smoe.py:244
+        if self.overlap < 0:
+            raise ValueError("overlap_of_batches must be >= 0")
         self.image = image
         self.dim_domain = image.ndim - 1
         self.num_pixel = int(np.prod(image.shape[:self.dim_domain]))
@@ -135,7 +137,6 @@ class Smoe:
                     raise ValueError("Required BatchSize is not compatible to input dimensions")
         else:
             self.batch_size_valued = tuple(self.batch_shape[:-1])
-        self.overlap = overlap_of_batches
         self.batch_size = tuple(np.array(self.batch_size_valued) + 2 * self.overlap)
         self.start_batches = int(np.prod(np.ceil(np.array(image.shape[:-1]) / np.array(self.batch_size_valued))))
 
@@ -166,6 +167,9 @@ class Smoe:
         if self._world > 1:
             if self.start_batches != 1:
                 raise NotImplementedError("pixel sharding over ranks needs start_batches == 1")
+            if self.ssim_opt or self.overlap > 0:
+                # SSIM windows and halos cross the band borders: a sharded SSIM loss needs a 5-pixel halo exchange
+                raise NotImplementedError("ssim_opt / overlap_of_batches on a sharded model")
             n0 = image.shape[0]
             self._band = (n0 * self._rank // self._world, n0 * (self._rank + 1) // self._world)
         else:
@@ -327,17 +331,44 @@ class Smoe:
             starts = [range(0, self.image.shape[a], self.batch_size_valued[a]) for a in range(d)]
             rects = [(org, self.batch_size_valued) for org in product(*starts)]
         max_tiles = 0
+        ov = self.overlap
+        self._batch_npix, self._batch_phantom = [], []
         for org, ext in rects:
             b = Batch()
+            clipped = False
             for a in range(3):
                 b.dims[a] = self._dims3[a]
-                b.origin[a] = org[a] if a < d else 0
-                b.extent[a] = ext[a] if a < d else 1
+                # the window plus its overlap halo, clipped to the image (smoe.py:18-35 pads with zeros instead;
+                # see _batch_phantom below)
+                lo = max(org[a] - ov, 0) if a < d else 0
+                hi = min(org[a] + ext[a] + ov, self._dims3[a]) if a < d else 1
+                clipped |= a < d and (org[a] - ov < 0 or org[a] + ext[a] + ov > self._dims3[a])
+                b.origin[a] = lo
+                b.extent[a] = hi - lo
                 b.tile[a] = self._tile[a]
             npix = int(np.prod(ext)) if self._world == 1 else self.num_pixel
             b.inv_count = 1.0 / npix
+            b.halo = ov
             self._batches.append(b)
+            self._batch_npix.append(npix)
+            # The reference zero-pads the JOINT domain, coordinates included (smoe.py:20, 28): a window at the image
+            # border is fed `overlap` rows of phantom pixels that all sit at coordinate (0,..,0).  They are cropped
+            # before the loss and can only add kernels to the window's influence list (smoe.py:829); one extra
+            # 1-pixel forward at the image origin reproduces that (pixel 0 IS at coordinate 0).
+            self._batch_phantom.append(ov > 0 and clipped)
             max_tiles = max(max_tiles, L.smoe_num_tiles(C.byref(b)))
+        self._phantom = None
+        if any(self._batch_phantom):
+            pb = Batch()
+            for a in range(3):
+                pb.dims[a], pb.origin[a], pb.extent[a], pb.tile[a] = self._dims3[a], 0, 1, self._tile[a]
+            pb.inv_count, pb.halo = 1.0, 0
+            self._phantom = (pb, torch.full((1,), _ffi.PIXEL_HALO, dtype=f32, device=dev))
+        self._ssim_ws = None
+        if self.ssim_opt:
+            self._d_res_pre = torch.zeros_like(self._d_res)      # the SSIM gradient needs the pre-clip values (STE)
+            nbytes = max(L.smoe_ssim_loss_workspace_bytes(C.byref(self._cfg), C.byref(b)) for b in self._batches)
+            self._ssim_ws = torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=dev)
         nb = len(self._batches)
         self._max_tiles = max_tiles
         self._klist = torch.ones((nb, K), dtype=torch.uint8, device=dev)
@@ -479,6 +510,10 @@ class Smoe:
                              "full-batch mask against the sampled pixels, smoe.py:1666-1677)")
         if sampling and self._world > 1:
             raise NotImplementedError("sampling_percentage < 100 on a sharded model")
+        if self.overlap > 0 and (sampling or use_loss_mask):
+            # smoe_test.py:322-325: sampling is "only working if ... batch overlap equal 0"; the mask is sliced
+            # with the un-padded window coordinates (smoe.py:1674-1676)
+            raise NotImplementedError("sampling_percentage < 100 / use_loss_mask with overlap_of_batches > 0")
         lossw, batches = (self._d_loss_mask if use_loss_mask else None), self._batches
         if sampling:
             lossw, batches = self._draw_samples(sampling_percentage)
@@ -540,7 +575,12 @@ class Smoe:
         num_pi = -1
         for ii, b in enumerate(batches):
             inv_n = float(b.inv_count)
-            if self.use_yuv:                               # smoe.py:933-935
+            if self.ssim_opt:                              # smoe.py:1006-1010
+                per = [h[ii, 8 + c] / self._batch_npix[ii] for c in range(Cc)]
+                ssim = (sum(p * wgt for p, wgt in zip(per, (6, 1, 1))) / 8 if Cc == 3 else per[0]) if self.use_yuv \
+                    else sum(per) / Cc
+                lp = 1 - ssim
+            elif self.use_yuv:                             # smoe.py:933-935
                 lp = 6 / 8 * h[ii, 0] * inv_n + 1 / 8 * sum(h[ii, c] * inv_n for c in range(1, Cc))
             else:
                 lp = sum(h[ii, c] for c in range(Cc)) * inv_n / Cc
@@ -549,7 +589,7 @@ class Smoe:
             mse_b = h[ii, 4] * inv_n / Cc * ((2 ** self.precision) ** 2)
             if h[ii, 5] > 0:
                 loss_b = float("nan")
-            frac = 1.0 if self._world > 1 else np.prod([b.extent[a] for a in range(self.dim_domain)]) / self.num_pixel
+            frac = 1.0 if self._world > 1 else self._batch_npix[ii] / self.num_pixel
             loss_val += loss_b * frac                       # smoe.py:1758-1759
             mse_val += mse_b * frac
             num_pi = int(h[ii, _ffi.NSCAL + 1])
@@ -595,7 +635,7 @@ class Smoe:
     def _update_sampling_probabilities(self):
         """sampl_prob = err_map / sum(err_map) per batch, err_map = mean_c (resq - target)^2 (smoe.py:906-907),
         kept on the device; replaces `random_sampling_per_batch[ii] = results[-1]` (smoe.py:1768-1769)."""
-        if self._world > 1:
+        if self._world > 1 or self.overlap > 0:
             return
         d, Cc = self.dim_domain, self.image.shape[-1]
         err = ((self._d_res.reshape(self._local_shape + (Cc,)) - self._d_image) ** 2).mean(dim=-1)
@@ -661,6 +701,20 @@ class Smoe:
                                      ptr(self._infl), ptr(self._pix) if train else ptr(None), ptr(self._tile_qmin),
                                      ptr(scal), ptr(self._partials), ptr(self._ticket), st), "smoe_forward")
                 self.gpu_launches += 1
+                if self._batch_phantom[ii]:
+                    pb, halo1 = self._phantom
+                    check(L.smoe_forward(C.byref(self._cfg), C.byref(pb), ptr(self._packed), ptr(self._indices),
+                                         ptr(counts), ptr(self._chunk_bounds), K, ptr(self._d_image), ptr(halo1),
+                                         ptr(self._d_axes[0]), ptr(self._d_axes[1]),
+                                         ptr(self._d_axes[2]) if self.dim_domain == 3 else ptr(None),
+                                         ptr(self._d_res), ptr(None), ptr(None), ptr(self._infl), ptr(None), ptr(None),
+                                         ptr(scal), ptr(self._partials), ptr(self._ticket), st), "smoe_forward (phantom)")
+                    self.gpu_launches += 1
+                if self.ssim_opt:
+                    check(L.smoe_ssim_loss(C.byref(self._cfg), C.byref(b), ptr(self._d_res), ptr(self._d_image),
+                                           ptr(self._d_res_pre), ptr(self._pix) if train else ptr(None), ptr(scal),
+                                           ptr(self._ssim_ws), st), "smoe_ssim_loss")
+                    self.gpu_launches += 2 * self.dim_domain + 2 if train else self.dim_domain + 1
             if train and pre:
                 check(L.smoe_backward(C.byref(self._cfg), C.byref(b), ptr(self._packed), ptr(counts), K,
                                       ptr(self._perm), ptr(self._pos), ptr(self._pix),
@@ -832,8 +886,13 @@ class Smoe:
         rects = self._batch_rects()
         for ii, (org, ext) in enumerate(rects):
             pts = []
+            ov = self.overlap
+            padded = ov > 0 and any(org[a] - ov < 0 or org[a] + ext[a] + ov > self.image.shape[a] for a in range(d))
             for a in range(d):
-                lo, hi = full_axes[a][org[a]], full_axes[a][org[a] + ext[a] - 1]
+                # min / max of the window's coordinates INCLUDING the overlap halo; the zero padding of border
+                # windows sits at coordinate 0 on every axis (smoe.py:18-35, 2324-2330)
+                lo = 0.0 if padded else full_axes[a][max(org[a] - ov, 0)]
+                hi = full_axes[a][min(org[a] + ext[a] + ov, self.image.shape[a]) - 1]
                 pts.append([lo, hi, (lo + hi) / 2])
             probe = torch.tensor(list(product(*pts)), dtype=torch.float32, device=self.device)      # (3^d, d)
             delta = probe[None, :, :] - mu[:, None, :]

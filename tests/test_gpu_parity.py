@@ -766,3 +766,59 @@ def test_random_sampling_of_training_pixels():
     l_start = m.run_batched(train=False)[0]
     m.train(30, val_iter=10, sampling_percentage=50, pis_l1=0.0)
     assert m.run_batched(train=False)[0] < l_start
+
+
+@pytest.mark.parametrize("case", ["mse_overlap", "ssim", "ssim_overlap", "ssim_video", "ssim_gray_yuv"])
+def test_ssim_loss_and_overlap_of_batches(case):
+    """ssim_opt (smoe.py:981-1010): loss = 1 - weighted custom_ssim of the SYMMETRIC-padded batch, gradient through
+    the SSIM map, the output fake-quant and the clip.  overlap_of_batches (smoe.py:18-35, 909-923, 985-991): every
+    window is forwarded with a halo that is cropped before the loss; halo pixels (and the zero padding at
+    coordinate 0 of border windows) only reach the influence lists.
+    Gradient tolerance with SSIM is 1e-3: sigma^2 = E[x^2] - mu^2 cancels in float32 (as it does in TF)."""
+    from oracle.model import OracleAdam, OracleSmoe
+    z = np.load(os.path.join(GOLDEN, "init_cases.npz"))
+    img, k = (z["vid_image"], [3, 4, 2]) if case == "ssim_video" else (z["rgb_image"], [6, 8])
+    if case == "ssim_gray_yuv":
+        img = np.ascontiguousarray(img[..., :1])
+    ssim = case.startswith("ssim")
+    ov = {"mse_overlap": 3, "ssim_overlap": 2}.get(case, 0)
+    kw = dict(use_determinant=True, train_inverse_cov=False, use_yuv=case != "ssim_video", ssim_opt=ssim,
+              overlap_of_batches=ov, start_batches=1 if case == "ssim_video" else 4)
+    m = _mk(img, k, **kw)
+    o = OracleSmoe(img, kernels_per_dim=k, dtype=torch.float64, **kw)
+    o.set_optimizer(OracleAdam(1e-3), OracleAdam(1e-5), OracleAdam(1.0))
+    (lg, mg, npg, _), (lo, mo, npo, _) = _train_pass_both(m, o, pis_l1=0.2, u_l1=1e-6)
+    assert npg == npo
+    assert abs(lg - lo) < (2e-5 if ssim else 2e-6) * max(1.0, abs(lo)) and abs(mg - mo) < 2e-3 * mo + 1e-3
+    if ssim:
+        assert 0 < lg < 1.2
+    g = m.get_gradients()
+    for kk, ref in o.last_grads.items():
+        assert _rel(g[kk], ref.numpy()) < (1e-3 if ssim else 1e-4), (kk, _rel(g[kk], ref.numpy()))
+    for a, b in zip(m.kernel_list_per_batch, o.kernel_list_per_batch):
+        assert (a != b).sum() <= 1
+    if ov:
+        # the halo only widens the influence lists
+        m0 = _mk(img, k, **dict(kw, overlap_of_batches=0))
+        m0.run_batched(train=True, update_reconstruction=True, pis_l1=0.2, u_l1=1e-6)
+        assert all(((a | b) == a).all() for a, b in zip(m.kernel_list_per_batch, m0.kernel_list_per_batch))
+        assert sum(int(a.sum()) - int(b.sum()) for a, b in zip(m.kernel_list_per_batch, m0.kernel_list_per_batch)) > 0
+        if not ssim:
+            np.testing.assert_array_equal(m.get_reconstruction(), m0.get_reconstruction())
+        m.update_kernel_list()
+        o.update_kernel_list()
+        for a, b in zip(m.kernel_list_per_batch, o.kernel_list_per_batch):
+            assert (a != b).sum() <= 1
+    # training (CUDA-graph replay from the second plain step on) follows the oracle and lowers the loss
+    first = None
+    for _ in range(6):
+        a = m.run_batched(train=True, pis_l1=0.2, u_l1=1e-6)
+        b = o.run_batched(train=True, pis_l1=0.2, u_l1=1e-6)
+        first = first if first is not None else a[0]
+        assert abs(a[0] - b[0]) < 5e-4 * max(1.0, abs(b[0]))
+    assert a[0] < first
+    if ssim:
+        # the loss value is the SSIM metric kernel's value on the same reconstruction (1 batch only)
+        if m.start_batches == 1:
+            l, _, _, _ = m.run_batched(train=False, update_reconstruction=True)
+            assert abs((1 - m.ssim()[0]) - l) < 1e-5

@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(libpath):
 def test_struct_sizes_match_header(libpath):
     from smoe_b200 import _ffi
     assert ctypes.sizeof(_ffi.Cfg) == (14 + 1 + 15 + 2) * 4
-    assert ctypes.sizeof(_ffi.Batch) == 13 * 4
+    assert ctypes.sizeof(_ffi.Batch) == 14 * 4
     assert ctypes.sizeof(_ffi.Adam) == 15 * 4
 
 

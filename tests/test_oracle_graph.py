@@ -180,3 +180,51 @@ def test_diff_center_and_kernel_count_norm():
     live = out3["indices"].numpy()
     num_pi = int((p["pis"] > 0).sum())
     np.testing.assert_allclose((g3["pis"] - g2["pis"])[live], 0.5 / num_pi - 0.5 / cfg.start_pis, atol=1e-12)
+
+
+# ----------------------------------------------------------------------------------------------------
+# SSIM loss (ssim_opt, smoe.py:981-1010) and overlap_of_batches (smoe.py:18-35, 909-923)
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nd", [2, 3])
+def test_torch_ssim_matches_the_numpy_restatement(nd):
+    from oracle.graph import _symmetric_pad, custom_ssim_torch
+    from oracle.ssim import smoe_ssim
+    rs = np.random.RandomState(nd)
+    shp = (14, 17, 3) if nd == 2 else (7, 12, 6, 3)
+    a, b = rs.uniform(0, 1, shp), rs.uniform(0, 1, shp)
+    per = custom_ssim_torch(_symmetric_pad(torch.tensor(a), nd), _symmetric_pad(torch.tensor(b), nd), nd).numpy()
+    _, ref = smoe_ssim(a, b, use_yuv=False, dtype=np.float64)
+    np.testing.assert_allclose(per, ref, rtol=1e-10)
+    assert abs(float(custom_ssim_torch(_symmetric_pad(torch.tensor(a), nd), _symmetric_pad(torch.tensor(a), nd), nd)
+                     .mean()) - 1) < 1e-12
+
+
+def test_ssim_loss_and_overlap_in_the_oracle_model():
+    from oracle.model import OracleAdam, OracleSmoe
+    rs = np.random.RandomState(0)
+    v, u = np.meshgrid(np.linspace(0, 1, 24), np.linspace(0, 1, 32), indexing="ij")
+    img = np.clip(0.5 + 0.3 * np.sin(5 * u + 3 * v)[..., None] + 0.05 * rs.standard_normal((24, 32, 3)), 0, 1)
+    img = (np.round(img * 255) / 255).astype(np.float32)
+    kw = dict(use_determinant=True, train_inverse_cov=False, use_yuv=True, start_batches=4, dtype=torch.float64)
+    o0 = OracleSmoe(img, kernels_per_dim=[4, 4], **kw)
+    o1 = OracleSmoe(img, kernels_per_dim=[4, 4], overlap_of_batches=3, **kw)
+    for o in (o0, o1):
+        o.set_optimizer(OracleAdam(1e-3), OracleAdam(1e-5), OracleAdam(1.0))
+    r0 = o0.run_batched(train=True, update_reconstruction=True)
+    r1 = o1.run_batched(train=True, update_reconstruction=True)
+    # the halo is cropped before the loss: same loss, same gradients, same reconstruction ...
+    assert abs(r0[0] - r1[0]) < 1e-12 and abs(r0[1] - r1[1]) < 1e-9
+    for k in o0.last_grads:
+        np.testing.assert_allclose(o0.last_grads[k], o1.last_grads[k], atol=1e-12)
+    np.testing.assert_array_equal(o0.reconstruction_image, o1.reconstruction_image)
+    # ... but the influence lists also see the halo pixels (and the zero padding at coordinate 0)
+    assert all((b1 | b0 == b1).all() for b0, b1 in zip(o0.kernel_list_per_batch, o1.kernel_list_per_batch))
+    assert sum(int(b1.sum() - b0.sum()) for b0, b1 in zip(o0.kernel_list_per_batch, o1.kernel_list_per_batch)) > 0
+    # SSIM loss: 1 - weighted SSIM per batch; decreases under training
+    o2 = OracleSmoe(img, kernels_per_dim=[4, 4], ssim_opt=True, overlap_of_batches=2, **kw)
+    o2.set_optimizer(OracleAdam(1e-3), OracleAdam(1e-5), OracleAdam(0.1))
+    l_first = o2.run_batched(train=True)[0]
+    assert 0 < l_first < 1
+    for _ in range(15):
+        l_last = o2.run_batched(train=True)[0]
+    assert l_last < l_first

@@ -343,7 +343,7 @@ def kernel_times(m, steps, with_step=True):
     b = m._batches[0]
     counts, regs, scal = m._counts[0], m._regsums[0], m._scalars[0]
     ax2 = ptr(m._d_axes[2]) if m.dim_domain == 3 else ptr(None)
-    check(L.smoe_pack(C.byref(m._cfg), ptr(m._theta), ptr(m._mus_grid), ptr(m._klist[0]), m.start_pis, ptr(m._packed), ptr(m._indices),
+    check(L.smoe_pack(C.byref(m._cfg), ptr(m._theta), ptr(m._mus_grid), ptr(None), ptr(m._klist[0]), m.start_pis, ptr(m._packed), ptr(m._indices),
                       ptr(m._pos), ptr(counts), ptr(regs), ptr(m._chunk_bounds), ptr(m._pack_ws), st), "pack")
     fw, bw = [], []
     for _ in range(steps + 1):

@@ -72,6 +72,8 @@ typedef struct smoe_cfg {
     int32_t pis_bits;          /* bit_depths[3]                                             */
     int32_t quantization_mode; /* 2: every parameter is fake-quantised with the fixed bounds below before use,
                                   gradients pass straight through inside the bounds (smoe.py:482-496);
+                                  3: the same with the min / max of the surviving kernels instead of fixed
+                                  bounds (smoe.py:497-531; q_bits only, see smoe_quant_ranges);
                                   0/1: parameters are used as they are (mode 1 quantises on the host only) */
     float   q_lb[5], q_ub[5];  /* lower_bounds / upper_bounds in the reference's order: A, musX, nu_e, pis,
                                   gamma_e (smoe_test.py:306-309)                                        */
@@ -127,6 +129,7 @@ size_t      smoe_backward_workspace_bytes(const smoe_cfg* cfg, int K_cap, int nu
  *   chunk_bounds: per 128 consecutive active kernels, bounding box of the centres, smallest
  *   eigenvalue bound and largest c0 -- the coarse level of the exact culling in smoe_forward */
 int smoe_pack(const smoe_cfg* cfg, const float* theta, const float* mus_grid /*[K_all][d], use_diff_center only*/,
+              const void* quant_ranges /* quantization_mode 3 only, from smoe_quant_ranges */,
               const uint8_t* kernel_list, int K_all,
               float* packed, int32_t* indices, int32_t* pos /*[K_all]: packed row of each kernel or -1*/,
               int32_t* counts, float* regsums,
@@ -191,8 +194,29 @@ int smoe_reduce_splits(const smoe_cfg* cfg, const int32_t* counts, int K_cap, in
  * (assign_add, smoe.py:1150).  Also rewrites kernel_list[indices[k]] = infl[k] when infl != NULL
  * (smoe.py:1763-1766). */
 int smoe_grad_finalize(const smoe_cfg* cfg, const float* raw, int num_splits, int K_cap, const float* theta,
+                       const void* quant_ranges /* quantization_mode 3 only */,
                        const int32_t* indices, const int32_t* counts, float pis_l1, float l1_norm /* start_pis */,
                        float u_l1, float* grads, void* stream);
+
+/* quantization_mode 3 (smoe.py:497-531): fake_quant_with_min_max_vars whose min / max are reduce_min / reduce_max
+ * over the kernels with a positive (fake-quantised) pi.  smoe_quant_ranges computes those ranges and TF's nudged
+ * scales on the device (no host read-back) into an opaque block of smoe_quant_ranges_bytes() that smoe_pack,
+ * smoe_grad_finalize, smoe_fake_quant_theta and smoe_quant_route take; call it once per training step, before the
+ * first smoe_pack.  A_diagonal (over its diagonal) and nu_e use the shifted form fq(x - min; 0, max - min) + min,
+ * A_corr, musX (only when train_musx) and gamma_e the plain form; pis keep their fixed bounds.
+ * smoe_quant_route finishes the gradient of the plain groups on the ACCUMULATED `grads`, once per step before
+ * smoe_adam_step: elements outside the nudged range lose their gradient to `min` / `max`, i.e. to the extreme
+ * elements of the kept kernels (equal shares among ties).
+ * smoe_fake_quant_theta writes the variables as the graph uses them (modes 2 and 3 and quantize_pis; what
+ * get_params returns, smoe.py:1796-1798); structural[0..1] (optional) receive what the structural zeros of
+ * A_diagonal (off-diagonal) and A_corr (diagonal and above) turn into. */
+size_t smoe_quant_ranges_bytes(void);
+int smoe_quant_ranges(const smoe_cfg* cfg, const float* theta, int K_all, int train_musx, void* quant_ranges,
+                      void* stream);
+int smoe_quant_route(const smoe_cfg* cfg, const float* theta, const void* quant_ranges, int K_all, float* grads,
+                     void* stream);
+int smoe_fake_quant_theta(const smoe_cfg* cfg, const float* theta, const void* quant_ranges, int K_all, float* out,
+                          float* structural /*[2]*/, void* stream);
 
 /* kernel_list[i] = 0 for all i, then kernel_list[indices[k]] = infl[k] (smoe.py:1763-1766). */
 int smoe_update_kernel_list(const int32_t* indices, const int32_t* counts, const uint8_t* infl,

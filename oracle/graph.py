@@ -122,10 +122,74 @@ def fake_quant_var(x, mn, mx, bits):
     return x * mask + (q - x * mask).detach()                   # value q, gradient = straight-through mask
 
 
-def effective_params(params, cfg):
-    """The q* tensors of smoe.py:482-496, 534-538: mode 2 fake-quantises every variable with the fixed
-    bounds (order A, musX, nu_e, pis, gamma_e: smoe_test.py:302-309); modes 0/1 use them as they are.
-    `pis` is handled by the caller (smoe.py:474-478)."""
+class _FakeQuantVarsMasked(torch.autograd.Function):
+    """tf.quantization.fake_quant_with_min_max_vars whose min / max are reduce_min / reduce_max over the rows
+    with pis > 0 (smoe.py:497-531), in the two forms the reference uses:
+      plain   q = fq(x; min, max)                      (A_corr, musX, gamma_e)
+      shifted q = fq(x - min; 0, max - min) + min      (A_diagonal over its diagonal entries, nu_e)
+    TF kernel semantics (FakeQuantWithMinMaxVarsFunctor / ...GradientFunctor, float32): min == max == 0 returns
+    zeros and passes the gradient; otherwise Nudge(), clamp, round; the gradient passes where
+    nudged_min <= x <= nudged_max, the gradients of elements below / above go to `min` / `max`, and from there
+    through reduce_min / reduce_max (equal shares among ties) back to the extreme kept elements.  For the shifted
+    form all of that cancels to a plain pass-through for the kept elements (d q_i / d min = -1 + 1)."""
+
+    @staticmethod
+    def forward(ctx, x, keep_rows, bits, shifted, sel):
+        f = np.float32
+        x32 = x.detach().to(torch.float32)
+        keep = keep_rows.reshape((-1,) + (1,) * (x.dim() - 1)).expand_as(x32)
+        pool = keep if sel is None else (keep & sel)          # elements the reduce_min / reduce_max run over
+        if not bool(pool.any()):
+            ctx.mode = "pass"
+            return x.clone()
+        mn, mx = f(x32[pool].min().item()), f(x32[pool].max().item())
+        lo, hi = (f(0.0), f(mx - mn)) if shifted else (mn, mx)
+        shift = mn if shifted else f(0.0)
+        if lo == 0 and hi == 0:
+            ctx.mode = "pass"
+            return (torch.zeros_like(x32) + float(shift)).to(x.dtype)
+        nmin, nmax, scale = _nudge(float(lo), float(hi), bits)
+        xs = x32 - float(shift)
+        q = fq_values(xs, nmin, nmax, scale) + float(shift)
+        if shifted:
+            ctx.mode = "pass"
+        else:
+            ctx.mode = "route"
+            below, above = xs < nmin, xs > nmax
+            ctx.save_for_backward(below, above, pool & (x32 == float(mn)), pool & (x32 == float(mx)))
+        return q.to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.mode == "pass":
+            return g, None, None, None, None
+        below, above, is_min, is_max = ctx.saved_tensors
+        gin = g * (~(below | above)).to(g.dtype)
+        gin = gin + is_min.to(g.dtype) * ((g * below.to(g.dtype)).sum() / is_min.sum())
+        gin = gin + is_max.to(g.dtype) * ((g * above.to(g.dtype)).sum() / is_max.sum())
+        return gin, None, None, None, None
+
+
+def effective_params(params, cfg, train_musx=True):
+    """The q* tensors of smoe.py:482-538: mode 2 fake-quantises every variable with the fixed bounds (order
+    A, musX, nu_e, pis, gamma_e: smoe_test.py:302-309), mode 3 with the min / max over the kernels whose
+    quantised pi is positive (pis keep their fixed bounds); modes 0/1 use the variables as they are.
+    `pis` itself is handled by the caller (smoe.py:474-478)."""
+    if cfg.quantization_mode == 3:
+        bd = cfg.bit_depths
+        qpis = fake_quant_args(params["pis"].detach(), cfg.lower_bounds[3], cfg.upper_bounds[3], bd[3])
+        keep = qpis > 0                                                          # pis_mask, smoe.py:480
+        d = params["A_diagonal"].shape[-1]
+        eye = torch.eye(d, dtype=torch.bool).expand_as(params["A_diagonal"])
+        out = dict(params)
+        fqv = _FakeQuantVarsMasked.apply
+        out["A_diagonal"] = fqv(params["A_diagonal"], keep, bd[0], True, eye)    # smoe.py:506-511 (diag_part)
+        out["A_corr"] = fqv(params["A_corr"], keep, bd[0], False, None)          # smoe.py:512-515
+        if train_musx:
+            out["musX"] = fqv(params["musX"], keep, bd[1], False, None)          # smoe.py:516-522
+        out["nu_e"] = fqv(params["nu_e"], keep, bd[2], True, None)               # smoe.py:524-527
+        out["gamma_e"] = fqv(params["gamma_e"], keep, bd[4], False, None)        # smoe.py:529-532
+        return out
     if cfg.quantization_mode != 2:
         return params
     lb, ub, bd = cfg.lower_bounds, cfg.upper_bounds, cfg.bit_depths
@@ -219,7 +283,8 @@ def _maha(x_sub_mu, A, train_inverse_cov, mode):
 def graph_forward(params: Dict[str, torch.Tensor], kernel_list, domain, target, cfg: GraphCfg,
                   pis_l1=0.0, u_l1=0.0, loss_weights=None, musX_grid=None,
                   feed: Optional[Dict[str, torch.Tensor]] = None,
-                  resq_override: Optional[torch.Tensor] = None, crop=None) -> Dict[str, torch.Tensor]:
+                  resq_override: Optional[torch.Tensor] = None, crop=None,
+                  train_musx: bool = True) -> Dict[str, torch.Tensor]:
     """One `session.run` of the reference graph on one batch of pixels.
 
     params : K_all-sized variables (pis, musX, A_diagonal, A_corr, gamma_e, nu_e)
@@ -236,8 +301,8 @@ def graph_forward(params: Dict[str, torch.Tensor], kernel_list, domain, target, 
     """
     dt = domain.dtype
     d, C = cfg.dim_domain, cfg.num_channels
-    if cfg.quantization_mode >= 3:
-        raise NotImplementedError("fake-quant training mode 3 is a 'next' row (SURVEY 8f-3)")
+    if cfg.quantization_mode > 3:
+        raise ValueError("quantization_mode must be 0..3")
 
     pis_var = params["pis"]
     # smoe.py:474-480
@@ -249,7 +314,7 @@ def graph_forward(params: Dict[str, torch.Tensor], kernel_list, domain, target, 
     bool_mask = torch.as_tensor(kernel_list, dtype=torch.bool) & pis_mask.detach()
     indices = torch.nonzero(bool_mask).flatten()
 
-    params = effective_params(params, cfg)                          # smoe.py:482-496 (mode 2), else identity
+    params = effective_params(params, cfg, train_musx)              # smoe.py:482-538 (modes 2, 3), else identity
     gamma_all = params["gamma_e"]
     if cfg.use_yuv and cfg.train_gammas and cfg.only_y_gamma:       # smoe.py:725-729
         gmask = torch.zeros(d, C, dtype=dt)

@@ -190,7 +190,7 @@ class OracleSmoe:
                     ovr = ovr[torch.as_tensor(samples)]
             out = graph_forward(leaf, self.kernel_list_per_batch[ii], domain, target, self.cfg,
                                 pis_l1, u_l1, musX_grid=self.musX_grid, feed=feed, resq_override=ovr,
-                                loss_weights=lw, crop=(batch.shape[:-1], ov))
+                                loss_weights=lw, crop=(batch.shape[:-1], ov), train_musx=self.train_musx)
             if train and trainable:
                 gs = torch.autograd.grad(out["loss"], [leaf[n] for n in trainable], allow_unused=True)
                 for n, g in zip(trainable, gs):
@@ -233,7 +233,7 @@ class OracleSmoe:
         from itertools import product as _product
         from .graph import assemble_A, effective_params
         d = self.dim_domain
-        eff = effective_params({k: v.detach() for k, v in self.vars.items()}, self.cfg)
+        eff = effective_params({k: v.detach() for k, v in self.vars.items()}, self.cfg, self.train_musx)
         A = assemble_A(eff["A_diagonal"], eff["A_corr"], self.cfg.train_inverse_cov).double()
         mu = eff["musX"].double()
         if self.use_diff_center:
@@ -311,7 +311,7 @@ class OracleSmoe:
     # -- getters --------------------------------------------------------------------
     def get_params(self):
         from .graph import effective_params
-        eff = effective_params({k: v.detach() for k, v in self.vars.items()}, self.cfg)   # smoe.py:1796-1798
+        eff = effective_params({k: v.detach() for k, v in self.vars.items()}, self.cfg, self.train_musx)   # smoe.py:1796-1798
         out = {k: v.numpy().astype(np.float32).copy() for k, v in eff.items()}
         if self.quantize_pis or self.quantization_mode >= 2:
             from .graph import fake_quant_args

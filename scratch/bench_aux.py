@@ -60,7 +60,7 @@ out["psnr_4k"] = {"ms": ms_sq, "algorithmic_GBps": alg / ms_sq / 1e6, "frac_of_m
 # ---- pi-mask compaction on the 518,400-kernel grid of config 5 ----------------------------------------
 Kall, P, PK = smoe.start_pis, smoe._P, smoe._PK
 smoe._theta[:, smoe._off["pi"]] = torch.where(torch.rand(Kall, device="cuda") < 0.7, 1.0, -1.0)
-ms_pack = timeit(lambda: check(lib().smoe_pack(C.byref(smoe._cfg), ptr(smoe._theta), ptr(smoe._mus_grid), ptr(smoe._klist[0]), Kall, ptr(smoe._packed),
+ms_pack = timeit(lambda: check(lib().smoe_pack(C.byref(smoe._cfg), ptr(smoe._theta), ptr(smoe._mus_grid), ptr(None), ptr(smoe._klist[0]), Kall, ptr(smoe._packed),
                                                ptr(smoe._indices), ptr(smoe._pos), ptr(smoe._counts[0]), ptr(smoe._regsums[0]),
                                                ptr(smoe._chunk_bounds), ptr(smoe._pack_ws), stream_ptr()), "pack"))
 Ka = int(smoe._counts[0, 0])

@@ -20,7 +20,7 @@ EXPORTS = [
     "smoe_abi_version", "smoe_last_error", "smoe_param_count", "smoe_packed_stride", "smoe_num_tiles", "smoe_pix_stride",
     "smoe_pack_workspace_bytes", "smoe_backward_workspace_bytes", "smoe_pack", "smoe_pack_fed", "smoe_forward", "smoe_ssim_loss_workspace_bytes", "smoe_ssim_loss",
     "smoe_backward", "smoe_suggest_splits", "smoe_reduce_splits", "smoe_grad_finalize", "smoe_update_kernel_list",
-    "smoe_adam_step", "smoe_ssim_workspace_bytes", "smoe_ssim", "smoe_sqerr", "smoe_quantize", "smoe_rescale",
+    "smoe_adam_step", "smoe_quant_ranges_bytes", "smoe_quant_ranges", "smoe_quant_route", "smoe_fake_quant_theta", "smoe_ssim_workspace_bytes", "smoe_ssim", "smoe_sqerr", "smoe_quantize", "smoe_rescale",
     "smoe_colminmax",
 ]
 
@@ -62,7 +62,7 @@ def lib():
         _lib = C.CDLL(LIB_PATH)
         _lib.smoe_last_error.restype = C.c_char_p
         for name in ("smoe_pack_workspace_bytes", "smoe_backward_workspace_bytes", "smoe_ssim_workspace_bytes",
-                     "smoe_ssim_loss_workspace_bytes"):
+                     "smoe_ssim_loss_workspace_bytes", "smoe_quant_ranges_bytes"):
             getattr(_lib, name).restype = C.c_size_t
         if _lib.smoe_abi_version() != 1:
             raise RuntimeError("libsmoe_b200.so ABI version mismatch")

@@ -466,7 +466,8 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(smoe_cfg cfg, const 
                                                             int K_cap, const float* __restrict__ theta,
                                                             const int32_t* __restrict__ indices,
                                                             const int32_t* __restrict__ counts, float pis_l1,
-                                                            float l1_norm, float u_l1, QuantSet qs,
+                                                            float l1_norm, float u_l1, QuantSet qs_in,
+                                                            const QuantDyn* __restrict__ qdyn,
                                                             float* __restrict__ grads) {
     constexpr int T = tri(D);
     constexpr int P = nparam(D, C);
@@ -483,7 +484,8 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(smoe_cfg cfg, const 
     const int row = indices[k];
     const float* th = theta + (size_t)row * P;
     float* gr = grads + (size_t)row * P;
-    const bool fq = qs.mode == 2;
+    const QuantSet qs = qs_in.mode == 3 ? qdyn->qs : qs_in;
+    const bool fq = qs.mode >= 2;
     const float l1 = pis_l1 / (cfg.kernel_count_as_norm_l1 ? (float)counts[1] : l1_norm);     // smoe.py:1022-1027
     float A[D][D], steA[D][D];
 #pragma unroll
@@ -491,8 +493,8 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(smoe_cfg cfg, const 
 #pragma unroll
         for (int m = 0; m < D; ++m) {
             float v = (m <= l) ? th[off_A(D, C) + lt(l, m)] : 0.f;
-            steA[l][m] = (fq && m <= l) ? ste_mask(v, qs.g[0]) : 1.f;
-            if (fq && m <= l) v = fake_quant(v, qs.g[0]);
+            steA[l][m] = (fq && m <= l) ? ste_mask(v, qs.g[m == l ? QG_AD : QG_AC]) : 1.f;
+            if (fq && m <= l) v = fake_quant(v, qs.g[m == l ? QG_AD : QG_AC]);
             A[l][m] = v;
         }
     float V[D], Dm[D][D];
@@ -507,8 +509,8 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(smoe_cfg cfg, const 
     float pi = th[off_pi(D, C)];
     float ste = 1.f;
     if (cfg.quantize_pis) {
-        ste = ste_mask(pi, qs.g[3]);
-        pi = fake_quant(pi, qs.g[3]);
+        ste = ste_mask(pi, qs.g[QG_PI]);
+        pi = fake_quant(pi, qs.g[QG_PI]);
     }
     gr[off_pi(D, C)] += (M0 / pi + l1) * ste;
     // mu and A
@@ -555,7 +557,7 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(smoe_cfg cfg, const 
     }
 #pragma unroll
     for (int l = 0; l < D; ++l) {
-        gr[off_mu(D, C) + l] += fq ? gmu[l] * ste_mask(th[off_mu(D, C) + l], qs.g[1]) : gmu[l];
+        gr[off_mu(D, C) + l] += fq ? gmu[l] * ste_mask(th[off_mu(D, C) + l], qs.g[QG_MU]) : gmu[l];
 #pragma unroll
         for (int m = 0; m <= l; ++m) {
             float gv = gA[l][m];
@@ -568,13 +570,13 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(smoe_cfg cfg, const 
     }
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        gr[off_nu(D, C) + c] += fq ? s[off_nu(D, C) + c] * ste_mask(th[off_nu(D, C) + c], qs.g[2]) : s[off_nu(D, C) + c];
+        gr[off_nu(D, C) + c] += fq ? s[off_nu(D, C) + c] * ste_mask(th[off_nu(D, C) + c], qs.g[QG_NU]) : s[off_nu(D, C) + c];
 #pragma unroll
         for (int l = 0; l < D; ++l) {
             float gv = s[off_ga(D, C) + l * C + c];
             if (!cfg.train_gammas) gv = 0.f;
             if (cfg.use_yuv && cfg.only_y_gamma && c > 0) gv = 0.f;
-            if (fq) gv *= ste_mask(th[off_ga(D, C) + l * C + c], qs.g[4]);
+            if (fq) gv *= ste_mask(th[off_ga(D, C) + l * C + c], qs.g[QG_GA]);
             gr[off_ga(D, C) + l * C + c] += gv;
         }
     }
@@ -665,16 +667,17 @@ int smoe_reduce_splits(const smoe_cfg* cfg, const int32_t* counts, int K_cap, in
 }
 
 int smoe_grad_finalize(const smoe_cfg* cfg, const float* raw, int num_splits, int K_cap, const float* theta,
-                       const int32_t* indices, const int32_t* counts, float pis_l1, float l1_norm, float u_l1,
-                       float* grads, void* stream) {
+                       const void* quant_ranges, const int32_t* indices, const int32_t* counts, float pis_l1,
+                       float l1_norm, float u_l1, float* grads, void* stream) {
     SMOE_REQUIRE(cfg && raw && theta && indices && counts && grads && K_cap > 0 && num_splits > 0, "bad argument");
+    SMOE_REQUIRE(cfg->quantization_mode != 3 || quant_ranges, "quantization_mode 3 needs quant_ranges");
     SMOE_REQUIRE(cfg->kernel_count_as_norm_l1 || l1_norm > 0.f, "l1_norm must be positive");
     const QuantSet qs = make_quantset(cfg);
     int nb = (K_cap + 255) / 256;
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL(D, C)                                                                                              \
     grad_finalize_kernel<D, C><<<nb, 256, 0, st>>>(*cfg, raw, num_splits, K_cap, theta, indices, counts, pis_l1, \
-                                                   l1_norm, u_l1, qs, grads);
+                                                   l1_norm, u_l1, qs, (const QuantDyn*)quant_ranges, grads);
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL
     return check_launch("smoe_grad_finalize");

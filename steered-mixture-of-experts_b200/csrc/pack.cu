@@ -33,7 +33,9 @@ struct PackBlk { int32_t count, numpi, nonpos, pad; float sum_pi, sum_diag; };
 template <int D, int C>
 __global__ void __launch_bounds__(256) pack_count_kernel(const float* __restrict__ theta,
                                                          const uint8_t* __restrict__ klist, int K_all,
-                                                         int quantize_pis, QuantSet qs, PackBlk* __restrict__ blk) {
+                                                         int quantize_pis, QuantSet qs_in,
+                                                         const QuantDyn* __restrict__ qdyn, PackBlk* __restrict__ blk) {
+    const QuantSet qs = qs_in.mode == 3 ? qdyn->qs : qs_in;
     constexpr int P = nparam(D, C);
     int i = blockIdx.x * 256 + threadIdx.x;
     int flag = 0, numpi = 0;
@@ -41,7 +43,7 @@ __global__ void __launch_bounds__(256) pack_count_kernel(const float* __restrict
     if (i < K_all) {
         const float* row = theta + (size_t)i * P;
         float pi = row[off_pi(D, C)];
-        if (quantize_pis) pi = fake_quant(pi, qs.g[3]);
+        if (quantize_pis) pi = fake_quant(pi, qs.g[QG_PI]);
         numpi = pi > 0.f;
         flag = numpi && klist[i];
         if (flag) {
@@ -49,7 +51,7 @@ __global__ void __launch_bounds__(256) pack_count_kernel(const float* __restrict
 #pragma unroll
             for (int l = 0; l < D; ++l) {
                 float a = row[off_A(D, C) + lt(l, l)];
-                if (qs.mode == 2) a = fake_quant(a, qs.g[0]);
+                if (qs.mode >= 2) a = fake_quant(a, qs.g[QG_AD]);
                 sdiag += a;
             }
         }
@@ -220,12 +222,14 @@ __global__ void __launch_bounds__(kChunk) chunk_bounds_kernel(const float* __res
 template <int D, int C>
 __global__ void __launch_bounds__(256) pack_scatter_kernel(smoe_cfg cfg, const float* __restrict__ theta,
                                                            const float* __restrict__ mus_grid,
-                                                           const uint8_t* __restrict__ klist, int K_all, QuantSet qs,
+                                                           const uint8_t* __restrict__ klist, int K_all, QuantSet qs_in,
+                                                           const QuantDyn* __restrict__ qdyn,
                                                            const PackBlk* __restrict__ blk, float* __restrict__ packed,
                                                            int32_t* __restrict__ indices, int32_t* __restrict__ pos,
                                                            int32_t* __restrict__ counts,
                                                            float* __restrict__ regsums, int32_t* __restrict__ nonpos_blk) {
     constexpr int P = nparam(D, C), PK = pstride(D, C);
+    const QuantSet qs = qs_in.mode == 3 ? qdyn->qs : qs_in;
     __shared__ int s_red[8];
     __shared__ int s_warp[8];
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -245,7 +249,7 @@ __global__ void __launch_bounds__(256) pack_scatter_kernel(smoe_cfg cfg, const f
     const float* row = theta + (size_t)min(i, K_all - 1) * P;
     if (i < K_all) {
         pi = row[off_pi(D, C)];
-        if (cfg.quantize_pis) pi = fake_quant(pi, qs.g[3]);
+        if (cfg.quantize_pis) pi = fake_quant(pi, qs.g[QG_PI]);
         flag = (pi > 0.f) && klist[i];
     }
     unsigned bal = __ballot_sync(0xffffffffu, flag);
@@ -260,13 +264,13 @@ __global__ void __launch_bounds__(256) pack_scatter_kernel(smoe_cfg cfg, const f
         indices[dst] = i;
         // the variables, fake-quantised when quantization_mode == 2 (smoe.py:482-496)
         float A[D][D], mu[D], nu[C], ga[D * C];
-        const bool fq = qs.mode == 2;
+        const bool fq = qs.mode >= 2;
 #pragma unroll
         for (int l = 0; l < D; ++l)
 #pragma unroll
             for (int m = 0; m < D; ++m) {
                 float v = (m <= l) ? row[off_A(D, C) + lt(l, m)] : 0.f;
-                if (fq && m <= l) v = fake_quant(v, qs.g[0]);
+                if (fq && m <= l) v = fake_quant(v, qs.g[m == l ? QG_AD : QG_AC]);
                 A[l][m] = v;
             }
         if (cfg.train_inverse_cov) {
@@ -278,14 +282,14 @@ __global__ void __launch_bounds__(256) pack_scatter_kernel(smoe_cfg cfg, const f
 #pragma unroll
         for (int l = 0; l < D; ++l) {
             float v = row[off_mu(D, C) + l];
-            if (fq) v = fake_quant(v, qs.g[1]);
+            if (fq) v = fake_quant(v, qs.g[QG_MU]);
             if (cfg.use_diff_center) v += mus_grid[(size_t)i * D + l];       // smoe.py:746-747
             mu[l] = v;
         }
 #pragma unroll
-        for (int c = 0; c < C; ++c) nu[c] = fq ? fake_quant(row[off_nu(D, C) + c], qs.g[2]) : row[off_nu(D, C) + c];
+        for (int c = 0; c < C; ++c) nu[c] = fq ? fake_quant(row[off_nu(D, C) + c], qs.g[QG_NU]) : row[off_nu(D, C) + c];
 #pragma unroll
-        for (int j = 0; j < D * C; ++j) ga[j] = fq ? fake_quant(row[off_ga(D, C) + j], qs.g[4]) : row[off_ga(D, C) + j];
+        for (int j = 0; j < D * C; ++j) ga[j] = fq ? fake_quant(row[off_ga(D, C) + j], qs.g[QG_GA]) : row[off_ga(D, C) + j];
         neg = stage_record<D, C>(cfg, A, mu, pi, nu, ga, packed + (size_t)dst * PK);
     }
     int negs = __syncthreads_count(neg);
@@ -337,6 +341,208 @@ __global__ void klist_set_kernel(const int32_t* __restrict__ indices, const int3
     if (k < counts[0] && infl[k]) klist[indices[k]] = 1;
 }
 
+
+// ---- quantization_mode 3: data-dependent fake-quant ranges (smoe.py:497-531) ---------------------------------
+// min / max of every parameter group over the kernels whose (fake-quantised) pi is positive, then TF's Nudge().
+// One CTA, fixed-order reductions.  Forms (oracle/graph.py:_FakeQuantVarsMasked):
+//   A diagonal, nu_e : q = fq(x - min; 0, max - min) + min         (shifted; straight-through)
+//   A_corr, musX, gamma_e : q = fq(x; min, max)                    (plain; clipped gradients go to the extremes)
+// A_corr's reduce_min / reduce_max run over the whole (d, d) blocks of the variable, whose diagonal and upper
+// entries are structural zeros, so 0 always takes part.
+template <int D, int C>
+__global__ void __launch_bounds__(1024) quant_ranges_kernel(smoe_cfg cfg, QuantSet qs_static, int train_musx,
+                                                            const float* __restrict__ theta, int K_all,
+                                                            QuantDyn* __restrict__ out) {
+    constexpr int P = nparam(D, C);
+    float mn[6], mx[6];
+#pragma unroll
+    for (int g = 0; g < 6; ++g) { mn[g] = INFINITY; mx[g] = -INFINITY; }
+    int kept = 0;
+    for (int i = threadIdx.x; i < K_all; i += 1024) {
+        const float* row = theta + (size_t)i * P;
+        if (!(fake_quant(row[off_pi(D, C)], qs_static.g[QG_PI]) > 0.f)) continue;          // pis_mask, smoe.py:480
+        kept = 1;
+        auto upd = [&](int g, float v) { mn[g] = fminf(mn[g], v); mx[g] = fmaxf(mx[g], v); };
+#pragma unroll
+        for (int l = 0; l < D; ++l) {
+            upd(QG_MU, row[off_mu(D, C) + l]);
+#pragma unroll
+            for (int m = 0; m <= l; ++m) upd(m == l ? QG_AD : QG_AC, row[off_A(D, C) + lt(l, m)]);
+        }
+        upd(QG_AC, 0.f);
+#pragma unroll
+        for (int c = 0; c < C; ++c) upd(QG_NU, row[off_nu(D, C) + c]);
+#pragma unroll
+        for (int j = 0; j < D * C; ++j) upd(QG_GA, row[off_ga(D, C) + j]);
+    }
+    __shared__ float s_mn[32][6], s_mx[32][6];
+    __shared__ int s_kept[32];
+#pragma unroll
+    for (int g = 0; g < 6; ++g)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[g] = fminf(mn[g], __shfl_xor_sync(0xffffffffu, mn[g], o));
+            mx[g] = fmaxf(mx[g], __shfl_xor_sync(0xffffffffu, mx[g], o));
+        }
+    kept = __any_sync(0xffffffffu, kept);
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int g = 0; g < 6; ++g) { s_mn[threadIdx.x >> 5][g] = mn[g]; s_mx[threadIdx.x >> 5][g] = mx[g]; }
+        s_kept[threadIdx.x >> 5] = kept;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    kept = 0;
+    for (int w = 0; w < 32; ++w) {
+        kept |= s_kept[w];
+#pragma unroll
+        for (int g = 0; g < 6; ++g) { mn[g] = fminf(mn[g], s_mn[w][g]); mx[g] = fmaxf(mx[g], s_mx[w][g]); }
+    }
+    QuantDyn q;
+    q.qs = qs_static;
+    q.qs.mode = 3;
+    const int bits[6] = {cfg.q_bits[0], cfg.q_bits[1], cfg.q_bits[2], cfg.q_bits[3], cfg.q_bits[4], cfg.q_bits[0]};
+    for (int g = 0; g < 6; ++g) {
+        q.mn[g] = mn[g];
+        q.mx[g] = mx[g];
+        if (g == QG_PI) continue;                                  // pis keep their fixed bounds (smoe.py:474-478)
+        Nudged n = {0.f, 0.f, 1.f, 1.f, 0.f, QF_IDENT};
+        const bool shifted = g == QG_AD || g == QG_NU;
+        if (kept && !(g == QG_MU && !train_musx)) {
+            const float lo = shifted ? 0.f : mn[g], hi = shifted ? __fsub_rn(mx[g], mn[g]) : mx[g];
+            if (lo == 0.f && hi == 0.f) {
+                n.flags = QF_ZERO;
+            } else {
+                n = nudge(lo, hi, bits[g]);
+                n.flags = shifted ? QF_PASS : QF_ROUTE;
+            }
+            n.shift = shifted ? mn[g] : 0.f;
+        }
+        q.qs.g[g] = n;
+    }
+    *out = q;
+}
+
+// The variables as the graph uses them (the q* tensors, smoe.py:482-538; what get_params returns, smoe.py:1796-1798)
+template <int D, int C>
+__global__ void __launch_bounds__(256) fake_quant_theta_kernel(smoe_cfg cfg, QuantSet qs_in,
+                                                               const QuantDyn* __restrict__ qdyn,
+                                                               const float* __restrict__ theta, int K_all,
+                                                               float* __restrict__ out,
+                                                               float* __restrict__ structural) {
+    constexpr int P = nparam(D, C);
+    const QuantSet qs = qs_in.mode == 3 ? qdyn->qs : qs_in;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= K_all) return;
+    const float* row = theta + (size_t)i * P;
+    float* o = out + (size_t)i * P;
+    const bool fq = qs.mode >= 2;
+#pragma unroll
+    for (int l = 0; l < D; ++l) {
+        o[off_mu(D, C) + l] = fq ? fake_quant(row[off_mu(D, C) + l], qs.g[QG_MU]) : row[off_mu(D, C) + l];
+#pragma unroll
+        for (int m = 0; m <= l; ++m) {
+            const float v = row[off_A(D, C) + lt(l, m)];
+            o[off_A(D, C) + lt(l, m)] = fq ? fake_quant(v, qs.g[m == l ? QG_AD : QG_AC]) : v;
+        }
+    }
+    o[off_pi(D, C)] = cfg.quantize_pis ? fake_quant(row[off_pi(D, C)], qs.g[QG_PI]) : row[off_pi(D, C)];
+#pragma unroll
+    for (int c = 0; c < C; ++c) o[off_nu(D, C) + c] = fq ? fake_quant(row[off_nu(D, C) + c], qs.g[QG_NU]) : row[off_nu(D, C) + c];
+#pragma unroll
+    for (int j = 0; j < D * C; ++j) o[off_ga(D, C) + j] = fq ? fake_quant(row[off_ga(D, C) + j], qs.g[QG_GA]) : row[off_ga(D, C) + j];
+    if (i == 0 && structural) {   // what the structural zeros of A_diagonal (off-diagonal) / A_corr (diagonal, upper) become
+        structural[0] = fq ? fake_quant(0.f, qs.g[QG_AD]) : 0.f;
+        structural[1] = fq ? fake_quant(0.f, qs.g[QG_AC]) : 0.f;
+    }
+}
+
+// Mode-3 gradient routing for the plain groups (A_corr, musX, gamma_e), applied once to the accumulated gradient
+// before Adam: in-range elements keep their gradient; the gradients of elements below nudged_min / above
+// nudged_max go to the `min` / `max` inputs of fake_quant_with_min_max_vars and from there, through
+// reduce_min / reduce_max (equal shares among ties), to the extreme elements of the kept kernels.  When the
+// extreme of A_corr is one of its structural zeros, that share lands on a variable entry the graph never reads;
+// it is dropped here (deviation from HEAD, which would start moving that unused entry).
+template <int D, int C>
+__global__ void __launch_bounds__(1024) quant_route_kernel(QuantSet qs_static, const QuantDyn* __restrict__ qdyn,
+                                                           const float* __restrict__ theta, int K_all,
+                                                           float* __restrict__ grads) {
+    constexpr int P = nparam(D, C);
+    const QuantSet qs = qdyn->qs;
+    const int groups[3] = {QG_AC, QG_MU, QG_GA};
+    __shared__ float s_sum[32][6];
+    __shared__ int s_cnt[32][6];
+    __shared__ float s_share[6];
+    float sum[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // [2*j]: below, [2*j+1]: above
+    int cnt[6] = {0, 0, 0, 0, 0, 0};                    // ties at min / max
+    auto visit = [&](auto&& fn) {
+        for (int i = threadIdx.x; i < K_all; i += 1024) {
+            const float* row = theta + (size_t)i * P;
+            if (!(fake_quant(row[off_pi(D, C)], qs_static.g[QG_PI]) > 0.f)) continue;
+            float* gr = grads + (size_t)i * P;
+#pragma unroll
+            for (int l = 0; l < D; ++l) {
+                fn(1, row[off_mu(D, C) + l], gr[off_mu(D, C) + l]);
+#pragma unroll
+                for (int m = 0; m < l; ++m) fn(0, row[off_A(D, C) + lt(l, m)], gr[off_A(D, C) + lt(l, m)]);
+            }
+#pragma unroll
+            for (int j = 0; j < D * C; ++j) fn(2, row[off_ga(D, C) + j], gr[off_ga(D, C) + j]);
+            // structural zeros of A_corr take part in the ties at min / max
+            if (qdyn->mn[QG_AC] == 0.f) cnt[0] += D * D - D * (D - 1) / 2;
+            if (qdyn->mx[QG_AC] == 0.f) cnt[1] += D * D - D * (D - 1) / 2;
+        }
+    };
+    visit([&](int j, float x, float& g) {
+        const Nudged n = qs.g[groups[j]];
+        if (!(n.flags & QF_ROUTE)) return;
+        if (x < n.nmin) sum[2 * j] += g;
+        if (x > n.nmax) sum[2 * j + 1] += g;
+        if (x == qdyn->mn[groups[j]]) cnt[2 * j] += 1;
+        if (x == qdyn->mx[groups[j]]) cnt[2 * j + 1] += 1;
+    });
+#pragma unroll
+    for (int q = 0; q < 6; ++q)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sum[q] += __shfl_down_sync(0xffffffffu, sum[q], o);
+            cnt[q] += __shfl_down_sync(0xffffffffu, cnt[q], o);
+        }
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+        for (int q = 0; q < 6; ++q) { s_sum[threadIdx.x >> 5][q] = sum[q]; s_cnt[threadIdx.x >> 5][q] = cnt[q]; }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float t = 0.f;
+        int c = 0;
+        for (int w = 0; w < 32; ++w) { t += s_sum[w][threadIdx.x]; c += s_cnt[w][threadIdx.x]; }
+        s_share[threadIdx.x] = c > 0 ? t / (float)c : 0.f;
+    }
+    __syncthreads();
+    // second sweep: mask + shares (cnt / sum are dead from here on)
+    for (int i = threadIdx.x; i < K_all; i += 1024) {
+        const float* row = theta + (size_t)i * P;
+        if (!(fake_quant(row[off_pi(D, C)], qs_static.g[QG_PI]) > 0.f)) continue;
+        float* gr = grads + (size_t)i * P;
+        auto fix = [&](int j, float x, float& g) {
+            const Nudged n = qs.g[groups[j]];
+            if (!(n.flags & QF_ROUTE)) return;
+            float v = (x >= n.nmin && x <= n.nmax) ? g : 0.f;
+            if (x == qdyn->mn[groups[j]]) v += s_share[2 * j];
+            if (x == qdyn->mx[groups[j]]) v += s_share[2 * j + 1];
+            g = v;
+        };
+#pragma unroll
+        for (int l = 0; l < D; ++l) {
+            fix(1, row[off_mu(D, C) + l], gr[off_mu(D, C) + l]);
+#pragma unroll
+            for (int m = 0; m < l; ++m) fix(0, row[off_A(D, C) + lt(l, m)], gr[off_A(D, C) + lt(l, m)]);
+        }
+#pragma unroll
+        for (int j = 0; j < D * C; ++j) fix(2, row[off_ga(D, C) + j], gr[off_ga(D, C) + j]);
+    }
+}
+
 }  // namespace smoe
 
 using namespace smoe;
@@ -358,11 +564,12 @@ size_t smoe_pack_workspace_bytes(int K_all) {
     return nb * sizeof(PackBlk) + nb * sizeof(int32_t) + 256;
 }
 
-int smoe_pack(const smoe_cfg* cfg, const float* theta, const float* mus_grid, const uint8_t* kernel_list, int K_all,
-              float* packed, int32_t* indices, int32_t* pos, int32_t* counts, float* regsums, float* chunk_bounds,
-              void* workspace, void* stream) {
+int smoe_pack(const smoe_cfg* cfg, const float* theta, const float* mus_grid, const void* quant_ranges,
+              const uint8_t* kernel_list, int K_all, float* packed, int32_t* indices, int32_t* pos, int32_t* counts,
+              float* regsums, float* chunk_bounds, void* workspace, void* stream) {
     SMOE_REQUIRE(!cfg || !cfg->use_diff_center || mus_grid, "use_diff_center needs mus_grid");
-    SMOE_REQUIRE(!cfg || cfg->quantization_mode <= 2, "quantization_mode 3 is not implemented");
+    SMOE_REQUIRE(!cfg || cfg->quantization_mode != 3 || quant_ranges, "quantization_mode 3 needs quant_ranges");
+    const QuantDyn* qdyn = (const QuantDyn*)quant_ranges;
     SMOE_REQUIRE(cfg && theta && kernel_list && packed && indices && pos && counts && regsums && chunk_bounds && workspace,
                  "null argument");
     SMOE_REQUIRE(K_all > 0, "K_all must be positive");
@@ -372,9 +579,9 @@ int smoe_pack(const smoe_cfg* cfg, const float* theta, const float* mus_grid, co
     int32_t* nonpos_blk = (int32_t*)((char*)workspace + (size_t)nb * sizeof(PackBlk));
     const QuantSet qs = make_quantset(cfg);
 #define CALL(D, C)                                                                                              \
-    pack_count_kernel<D, C><<<nb, 256, 0, st>>>(theta, kernel_list, K_all, cfg->quantize_pis, qs, blk);         \
-    pack_scatter_kernel<D, C><<<nb, 256, 0, st>>>(*cfg, theta, mus_grid, kernel_list, K_all, qs, blk, packed,   \
-                                                  indices, pos, counts, regsums, nonpos_blk);
+    pack_count_kernel<D, C><<<nb, 256, 0, st>>>(theta, kernel_list, K_all, cfg->quantize_pis, qs, qdyn, blk);   \
+    pack_scatter_kernel<D, C><<<nb, 256, 0, st>>>(*cfg, theta, mus_grid, kernel_list, K_all, qs, qdyn, blk,     \
+                                                  packed, indices, pos, counts, regsums, nonpos_blk);
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL
     nonpos_total_kernel<<<1, 1, 0, st>>>(nonpos_blk, nb, counts);
@@ -383,6 +590,48 @@ int smoe_pack(const smoe_cfg* cfg, const float* theta, const float* mus_grid, co
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL
     return check_launch("smoe_pack");
+}
+
+size_t smoe_quant_ranges_bytes(void) { return sizeof(QuantDyn); }
+
+int smoe_quant_ranges(const smoe_cfg* cfg, const float* theta, int K_all, int train_musx, void* quant_ranges,
+                      void* stream) {
+    SMOE_REQUIRE(cfg && theta && quant_ranges && K_all > 0, "bad argument");
+    SMOE_REQUIRE(cfg->quantization_mode == 3, "only meaningful for quantization_mode 3");
+    QuantSet qs = make_quantset(cfg);
+    qs.g[QG_PI] = nudge(cfg->pis_lb, cfg->pis_ub, cfg->pis_bits);
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(D, C) quant_ranges_kernel<D, C><<<1, 1024, 0, st>>>(*cfg, qs, train_musx, theta, K_all, (QuantDyn*)quant_ranges);
+    SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
+#undef CALL
+    return check_launch("smoe_quant_ranges");
+}
+
+int smoe_fake_quant_theta(const smoe_cfg* cfg, const float* theta, const void* quant_ranges, int K_all, float* out,
+                          float* structural, void* stream) {
+    SMOE_REQUIRE(cfg && theta && out && K_all > 0, "bad argument");
+    SMOE_REQUIRE(cfg->quantization_mode != 3 || quant_ranges, "quantization_mode 3 needs quant_ranges");
+    const QuantSet qs = make_quantset(cfg);
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(D, C)                                                                                              \
+    fake_quant_theta_kernel<D, C><<<(K_all + 255) / 256, 256, 0, st>>>(*cfg, qs, (const QuantDyn*)quant_ranges, \
+                                                                       theta, K_all, out, structural);
+    SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
+#undef CALL
+    return check_launch("smoe_fake_quant_theta");
+}
+
+int smoe_quant_route(const smoe_cfg* cfg, const float* theta, const void* quant_ranges, int K_all, float* grads,
+                     void* stream) {
+    SMOE_REQUIRE(cfg && theta && quant_ranges && grads && K_all > 0, "bad argument");
+    SMOE_REQUIRE(cfg->quantization_mode == 3, "only meaningful for quantization_mode 3");
+    QuantSet qs = make_quantset(cfg);
+    qs.g[QG_PI] = nudge(cfg->pis_lb, cfg->pis_ub, cfg->pis_bits);
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(D, C) quant_route_kernel<D, C><<<1, 1024, 0, st>>>(qs, (const QuantDyn*)quant_ranges, theta, K_all, grads);
+    SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
+#undef CALL
+    return check_launch("smoe_quant_route");
 }
 
 int smoe_pack_fed(const smoe_cfg* cfg, const float* A, const float* musX, const float* nu_e, const float* gamma_e,

@@ -44,10 +44,18 @@ __host__ __device__ inline int pix_stride(int d, int C, int RL) {
     return pix_rowc_offset(C) + ((d - 1) * (SMOE_TPIX / RL) + 3) / 4 * 4;
 }
 
-// TF FakeQuantWithMinMaxArgs (float32): nudged range and scale, see oracle/graph.py:_nudge
-struct Nudged { float nmin, nmax, scale, inv_scale; };
-struct QuantSet { Nudged g[5]; int mode; };        // groups: A, musX, nu_e, pis, gamma_e
-static inline Nudged nudge(float mn, float mx, int bits) {
+// TF FakeQuantWithMinMaxArgs / ...Vars (float32): nudged range and scale, see oracle/graph.py:_nudge.
+//   value = fq(x - shift; nmin, nmax) + shift   (shift = 0 except for the "shifted" groups of mode 3)
+//   flags: QF_ZERO  min == max == 0: the op returns zeros and passes the gradient (TF kernel special case)
+//          QF_PASS  straight-through for every element (the shifted form of mode 3, smoe.py:506-511, 524-527)
+//          QF_IDENT the group is not quantised at all (musX with train_musx == False in mode 3, smoe.py:516-522)
+//          QF_ROUTE mode-3 plain group: the in-range mask is applied by smoe_quant_route, not by grad_finalize
+struct Nudged { float nmin, nmax, scale, inv_scale, shift; int flags; };
+constexpr int QF_ZERO = 1, QF_PASS = 2, QF_IDENT = 4, QF_ROUTE = 8;
+constexpr int QG_AD = 0, QG_MU = 1, QG_NU = 2, QG_PI = 3, QG_GA = 4, QG_AC = 5;   // A diagonal | musX | nu_e | pis | gamma_e | A_corr
+struct QuantSet { Nudged g[6]; int mode; int pad; };
+struct QuantDyn { QuantSet qs; float mn[6], mx[6]; };       // mode 3: ranges computed on the device (smoe_quant_ranges)
+__host__ __device__ inline Nudged nudge(float mn, float mx, int bits) {
     float qmin = 0.f, qmax = (float)((1 << bits) - 1);
     float scale = (mx - mn) / (qmax - qmin);
     float zp = qmin - mn / scale;
@@ -57,16 +65,21 @@ static inline Nudged nudge(float mn, float mx, int bits) {
     n.nmax = (qmax - nzp) * scale;
     n.scale = scale;
     n.inv_scale = 1.0f / scale;
+    n.shift = 0.f;
+    n.flags = 0;
     return n;
 }
 static inline QuantSet make_quantset(const smoe_cfg* cfg) {
     QuantSet q;
     q.mode = cfg->quantization_mode;
-    for (int i = 0; i < 5; ++i) {
-        q.g[i].nmin = 0.f; q.g[i].nmax = 0.f; q.g[i].scale = 1.f; q.g[i].inv_scale = 1.f;
-        if (cfg->quantization_mode == 2) q.g[i] = nudge(cfg->q_lb[i], cfg->q_ub[i], cfg->q_bits[i]);
+    q.pad = 0;
+    for (int i = 0; i < 6; ++i) {
+        q.g[i].nmin = 0.f; q.g[i].nmax = 0.f; q.g[i].scale = 1.f; q.g[i].inv_scale = 1.f; q.g[i].shift = 0.f;
+        q.g[i].flags = QF_IDENT;
+        const int b = i == QG_AC ? 0 : i;                    // A_corr shares the bounds of A (smoe.py:483-486)
+        if (cfg->quantization_mode == 2) q.g[i] = nudge(cfg->q_lb[b], cfg->q_ub[b], cfg->q_bits[b]);
     }
-    if (cfg->quantization_mode != 2 && cfg->quantize_pis) q.g[3] = nudge(cfg->pis_lb, cfg->pis_ub, cfg->pis_bits);
+    if (cfg->quantization_mode != 2 && cfg->quantize_pis) q.g[QG_PI] = nudge(cfg->pis_lb, cfg->pis_ub, cfg->pis_bits);
     return q;
 }
 
@@ -91,11 +104,20 @@ int check_launch(const char* what);
 
 #ifdef __CUDACC__
 __device__ __forceinline__ float fake_quant(float x, Nudged n) {
-    float c = fminf(fmaxf(x, n.nmin), n.nmax);
+    if (n.flags & QF_IDENT) return x;
+    if (n.flags & QF_ZERO) return n.shift;
+    float c = fminf(fmaxf(__fsub_rn(x, n.shift), n.nmin), n.nmax);
     float k = floorf(__fadd_rn(__fmul_rn(__fsub_rn(c, n.nmin), n.inv_scale), 0.5f));
-    return __fadd_rn(__fmul_rn(k, n.scale), n.nmin);
+    return __fadd_rn(__fadd_rn(__fmul_rn(k, n.scale), n.nmin), n.shift);
 }
-__device__ __forceinline__ float ste_mask(float x, Nudged n) { return (x >= n.nmin && x <= n.nmax) ? 1.f : 0.f; }
+__device__ __forceinline__ bool quant_in_range(float x, Nudged n) {
+    const float xs = __fsub_rn(x, n.shift);
+    return xs >= n.nmin && xs <= n.nmax;
+}
+__device__ __forceinline__ float ste_mask(float x, Nudged n) {
+    if (n.flags & (QF_IDENT | QF_ZERO | QF_PASS | QF_ROUTE)) return 1.f;
+    return quant_in_range(x, n) ? 1.f : 0.f;
+}
 __device__ __forceinline__ float ex2f(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -76,8 +76,7 @@ class Smoe:
         _ffi.require_cuda()
         lib()
         unsupported = {"affines": affines is not None, "train_trafo": train_trafo, "train_svs": train_svs,
-                       "add_kernel_slots": add_kernel_slots > 0, "radial_as": radial_as,
-                       "quantization_mode 3": quantization_mode >= 3}
+                       "add_kernel_slots": add_kernel_slots > 0, "radial_as": radial_as}
         for k, v in unsupported.items():
             if v:
                 raise NotImplementedError(f"{k}: outside the single-model hot path (SURVEY.md 8, decision D1)")
@@ -110,6 +109,8 @@ class Smoe:
         self.only_rec_from_checkpoint = only_rec_from_checkpoint
         self.optimizer1 = self.optimizer2 = self.optimizer3 = None
         self.grad_clip_value_abs = None
+        if quantization_mode not in (0, 1, 2, 3):
+            raise ValueError("quantization_mode must be 0, 1, 2 or 3")
         if quantization_mode >= 2:
             self.quantize_pis = quantize_pis = True          # smoe.py:474 (and smoe_test.py:36-37)
         if quantize_pis and (lower_bounds is None or upper_bounds is None or bit_depths is None):
@@ -273,14 +274,17 @@ class Smoe:
         lb3 = float(self.lower_bounds[3]) if self.quantize_pis else 0.0
         ub3 = float(self.upper_bounds[3]) if self.quantize_pis else 1.0
         bits3 = int(self.bit_depths[3]) if self.quantize_pis else 8
-        qm2 = self.quantization_mode == 2
+        qm2 = self.quantization_mode >= 2
         q_lb = (C.c_float * 5)(*([float(v) for v in self.lower_bounds] if qm2 else [0.0] * 5))
         q_ub = (C.c_float * 5)(*([float(v) for v in self.upper_bounds] if qm2 else [1.0] * 5))
         q_bits = (C.c_int32 * 5)(*([int(v) for v in self.bit_depths] if qm2 else [8] * 5))
+        # mode 3: fake-quant ranges from the surviving kernels, computed on the device once per step
+        self._qdyn = (torch.zeros((L.smoe_quant_ranges_bytes() + 3) // 4, dtype=torch.int32, device=dev)
+                      if self.quantization_mode == 3 else None)
         self._cfg = Cfg(d, Cc, int(self.precision), float(self.margin), int(self.use_determinant),
                         int(self.train_inverse_cov), int(self.use_yuv), int(self.train_gammas),
                         int(self.only_y_gamma), int(self.quantize_pis), lb3, ub3, bits3,
-                        2 if qm2 else 0, q_lb, q_ub, q_bits, int(self.use_diff_center),
+                        int(self.quantization_mode) if qm2 else 0, q_lb, q_ub, q_bits, int(self.use_diff_center),
                         int(self.kernel_count_as_norm_l1), int(dense_exec))   # dense_exec: 0 cull+skip, 1 dense, 2 skip only
         # variables
         A0 = np.asarray(self.A_init, dtype=np.float64)
@@ -673,6 +677,10 @@ class Smoe:
             if Kf > K:
                 raise ValueError("more fed kernels than model kernels")
         norm = float(self.start_pis)
+        if pre and self._qdyn is not None and not fed:
+            check(L.smoe_quant_ranges(C.byref(self._cfg), ptr(self._theta), K, int(self.train_musx), ptr(self._qdyn), st),
+                  "smoe_quant_ranges")
+            self.gpu_launches += 1
         for ii, b in enumerate(batches):
             counts, regs, scal = self._counts[ii], self._regsums[ii], self._scalars[ii]
             if not pre:
@@ -685,8 +693,8 @@ class Smoe:
                 regs.zero_()
                 self.gpu_launches += 2
             else:
-                check(L.smoe_pack(C.byref(self._cfg), ptr(self._theta), ptr(self._mus_grid), ptr(self._klist[ii]), K,
-                                  ptr(self._packed),
+                check(L.smoe_pack(C.byref(self._cfg), ptr(self._theta), ptr(self._mus_grid), ptr(self._qdyn),
+                                  ptr(self._klist[ii]), K, ptr(self._packed),
                                   ptr(self._indices), ptr(self._pos), ptr(counts), ptr(regs), ptr(self._chunk_bounds),
                                   ptr(self._pack_ws), st), "smoe_pack")
                 self.gpu_launches += 4
@@ -728,8 +736,8 @@ class Smoe:
                 continue
             if train:
                 raw, ns = (self._xbuf, 1) if self._world > 1 else (self._raw_part, self._splits)
-                check(L.smoe_grad_finalize(C.byref(self._cfg), ptr(raw), ns, K, ptr(self._theta), ptr(self._indices),
-                                           ptr(counts), C.c_float(float(pis_l1)), C.c_float(norm),
+                check(L.smoe_grad_finalize(C.byref(self._cfg), ptr(raw), ns, K, ptr(self._theta), ptr(self._qdyn),
+                                           ptr(self._indices), ptr(counts), C.c_float(float(pis_l1)), C.c_float(norm),
                                            C.c_float(float(u_l1)), ptr(self._grads), st), "smoe_grad_finalize")
                 self.gpu_launches += 1
             if not with_quantized_params:                 # smoe.py:1763-1766
@@ -738,6 +746,10 @@ class Smoe:
                 self.gpu_launches += 2
         if not post:
             return
+        if train and self._qdyn is not None:             # clipped gradients of the plain groups -> extreme elements
+            check(L.smoe_quant_route(C.byref(self._cfg), ptr(self._theta), ptr(self._qdyn), K, ptr(self._grads), st),
+                  "smoe_quant_route")
+            self.gpu_launches += 1
         if train:
             self._adam_launch()
         # one small device->host read per call: scalars, counts, regulariser sums
@@ -934,8 +946,18 @@ class Smoe:
         """The variables as the graph uses them: fake-quantised per group when quantization_mode == 2
         (smoe.py:482-496); pis also under quantize_pis."""
         theta = self._theta if theta is None else theta
-        if self.quantization_mode != 2 and not self.quantize_pis:
+        if self.quantization_mode < 2 and not self.quantize_pis:
             return theta
+        if self.quantization_mode == 3:                       # ranges of THIS theta, then the device's own rounding
+            L, st = lib(), stream_ptr()
+            qd = torch.zeros_like(self._qdyn)
+            out = torch.empty_like(theta)
+            self._structural = torch.zeros((2,), dtype=torch.float32, device=self.device)
+            check(L.smoe_quant_ranges(C.byref(self._cfg), ptr(theta), self.start_pis, int(self.train_musx), ptr(qd), st),
+                  "smoe_quant_ranges")
+            check(L.smoe_fake_quant_theta(C.byref(self._cfg), ptr(theta), ptr(qd), self.start_pis, ptr(out),
+                                          ptr(self._structural), st), "smoe_fake_quant_theta")
+            return out
         out = theta.clone()
         o = self._off
         out[:, o["pi"]] = self._effective_pis(theta)
@@ -964,6 +986,9 @@ class Smoe:
         if self.quantization_mode == 2:      # the reference fake-quantises the whole (K,d,d) variables (smoe.py:483-486)
             A_diag[:] = A_corr[:] = float(_fake_quant_torch(torch.zeros(1), self.lower_bounds[0], self.upper_bounds[0],
                                                             self.bit_depths[0]))
+        elif self.quantization_mode == 3:    # (smoe.py:506-515)
+            sv = self._structural.cpu().numpy()
+            A_diag[:], A_corr[:] = sv[0], sv[1]
         for l in range(d):
             for m in range(l + 1):
                 (A_diag if l == m else A_corr)[:, l, m] = th[:, d + l * (l + 1) // 2 + m]

@@ -822,3 +822,57 @@ def test_ssim_loss_and_overlap_of_batches(case):
         if m.start_batches == 1:
             l, _, _, _ = m.run_batched(train=False, update_reconstruction=True)
             assert abs((1 - m.ssim()[0]) - l) < 1e-5
+
+
+@pytest.mark.parametrize("case", ["img_diff_center", "video_abs_centres"])
+def test_fake_quant_training_mode3_ranges_of_the_surviving_kernels(case):
+    """quantization_mode 3 (smoe.py:497-531): fake_quant_with_min_max_vars with reduce_min / reduce_max over the
+    kernels whose quantised pi is positive -- shifted form for A_diagonal / nu_e, plain form (with TF's nudging,
+    clamping and gradient routing to the extremes) for A_corr / musX / gamma_e, fixed bounds for pis."""
+    from oracle.model import OracleAdam, OracleSmoe
+    z = np.load(os.path.join(GOLDEN, "init_cases.npz"))
+    img, k = (z["rgb_image"], [6, 8]) if case == "img_diff_center" else (z["vid_image"], [3, 4, 2])
+    kw = dict(use_determinant=True, train_inverse_cov=False, use_yuv=False, normalize_pis=False,
+              quantization_mode=3, lower_bounds=[0, 0, 0, 0.0, 0], upper_bounds=[0, 0, 0, 2.0, 0],
+              bit_depths=[8, 9, 6, 10, 5], use_diff_center=(case == "img_diff_center"))
+    m = _mk(img, k, **kw)
+    o = OracleSmoe(img, kernels_per_dim=k, dtype=torch.float64, **kw)
+    o.set_optimizer(OracleAdam(1e-3), OracleAdam(1e-5), OracleAdam(1.0))
+    K, d, C = m.start_pis, m.dim_domain, img.shape[-1]
+    rs = np.random.RandomState(12)
+    pert = {"pis": rs.uniform(0.3, 1.7, K), "gamma_e": rs.normal(0, 0.3, (K, d, C)),
+            "nu_e": o.vars["nu_e"].numpy() + rs.normal(0, 0.05, (K, C)),
+            "A_corr": np.tril(rs.normal(0, 2.0, (K, d, d)), -1),
+            "A_diagonal": o.vars["A_diagonal"].numpy() * (1 + 0.2 * rs.uniform(-1, 1, (K, 1, 1)))}
+    if case == "img_diff_center":
+        pert["musX"] = rs.uniform(-0.02, 0.02, (K, d))
+    pert["pis"][[1, 7]] = -0.3
+    pert["nu_e"][1] = 9.0                                   # a pruned kernel must not widen the range
+    pert["gamma_e"][7] = -50.0
+    pert = {kk: v.astype(np.float32) for kk, v in pert.items()}
+    m.set_params(pert)
+    for kk, v in pert.items():
+        o.vars[kk] = torch.tensor(v.astype(np.float64))
+    pg, po = m.get_params(), o.get_params()
+    keep = po["pis"] > 0
+    assert keep.sum() == K - 2
+    for kk in PARAM_KEYS:                                   # bit for bit on the rows the graph reads
+        np.testing.assert_array_equal(pg[kk][keep], po[kk][keep], err_msg=kk)
+    assert pg["nu_e"][keep].max() < 2 and abs(pg["gamma_e"][keep]).max() < 5
+    clamped = sum(int((np.abs(po[kk][keep] - pert[kk][keep]) > 0.5001 * (pert[kk][keep].max() - pert[kk][keep].min())
+                       / (2 ** b - 1)).sum()) for kk, b in (("gamma_e", 5),))
+    (lg, mg, npg, _), (lo, mo, npo, _) = _train_pass_both(m, o, pis_l1=0.3, u_l1=1e-5)
+    assert npg == npo == K - 2
+    assert abs(lg - lo) < 2e-6 * max(1.0, abs(lo)) and abs(mg - mo) < 2e-3 * mo + 1e-3
+    g = m.get_gradients()
+    for kk, ref in o.last_grads.items():
+        assert _rel(g[kk], ref.numpy()) < 1e-4, (kk, _rel(g[kk], ref.numpy()), clamped)
+    assert np.abs(g["pis"][[1, 7]]).max() == 0 and np.abs(g["nu_e"][[1, 7]]).max() == 0
+    for _ in range(3):
+        a = m.run_batched(train=True, pis_l1=0.3, u_l1=1e-5)
+        b = o.run_batched(train=True, pis_l1=0.3, u_l1=1e-5)
+        assert abs(a[0] - b[0]) < 1e-3 * max(1.0, abs(b[0]))
+    pg, po = m.get_params(), o.get_params()
+    for kk in ("nu_e", "musX", "pis"):
+        span = po[kk][keep].max() - po[kk][keep].min() + 1e-9
+        assert (np.abs(pg[kk][keep] - po[kk][keep]) > 0.02 * span).mean() < 0.1, kk

@@ -228,3 +228,55 @@ def test_ssim_loss_and_overlap_in_the_oracle_model():
     for _ in range(15):
         l_last = o2.run_batched(train=True)[0]
     assert l_last < l_first
+
+
+# ----------------------------------------------------------------------------------------------------
+# quantization_mode 3 (fake-quant with the min / max of the surviving kernels, smoe.py:497-531)
+# ----------------------------------------------------------------------------------------------------
+def test_mode3_ranges_follow_the_surviving_kernels_and_route_clipped_gradients():
+    from oracle.graph import effective_params
+    p, x, t, kl, cfg = _rand_case(2, 3, False, True, True, 8, K=12)
+    cfg.quantization_mode, cfg.bit_depths = 3, [6, 7, 5, 10, 4]
+    cfg.lower_bounds, cfg.upper_bounds = [0, 0, 0, 0.0, 0], [0, 0, 0, 2.0, 0]      # only the pis bounds are used
+    p = {k: v.astype(np.float32).astype(np.float64) for k, v in p.items()}
+    p["nu_e"][1] = 7.0                                  # kernel 1 has pi < 0: it must not widen any range
+    tp = {k: torch.tensor(v) for k, v in p.items()}
+    eff = effective_params(tp, cfg)
+    keep = p["pis"] > 1.0 / 1023                        # fake-quantised pi > 0
+    # shifted form: the extremes of the kept rows are reproduced exactly, values lie on min + k * scale
+    nu_k = p["nu_e"][keep]
+    q = eff["nu_e"].numpy()[keep]
+    assert q.min() == nu_k.min() and abs(q.max() - nu_k.max()) < 1e-6
+    scale = (np.float32(nu_k.max()) - np.float32(nu_k.min())) / np.float32(31)
+    code = (q - nu_k.min()) / scale
+    assert np.abs(code - np.round(code)).max() < 1e-3 and np.abs(q - nu_k).max() <= scale / 2 * 1.001
+    # plain form (gamma_e, 4 bits): zero is a code; elements beyond the nudged range are clamped
+    ga = eff["gamma_e"].numpy()[keep]
+    gscale = (p["gamma_e"][keep].max() - p["gamma_e"][keep].min()) / 15
+    assert np.abs(ga / gscale - np.round(ga / gscale)).max() < 1e-3
+    # gradients: shifted groups pass straight through; in a plain group the gradient of a clamped element goes
+    # to the extreme element of the kept rows, and the total is conserved
+    out, g = graph_grads(tp, kl, torch.tensor(x), torch.tensor(t), cfg, pis_l1=0.1)
+    cfg0 = GraphCfg(**{**cfg.__dict__, "quantization_mode": 0})
+    eff_leaf = {k: v.detach().clone().requires_grad_(True) for k, v in eff.items()}
+    eff_leaf["pis"] = out["pis"].new_tensor(p["pis"]).requires_grad_(True)
+    cfg0.quantize_pis = True
+    out0, g0 = graph_grads({k: v.detach() for k, v in eff_leaf.items()}, kl, torch.tensor(x), torch.tensor(t), cfg0,
+                           pis_l1=0.1)
+    np.testing.assert_allclose(g["nu_e"], g0["nu_e"], atol=1e-14)
+    np.testing.assert_allclose(torch.diagonal(g["A_diagonal"], dim1=1, dim2=2),
+                               torch.diagonal(g0["A_diagonal"], dim1=1, dim2=2), atol=1e-14)
+    assert abs(float(g["gamma_e"].sum()) - float(g0["gamma_e"].sum())) < 1e-12 * max(1, float(g0["gamma_e"].abs().sum()))
+    assert abs(float(out["loss"].detach()) - float(out0["loss"].detach())) < 1e-12
+
+
+def test_mode3_all_zero_group_is_passed_through():
+    p, x, t, kl, cfg = _rand_case(2, 1, False, True, False, 9)
+    p["A_corr"][:] = 0.0
+    p["gamma_e"][:] = 0.0
+    cfg.quantization_mode, cfg.bit_depths = 3, [8, 8, 8, 10, 8]
+    cfg.lower_bounds, cfg.upper_bounds = [0, 0, 0, 0.0, 0], [0, 0, 0, 2.0, 0]
+    tp = {k: torch.tensor(v.astype(np.float32).astype(np.float64)) for k, v in p.items()}
+    out, g = graph_grads(tp, kl, torch.tensor(x), torch.tensor(t), cfg)
+    assert float(out["gamma_e"].detach().abs().max()) == 0
+    assert float(g["gamma_e"].abs().max()) > 0 and float(g["A_corr"][:, 1, 0].abs().max()) > 0

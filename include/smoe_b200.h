@@ -222,6 +222,18 @@ int smoe_fake_quant_theta(const smoe_cfg* cfg, const float* theta, const void* q
 int smoe_update_kernel_list(const int32_t* indices, const int32_t* counts, const uint8_t* infl,
                             uint8_t* kernel_list, int K_all, void* stream);
 
+/* Start of a run_batched pass in one launch: zero the gradient accumulators (zero_op, smoe.py:1612-1613; grads may
+ * be NULL for an evaluation pass), the SMOE_NSCAL-float scalar block of each of n_rows batches (row_stride floats
+ * apart) and the influence flags (infl may be NULL). */
+int smoe_step_begin(float* grads, size_t n_grads, float* scalars, int n_rows, int row_stride, uint8_t* infl, int K,
+                    void* stream);
+
+/* Sharded step: the tail [scalars(SMOE_NSCAL) | influence flags as floats (K)] of the buffer that is
+ * all-reduced (sum) over the ranks next to the per-kernel statistics of smoe_reduce_splits, and its unpacking
+ * (flags: any rank). */
+int smoe_exchange_pack(const float* scalars, const uint8_t* infl, int K, float* tail, void* stream);
+int smoe_exchange_unpack(const float* tail, int K, float* scalars, uint8_t* infl, void* stream);
+
 /* TF1 ApplyAdam on every K_all row (dense, pruned rows included), three groups.  Replaces
  * session.run(train_op) at smoe.py:1788 (apply_gradients at smoe.py:1173-1193). */
 int smoe_adam_step(const smoe_cfg* cfg, const smoe_adam* hp, const float* alpha_dev /* optional device [3]:

@@ -180,9 +180,15 @@ __device__ __forceinline__ int stage_record(const smoe_cfg& cfg, const float (&A
 // (coarse level of the exact culling; layout [mu_min[3] | mu_max[3] | lam_min | c0_max | kap_min[3] | -], stride kCB).
 template <int D, int C>
 __global__ void __launch_bounds__(kChunk) chunk_bounds_kernel(const float* __restrict__ packed,
-                                                              const int32_t* __restrict__ counts,
-                                                              float* __restrict__ cb) {
+                                                              int32_t* __restrict__ counts,
+                                                              float* __restrict__ cb,
+                                                              const int32_t* __restrict__ nonpos_blk, int nb) {
     constexpr int PK = pstride(D, C);
+    if (nonpos_blk && blockIdx.x == 0 && threadIdx.x == 0) {        // counts[2]: kernels with pi * det <= 0
+        int s = 0;
+        for (int b = 0; b < nb; ++b) s += nonpos_blk[b];
+        counts[2] = s;
+    }
     const int K = counts[0];
     const int k = blockIdx.x * kChunk + threadIdx.x;
     if ((int)blockIdx.x * kChunk >= K) return;
@@ -307,11 +313,6 @@ __global__ void __launch_bounds__(256) pack_scatter_kernel(smoe_cfg cfg, const f
     }
 }
 
-__global__ void nonpos_total_kernel(const int32_t* __restrict__ nonpos_blk, int nb, int32_t* __restrict__ counts) {
-    int s = 0;
-    for (int b = 0; b < nb; ++b) s += nonpos_blk[b];
-    counts[2] = s;
-}
 
 template <int D, int C>
 __global__ void __launch_bounds__(256) pack_fed_kernel(smoe_cfg cfg, const float* __restrict__ A_, const float* __restrict__ mus,
@@ -331,14 +332,50 @@ __global__ void __launch_bounds__(256) pack_fed_kernel(smoe_cfg cfg, const float
                        packed + (size_t)i * PK);
 }
 
-__global__ void klist_clear_kernel(uint8_t* __restrict__ klist, int K_all) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < K_all) klist[i] = 0;
+// kernel_list[i] = infl[k] if i == indices[k] for an active k, else 0.  `indices` is ascending (stream compaction
+// keeps the original order), so every original index finds its packed row by bisection: one launch, no clear pass.
+__global__ void __launch_bounds__(256) klist_update_kernel(const int32_t* __restrict__ indices,
+                                                           const int32_t* __restrict__ counts,
+                                                           const uint8_t* __restrict__ infl,
+                                                           uint8_t* __restrict__ klist, int K_all) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= K_all) return;
+    int lo = 0, hi = counts[0];
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (indices[mid] < i) lo = mid + 1; else hi = mid;
+    }
+    klist[i] = (lo < counts[0] && indices[lo] == i) ? (infl[lo] ? 1 : 0) : 0;
 }
-__global__ void klist_set_kernel(const int32_t* __restrict__ indices, const int32_t* __restrict__ counts,
-                                 const uint8_t* __restrict__ infl, uint8_t* __restrict__ klist) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < counts[0] && infl[k]) klist[indices[k]] = 1;
+
+// start of a training / evaluation pass: zero the gradient accumulators (zero_op, smoe.py:1612-1613), the scalar
+// blocks of all batches and the influence flags of the first batch -- one launch instead of three fills
+__global__ void __launch_bounds__(256) step_begin_kernel(float* __restrict__ grads, size_t n_grads,
+                                                         float* __restrict__ scalars, int n_scalars, int scalar_stride,
+                                                         int n_rows, uint8_t* __restrict__ infl, int K) {
+    const size_t stride = (size_t)gridDim.x * 256;
+    const size_t i0 = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (grads)
+        for (size_t i = i0; i < n_grads; i += stride) grads[i] = 0.f;
+    for (size_t i = i0; i < (size_t)n_rows * n_scalars; i += stride)
+        scalars[(i / n_scalars) * scalar_stride + i % n_scalars] = 0.f;
+    if (infl)
+        for (size_t i = i0; i < (size_t)K; i += stride) infl[i] = 0;
+}
+
+// the tail of the buffer a sharded step all-reduces: [scalars | influence flags as floats], and back
+__global__ void __launch_bounds__(256) exchange_pack_kernel(const float* __restrict__ scalars,
+                                                            const uint8_t* __restrict__ infl, int K,
+                                                            float* __restrict__ tail) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < SMOE_NSCAL) tail[i] = scalars[i];
+    if (i < K) tail[SMOE_NSCAL + i] = infl[i] ? 1.f : 0.f;
+}
+__global__ void __launch_bounds__(256) exchange_unpack_kernel(const float* __restrict__ tail, int K,
+                                                              float* __restrict__ scalars, uint8_t* __restrict__ infl) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < SMOE_NSCAL) scalars[i] = tail[i];
+    if (i < K) infl[i] = tail[SMOE_NSCAL + i] > 0.f ? 1 : 0;
 }
 
 
@@ -584,9 +621,8 @@ int smoe_pack(const smoe_cfg* cfg, const float* theta, const float* mus_grid, co
                                                   packed, indices, pos, counts, regsums, nonpos_blk);
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL
-    nonpos_total_kernel<<<1, 1, 0, st>>>(nonpos_blk, nb, counts);
     const int nchunks = (K_all + kChunk - 1) / kChunk;
-#define CALL(D, C) chunk_bounds_kernel<D, C><<<nchunks, kChunk, 0, st>>>(packed, counts, chunk_bounds);
+#define CALL(D, C) chunk_bounds_kernel<D, C><<<nchunks, kChunk, 0, st>>>(packed, counts, chunk_bounds, nonpos_blk, nb);
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL
     return check_launch("smoe_pack");
@@ -644,7 +680,7 @@ int smoe_pack_fed(const smoe_cfg* cfg, const float* A, const float* musX, const 
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL
     const int nchunks = (K + kChunk - 1) / kChunk;
-#define CALL(D, C) chunk_bounds_kernel<D, C><<<nchunks, kChunk, 0, st>>>(packed, counts, chunk_bounds);
+#define CALL(D, C) chunk_bounds_kernel<D, C><<<nchunks, kChunk, 0, st>>>(packed, counts, chunk_bounds, nullptr, 0);
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL
     return check_launch("smoe_pack_fed");
@@ -655,9 +691,34 @@ int smoe_update_kernel_list(const int32_t* indices, const int32_t* counts, const
     SMOE_REQUIRE(indices && counts && infl && kernel_list && K_all > 0, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     int nb = (K_all + 255) / 256;
-    klist_clear_kernel<<<nb, 256, 0, st>>>(kernel_list, K_all);
-    klist_set_kernel<<<nb, 256, 0, st>>>(indices, counts, infl, kernel_list);
+    klist_update_kernel<<<nb, 256, 0, st>>>(indices, counts, infl, kernel_list, K_all);
     return check_launch("smoe_update_kernel_list");
+}
+
+int smoe_step_begin(float* grads, size_t n_grads, float* scalars, int n_rows, int row_stride, uint8_t* infl, int K,
+                    void* stream) {
+    SMOE_REQUIRE(scalars && n_rows > 0 && row_stride >= SMOE_NSCAL, "bad argument");
+    size_t n = n_grads > (size_t)K ? n_grads : (size_t)K;
+    if (n < (size_t)n_rows * SMOE_NSCAL) n = (size_t)n_rows * SMOE_NSCAL;
+    int nb = (int)((n + 255) / 256);
+    if (nb > 148 * 8) nb = 148 * 8;
+    step_begin_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(grads, grads ? n_grads : 0, scalars, SMOE_NSCAL, row_stride,
+                                                           n_rows, infl, infl ? K : 0);
+    return check_launch("smoe_step_begin");
+}
+
+int smoe_exchange_pack(const float* scalars, const uint8_t* infl, int K, float* tail, void* stream) {
+    SMOE_REQUIRE(scalars && infl && tail && K > 0, "bad argument");
+    const int n = K > SMOE_NSCAL ? K : SMOE_NSCAL;
+    exchange_pack_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(scalars, infl, K, tail);
+    return check_launch("smoe_exchange_pack");
+}
+
+int smoe_exchange_unpack(const float* tail, int K, float* scalars, uint8_t* infl, void* stream) {
+    SMOE_REQUIRE(scalars && infl && tail && K > 0, "bad argument");
+    const int n = K > SMOE_NSCAL ? K : SMOE_NSCAL;
+    exchange_unpack_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(tail, K, scalars, infl);
+    return check_launch("smoe_exchange_unpack");
 }
 
 }  // extern "C"

@@ -381,9 +381,12 @@ class Smoe:
         self._pos = torch.zeros((K,), dtype=torch.int32, device=dev)
         self._perm = None
         self._refresh_perm()
-        self._counts = torch.zeros((nb, 4), dtype=torch.int32, device=dev)
-        self._regsums = torch.zeros((nb, 2), dtype=f32, device=dev)
-        self._scalars = torch.zeros((nb, _ffi.NSCAL), dtype=f32, device=dev)
+        # one block per batch [scalars (NSCAL) | counts (4 x int32) | regulariser sums (2) | pad]: a single
+        # device->host copy per run_batched call brings back everything the host needs
+        self._stats = torch.zeros((nb, _ffi.STATS_STRIDE), dtype=f32, device=dev)
+        self._scalars = self._stats[:, :_ffi.NSCAL]
+        self._counts = self._stats.view(torch.int32)[:, _ffi.NSCAL:_ffi.NSCAL + 4]
+        self._regsums = self._stats[:, _ffi.NSCAL + 4:_ffi.NSCAL + 6]
         self._infl = torch.zeros((K,), dtype=torch.uint8, device=dev)
         self._pix = torch.zeros((max_tiles * L.smoe_pix_stride(d, Cc, C.byref(self._batches[0])),), dtype=f32, device=dev)
         self._tile_qmin = torch.zeros((max_tiles,), dtype=f32, device=dev)
@@ -398,7 +401,7 @@ class Smoe:
         self._raw_part = None           # allocated on the first training pass
         # [raw statistics | scalars | influence flags]: the buffer a multi-GPU run all-reduces
         self._xbuf = torch.zeros((K * self._P + _ffi.NSCAL + K,), dtype=f32, device=dev) if self._world > 1 else None
-        self._host_stats = torch.zeros((nb, _ffi.NSCAL + 4 + 2), dtype=f32).pin_memory()
+        self._host_stats = torch.zeros((nb, _ffi.STATS_STRIDE), dtype=f32).pin_memory()
         self._alpha_host = torch.zeros((4,), dtype=f32).pin_memory()
         self._alpha_dev = torch.zeros((4,), dtype=f32, device=dev)
         self._graphs = {}
@@ -573,6 +576,7 @@ class Smoe:
                           lossw=lossw, batches=batches)
         torch.cuda.current_stream().synchronize()
         h = self._host_stats.numpy().astype(np.float64)
+        h[:, _ffi.NSCAL:_ffi.NSCAL + 4] = self._host_stats.view(torch.int32).numpy()[:, _ffi.NSCAL:_ffi.NSCAL + 4]
         norm = float(self.start_pis)
         Cc = self.image.shape[-1]
         loss_val = mse_val = 0.0
@@ -666,9 +670,10 @@ class Smoe:
                     torch.div(self._d_image_u8.to(torch.float32), 255.0, out=self._d_image)
                 else:
                     self._d_image.copy_(_host_image, non_blocking=True)
-            if train:
-                self._grads.zero_()
-            self._scalars.zero_()
+            check(L.smoe_step_begin(ptr(self._grads) if train else ptr(None), C.c_size_t(self._grads.numel()),
+                                    ptr(self._stats), len(self._batches), _ffi.STATS_STRIDE, ptr(self._infl), K, st),
+                  "smoe_step_begin")
+            self.gpu_launches += 1
         fed = with_quantized_params and update_reconstruction
         if fed:
             rp = {k: torch.as_tensor(np.ascontiguousarray(np.asarray(v, dtype=np.float32)), device=self.device)
@@ -691,15 +696,16 @@ class Smoe:
                                       ptr(self._chunk_bounds), st), "smoe_pack_fed")
                 self._indices[:Kf] = torch.arange(Kf, dtype=torch.int32, device=self.device)
                 regs.zero_()
-                self.gpu_launches += 2
+                self.gpu_launches += 3
             else:
                 check(L.smoe_pack(C.byref(self._cfg), ptr(self._theta), ptr(self._mus_grid), ptr(self._qdyn),
                                   ptr(self._klist[ii]), K, ptr(self._packed),
                                   ptr(self._indices), ptr(self._pos), ptr(counts), ptr(regs), ptr(self._chunk_bounds),
                                   ptr(self._pack_ws), st), "smoe_pack")
-                self.gpu_launches += 4
+                self.gpu_launches += 3
             if pre:
-                self._infl.zero_()
+                if ii > 0:
+                    self._infl.zero_()
                 check(L.smoe_forward(C.byref(self._cfg), C.byref(b), ptr(self._packed), ptr(self._indices), ptr(counts),
                                      ptr(self._chunk_bounds), K,
                                      ptr(self._d_image), ptr(lossw), ptr(self._d_axes[0]), ptr(self._d_axes[1]),
@@ -743,7 +749,7 @@ class Smoe:
             if not with_quantized_params:                 # smoe.py:1763-1766
                 check(L.smoe_update_kernel_list(ptr(self._indices), ptr(counts), ptr(self._infl), ptr(self._klist[ii]),
                                                 K, st), "smoe_update_kernel_list")
-                self.gpu_launches += 2
+                self.gpu_launches += 1
         if not post:
             return
         if train and self._qdyn is not None:             # clipped gradients of the plain groups -> extreme elements
@@ -753,10 +759,7 @@ class Smoe:
         if train:
             self._adam_launch()
         # one small device->host read per call: scalars, counts, regulariser sums
-        hs = self._host_stats
-        hs[:, :_ffi.NSCAL].copy_(self._scalars, non_blocking=True)
-        hs[:, _ffi.NSCAL:_ffi.NSCAL + 4].copy_(self._counts.to(torch.float32), non_blocking=True)
-        hs[:, _ffi.NSCAL + 4:].copy_(self._regsums, non_blocking=True)
+        self._host_stats.copy_(self._stats, non_blocking=True)
 
     def _exchange(self, train, counts, scal, phase="all"):
         """The one exchange step of the sharded path: sum over ranks of the
@@ -770,13 +773,14 @@ class Smoe:
                 self.gpu_launches += 1
             else:
                 self._xbuf[:K * P].zero_()
-            self._xbuf[K * P:K * P + _ffi.NSCAL] = scal
-            self._xbuf[K * P + _ffi.NSCAL:] = self._infl.to(torch.float32)
+            check(L.smoe_exchange_pack(ptr(scal), ptr(self._infl), K, ptr(self._xbuf[K * P:]), st), "smoe_exchange_pack")
+            self.gpu_launches += 1
         if phase == "all":
             torch.distributed.all_reduce(self._xbuf, group=self._pg)
         if phase in ("all", "post"):
-            scal.copy_(self._xbuf[K * P:K * P + _ffi.NSCAL])
-            self._infl.copy_((self._xbuf[K * P + _ffi.NSCAL:] > 0).to(torch.uint8))
+            check(L.smoe_exchange_unpack(ptr(self._xbuf[K * P:]), K, ptr(scal), ptr(self._infl), st),
+                  "smoe_exchange_unpack")
+            self.gpu_launches += 1
 
     def _gather_reconstruction(self):
         Cc = self.image.shape[-1]

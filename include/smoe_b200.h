@@ -80,6 +80,10 @@ typedef struct smoe_cfg {
     int32_t q_bits[5];         /* bit_depths, same order (smoe_test.py:302)                            */
     int32_t use_diff_center;   /* the musX variable holds offsets from a fixed grid (smoe.py:390-394, 746-747) */
     int32_t kernel_count_as_norm_l1; /* L1 on pis normalised by the live kernel count (smoe.py:1022-1025) */
+    int32_t radial_as;         /* A = a * I with ONE trainable scalar per kernel and a frozen A_corr = 0
+                                  (smoe.py:429-434, 714-721): the d diagonal entries of a theta row are kept
+                                  equal -- each receives the sum of the d diagonal gradients -- and the
+                                  strictly-lower entries receive none                                    */
     int32_t dense_exec;        /* 0: exact culling + exact-zero skipping (default);
                                   1: execute every (pixel, kernel) pair in full;
                                   2: exact-zero skipping inside the dense sweeps, no tile-level

@@ -254,7 +254,11 @@ def custom_ssim_torch(img1, img2, ndim, max_val=1.0):
 
 def assemble_A(A_diagonal, A_corr, train_inverse_cov):
     """smoe.py:732-735: band_part(A_diag,0,0) + strict-lower(A_corr) (+ its transpose)."""
-    diag = torch.diag_embed(torch.diagonal(A_diagonal, dim1=-2, dim2=-1))
+    if A_diagonal.dim() == 1:        # radial_as: tile the scalar, band_part keeps the diagonal (smoe.py:714-721)
+        d = A_corr.shape[-1]
+        diag = A_diagonal[:, None, None] * torch.eye(d, dtype=A_diagonal.dtype)
+    else:
+        diag = torch.diag_embed(torch.diagonal(A_diagonal, dim1=-2, dim2=-1))
     low = torch.tril(A_corr, diagonal=-1)
     A = diag + low
     if train_inverse_cov:

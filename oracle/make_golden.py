@@ -178,6 +178,42 @@ def golden_quant(ref_quantizer):
     np.savez_compressed(os.path.join(OUT, "quant_cases.npz"), **out)
 
 
+def golden_quant_radial(ref_quantizer):
+    """radial_as (smoe.py:429-434, 714-721): A_diagonal is one scalar per kernel, A_corr is not quantised
+    (quantizer.py:11, 45, 61, 80, 97-136)."""
+    out = {}
+    cases = [(qm, qp, d, C) for qm in (1, 2, 3) for qp in (False, True) if not (qm == 3 and not qp)
+             for (d, C) in ((2, 3), (3, 1))]
+    for ci, (qm, qp, d, C) in enumerate(cases):
+        rs = np.random.RandomState(300 + ci)
+        K = 29 + ci
+        p = random_params(rs, K, d, C)
+        p["A_diagonal"] = rs.uniform(5, 60, K).astype(np.float32)
+        p["A_corr"] = np.zeros((K, d, d), np.float32)
+        s = _Shim()
+        s.quantization_mode, s.quantize_pis, s.radial_as, s.dim_domain = qm, qp, True, d
+        s.image = np.zeros((4,) * d + (C,), np.float32)
+        s.lower_bounds, s.upper_bounds = [-2500, -.3, -5, 0, -32], [2500, 1.3, 5, 2, 32]
+        s.bit_depths = [12, 11, 8, 7, 9] if ci % 2 == 0 else [20, 18, 6, 10, 10]
+        s.use_diff_center = False
+        s.musX_init = None
+        q = ref_quantizer.quantize_params(s, copy.deepcopy(p))
+        r = ref_quantizer.rescaler(s, q)
+        pre = f"case{ci}_"
+        out[pre + "meta"] = np.array([qm, int(qp), d, C, K] + list(s.bit_depths))
+        for k, v in p.items():
+            out[pre + "in_" + k] = v
+        assert "A_corr" not in q
+        for k in ("A_diagonal", "musX", "nu_e", "pis", "gamma_e"):
+            out[pre + "q_" + k] = q[k]
+            out[pre + "lb_" + k] = np.asarray(q["lower_bounds"][k])
+            out[pre + "ub_" + k] = np.asarray(q["upper_bounds"][k])
+        for k, v in r.items():
+            out[pre + "r_" + k] = v
+    out["num_cases"] = np.array(len(cases))
+    np.savez_compressed(os.path.join(OUT, "quant_radial_cases.npz"), **out)
+
+
 def golden_graph():
     """Graph fixtures from the float64 restatement (NOT TensorFlow output: pinned=False)."""
     import torch
@@ -241,6 +277,7 @@ def main():
     ref_smoe, ref_quantizer, _ = import_reference()
     golden_init(ref_smoe)
     golden_quant(ref_quantizer)
+    golden_quant_radial(ref_quantizer)
     golden_graph()
     print("golden vectors written to", OUT)
 

@@ -58,14 +58,14 @@ class OracleSmoe:
                  quantize_pis=False, lower_bounds=None, upper_bounds=None, use_yuv=True,
                  only_y_gamma=False, precision=8, iter_offset=0, margin=0.5,
                  kernel_count_as_norm_l1=False, train_inverse_cov=True, dtype=torch.float32,
-                 einsum_mode="einsum", loss_mask=None, ssim_opt=False, overlap_of_batches=0):
+                 einsum_mode="einsum", loss_mask=None, ssim_opt=False, overlap_of_batches=0, radial_as=False):
         self.image = np.asarray(image)
         self.dtype = dtype
         self.dim_domain = self.image.ndim - 1
         self.num_pixel = int(np.prod(self.image.shape[:self.dim_domain]))
         self.precision = precision
         self.use_yuv = use_yuv
-        self.radial_as = False
+        self.radial_as = radial_as
         self.use_diff_center = use_diff_center
         self.quantization_mode = quantization_mode
         self.quantize_pis = quantize_pis
@@ -103,8 +103,9 @@ class OracleSmoe:
         self.vars = {
             "pis": tt(pis0),
             "musX": tt(np.zeros_like(mus0) if use_diff_center else mus0),
-            "A_diagonal": tt(np.where(eye, A0, 0.0)),
-            "A_corr": tt(np.where(np.tril(np.ones((d, d), bool), -1)[None], A0, 0.0)),
+            "A_diagonal": tt(A0[:, 0, 0]) if radial_as else tt(np.where(eye, A0, 0.0)),     # smoe.py:429-434
+            "A_corr": tt(np.zeros_like(A0)) if radial_as
+            else tt(np.where(np.tril(np.ones((d, d), bool), -1)[None], A0, 0.0)),
             "gamma_e": tt(ga0),
             "nu_e": tt(nu0),
         }
@@ -141,7 +142,7 @@ class OracleSmoe:
         o1, o2, o3 = self.optimizers
         g1 = ["nu_e"] + (["gamma_e"] if self.train_gammas else []) + (["musX"] if self.train_musx else [])
         g2 = ["pis"] if self.train_pis else []
-        g3 = ["A_diagonal", "A_corr"]
+        g3 = ["A_diagonal"] if self.radial_as else ["A_diagonal", "A_corr"]
         return [(o, names) for o, names in ((o1, g1), (o2, g2), (o3, g3)) if not o._lr == 0]
 
     # -- the batched executor -----------------------------------------------------------

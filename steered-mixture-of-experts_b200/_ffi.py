@@ -33,7 +33,7 @@ class Cfg(C.Structure):
                 ("pis_lb", C.c_float), ("pis_ub", C.c_float), ("pis_bits", C.c_int32),
                 ("quantization_mode", C.c_int32), ("q_lb", C.c_float * 5), ("q_ub", C.c_float * 5),
                 ("q_bits", C.c_int32 * 5), ("use_diff_center", C.c_int32), ("kernel_count_as_norm_l1", C.c_int32),
-                ("dense_exec", C.c_int32)]
+                ("radial_as", C.c_int32), ("dense_exec", C.c_int32)]
 
 
 PIXEL_ABSENT, PIXEL_HALO = -1.0, -2.0          # SMOE_PIXEL_ABSENT / SMOE_PIXEL_HALO

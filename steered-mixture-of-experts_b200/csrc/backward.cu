@@ -557,16 +557,23 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(smoe_cfg cfg, const 
     }
 #pragma unroll
     for (int l = 0; l < D; ++l) {
+        gA[l][l] += u_l1;                                               // smoe.py:1044
+        if (cfg.use_determinant) gA[l][l] += M0 / A[l][l];              // smoe.py:810
+    }
+    if (cfg.radial_as) {        // one scalar a per kernel, A = a * I (smoe.py:429-434, 714-721): d/da = sum_l d/dA_ll
+        float gs = 0.f;
+#pragma unroll
+        for (int l = 0; l < D; ++l) gs += gA[l][l];
+#pragma unroll
+        for (int l = 0; l < D; ++l)
+#pragma unroll
+            for (int m = 0; m <= l; ++m) gA[l][m] = (l == m) ? gs : 0.f;      // A_corr is not trainable
+    }
+#pragma unroll
+    for (int l = 0; l < D; ++l) {
         gr[off_mu(D, C) + l] += fq ? gmu[l] * ste_mask(th[off_mu(D, C) + l], qs.g[QG_MU]) : gmu[l];
 #pragma unroll
-        for (int m = 0; m <= l; ++m) {
-            float gv = gA[l][m];
-            if (l == m) {
-                gv += u_l1;                                             // smoe.py:1044
-                if (cfg.use_determinant) gv += M0 / A[l][l];            // smoe.py:810
-            }
-            gr[off_A(D, C) + lt(l, m)] += gv * steA[l][m];
-        }
+        for (int m = 0; m <= l; ++m) gr[off_A(D, C) + lt(l, m)] += gA[l][m] * steA[l][m];
     }
 #pragma unroll
     for (int c = 0; c < C; ++c) {

@@ -352,6 +352,7 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
         __syncthreads();
         if (tid == 0 && a.tile_qmin) a.tile_qmin[tile] = qmin;
         {
+            const bool want_argmax = a.argmax != nullptr;        // training passes do not fetch w_e_max (smoe.py:1690)
             const float thrB = qmin - 0.01f;
             const int nlist = build_chunk_list(thrB);
             sweep(nlist, thrB, [&](const float* rec) {
@@ -378,6 +379,15 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
                         f[4 * j] = v.x; f[4 * j + 1] = v.y; f[4 * j + 2] = v.z; f[4 * j + 3] = v.w;
                     }
                     const int kglob = __float_as_int(f[R::OK]);
+                    // expert value E_c(x) = nu'_c + gamma_c . x': the part that does not depend on x'_0 once per
+                    // (thread, kernel), one FFMA per pixel and channel
+                    float Eb[C];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        Eb[c] = f[R::ONU + c];
+#pragma unroll
+                        for (int l = 1; l < D; ++l) Eb[c] = fmaf(f[R::OGA + l * C + c], xs[l], Eb[c]);
+                    }
 #pragma unroll
                     for (int p = 0; p < PPT; ++p) {
                         // w = e/S = tau * 2^(q - log2(tau*S)), the form the backward recomputes
@@ -385,14 +395,9 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
                         const bool pass = q[p] > qthr[p];
                         const float wm = pass ? w : 0.f;
 #pragma unroll
-                        for (int c = 0; c < C; ++c) {
-                            float E = f[R::ONU + c];
-                            E = fmaf(f[R::OGA + c], x0[p], E);
-#pragma unroll
-                            for (int l = 1; l < D; ++l) E = fmaf(f[R::OGA + l * C + c], xs[l], E);
-                            r[p][c] = fmaf(wm, E, r[p][c]);
-                        }
-                        if (pass && w > bestw[p]) { bestw[p] = w; bestk[p] = kglob; }
+                        for (int c = 0; c < C; ++c) r[p][c] = fmaf(wm, fmaf(f[R::OGA + c], x0[p], Eb[c]), r[p][c]);
+                        // tf.argmax keeps the first maximum: kernels arrive in ascending index, so strictly greater
+                        if (want_argmax && pass && w > bestw[p]) { bestw[p] = w; bestk[p] = kglob; }
                     }
                     if (any && a.infl) a.infl[kglob] = 1;
                 }

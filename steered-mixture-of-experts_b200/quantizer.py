@@ -58,14 +58,15 @@ def _bounds_for(smoe, name, x_dev, rows, cols, shape_tail):
 def quantize_params(smoe, params):
     _ffi.require_cuda()
     params, _ = reduce_params(params)
-    if getattr(smoe, "radial_as", False):
-        raise NotImplementedError("radial_as")
+    radial = bool(getattr(smoe, "radial_as", False))       # A_diagonal is (K,), A_corr is not quantised
     dev = _device(smoe)
     bd = smoe.bit_depths
     steps = {"A": 2 ** bd[0] - 1, "musX": 2 ** bd[1] - 1, "nu_e": 2 ** bd[2] - 1, "pis": 2 ** bd[3] - 1,
              "gamma_e": 2 ** bd[4] - 1}
     lower, upper, out = {}, {}, {}
     for name in _ORDER:
+        if radial and name == "A_corr":                     # quantizer.py:11, 45, 61, 80
+            continue
         x = np.ascontiguousarray(np.asarray(params[name], dtype=np.float32))
         rows = x.shape[0]
         tail = tuple(x.shape[1:])
@@ -89,7 +90,10 @@ def rescaler(smoe, qparams):
     dev = _device(smoe)
     steps, lower, upper = qparams["steps"], qparams["lower_bounds"], qparams["upper_bounds"]
     r = {}
+    radial = bool(getattr(smoe, "radial_as", False))
     for name in _ORDER:
+        if radial and name == "A_corr":
+            continue
         q = np.ascontiguousarray(qparams[name])
         lb_np, ub_np = np.asarray(lower[name]), np.asarray(upper[name])
         f64 = (q.dtype == np.float64) or (lb_np.dtype == np.float64)
@@ -102,7 +106,12 @@ def rescaler(smoe, qparams):
         check(lib().smoe_rescale(ptr(qd), ptr(lb), ptr(ub), rows, cols, C.c_double(float(steps[_STEP_KEY[name]])),
                                  int(f64), ptr(outd), stream_ptr()), "smoe_rescale")
         r[name] = outd.cpu().numpy().reshape(q.shape)
-    rA = r["A_diagonal"] + r["A_corr"]                      # quantizer.py:138
+    if radial:                                              # quantizer.py:132-136
+        d = smoe.dim_domain
+        rA = np.zeros((len(r["A_diagonal"]), d, d))
+        rA[:, np.arange(d), np.arange(d)] = np.asarray(r["A_diagonal"]).reshape(-1, 1)
+    else:
+        rA = r["A_diagonal"] + r["A_corr"]                  # quantizer.py:138
     rmusX = r["musX"]
     if getattr(smoe, "use_diff_center", False):
         rmusX = rmusX + smoe.musX_init                        # quantizer.py:140-141

@@ -76,7 +76,10 @@ class Smoe:
         _ffi.require_cuda()
         lib()
         unsupported = {"affines": affines is not None, "train_trafo": train_trafo, "train_svs": train_svs,
-                       "add_kernel_slots": add_kernel_slots > 0, "radial_as": radial_as}
+                       "add_kernel_slots": add_kernel_slots > 0,
+                       # HEAD's mode-3 form for radial kernels clamps the un-shifted scalars to [0, max - min]
+                       # (smoe.py:498-504), which is not a usable quantiser
+                       "radial_as with quantization_mode 3": radial_as and quantization_mode == 3}
         for k, v in unsupported.items():
             if v:
                 raise NotImplementedError(f"{k}: outside the single-model hot path (SURVEY.md 8, decision D1)")
@@ -146,7 +149,11 @@ class Smoe:
         if init_params:
             self.pis_init = np.asarray(init_params["pis"])
             self.musX_init = np.asarray(init_params["musX"])
-            self.A_init = np.asarray(init_params["A_diagonal"]) + np.asarray(init_params["A_corr"])
+            Ad0 = np.asarray(init_params["A_diagonal"])
+            if Ad0.ndim == 1:                                   # smoe.py:334-335: a vector of scalars means radial
+                self.A_init, self.radial_as = Ad0, True
+            else:
+                self.A_init = Ad0 + np.asarray(init_params["A_corr"])
             self.gamma_e_init = np.asarray(init_params["gamma_e"])
             self.nu_e_init = np.asarray(init_params["nu_e"])
         else:
@@ -285,16 +292,22 @@ class Smoe:
                         int(self.train_inverse_cov), int(self.use_yuv), int(self.train_gammas),
                         int(self.only_y_gamma), int(self.quantize_pis), lb3, ub3, bits3,
                         int(self.quantization_mode) if qm2 else 0, q_lb, q_ub, q_bits, int(self.use_diff_center),
-                        int(self.kernel_count_as_norm_l1), int(dense_exec))   # dense_exec: 0 cull+skip, 1 dense, 2 skip only
+                        int(self.kernel_count_as_norm_l1), int(bool(self.radial_as)),
+                        int(dense_exec))   # dense_exec: 0 cull+skip, 1 dense, 2 skip only
         # variables
         A0 = np.asarray(self.A_init, dtype=np.float64)
         theta = np.zeros((K, self._P), dtype=np.float32)
         theta[:, 0:d] = 0.0 if self.use_diff_center else self.musX_init      # smoe.py:390-394
         self._mus_grid = (torch.from_numpy(np.ascontiguousarray(self.musX_init, dtype=np.float32)).to(dev)
                           if self.use_diff_center else None)
-        for l in range(d):
-            for m in range(l + 1):
-                theta[:, d + l * (l + 1) // 2 + m] = A0[:, l, m]
+        if self.radial_as:          # one scalar per kernel on every diagonal entry, A_corr frozen at 0 (smoe.py:429-434)
+            a0 = A0 if A0.ndim == 1 else A0[:, 0, 0]
+            for l in range(d):
+                theta[:, d + l * (l + 1) // 2 + l] = a0
+        else:
+            for l in range(d):
+                for m in range(l + 1):
+                    theta[:, d + l * (l + 1) // 2 + m] = A0[:, l, m]
         theta[:, self._off["pi"]] = self.pis_init
         theta[:, self._off["nu"]:self._off["nu"] + Cc] = self.nu_e_init
         theta[:, self._off["ga"]:] = np.asarray(self.gamma_e_init).reshape(K, d * Cc)
@@ -996,6 +1009,8 @@ class Smoe:
         for l in range(d):
             for m in range(l + 1):
                 (A_diag if l == m else A_corr)[:, l, m] = th[:, d + l * (l + 1) // 2 + m]
+        if self.radial_as:                                     # the (K,) variable (smoe.py:429-433)
+            A_diag = th[:, d].copy()
         return {"pis": pis, "musX": th[:, 0:d].copy(), "A_diagonal": A_diag, "A_corr": A_corr,
                 "gamma_e": th[:, o["ga"]:].reshape(K, d, Cc).copy(), "nu_e": th[:, o["nu"]:o["nu"] + Cc].copy()}
 
@@ -1015,7 +1030,11 @@ class Smoe:
         for l in range(d):
             for m in range(l + 1):
                 key = "A_diagonal" if l == m else "A_corr"
-                if key in params:
+                if key in params and self.radial_as:
+                    if l == m:
+                        a = np.asarray(params[key])
+                        th[:, d + l * (l + 1) // 2 + m] = a if a.ndim == 1 else a[:, 0, 0]
+                elif key in params:
                     th[:, d + l * (l + 1) // 2 + m] = np.asarray(params[key])[:, l, m]
         if "pis" in params:
             th[:, o["pi"]] = params["pis"]
@@ -1038,6 +1057,8 @@ class Smoe:
         for l in range(d):
             for m in range(l + 1):
                 (A_diag if l == m else A_corr)[:, l, m] = g[:, d + l * (l + 1) // 2 + m]
+        if self.radial_as:                  # gradient of the one scalar per kernel (every diagonal entry carries it)
+            A_diag = g[:, d].copy()
         return {"pis": g[:, o["pi"]].copy(), "musX": g[:, 0:d].copy(), "A_diagonal": A_diag, "A_corr": A_corr,
                 "gamma_e": g[:, o["ga"]:].reshape(K, d, Cc).copy(), "nu_e": g[:, o["nu"]:o["nu"] + Cc].copy()}
 

@@ -621,9 +621,16 @@ def test_pi_sparsification_prunes_and_index_sets_follow_pis():
             np.testing.assert_array_equal(m._indices[:K].cpu().numpy(), np.nonzero(kl_before & (pis_before > 0))[0])
             assert counts_g[-1] == int((pis_before > 0).sum())
         counts_o.append(o.run_batched(pis_l1=10.0, train=True)[2])
+        if it == 379:
+            # just before the first pi reaches 0 (pi = 1/256 shrinks by ~lr2 = 1e-5 per step): the pis themselves
+            # -- a continuous quantity -- must track the float64 oracle to a few Adam steps
+            dp = np.abs(m.get_params()["pis"] - o.get_params()["pis"])
+            assert counts_g[-1] == counts_o[-1] == 256 and np.quantile(dp, 0.99) < 3e-5 and dp.max() < 1e-4, dp.max()
     assert counts_g[0] == 256 and counts_g[-1] <= 0.7 * 256          # >= 30 % pruned
-    # same trajectory: a pi crosses 0 a few iterations earlier or later in float32 than in float64
-    assert np.abs(np.array(counts_g) - np.array(counts_o)).max() <= 16 and abs(counts_g[-1] - counts_o[-1]) <= 8
+    # Same trajectory.  Most pis cross 0 within a few iterations of each other (iterations ~390-420), so the COUNT
+    # is steep there and a crossing that happens two iterations earlier or later moves it by tens; the float32
+    # and float64 runs of the oracle itself differ by up to 12 kernels on this case.
+    assert np.abs(np.array(counts_g) - np.array(counts_o)).max() <= 40 and abs(counts_g[-1] - counts_o[-1]) <= 26
     assert np.isfinite(m.run_batched(train=False)[0])
 
 
@@ -876,3 +883,70 @@ def test_fake_quant_training_mode3_ranges_of_the_surviving_kernels(case):
     for kk in ("nu_e", "musX", "pis"):
         span = po[kk][keep].max() - po[kk][keep].min() + 1e-9
         assert (np.abs(pg[kk][keep] - po[kk][keep]) > 0.02 * span).mean() < 0.1, kk
+
+
+@pytest.mark.parametrize("case", ["img", "video_mode2"])
+def test_radial_kernels(case):
+    """radial_as (smoe.py:429-434, 714-721): one trainable scalar a per kernel, A = a * I, A_corr frozen at 0;
+    get_params returns A_diagonal as a (K,) vector; the quantiser leaves A_corr out (quantizer.py:11, 45, 132-136)."""
+    from oracle.model import OracleAdam, OracleSmoe
+    from smoe_b200 import quantize_params, rescaler
+    z = np.load(os.path.join(GOLDEN, "init_cases.npz"))
+    img, k = (z["rgb_image"], [6, 8]) if case == "img" else (z["vid_image"], [3, 4, 2])
+    kw = dict(use_determinant=True, train_inverse_cov=False, use_yuv=False, radial_as=True, normalize_pis=False)
+    if case == "video_mode2":
+        kw.update(quantization_mode=2, lower_bounds=[-40.0, -0.3, -1.0, 0.0, -2.0], upper_bounds=[40.0, 1.3, 2.0, 2.0, 2.0],
+                  bit_depths=[12, 12, 8, 10, 8])
+    m = _mk(img, k, **kw)
+    o = OracleSmoe(img, kernels_per_dim=k, dtype=torch.float64, **kw)
+    o.set_optimizer(OracleAdam(1e-3), OracleAdam(1e-5), OracleAdam(1.0))
+    K, d = m.start_pis, m.dim_domain
+    pg, po = m.get_params(), o.get_params()
+    assert pg["A_diagonal"].shape == (K,) and pg["A_corr"].shape == (K, d, d)
+    for kk in PARAM_KEYS:
+        np.testing.assert_array_equal(pg[kk], po[kk], err_msg=kk)
+    a = (pg["A_diagonal"] * (1 + 0.2 * np.random.RandomState(4).uniform(-1, 1, K))).astype(np.float32)
+    m.set_params({"A_diagonal": a})
+    o.vars["A_diagonal"] = torch.tensor(a.astype(np.float64))
+    (lg, mg, _, _), (lo, mo, _, _) = _train_pass_both(m, o, pis_l1=0.1, u_l1=1e-5)
+    assert abs(lg - lo) < 2e-6 * max(1.0, abs(lo)) and abs(mg - mo) < 2e-3 * mo + 1e-3
+    g = m.get_gradients()
+    assert g["A_diagonal"].shape == (K,)
+    for kk, ref in o.last_grads.items():
+        assert _rel(g[kk], ref.numpy()) < 1e-4, kk
+    assert np.abs(g["A_corr"]).max() == 0
+    for _ in range(4):
+        x = m.run_batched(train=True, pis_l1=0.1, u_l1=1e-5)
+        y = o.run_batched(train=True, pis_l1=0.1, u_l1=1e-5)
+        assert abs(x[0] - y[0]) < 1e-3 * max(1.0, abs(y[0]))
+    p1 = m.get_params()
+    assert np.abs(p1["A_corr"]).max() == 0 and np.abs(p1["A_diagonal"] - a).max() > 0
+    if case == "img":
+        # quantiser round trip of the radial dict: bit-exact with the reference's own vectors, and usable as rparams
+        zq = np.load(os.path.join(GOLDEN, "quant_radial_cases.npz"))
+
+        class Shim:
+            pass
+        for ci in range(int(zq["num_cases"])):
+            pre = f"case{ci}_"
+            qm, qp, dd, C, _ = [int(v) for v in zq[pre + "meta"][:5]]
+            s = Shim()
+            s.quantization_mode, s.quantize_pis, s.radial_as, s.dim_domain = qm, bool(qp), True, dd
+            s.image = np.zeros((4,) * dd + (C,), np.float32)
+            s.lower_bounds, s.upper_bounds = [-2500, -.3, -5, 0, -32], [2500, 1.3, 5, 2, 32]
+            s.bit_depths = [int(v) for v in zq[pre + "meta"][5:]]
+            s.use_diff_center, s.musX_init = False, None
+            q = quantize_params(s, {kk: zq[pre + "in_" + kk].copy() for kk in PARAM_KEYS})
+            r = rescaler(s, q)
+            assert "A_corr" not in q
+            for kk in ("A_diagonal", "musX", "nu_e", "pis", "gamma_e"):
+                np.testing.assert_array_equal(q[kk], zq[pre + "q_" + kk], err_msg=f"case {ci} codes {kk}")
+                assert q[kk].dtype == zq[pre + "q_" + kk].dtype
+            for kk in ("A", "musX", "nu_e", "pis", "gamma_e"):
+                np.testing.assert_array_equal(r[kk], zq[pre + "r_" + kk], err_msg=f"case {ci} rescaled {kk}")
+        m.quantization_mode, m.bit_depths = 1, [12, 12, 8, 10, 8]
+        m.qparams = quantize_params(m, m.get_params())
+        m.rparams = rescaler(m, m.qparams)
+        lq, _, _, _ = m.run_batched(train=False, update_reconstruction=True, with_quantized_params=True)
+        l0, _, _, _ = m.run_batched(train=False, update_reconstruction=True)
+        assert abs(lq - l0) < 0.2 * l0 + 1e-3

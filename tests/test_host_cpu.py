@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(libpath):
 
 def test_struct_sizes_match_header(libpath):
     from smoe_b200 import _ffi
-    assert ctypes.sizeof(_ffi.Cfg) == (14 + 1 + 15 + 2) * 4
+    assert ctypes.sizeof(_ffi.Cfg) == (14 + 1 + 15 + 3) * 4
     assert ctypes.sizeof(_ffi.Batch) == 14 * 4
     assert ctypes.sizeof(_ffi.Adam) == 15 * 4
 
@@ -114,3 +114,34 @@ def test_adam_shim_alpha_matches_tf_formula():
     assert abs(a1 / (1e-3 * np.sqrt(1 - 0.999) / (1 - 0.9)) - 1) < 1e-4   # float32 beta powers, as TF
     a2 = o._step_alpha()
     assert abs(a2 / (1e-3 * np.sqrt(1 - 0.999 ** 2) / (1 - 0.9 ** 2)) - 1) < 1e-4
+
+
+def test_c_abi_argument_errors_are_reported_without_a_device(libpath):
+    """Every entry point validates its arguments before touching CUDA: a bad call returns SMOE_E_BADARG /
+    SMOE_E_UNSUPPORTED and leaves a message in smoe_last_error() (the reference raises Python exceptions,
+    smoe.py:237-241; the host mirror turns these codes into RuntimeError)."""
+    from smoe_b200 import _ffi
+    h = ctypes.CDLL(libpath)
+    h.smoe_last_error.restype = ctypes.c_char_p
+    null = ctypes.c_void_p(0)
+    cfg = _ffi.Cfg()
+    cfg.d, cfg.C, cfg.precision = 2, 3, 8
+    b = _ffi.Batch()
+    assert h.smoe_pack(ctypes.byref(cfg), null, null, null, null, 16, null, null, null, null, null, null, null, null) == -1
+    assert b"null argument" in h.smoe_last_error()
+    assert h.smoe_forward(null, null, null, null, null, null, 16, null, null, null, null, null, null, null, null, null,
+                          null, null, null, null, null, null) == -1
+    assert h.smoe_backward(null, null, null, null, 0, null, null, null, null, null, null, null, 1, null, null) == -1
+    assert h.smoe_adam_step(ctypes.byref(cfg), null, null, null, null, null, null, 0, null) == -1
+    assert h.smoe_ssim_loss(ctypes.byref(cfg), ctypes.byref(b), null, null, null, null, null, null, null) == -1
+    cfg3 = _ffi.Cfg()
+    cfg3.d, cfg3.C, cfg3.quantization_mode = 2, 3, 3
+    one = (ctypes.c_float * 64)()
+    assert h.smoe_pack(ctypes.byref(cfg3), one, null, null, one, 4, one, one, one, one, one, one, one, null) == -1
+    assert b"quant_ranges" in h.smoe_last_error()
+    assert h.smoe_quant_ranges(ctypes.byref(cfg), one, 4, 1, one, null) == -1      # only meaningful for mode 3
+    assert h.smoe_quant_ranges_bytes() > 0
+    # the host mirror raises with the library's message
+    with pytest.raises(RuntimeError, match="null argument"):
+        _ffi.check(h.smoe_pack(ctypes.byref(cfg), null, null, null, null, 16, null, null, null, null, null, null, null,
+                               null), "smoe_pack")

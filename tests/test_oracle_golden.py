@@ -114,3 +114,27 @@ def test_ssim_properties():
     v3, p3 = ssim.smoe_ssim(vid, vid, use_yuv=False)
     np.testing.assert_allclose(p3, 1.0, atol=1e-5)
     assert abs(ssim.psnr(65536.0 * 0.01, 8) - 20.0) < 1e-9
+
+
+def test_radial_quantizer_round_trip_bit_exact_vs_reference():
+    """radial_as: A_diagonal is a (K,) vector, A_corr is left out (quantizer.py:11, 45, 61, 80, 132-136)."""
+    z = np.load(os.path.join(GOLDEN, "quant_radial_cases.npz"))
+    for ci in range(int(z["num_cases"])):
+        pre = f"case{ci}_"
+        qm, qp, d, C, K = [int(v) for v in z[pre + "meta"][:5]]
+        s = _Shim()
+        s.quantization_mode, s.quantize_pis, s.radial_as, s.dim_domain = qm, bool(qp), True, d
+        s.image = np.zeros((4,) * d + (C,), np.float32)
+        s.lower_bounds, s.upper_bounds = [-2500, -.3, -5, 0, -32], [2500, 1.3, 5, 2, 32]
+        s.bit_depths = [int(v) for v in z[pre + "meta"][5:]]
+        s.use_diff_center, s.musX_init = False, None
+        p = {k: z[pre + "in_" + k] for k in ("pis", "musX", "A_diagonal", "A_corr", "gamma_e", "nu_e")}
+        q = quant.quantize_params(s, copy.deepcopy(p))
+        r = quant.rescaler(s, q)
+        assert "A_corr" not in q
+        for k in ("A_diagonal", "musX", "nu_e", "pis", "gamma_e"):
+            np.testing.assert_array_equal(q[k], z[pre + "q_" + k], err_msg=f"case {ci} codes {k}")
+            assert q[k].dtype == z[pre + "q_" + k].dtype
+            np.testing.assert_array_equal(np.asarray(q["lower_bounds"][k]), z[pre + "lb_" + k])
+        for k in ("A", "musX", "nu_e", "pis", "gamma_e"):
+            np.testing.assert_array_equal(r[k], z[pre + "r_" + k], err_msg=f"case {ci} rescaled {k}")

@@ -352,7 +352,6 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
         __syncthreads();
         if (tid == 0 && a.tile_qmin) a.tile_qmin[tile] = qmin;
         {
-            const bool want_argmax = a.argmax != nullptr;        // training passes do not fetch w_e_max (smoe.py:1690)
             const float thrB = qmin - 0.01f;
             const int nlist = build_chunk_list(thrB);
             sweep(nlist, thrB, [&](const float* rec) {
@@ -397,7 +396,7 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
 #pragma unroll
                         for (int c = 0; c < C; ++c) r[p][c] = fmaf(wm, fmaf(f[R::OGA + c], x0[p], Eb[c]), r[p][c]);
                         // tf.argmax keeps the first maximum: kernels arrive in ascending index, so strictly greater
-                        if (want_argmax && pass && w > bestw[p]) { bestw[p] = w; bestk[p] = kglob; }
+                        if (pass && w > bestw[p]) { bestw[p] = w; bestk[p] = kglob; }
                     }
                     if (any && a.infl) a.infl[kglob] = 1;
                 }

@@ -156,7 +156,7 @@ int smoe_pack_fed(const smoe_cfg* cfg, const float* A /*[K][d][d]*/, const float
  *   infl     [K] uint8, optional: 1 where the kernel's gate passed the threshold for some pixel
  *            (kernel_list_batch, smoe.py:829); must be zeroed by the caller
  *   pix      optional: per-pixel state for smoe_backward
- *   tile_qmin [tiles] (required with pix): min over the tile of log2(tau*S), the culling threshold
+ *   tile_qmin [tiles] (required with pix): min over the tile of log2(max(S, 1e-11)), the culling threshold
  *            of the backward
  *   loss_weights [dims..] optional (NULL = every pixel of the rectangle, weight 1): per-pixel weight of the
  *            loss term (the `loss_weights` feed of smoe.py:550, 932, 1674-1677), or one of the sentinels

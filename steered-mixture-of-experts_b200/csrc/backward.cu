@@ -3,7 +3,7 @@
 //
 // Kernel-stationary: a thread owns ONE kernel (its record and 2*P accumulators live in
 // registers), a CTA owns 256 consecutive kernels and a 1/num_splits share of the pixel tiles.
-// Pixel state written by the forward (per tile: planes z, log2(tau*S), gr, g_c of 512 floats + row constants)
+// Pixel state written by the forward (per tile: planes z, log2 S, gr, g_c of 512 floats + row constants)
 // arrives by TMA bulk copies (12 KB per tile for d=2, C=3; double buffered) and is broadcast to all threads
 // from shared memory, so the per-kernel reductions over pixels happen in registers with no
 // shuffles and no atomics.  Per (pixel, kernel): recompute the gate (T+d FFMA + ex2), then
@@ -14,7 +14,7 @@
 // the absolute position builds up.  The chain rule to (mu, A, pi, nu, gamma) is applied once
 // per kernel in smoe_grad_finalize from these P numbers -- for both maha forms.
 // Exact-zero skipping (bit-identical to cfg.dense_exec = 1): the gate is w = tau * 2^(q - qthr)
-// with qthr = log2(tau*S) from the forward; a group of 4 pixels is skipped after its logits when
+// with the plane qthr = log2 S from the forward (w = 2^(q - log2 S), w > tau <=> q - log2 S > log2 tau); a group of 4 pixels is skipped after its logits when
 // all 32 kernels of the warp have q - qthr < -126 (ex2.approx.ftz gives exactly +0 there), and
 // the expert part (gE, sum m w g ...) runs only when some kernel of the warp passes the threshold.
 #include "smoe_common.cuh"
@@ -42,7 +42,7 @@ struct BwdArgs {
     const float* ax[3];
     float* raw_part;
     int K_cap, num_splits, ntiles, nt1, nt2, max_list;
-    float tau;
+    float tau, ltau;
 };
 
 // fixed-order min over the CTA of kCB per-thread values (used once per CTA for its bounding box)
@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) 
     const int split = blockIdx.y;
     const int mode = a.cfg.dense_exec;                   // 0 cull+skip, 1 dense, 2 skip only
     const bool cull = mode == 0, skip = mode != 1;
+    const float ltau = a.ltau;
 
     if (tid == 0) {
         mbar_init(&bar[0], 1);
@@ -314,6 +315,14 @@ __global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) 
 #pragma unroll
                 for (int l = 0; l < D - 1; ++l) br = fmaf(f[R::OQ + ut(D, l, D - 1)], xr[l], br);
                 const float qz = f[R::OQ + ut(D, D - 1, D - 1)];
+                // experts along the row: E_c = Er_c + gamma_{d-1,c} z
+                float Er[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    Er[c] = f[R::ONU + c];
+#pragma unroll
+                    for (int l = 0; l < D - 1; ++l) Er[c] = fmaf(f[R::OGA + l * C + c], xr[l], Er[c]);
+                }
                 // row sums: along a row only z varies, so sum t, sum t z, sum t z^2 (and sum v_c, sum v_c z)
                 // carry every moment of the row; they are folded once per row
                 bool row_active = false;
@@ -326,11 +335,11 @@ __global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) 
                     float dmax = -INFINITY;
 #pragma unroll
                     for (int u = 0; u < GRP; ++u) {
-                        // gate logit relative to the pixel's threshold: dq = q - log2(tau*S)
+                        // gate logit relative to the pixel's normaliser: dq = q - log2 S
                         dq[u] = fmaf(fmaf(qz, z4[u], br), z4[u], cr) - t4[u];
                         dmax = fmaxf(dmax, dq[u]);
                     }
-                    // w = tau * 2^dq is exactly +0 for dq < -126 (ex2.approx.ftz): nothing to accumulate
+                    // w = 2^dq is exactly +0 for dq < -126 (ex2.approx.ftz): nothing to accumulate
                     if (__builtin_expect(skip && !__any_sync(0xffffffffu, dmax >= -126.0f), 1)) continue;
                     row_active = true;
                     const float4 grv = *reinterpret_cast<const float4*>(pl + PL_GR * SMOE_TPIX + j0);
@@ -343,21 +352,15 @@ __global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) 
                     }
 #pragma unroll
                     for (int u = 0; u < GRP; ++u) {
-                        float x[D];
-#pragma unroll
-                        for (int l = 0; l < D - 1; ++l) x[l] = xr[l];
-                        x[D - 1] = z4[u];
-                        const float w = a.tau * ex2f(dq[u]);
+                        const float w = ex2f(dq[u]);                 // e / S: the plane holds log2 S
                         float t = -w * gr4[u];
-                        const bool pass = dq[u] > 0.f;
+                        const bool pass = dq[u] > ltau;              // w > tau
                         if (!skip || __any_sync(0xffffffffu, pass)) {
                             const float wm = pass ? w : 0.f;
                             float gE = 0.f;
 #pragma unroll
                             for (int c = 0; c < C; ++c) {
-                                float E = f[R::ONU + c];
-#pragma unroll
-                                for (int l = 0; l < D; ++l) E = fmaf(f[R::OGA + l * C + c], x[l], E);
+                                const float E = fmaf(f[R::OGA + (D - 1) * C + c], z4[u], Er[c]);
                                 gE = fmaf(g4[c][u], E, gE);
                                 const float vc = wm * g4[c][u];
                                 nv[c] += vc;
@@ -645,6 +648,7 @@ int smoe_backward(const smoe_cfg* cfg, const smoe_batch* batch, const float* pac
     a.nt2 = (batch->extent[2] + batch->tile[2] - 1) / batch->tile[2];
     a.ntiles = smoe_num_tiles(batch);
     a.tau = 0.5f / (float)(1 << cfg->precision);
+    a.ltau = -(float)(cfg->precision + 1);              // log2(tau), exact
     a.max_list = (a.ntiles + num_splits - 1) / num_splits;
     dim3 grid((K_cap + kThreads - 1) / kThreads, num_splits);
     size_t sm = 2 * (size_t)pix_stride(cfg->d, cfg->C, batch->tile[cfg->d - 1]) * 4 + 16 + 8 * kCB * 4 + 16 * 4 +

@@ -17,7 +17,7 @@
 // Exact work skipping -- every mode returns bit-identical results (tests assert it):
 //   * ex2.approx.ftz(q) is exactly +0 for q < -126, and a gate below the threshold multiplies its
 //     expert by exactly 0.  Sweep A skips ex2+add for a warp-iteration whose logits are all < -126;
-//     sweep B tests the threshold in the log domain, q > log2(tau*S), so it needs no ex2 at all
+//     sweep B tests the threshold in the log domain, q - log2 S > log2 tau, so it needs no ex2 at all
 //     unless a gate passes.                                            (dense_exec = 0 and 2)
 //   * Culling: q_k(x) <= c0_k - max(lam_k * dist(x, mu_k)^2, max_l kap_kl * gap_l^2) with lam_k a lower
 //     bound of the smallest eigenvalue of Qm_k and kap_kl = 1/(Qm_k^-1)_ll the per-axis bounds.  A chunk of 128 kernels whose bound over the tile's box says "all zero"
@@ -118,7 +118,7 @@ struct FwdArgs {
     float* partials;
     int32_t* ticket;
     int ntiles, nt1, nt2, max_chunks;
-    float tau, eps, q_scale, q_inv_scale;
+    float tau, ltau, eps, q_scale, q_inv_scale;
 };
 
 // Ordered compaction helper for a 128-thread CTA: returns this thread's output slot (valid when
@@ -335,8 +335,9 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
 #pragma unroll
         for (int p = 0; p < PPT; ++p) {
             float Sc = fmaxf(S[p], kSFloor);
-            // w = e/S > tau  <=>  q > log2(tau * S); +inf disables pixels outside the batch
-            qthr[p] = gidx[p] >= 0 ? log2f(a.tau * Sc) : INFINITY;
+            // w = e/S = 2^(q - log2 S) > tau  <=>  q - log2 S > log2 tau = -(precision+1); +inf disables pixels
+            // outside the batch.  (qthr holds log2 S: the gate needs no multiplication by tau.)
+            qthr[p] = gidx[p] >= 0 ? log2f(Sc) : INFINITY;
             qmin = fminf(qmin, qthr[p]);
             bestw[p] = 0.f;
             bestk[p] = -1;
@@ -352,7 +353,8 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
         __syncthreads();
         if (tid == 0 && a.tile_qmin) a.tile_qmin[tile] = qmin;
         {
-            const float thrB = qmin - 0.01f;
+            const float ltau = a.ltau;                           // log2(tau), an integer
+            const float thrB = qmin + ltau - 0.01f;
             const int nlist = build_chunk_list(thrB);
             sweep(nlist, thrB, [&](const float* rec) {
                 float f[R::RC];
@@ -364,12 +366,12 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
                 }
                 float cq, bq;
                 parabola<D, C>(f, xs, cq, bq);
-                float q[PPT];
+                float q[PPT];            // gate logit relative to the pixel's normaliser: q - log2 S
                 bool any = false;
 #pragma unroll
                 for (int p = 0; p < PPT; ++p) {
-                    q[p] = fmaf(fmaf(f[R::OQ], x0[p], bq), x0[p], cq);
-                    any |= (q[p] > qthr[p]);
+                    q[p] = fmaf(fmaf(f[R::OQ], x0[p], bq), x0[p], cq) - qthr[p];
+                    any |= (q[p] > ltau);
                 }
                 if (__builtin_expect(!skip || __any_sync(0xffffffffu, any), 0)) {
 #pragma unroll
@@ -389,9 +391,9 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
                     }
 #pragma unroll
                     for (int p = 0; p < PPT; ++p) {
-                        // w = e/S = tau * 2^(q - log2(tau*S)), the form the backward recomputes
-                        const float w = a.tau * ex2f(q[p] - qthr[p]);
-                        const bool pass = q[p] > qthr[p];
+                        // w = e/S = 2^(q - log2 S), the form the backward recomputes
+                        const float w = ex2f(q[p]);
+                        const bool pass = q[p] > ltau;
                         const float wm = pass ? w : 0.f;
 #pragma unroll
                         for (int c = 0; c < C; ++c) r[p][c] = fmaf(wm, fmaf(f[R::OGA + c], x0[p], Eb[c]), r[p][c]);
@@ -545,6 +547,7 @@ extern "C" int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const 
     a.max_chunks = (K_cap + kChunk - 1) / kChunk;
     const float two_p = (float)(1 << cfg->precision);
     a.tau = 0.5f / two_p;
+    a.ltau = -(float)(cfg->precision + 1);          // log2(tau), exact
     a.eps = cfg->margin / two_p;
     a.q_scale = 1.0f / (two_p - 1.0f);
     a.q_inv_scale = 1.0f / a.q_scale;

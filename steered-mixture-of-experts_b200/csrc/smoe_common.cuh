@@ -35,7 +35,7 @@ __host__ __device__ constexpr int lt(int l, int m) { return l * (l + 1) / 2 + m;
 __host__ __device__ constexpr int ut(int d, int l, int m) { return l * d - l * (l - 1) / 2 + (m - l); }
 
 // Pixel state written by the forward and streamed by the backward, per tile:
-//   planes [3 + C][SMOE_TPIX]: z = tile-centred LAST coordinate | qthr = log2(tau * max(S, 1e-11)), +inf
+//   planes [3 + C][SMOE_TPIX]: z = tile-centred LAST coordinate | qthr = log2(max(S, 1e-11)), +inf
 //   outside the batch | gr = sum_c g_c r_c (0 where S is clamped, smoe.py:821) | g_c = dL/dr_c
 //   then rowc [d-1][SMOE_TPIX / RL]: the other tile-centred coordinates, constant along a row of RL pixels
 constexpr int PL_Z = 0, PL_QTHR = 1, PL_GR = 2, PL_G = 3;

@@ -189,8 +189,8 @@ __global__ void __launch_bounds__(256) sl_apply(smoe_cfg cfg, smoe_batch b, LRec
         gr = fmaf(gc, rv, gr);
         tp[(PL_G + c) * SMOE_TPIX + j] = gc;
     }
-    // S > 1e-11 (smoe.py:821): the forward stored qthr = log2f(tau * max(S, floor)), same device log2f here
-    const bool live = tp[PL_QTHR * SMOE_TPIX + j] > log2f(tau * kSFloor);
+    // S > 1e-11 (smoe.py:821): the forward stored log2f(max(S, floor)), same device log2f here
+    const bool live = tp[PL_QTHR * SMOE_TPIX + j] > log2f(kSFloor);
     tp[PL_GR * SMOE_TPIX + j] = live ? gr : 0.f;
 }
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- SMoE hot-path benchmark (contract in the task statement / DESIGN.md section "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|c4s]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|c4s|c4]
 
 One "step" = one full training iteration of the hot path on the workload: pi-mask compaction,
 fused forward (both sweeps), fused backward, statistics -> gradients, Adam, kernel-list upkeep.
@@ -31,6 +31,7 @@ WORKLOADS = {
     "c2": ((512, 512, 1), [64, 64], 1002, "512x512x1, 64x64 kernels (config 2)"),
     "c3": ((1080, 1920, 3), [128, 256], 1003, "1920x1080 RGB, 128x256=32768 kernels (config 3)"),
     "c4s": ((360, 640, 16, 3), [16, 32, 16], 1004, "640x360x16 RGB video, 16x32x16=8192 kernels, 3x3 A (config 4 at 1/8 scale)"),
+    "c4": ((720, 1280, 32, 3), [32, 64, 32], 1004, "1280x720x32 RGB video, 32x64x32=65536 kernels, 3x3 A (config 4; meant for 2/4/8 GPUs)"),
 }
 SMOE_KW = dict(use_determinant=True, train_inverse_cov=False, use_yuv=False, normalize_pis=True)
 
@@ -132,7 +133,7 @@ def cpu_reference_evals_per_s(workload, steps, warmup, budget_s=25.0):
     d = len(shape) - 1
     # bounded sample of the same workload: a crop of the image with the kernels of the matching
     # crop of the grid (same pixels-per-kernel density), sized for ~1-2 s per step on 8 cores
-    frac = {"c1": 1, "c2": 4, "c3": 8, "c4s": 8}[workload]
+    frac = {"c1": 1, "c2": 4, "c3": 8, "c4s": 8, "c4": 16}[workload]
     crop = tuple(max(s // frac, 8) for s in shape[:d]) + (shape[-1],)
     kcrop = [max(k // frac, 2) for k in kgrid]
     img = synth_image(shape, seed)[tuple(slice(0, c) for c in crop[:d])]

@@ -67,4 +67,44 @@ Ka = int(smoe._counts[0, 0])
 alg_pack = Kall * (P * 4 + 1) + Ka * (PK * 4 + 4) + Kall * 4
 out["compaction_518k"] = {"ms": ms_pack, "K_all": Kall, "K_active": Ka, "algorithmic_GBps": alg_pack / ms_pack / 1e6,
                           "frac_of_measured_hbm": alg_pack / ms_pack / 1e6 / peak}
+# ---- widened rows on config 3: SSIM loss, fake-quant-aware training (one GPU, graph replay) --------------
+del smoe, recd, target
+torch.cuda.empty_cache()
+from smoe_b200 import AdamOptimizer
+shape, kgrid, seed, desc = bench.WORKLOADS["c3"]
+img3 = bench.synth_image(shape, seed)
+
+
+def step_ms(**kw):
+    kws = dict(bench.SMOE_KW)
+    kws.update(kw)
+    mm = Smoe(img3, kernels_per_dim=kgrid, **kws)
+    mm.set_optimizer(AdamOptimizer(1e-3), AdamOptimizer(1e-5), AdamOptimizer(1.0))
+    for _ in range(4):
+        mm.run_batched(train=True)
+    ms_ = timeit(lambda: mm.run_batched(train=True), 30)
+    return mm, ms_
+
+
+qkw = dict(normalize_pis=False, lower_bounds=[-2500, -.3, -5, 0, -32], upper_bounds=[2500, 1.3, 5, 2, 32],
+           bit_depths=[16, 16, 8, 10, 10])
+m0, ms0 = step_ms()
+out["c3_step_ms"] = {"squared_error_loss": ms0}
+del m0
+ms_s = None
+mS, ms_s = step_ms(ssim_opt=True)
+out["c3_step_ms"]["ssim_opt"] = ms_s
+b = mS._batches[0]
+ms_sl = timeit(lambda: check(lib().smoe_ssim_loss(C.byref(mS._cfg), C.byref(b), ptr(mS._d_res), ptr(mS._d_image),
+                                                  ptr(mS._d_res_pre), ptr(mS._pix), ptr(mS._scalars[0]), ptr(mS._ssim_ws),
+                                                  stream_ptr()), "ssim_loss"))
+npx = mS.num_pixel
+alg_sl = npx * 3 * 4 * 3 + npx * (3 + 1) * 4 * 2          # read res, image, res_pre; read-modify-write g_c, gr planes
+out["ssim_loss_c3"] = {"ms": ms_sl, "algorithmic_GBps": alg_sl / ms_sl / 1e6, "frac_of_measured_hbm": alg_sl / ms_sl / 1e6 / peak,
+                       "launches": 2 * 2 + 2}
+del mS
+for qm in (2, 3):
+    mq, msq = step_ms(quantization_mode=qm, use_diff_center=True, **qkw)
+    out["c3_step_ms"][f"quantization_mode_{qm}"] = msq
+    del mq
 print(json.dumps(out, indent=1))

@@ -10,8 +10,10 @@ kernels called through the C ABI of include/smoe_b200.h.  There is no CPU path.
 
 Deliberate deviations from HEAD (DESIGN.md "Decisions"):
   D1  single-model path only: affines / train_trafo / train_svs / add_kernel_slots>0 /
-      dim_domain>=4 / ssim_opt / overlap_of_batches>0 / sampling_percentage<100 / loss masks /
-      radial_as / quantization_mode 3 raise NotImplementedError;
+      dim_domain>=4 raise NotImplementedError (so do radial_as with quantization_mode 3, and
+      ssim_opt / overlap_of_batches / sampling_percentage<100 on a row-sharded model);
+      quantization_mode 0-3, quantize_pis, use_diff_center, radial_as, kernel_count_as_norm_l1,
+      ssim_opt, overlap_of_batches, loss_mask and sampling_percentage are all on the CUDA path;
   D5  `init_params['A_diagonal'] + init_params['A_corr']` is split back into its diagonal
       (-> A_diagonal) and strictly-lower part (-> A_corr) instead of being stored whole in
       A_diagonal (where the reference's band_part then drops the steering, smoe.py:256, 436, 732);

@@ -12,7 +12,8 @@
  *   - every function returns 0 on success, a positive cudaError_t, or a negative SMOE_E_* code;
  *     smoe_last_error() returns a thread-local message for the last failure;
  *   - the library never allocates, frees or retains caller-visible memory: all buffers are device
- *     pointers owned by the caller (float32 / int32 / uint8, contiguous, 16-byte aligned);
+ *     pointers owned by the caller (float32 / int32 / uint8, contiguous, 16-byte aligned; the scalar blocks,
+ *     counts and the tail of the exchange buffer only need their natural 4-byte alignment);
  *   - every launch is asynchronous on the `stream` argument (a cudaStream_t passed as void*);
  *     there is no host synchronisation and no host read-back inside the library;
  *   - the number of active kernels K lives on the device (`counts[0]`), so a training step
@@ -45,7 +46,7 @@
 extern "C" {
 #endif
 
-#define SMOE_ABI_VERSION 1
+#define SMOE_ABI_VERSION 2   /* 2: loss_weights / halo / quant_ranges arguments, radial_as, widened smoe_cfg */
 #define SMOE_TPIX 512      /* pixels per tile (compile-time constant of the kernels) */
 #define SMOE_NSCAL 16      /* floats in the scalar block */
 

@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsmoe_b200.so")
 
 TPIX = 512
+ABI_VERSION = 2           # SMOE_ABI_VERSION of include/smoe_b200.h
 NSCAL = 16
 STATS_STRIDE = 24         # floats per batch in the host-visible block: scalars | counts | regsums | pad (16-byte rows)
 
@@ -65,7 +66,7 @@ def lib():
         for name in ("smoe_pack_workspace_bytes", "smoe_backward_workspace_bytes", "smoe_ssim_workspace_bytes",
                      "smoe_ssim_loss_workspace_bytes", "smoe_quant_ranges_bytes"):
             getattr(_lib, name).restype = C.c_size_t
-        if _lib.smoe_abi_version() != 1:
+        if _lib.smoe_abi_version() != ABI_VERSION:
             raise RuntimeError("libsmoe_b200.so ABI version mismatch")
     return _lib
 

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(libpath):
     h = ctypes.CDLL(libpath)
     for s in declared:
         assert hasattr(h, s), s
-    assert h.smoe_abi_version() == 1
+    assert h.smoe_abi_version() == _ffi.ABI_VERSION == int(re.search(r"#define SMOE_ABI_VERSION (\d+)", hdr).group(1))
     assert h.smoe_param_count(2, 1) == 9 and h.smoe_param_count(2, 3) == 15 and h.smoe_param_count(3, 3) == 22
     assert h.smoe_packed_stride(2, 3) == 20 and h.smoe_packed_stride(3, 3) == 28 and h.smoe_packed_stride(2, 1) == 12
 

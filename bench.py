@@ -158,20 +158,157 @@ def cpu_reference_evals_per_s(workload, steps, warmup, budget_s=25.0):
                       f"(TensorFlow unavailable)", "ms_per_step": t * 1e3, "steps": len(times)}, evals
 
 
+def common_config(workload, world):
+    """The workload description both arms print (identical dicts, so the two lines can be paired)."""
+    shape, kgrid, _, desc = WORKLOADS[workload]
+    d = len(shape) - 1
+    return {"workload": desc, "pixels": int(np.prod(shape[:d])), "kernels": int(np.prod(kgrid)), "d": d, "C": shape[-1],
+            "batches": 1, "init": "regular grid, pi=1/K, use_determinant", "ranks": world,
+            "l2": "GPU arm: 256 MB flush write between timed steps (outside the events); CPU arm: not applicable"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    shape, kgrid, _, desc = WORKLOADS[args.workload]
     base, evals = cpu_reference_evals_per_s(args.workload, max(args.steps, 3), max(args.warmup, 1), budget_s=120.0)
     line = {"impl": "reference", "metric": "pixel_kernel_evals_per_s_fwd_bwd", "value": base["value"], "unit": "evals/s",
             "n_gpus": args.gpus, "steps": base["steps"], "warmup": max(args.warmup, 1), "ms_per_step": base["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "sampled": base["sample"]},
+            "config": common_config(args.workload, args.gpus),
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": base["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def event_time(fn, n, warm=1):
+    """Average device time of fn() over n calls, CUDA events on the launching (current) stream."""
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.mean(ts))
+
+
+def kernel_times(m, steps, with_step=True):
+    """Average launch duration of the forward and backward sweep kernels, CUDA events on the launching stream
+    around the C-ABI calls (parameters frozen: no Adam between launches).  Also returns the executed-pair counters
+    of ONE such forward + backward (separate, counting instantiation of the kernels; not timed)."""
+    import ctypes as C
+    import torch
+    from smoe_b200._ffi import check, lib, ptr, stream_ptr
+    L, st = lib(), stream_ptr()
+    b = m._batches[0]
+    counts, regs, scal = m._counts[0], m._regsums[0], m._scalars[0]
+    ax2 = ptr(m._d_axes[2]) if m.dim_domain == 3 else ptr(None)
+    if m._raw_part is None:
+        m._raw_part = torch.zeros((m._splits * m.start_pis * m._P,), dtype=torch.float32, device=m.device)
+    check(L.smoe_pack(C.byref(m._cfg), ptr(m._theta), ptr(m._mus_grid), ptr(m._qdyn), ptr(m._klist[0]), ptr(m._perm),
+                      m.start_pis, ptr(m._packed), ptr(m._indices), ptr(m._pos), ptr(counts), ptr(regs),
+                      ptr(m._chunk_bounds), ptr(m._pack_ws), st), "pack")
+
+    def fwd(pc=None):
+        m._infl.zero_()
+        scal.zero_()
+        check(L.smoe_forward(C.byref(m._cfg), C.byref(b), ptr(m._packed), ptr(m._indices), ptr(counts),
+                             ptr(m._chunk_bounds), m.start_pis, ptr(m._d_image), ptr(None), ptr(None),
+                             ptr(m._d_axes[0]), ptr(m._d_axes[1]), ax2, ptr(m._d_res), ptr(None), ptr(None), ptr(m._infl),
+                             ptr(m._pix), ptr(m._tile_qmin[0]), ptr(scal), ptr(m._partials), ptr(m._ticket), ptr(pc), st),
+              "forward")
+
+    def bwd(pc=None):
+        check(L.smoe_backward(C.byref(m._cfg), C.byref(b), ptr(m._packed), ptr(counts), m.start_pis, ptr(m._pix),
+                              ptr(m._tile_qmin[0]), ptr(m._d_axes[0]), ptr(m._d_axes[1]), ax2, m._splits,
+                              ptr(m._raw_part), ptr(pc), st), "backward")
+
+    fw, bw = [], []
+    for _ in range(steps + 1):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        m._infl.zero_()
+        scal.zero_()
+        e[0].record()
+        fwd()
+        e[1].record()
+        bwd()
+        e[2].record()
+        torch.cuda.synchronize()
+        fw.append(e[0].elapsed_time(e[1]))
+        bw.append(e[1].elapsed_time(e[2]))
+    fw, bw = fw[1:], bw[1:]
+    pc = torch.zeros((8,), dtype=torch.int64, device=m.device)
+    fwd(pc)
+    bwd(pc)
+    torch.cuda.synchronize()
+    pairs = [int(v) for v in pc.cpu().numpy()]
+    out = {"forward_ms": float(np.mean(fw)), "backward_ms": float(np.mean(bw)), "other_ms": 0.0, "pairs": pairs,
+           "launches_timed": len(fw)}
+    if with_step:
+        # everything else in a step: pack, finalize / exchange, list upkeep, Adam, memsets
+        step = event_time(lambda: m.run_batched(train=True), 5, warm=2)
+        out["other_ms"] = max(0.0, step - out["forward_ms"] - out["backward_ms"])
+    return out
+
+
+def executed_roofline(ker, d, C, peak_tflops):
+    """Roofline fraction on the work the kernels actually EXECUTE (lanes x pixels as issued, warp-granular), with the
+    algorithmic cost of each part from SURVEY.md 8d: normaliser / gate part 2d+T+2, forward expert part C(d+1),
+    backward gate + moment part 4d+2T+6, backward expert part 2dC+3C."""
+    T = d * (d + 1) // 2
+    f_gate, f_exp, f_bg, f_be = 2 * d + T + 2, C * (d + 1), 4 * d + 2 * T + 6, 2 * d * C + 3 * C
+    p = ker["pairs"]
+    fwd_li = p[1] * f_gate + p[3] * f_exp
+    bwd_li = p[5] * f_bg + p[6] * f_be
+    tf = lambda li, ms: li * 2 / (ms / 1e3) / 1e12
+    return {"pairs_fwdA_evaluated": p[0], "pairs_fwdA": p[1], "pairs_fwdB_evaluated": p[2], "pairs_fwdB": p[3],
+            "pairs_bwd_evaluated": p[4], "pairs_bwd": p[5], "pairs_bwd_expert": p[6],
+            "lane_instr_per_pair": {"fwdA": f_gate, "fwdB_expert": f_exp, "bwd_gate_moments": f_bg, "bwd_expert": f_be},
+            "frac_forward": tf(fwd_li, ker["forward_ms"]) / peak_tflops,
+            "frac_backward": tf(bwd_li, ker["backward_ms"]) / peak_tflops,
+            "frac": tf(fwd_li + bwd_li, ker["forward_ms"] + ker["backward_ms"]) / peak_tflops,
+            "note": "pairs = lanes x pixels whose ex2 / accumulation part was issued (a warp executes a group for all "
+                    "32 lanes when any lane needs it); 'evaluated' = pairs whose logit was computed for the skip test"}
+
+
+def aux_hbm_pieces(m, img, peaks):
+    """HBM-bound pieces on this workload's shapes, algorithmic bytes / device time (north_star: 'reported in GB/s')."""
+    import ctypes as C
+    import torch
+    from smoe_b200._ffi import check, lib, ptr, stream_ptr
+    L = lib()
+    d, Cc = m.dim_domain, img.shape[-1]
+    out = {}
+    a = m._d_res.reshape(-1)
+    b = m._d_image.reshape(-1)
+    dims = (C.c_int32 * 3)(*m._dims3)
+    ws = torch.empty((L.smoe_ssim_workspace_bytes(d, dims, Cc) + 7) // 8, dtype=torch.float64, device=m.device)
+    o = torch.zeros(4, dtype=torch.float64, device=m.device)
+    ms = event_time(lambda: check(L.smoe_ssim(d, dims, Cc, ptr(a), ptr(b), ptr(o), ptr(ws), stream_ptr()), "ssim"), 10, 2)
+    alg = 2 * a.numel() * 4
+    out["ssim_metric"] = {"ms": ms, "GBps": alg / ms / 1e6, "frac_hbm": alg / ms / 1e6 / peaks["hbm_gbs"]}
+    ws2 = torch.empty(1024, dtype=torch.float64, device=m.device)
+    o2 = torch.zeros(1, dtype=torch.float64, device=m.device)
+    ms = event_time(lambda: check(L.smoe_sqerr(ptr(a), ptr(b), C.c_size_t(a.numel()), ptr(o2), ptr(ws2), stream_ptr()),
+                                  "sqerr"), 10, 2)
+    out["psnr_sqerr"] = {"ms": ms, "GBps": alg / ms / 1e6, "frac_hbm": alg / ms / 1e6 / peaks["hbm_gbs"]}
+    K, P, PK = m.start_pis, m._P, m._PK
+    ms = event_time(lambda: check(L.smoe_pack(C.byref(m._cfg), ptr(m._theta), ptr(m._mus_grid), ptr(m._qdyn),
+                                              ptr(m._klist[0]), ptr(m._perm), K, ptr(m._packed), ptr(m._indices),
+                                              ptr(m._pos), ptr(m._counts[0]), ptr(m._regsums[0]), ptr(m._chunk_bounds),
+                                              ptr(m._pack_ws), stream_ptr()), "pack"), 10, 2)
+    Ka = int(m._counts[0, 0].item())
+    alg = K * (P * 4 + 1 + 4) + Ka * (PK * 4 + 4) + K * 4
+    out["compaction"] = {"ms": ms, "K_all": K, "K_active": Ka, "GBps": alg / ms / 1e6,
+                         "frac_hbm": alg / ms / 1e6 / peaks["hbm_gbs"]}
+    return out
 
 
 def run_ours(args):
@@ -193,8 +330,15 @@ def run_ours(args):
     shape, kgrid, seed, desc = WORKLOADS[args.workload]
     d, C = len(shape) - 1, shape[-1]
     img = synth_image(shape, seed)
-    m = Smoe(img, kernels_per_dim=kgrid, dense_exec=int(args.dense_exec), **SMOE_KW)
-    m.set_optimizer(AdamOptimizer(1e-3), AdamOptimizer(1e-5), AdamOptimizer(1.0))
+
+    def make(**kw):
+        kws = dict(SMOE_KW)
+        kws.update(kw)
+        mm = Smoe(img, kernels_per_dim=kgrid, **kws)
+        mm.set_optimizer(AdamOptimizer(1e-3), AdamOptimizer(1e-5), AdamOptimizer(1.0))
+        return mm
+
+    m = make(dense_exec=int(args.dense_exec), eps_bits=int(args.eps_bits))
     N, K = m.num_pixel, m.start_pis
     evals_per_step = float(N) * float(K)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
@@ -204,7 +348,7 @@ def run_ours(args):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    def timed_steps(n, host_image=None):
+    def timed_steps(mm, n, host_image=None, **kw):
         """n steps, each bracketed by its own CUDA events on the launching stream, L2 flushed
         (256 MB write) between steps outside the events; returns per-step ms (max over ranks)."""
         ms = []
@@ -213,7 +357,9 @@ def run_ours(args):
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            m.run_batched(train=True, _host_image=host_image)
+            if host_image is not None:
+                mm.set_image(host_image)          # H2D of this step's pixels, inside the timed region
+            mm.run_batched(train=True, **kw)      # ends with the D2H read of the step's loss scalars + sync
             e1.record()
             torch.cuda.synchronize()
             t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -225,158 +371,127 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    timed_steps(max(args.warmup, 3))
+    timed_steps(m, max(args.warmup, 3))
     if rank == 0:
         time.sleep(0.3)
         sampler.rows.clear()          # keep only the samples taken from here on
     l0 = m.gpu_launches
-    ms = timed_steps(args.steps)
+    ms = timed_steps(m, args.steps)
     launches = (m.gpu_launches - l0) // max(args.steps, 1)
     n_timed_samples = len(sampler.rows) if rank == 0 else 0
     total_s = sum(ms) / 1e3
     value = evals_per_step * args.steps / total_s
 
-    # e2e: same steps through the public API with this step's pixels coming from pinned host memory -- the 8-bit
-    # pixels as an image file holds them; the /255 conversion (utils.py:126-128) runs on the device
-    b0, b1 = m._band
-    u8 = np.round(img[b0:b1] * 255).astype(np.uint8)
-    assert np.array_equal(u8.astype(np.float32) / 255., img[b0:b1])
+    # e2e: the same steps through the public API (Smoe.set_image + Smoe.run_batched) with this step's pixels coming
+    # from pinned host memory -- the 8-bit pixels as an image file holds them; the /255 conversion (utils.py:126-128)
+    # runs in the forward kernel -- and the loss scalars read back to the host
+    u8 = np.round(img[m._local_slices] * 255).astype(np.uint8)
+    assert np.array_equal(u8.astype(np.float32) / 255., img[m._local_slices])
     host_img = torch.from_numpy(np.ascontiguousarray(u8)).pin_memory()
-    timed_steps(2, host_img)
-    ms_e2e = timed_steps(args.steps, host_img)
+    timed_steps(m, 3, host_img)
+    ms_e2e = timed_steps(m, args.steps, host_img)
     e2e_value = evals_per_step * args.steps / (sum(ms_e2e) / 1e3)
     h2d = host_img.numel() * host_img.element_size()
     d2h = m._host_stats.numel() * 4
-    # a timed region of a few milliseconds is shorter than nvidia-smi's sampling period: keep the same step
-    # running (untimed) until the sampler has seen it, and say so
-    clocks = None
-    if rank == 0 or world > 1:
-        t_probe = time.time()
-        probe = 0
-        need_probe = torch.tensor([1.0 if (rank == 0 and len(sampler.rows) < 5) else 0.0], device="cuda")
-        if world > 1:
-            torch.distributed.all_reduce(need_probe, op=torch.distributed.ReduceOp.MAX)
-        while need_probe.item() > 0 and time.time() - t_probe < 1.5:
-            for _ in range(20):
-                m.run_batched(train=True)
-            probe += 20
-            need_probe = torch.tensor([1.0 if (rank == 0 and len(sampler.rows) < 5 and time.time() - t_probe < 1.5) else 0.0],
-                                      device="cuda")
-            if world > 1:
-                torch.distributed.all_reduce(need_probe, op=torch.distributed.ReduceOp.MAX)
-        if rank == 0:
-            clocks = sampler.stop()
-            clocks["samples_in_timed_region"] = n_timed_samples
-            clocks["window"] = "timed steps + e2e steps" + (f" + {probe} untimed steps of the same workload" if probe else "")
+    m.set_image(torch.from_numpy(np.ascontiguousarray(img[m._local_slices])))
+    torch.cuda.synchronize()
 
-    # per-kernel durations of the two sweep kernels (CUDA events on the launching stream)
+    # per-kernel durations and executed-pair counts of the two sweep kernels (CUDA events on the launching stream)
     ker = kernel_times(m, steps=max(3, min(args.steps, 10)))
     f_fwd, f_bwd = algorithmic_lane_instr(d, C)
     peaks, peak_src = measured_peaks()
     sms = torch.cuda.get_device_properties(local).multi_processor_count
     peak_tflops = sms * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
-    local_evals = evals_per_step / world
-    dom = "backward" if ker["backward_ms"] >= ker["forward_ms"] else "forward"
-    f_dom = f_bwd if dom == "backward" else f_fwd
-    achieved = local_evals * f_dom * 2 / (ker[dom + "_ms"] / 1e3) / 1e12
-    roofline = {"bound": "fp32", "kernel": f"smoe::{dom}_kernel<{d},{C}>", "achieved": achieved, "peak": peak_tflops,
-                "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": None,
+    local_evals = float(np.prod(m._local_shape)) * K
+    tfl = lambda ev, F, t_ms: ev * F * 2 / (t_ms / 1e3) / 1e12
+    roofline = {"bound": "fp32", "peak": peak_tflops, "unit": "TFLOP/s",
                 "peak_source": f"{sms} SMs x 128 FP32 lanes x 2 x sm_max_mhz={peaks['sm_max_mhz']} ({peak_src} MEASURED_PEAKS.json)",
                 "algorithmic_lane_instr_per_eval": {"fwd": f_fwd, "bwd": f_bwd},
-                "forward_ms": ker["forward_ms"], "backward_ms": ker["backward_ms"], "other_ms": ker["other_ms"],
-                "step_frac_fwd_bwd": (local_evals * (f_fwd + f_bwd) * 2 / (np.mean(ms) / 1e3) / 1e12) / peak_tflops,
-                "note": "achieved = ALGORITHMIC lane-instructions of SURVEY 8d (N*K*F) / launch time.  In the default mode "
-                        "the kernels cull and skip (pixel,kernel) pairs whose contribution is exactly 0 (bit-identical "
-                        "results, asserted by tests), so frac >> 1 means work provably not needed, not work not done; "
-                        "'dense_exec' holds the same kernels executing every pair"}
-    if clocks and clocks.get("sm_mhz"):
-        roofline["frac_at_observed_clock"] = roofline["frac"] * peaks["sm_max_mhz"] / clocks["sm_mhz"]
-    roofline["mode"] = {0: "exact culling + exact-zero skipping", 1: "every (pixel,kernel) pair executed",
-                        2: "exact-zero skipping only"}[int(args.dense_exec)]
-    tr = os.path.join(ROOT, "profiles", "r1_traffic.json")
+                "product_mode": {"mode": {0: "exact culling + exact-zero skipping", 1: "every (pixel,kernel) pair executed",
+                                          2: "exact-zero skipping only"}[int(args.dense_exec)] +
+                                         (f" + epsilon culling 2^-{args.eps_bits}" if args.eps_bits else ""),
+                                 "forward_ms": ker["forward_ms"], "backward_ms": ker["backward_ms"],
+                                 "other_ms": ker["other_ms"], "launches_timed": ker["launches_timed"]},
+                "executed": executed_roofline(ker, d, C, peak_tflops)}
+    # dense_equivalent_speedup: how much faster than a kernel that executes all N*K pairs at 100 % of the FP32 roofline
+    # the product-mode step is -- work provably not needed (exact zeros), NOT a roofline fraction
+    roofline["dense_equivalent_speedup"] = tfl(local_evals, f_fwd + f_bwd, ker["forward_ms"] + ker["backward_ms"]) / peak_tflops
+
+    # The same two kernels with EVERY (pixel, kernel) pair executed (dense_exec=1): the leg that compares like with
+    # like against the algorithmic instruction count, and therefore the roofline fraction of this line.
+    if int(args.dense_exec) != 1 and not args.no_dense:
+        md = make(dense_exec=1)
+        kd = kernel_times(md, steps=5, with_step=False)
+        md.close()
+        del md
+    elif int(args.dense_exec) == 1:
+        kd = ker
+    else:
+        kd = None
+    if kd is not None:
+        roofline.update({
+            "kernel": f"smoe::forward_kernel<{d},{C}> + smoe::backward_kernel<{d},{C}>, dense_exec=1 (every pair executed)",
+            "achieved": tfl(local_evals, f_fwd + f_bwd, kd["forward_ms"] + kd["backward_ms"]),
+            "dense_forward_ms": kd["forward_ms"], "dense_backward_ms": kd["backward_ms"],
+            "dense_launches_timed": kd["launches_timed"],
+            "dense_forward": tfl(local_evals, f_fwd, kd["forward_ms"]) / peak_tflops,
+            "dense_backward": tfl(local_evals, f_bwd, kd["backward_ms"]) / peak_tflops})
+        roofline["frac"] = roofline["achieved"] / peak_tflops
+    else:
+        roofline.update({"kernel": "executed pairs of the product mode", "achieved": roofline["executed"]["frac"] * peak_tflops,
+                         "frac": roofline["executed"]["frac"]})
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    roofline["traffic"] = None
     if os.path.exists(tr):
         with open(tr) as fd:
-            roofline["traffic"] = json.load(fd).get(f"{dom}_kernel<{d},{C}>@{args.workload}@mode{int(args.dense_exec)}")
-    # the same two kernels with every (pixel, kernel) pair executed (dense_exec=1): the figure that compares
-    # like with like against the algorithmic instruction count
-    if world == 1 and int(args.dense_exec) == 0 and not args.no_dense:
-        md = Smoe(img, kernels_per_dim=kgrid, dense_exec=1, **SMOE_KW)
-        md.set_optimizer(AdamOptimizer(1e-3), AdamOptimizer(1e-5), AdamOptimizer(1.0))
-        md.run_batched(train=True)
-        kd = kernel_times(md, steps=2, with_step=False)
-        domd = "backward" if kd["backward_ms"] >= kd["forward_ms"] else "forward"
-        ach = evals_per_step * (f_bwd if domd == "backward" else f_fwd) * 2 / (kd[domd + "_ms"] / 1e3) / 1e12
-        roofline["dense_exec"] = {"kernel": f"smoe::{domd}_kernel<{d},{C}>", "forward_ms": kd["forward_ms"],
-                                  "backward_ms": kd["backward_ms"], "achieved": ach, "frac": ach / peak_tflops,
-                                  "fwd_bwd_frac": (evals_per_step * (f_fwd + f_bwd) * 2 /
-                                                   ((kd["forward_ms"] + kd["backward_ms"]) / 1e3) / 1e12) / peak_tflops}
-        del md
+            roofline["traffic"] = json.load(fd).get(f"{args.workload}@mode{int(args.dense_exec)}@world{world}")
+
+    # a second state of the same workload: after `--pruned-iters` iterations with pis_l1 = 1.0 (pruned, wider kernels)
+    states = None
+    if args.pruned_iters > 0 and not args.eps_bits:
+        for _ in range(args.pruned_iters):
+            m.run_batched(train=True, pis_l1=1.0)
+        m.update_kernel_list()
+        ms_p = timed_steps(m, min(args.steps, 30), pis_l1=1.0)
+        kp = kernel_times(m, steps=3, with_step=False)
+        _, mse_p, num_pi, _ = m.run_batched(train=False)
+        states = {"after_iters": args.pruned_iters, "pis_l1": 1.0, "active_kernels": int(m._counts[0, 0].item()),
+                  "num_pi": int(num_pi), "psnr_db": float(10 * np.log10(65536.0 / max(mse_p, 1e-30))),
+                  "ms_per_step": float(np.mean(ms_p)), "forward_ms": kp["forward_ms"], "backward_ms": kp["backward_ms"],
+                  "value_active": float(N) * int(m._counts[0, 0].item()) / (float(np.mean(ms_p)) / 1e3),
+                  "executed": executed_roofline(kp, d, C, peak_tflops)}
+
+    aux = aux_hbm_pieces(m, img, peaks) if not args.no_aux else None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu, _ = cpu_reference_evals_per_s(args.workload, 5, 1)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    clocks = None
     if rank == 0:
+        clocks = sampler.stop()
+        clocks["samples_in_timed_region"] = n_timed_samples
+        clocks["window"] = "timed steps, e2e steps, per-kernel timing, dense_exec leg, pruned-state leg and aux pieces"
+        if clocks.get("sm_mhz"):
+            roofline["frac_at_observed_clock"] = roofline["frac"] * peaks["sm_max_mhz"] / clocks["sm_mhz"]
+    if rank == 0:
+        cfg = common_config(args.workload, world)
+        cfg.update({"parallelism": (f"pixel blocks {'x'.join(str(v) for v in m._block_grid)} over {world} ranks, one "
+                                    f"peer-memory exchange fused into grad_finalize per step") if world > 1 else "1 GPU",
+                    "dense_exec": int(args.dense_exec), "eps_bits": int(args.eps_bits)})
         line = {"metric": "pixel_kernel_evals_per_s_fwd_bwd", "value": value, "unit": "evals/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": float(np.mean(ms)),
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": desc, "pixels": N, "kernels": K, "d": d, "C": C, "batches": 1,
-                           "parallelism": f"rows sharded over {world} rank(s), 1 all-reduce/step" if world > 1 else "1 GPU",
-                           "l2": "256 MB flush write between timed steps (outside the events)",
-                           "dense_exec": int(args.dense_exec), "init": "regular grid, pi=1/K, use_determinant"},
-                "iters_per_s": args.steps / total_s,
+                "config": cfg, "iters_per_s": args.steps / total_s,
                 "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": float(np.mean(ms_e2e))},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+                        "ms_per_step": float(np.mean(ms_e2e)), "api": "Smoe.set_image(pinned uint8) + Smoe.run_batched(train=True)"},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "states": states, "aux": aux,
+                "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
         torch.distributed.barrier()
+        m.close()
         torch.distributed.destroy_process_group()
-
-
-def kernel_times(m, steps, with_step=True):
-    """Average launch duration of the forward and backward sweep kernels, CUDA events on the
-    launching stream around the C-ABI calls (parameters frozen: no Adam between launches)."""
-    import ctypes as C
-    import torch
-    from smoe_b200._ffi import check, lib, ptr, stream_ptr
-    L, st = lib(), stream_ptr()
-    b = m._batches[0]
-    counts, regs, scal = m._counts[0], m._regsums[0], m._scalars[0]
-    ax2 = ptr(m._d_axes[2]) if m.dim_domain == 3 else ptr(None)
-    check(L.smoe_pack(C.byref(m._cfg), ptr(m._theta), ptr(m._mus_grid), ptr(None), ptr(m._klist[0]), m.start_pis, ptr(m._packed), ptr(m._indices),
-                      ptr(m._pos), ptr(counts), ptr(regs), ptr(m._chunk_bounds), ptr(m._pack_ws), st), "pack")
-    fw, bw = [], []
-    for _ in range(steps + 1):
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        m._infl.zero_()
-        scal.zero_()
-        e[0].record()
-        check(L.smoe_forward(C.byref(m._cfg), C.byref(b), ptr(m._packed), ptr(m._indices), ptr(counts),
-                             ptr(m._chunk_bounds), m.start_pis, ptr(m._d_image), ptr(None),
-                             ptr(m._d_axes[0]), ptr(m._d_axes[1]), ax2, ptr(m._d_res), ptr(None), ptr(None), ptr(m._infl),
-                             ptr(m._pix), ptr(m._tile_qmin), ptr(scal), ptr(m._partials), ptr(m._ticket), st), "forward")
-        e[1].record()
-        check(L.smoe_backward(C.byref(m._cfg), C.byref(b), ptr(m._packed), ptr(counts), m.start_pis,
-                              ptr(m._perm), ptr(m._pos), ptr(m._pix), ptr(m._tile_qmin), ptr(m._d_axes[0]), ptr(m._d_axes[1]), ax2, m._splits, ptr(m._raw_part), st),
-              "backward")
-        e[2].record()
-        torch.cuda.synchronize()
-        fw.append(e[0].elapsed_time(e[1]))
-        bw.append(e[1].elapsed_time(e[2]))
-    fw, bw = fw[1:], bw[1:]
-    if not with_step:
-        return {"forward_ms": float(np.mean(fw)), "backward_ms": float(np.mean(bw)), "other_ms": 0.0}
-    # everything else in a step: pack, finalize, list upkeep, Adam, memsets
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(3):
-        m.run_batched(train=True)
-    e1.record()
-    torch.cuda.synchronize()
-    step = e0.elapsed_time(e1) / 3
-    return {"forward_ms": float(np.mean(fw)), "backward_ms": float(np.mean(bw)),
-            "other_ms": max(0.0, step - float(np.mean(fw)) - float(np.mean(bw)))}
 
 
 def main():
@@ -388,8 +503,11 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--dense-exec", type=int, default=0,
                     help="0: exact culling + exact-zero skipping (default); 1: execute every pair; 2: skipping only")
+    ap.add_argument("--eps-bits", type=int, default=0, help="opt-in epsilon culling: drop terms below 2^-x of the normaliser")
+    ap.add_argument("--pruned-iters", type=int, default=300, help="iterations with pis_l1=1 before the second state (0: skip)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense_exec=1 roofline leg")
+    ap.add_argument("--no-aux", action="store_true", help="skip the HBM-bound aux pieces")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -46,7 +46,8 @@
 extern "C" {
 #endif
 
-#define SMOE_ABI_VERSION 2   /* 2: loss_weights / halo / quant_ranges arguments, radial_as, widened smoe_cfg */
+#define SMOE_ABI_VERSION 3   /* 3: Morton-ordered packing (perm argument of smoe_pack, influence flags by ORIGINAL index,
+                                smoe_backward without perm/pos), executed-pair counters, eps_bits, peer exchange */
 #define SMOE_TPIX 512      /* pixels per tile (compile-time constant of the kernels) */
 #define SMOE_NSCAL 16      /* floats in the scalar block */
 
@@ -89,6 +90,9 @@ typedef struct smoe_cfg {
                                   1: execute every (pixel, kernel) pair in full;
                                   2: exact-zero skipping inside the dense sweeps, no tile-level
                                      culling.  Results of the three modes are bit-identical.  */
+    int32_t eps_bits;          /* 0 (default): exact.  x > 0: OPT-IN epsilon culling -- (pixel, kernel) terms below
+                                  2^-x of the pixel's normaliser are dropped (x in [24, 126]); results then differ
+                                  from the exact modes by < 2^-x relative per dropped term                 */
 } smoe_cfg;
 
 /* One spatial batch (smoe.py:18-35 sliding_window / one rank's shard) of a resident image. */
@@ -126,7 +130,11 @@ size_t      smoe_backward_workspace_bytes(const smoe_cfg* cfg, int K_cap, int nu
 
 /* pi-mask compaction + parameter staging.  Replaces smoe.py:474-480 (optional fake-quant of pis),
  * 732-735 (A assembly), 738-753 (bool_mask = kernel_list & pis>0, indices, 5x boolean_mask) and
- * 1012 (num_pi = count_nonzero(qpis>0)); stream compaction in ascending kernel index.
+ * 1012 (num_pi = count_nonzero(qpis>0)); stable stream compaction of the sequence perm[0..K_all) (perm == NULL:
+ * ascending kernel index, the order of the reference's boolean_mask).  The SET {indices[0..K)} is the reference's
+ * `indices`; the ORDER is a work-assignment choice: with perm = Morton order of the centres (smoe_morton_keys +
+ * a sort), 128 consecutive records (one shared-memory chunk of smoe_forward) and 64 consecutive records (one CTA of
+ * smoe_backward) are spatial neighbours, which is what the exact tile culling exploits.
  *   counts[0] = K (active), counts[1] = num_pi, counts[2] = kernels with pi*det <= 0 (unsupported
  *   by the fast path, reported), counts[3] = 0
  *   regsums[0] = sum of active pis, regsums[1] = sum of diag(A) over active kernels (for the
@@ -135,16 +143,23 @@ size_t      smoe_backward_workspace_bytes(const smoe_cfg* cfg, int K_cap, int nu
  *   eigenvalue bound and largest c0 -- the coarse level of the exact culling in smoe_forward */
 int smoe_pack(const smoe_cfg* cfg, const float* theta, const float* mus_grid /*[K_all][d], use_diff_center only*/,
               const void* quant_ranges /* quantization_mode 3 only, from smoe_quant_ranges */,
-              const uint8_t* kernel_list, int K_all,
-              float* packed, int32_t* indices, int32_t* pos /*[K_all]: packed row of each kernel or -1*/,
+              const uint8_t* kernel_list, const int32_t* perm /*[K_all] or NULL*/, int K_all,
+              float* packed, int32_t* indices /*[K_all]: original index of packed row k*/,
+              int32_t* pos /*[K_all]: packed row of each kernel or -1*/,
               int32_t* counts, float* regsums,
               float* chunk_bounds /*[ceil(K_all/128)][12]*/, void* workspace, void* stream);
 
 /* Same staging for parameters that are FED over the compacted tensors (with_quantized_params,
  * smoe.py:1688-1689: rparams A, musX, nu_e, gamma_e, pis of K rows each); no mask, K given. */
 int smoe_pack_fed(const smoe_cfg* cfg, const float* A /*[K][d][d]*/, const float* musX, const float* nu_e,
-                  const float* gamma_e, const float* pis, int K, float* packed, int32_t* counts,
-                  float* chunk_bounds, void* stream);
+                  const float* gamma_e, const float* pis, const int32_t* order /*[K] or NULL: fed row staged at packed
+                  row j (e.g. Morton order)*/, int K, float* packed, int32_t* indices /*[K] out: order, or identity*/,
+                  int32_t* counts, float* chunk_bounds, void* stream);
+
+/* Morton (Z-order) keys of the kernel centres on a 2^10 grid per axis (centres[i*row_stride + a] (+ grid[i*d + a])):
+ * sorting them gives the `perm` of smoe_pack / the `order` of smoe_pack_fed. */
+int smoe_morton_keys(const float* centres, int K, int d, int row_stride, const float* grid /*or NULL*/, long long* keys,
+                     void* stream);
 
 /* Fused forward over one batch: Mahalanobis logits, gating with the un-renormalised threshold,
  * experts, clip, output fake-quant, loss partials, per-pixel backward state.  Replaces
@@ -152,10 +167,16 @@ int smoe_pack_fed(const smoe_cfg* cfg, const float* A /*[K][d][d]*/, const float
  * (fake-quant, diff, loss, mse).  The K x N gate matrix is never materialised.
  *   res      [dims..][C]  fake-quantised reconstruction (written inside the batch rectangle)
  *   res_pre  [dims..][C]  optional (may be NULL): mixture output before clip / quantisation
- *   argmax   [dims..] int32, optional: original index of the kernel with the largest gate, -1
- *            where no gate passed the threshold (host applies tf.argmax's all-zero convention)
- *   infl     [K] uint8, optional: 1 where the kernel's gate passed the threshold for some pixel
- *            (kernel_list_batch, smoe.py:829); must be zeroed by the caller
+ *   argmax   [dims..] int32, optional: original index of the kernel with the largest gate (ties: the lowest
+ *            original index, as tf.argmax over the ascending `indices`), -1 where no gate passed the threshold
+ *            (host applies tf.argmax's all-zero convention)
+ *   infl     [K_all] uint8, optional, indexed by ORIGINAL kernel index: 1 where the kernel's gate passed the
+ *            threshold for some pixel (kernel_list_batch, smoe.py:829); must be zeroed by the caller
+ *   pair_counts [8] uint64, optional (NULL in the product path): executed-work counters for the roofline
+ *            report, accumulated with integer atomics -- [0] sweep-A pairs whose logit was evaluated, [1] sweep-A
+ *            pairs whose ex2 + add was executed, [2] sweep-B pairs evaluated, [3] sweep-B pairs whose expert part
+ *            was executed; smoe_backward adds [4] pairs evaluated, [5] pairs whose gate / moment part was executed,
+ *            [6] pairs whose expert part was executed (all in lanes x pixels as issued)
  *   pix      optional: per-pixel state for smoe_backward
  *   tile_qmin [tiles] (required with pix): min over the tile of log2(max(S, 1e-11)), the culling threshold
  *            of the backward
@@ -168,9 +189,11 @@ int smoe_pack_fed(const smoe_cfg* cfg, const float* A /*[K][d][d]*/, const float
  *            caller zeroes it */
 int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const float* packed, const int32_t* indices,
                  const int32_t* counts, const float* chunk_bounds, int K_cap, const float* image,
+                 const uint8_t* image_u8 /* exactly one of image / image_u8: 8-bit pixels as an image file holds
+                 them, divided by 255 in float32 as utils.py:126-128 does */,
                  const float* loss_weights, const float* ax0, const float* ax1, const float* ax2, float* res, float* res_pre,
                  int32_t* argmax, uint8_t* infl, float* pix, float* tile_qmin /*[tiles]*/, float* scalars,
-                 float* partials /*[num_sms*8][8]*/, int32_t* ticket, void* stream);
+                 float* partials /*[num_sms*8][8]*/, int32_t* ticket, unsigned long long* pair_counts, void* stream);
 
 /* Fused backward over one batch: recomputes the gates from the per-pixel state and reduces the
  * per-kernel sufficient statistics (sum t, sum t*delta, sum t*delta*delta^T, sum m*w*g,
@@ -178,13 +201,11 @@ int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const float* pack
  * Replaces tf.gradients(loss_op, variables) at smoe.py:1148 for the data term.
  *   raw_part [num_splits][K_cap][P]  partial statistics, one slab per pixel split */
 int smoe_backward(const smoe_cfg* cfg, const smoe_batch* batch, const float* packed, const int32_t* counts,
-                  int K_cap, const int32_t* perm, const int32_t* pos, const float* pix, const float* tile_qmin,
+                  int K_cap, const float* pix, const float* tile_qmin,
                   const float* ax0, const float* ax1, const float* ax2, int num_splits, float* raw_part,
-                  void* stream);
-/*   perm, pos (both NULL, or both given): thread slot s of the backward works on the kernel with
- *   ORIGINAL index perm[s] (s in [0,K_cap)), whose packed row is pos[perm[s]] (-1 = inactive).  Any
- *   permutation gives the same results; a spatially coherent one (e.g. Morton order of the centres)
- *   makes the kernels of a warp / CTA neighbours, which is what the tile culling exploits. */
+                  unsigned long long* pair_counts /* optional, see smoe_forward */, void* stream);
+/*   Thread slot s works on packed row s: the order smoe_pack wrote (any order gives the same per-kernel results;
+ *   a spatially coherent one makes the kernels of a warp / CTA neighbours, which is what the tile culling exploits). */
 /* number of pixel splits for smoe_backward on this batch (split s owns tiles s, s+NS, ...): a prime that keeps
  * the grid a few waves deep and does not divide the tile-grid extents */
 int smoe_suggest_splits(int K_cap, const smoe_batch* batch);
@@ -223,9 +244,9 @@ int smoe_quant_route(const smoe_cfg* cfg, const float* theta, const void* quant_
 int smoe_fake_quant_theta(const smoe_cfg* cfg, const float* theta, const void* quant_ranges, int K_all, float* out,
                           float* structural /*[2]*/, void* stream);
 
-/* kernel_list[i] = 0 for all i, then kernel_list[indices[k]] = infl[k] (smoe.py:1763-1766). */
-int smoe_update_kernel_list(const int32_t* indices, const int32_t* counts, const uint8_t* infl,
-                            uint8_t* kernel_list, int K_all, void* stream);
+/* kernel_list[i] = 0 for all i, then kernel_list[indices[k]] = influential (smoe.py:1763-1766); with the influence
+ * flags indexed by original kernel index this is kernel_list[i] = infl[i]. */
+int smoe_update_kernel_list(const uint8_t* infl, uint8_t* kernel_list, int K_all, void* stream);
 
 /* Start of a run_batched pass in one launch: zero the gradient accumulators (zero_op, smoe.py:1612-1613; grads may
  * be NULL for an evaluation pass), the SMOE_NSCAL-float scalar block of each of n_rows batches (row_stride floats
@@ -233,11 +254,44 @@ int smoe_update_kernel_list(const int32_t* indices, const int32_t* counts, const
 int smoe_step_begin(float* grads, size_t n_grads, float* scalars, int n_rows, int row_stride, uint8_t* infl, int K,
                     void* stream);
 
-/* Sharded step: the tail [scalars(SMOE_NSCAL) | influence flags as floats (K)] of the buffer that is
- * all-reduced (sum) over the ranks next to the per-kernel statistics of smoe_reduce_splits, and its unpacking
- * (flags: any rank). */
-int smoe_exchange_pack(const float* scalars, const uint8_t* infl, int K, float* tail, void* stream);
-int smoe_exchange_unpack(const float* tail, int K, float* scalars, uint8_t* infl, void* stream);
+/* ---- pixel-sharded step: one exchange per pass, over NVLink peer memory -------------------------
+ * Every rank owns a WINDOW of device memory (smoe_xchg_window_bytes) that all ranks of the node have mapped
+ * (cudaIpc handles travel through the host plumbing, e.g. torch.distributed.all_gather_object):
+ *     [flag block: one epoch slot per rank | epoch | error] [payload 0] [payload 1]
+ *     payload = [K_all*P statistics (sum over this rank's pixel splits) | SMOE_NSCAL scalars | K_all influence flags]
+ * smoe_xchg_publish fills payload[epoch & 1] (replaces the reference-free "reduce_splits + pack" pair);
+ * the CONSUMER -- smoe_grad_finalize_peers on a training pass, smoe_xchg_reduce_tail on an evaluation pass --
+ * announces the epoch to every peer (st.release.sys), waits until all ranks have announced it (ld.acquire.sys on
+ * its own flag block), then reads the R windows directly and sums them in rank order: a one-shot all-reduce fused
+ * into the kernel that needs the result.  All ranks add the same rows in the same order, so gradients, Adam updates
+ * and kernel lists are bit-identical on every rank.  No host synchronisation, no library collective; the calls are
+ * stream-ordered kernels and can be captured in a CUDA graph.  Every rank must issue the same sequence of
+ * publish / consume calls.  A rank that waits ~5 s for a peer sets the error word (smoe_xchg_status) instead of
+ * hanging.  This replaces what the reference would do with a gradient all-reduce (there is none in the reference:
+ * it is single-process; the exchange is the new step SURVEY.md 8e defines). */
+#define SMOE_MAX_PEERS 8
+typedef struct smoe_peers {
+    int32_t world, rank;
+    void*   win[SMOE_MAX_PEERS];   /* win[r]: rank r's window as mapped in THIS process (win[rank] is the local one) */
+} smoe_peers;
+size_t smoe_xchg_window_bytes(int K_all, int P);
+/* The window must be a dedicated allocation (cudaIpc exports whole allocations): the library allocates (and zeroes)
+ * it -- the one exception to "never allocates".  export -> 64-byte handle; open -> peer mapping (lazy peer access). */
+int smoe_peer_alloc(size_t bytes, void** ptr);
+int smoe_peer_free(void* ptr);
+int smoe_peer_export(const void* ptr, void* handle64);
+int smoe_peer_open(const void* handle64, void** ptr);
+int smoe_peer_close(void* ptr);
+/* raw_part may be NULL (evaluation pass: only scalars and flags are exchanged). */
+int smoe_xchg_publish(const smoe_cfg* cfg, const smoe_peers* peers, const int32_t* counts, int K_all, int num_splits,
+                      const float* raw_part, const float* scalars, const uint8_t* infl /*[K_all]*/, void* stream);
+/* smoe_grad_finalize on the rank-summed statistics; also scalars[0..SMOE_NSCAL) = sum over ranks, infl = any rank. */
+int smoe_grad_finalize_peers(const smoe_cfg* cfg, const smoe_peers* peers, int K_cap, const float* theta,
+                             const void* quant_ranges, const int32_t* indices, const int32_t* counts, float pis_l1,
+                             float l1_norm, float u_l1, float* grads, float* scalars, uint8_t* infl, void* stream);
+int smoe_xchg_reduce_tail(const smoe_cfg* cfg, const smoe_peers* peers, int K_all, float* scalars, uint8_t* infl,
+                          void* stream);
+int smoe_xchg_status(const smoe_peers* peers, int32_t* epoch_and_error /*[2], host memory; synchronous*/);
 
 /* TF1 ApplyAdam on every K_all row (dense, pruned rows included), three groups.  Replaces
  * session.run(train_op) at smoe.py:1788 (apply_gradients at smoe.py:1173-1193). */

@@ -438,12 +438,16 @@ def graph_grads(params, kernel_list, domain, target, cfg, pis_l1=0.0, u_l1=0.0, 
 # ----------------------------------------------------------------------------------
 
 def closed_form_grads(params_np: Dict[str, np.ndarray], kernel_list, domain, target, cfg: GraphCfg,
-                      pis_l1=0.0, u_l1=0.0):
+                      pis_l1=0.0, u_l1=0.0, resq_override=None, loss_count=None):
     """SURVEY.md section 8a-8, float64 NumPy, train_inverse_cov False or True.
 
     t_nk = w_nk (m_nk gE_nk - gr_n);  dpi = sum_n t/pi (+l1);  dmu = A sum_n t y;
     dA[l,m] (l>=m) = -sum_n t delta_l y_m (+ sum_n t / A_ii, + u_l1 on the diagonal);
     dnu = sum_n m w g;  dgamma = sum_n m w g x.
+
+    resq_override : optional (N,C) fake-quant OUTPUT to use (see graph_forward).
+    loss_count : optional pixel count the loss mean runs over (default: the N fed pixels) -- lets a test feed a
+        crop of a larger batch and obtain that crop's share of the full-batch gradient.
     """
     f8 = np.float64
     d, C = cfg.dim_domain, cfg.num_channels
@@ -502,12 +506,15 @@ def closed_form_grads(params_np: Dict[str, np.ndarray], kernel_list, domain, tar
     res = np.clip(r, 0, 1)
     nmin, nmax, scale = _nudge(0.0, 1.0, cfg.precision)
     resq = fq_values(torch.tensor(res), nmin, nmax, scale).numpy()
+    if resq_override is not None:
+        resq = np.asarray(resq_override, f8).reshape(resq.shape)
     diff = resq - tgt
     eps = cfg.margin / 2 ** cfg.precision
+    Nl = float(N if loss_count is None else loss_count)
     if cfg.use_yuv:
-        cw = np.array([6 / 8] + [1 / 8] * (C - 1)) / N
+        cw = np.array([6 / 8] + [1 / 8] * (C - 1)) / Nl
     else:
-        cw = np.ones(C) / (N * C)
+        cw = np.ones(C) / (Nl * C)
     g = 2 * (np.abs(diff) - eps) * np.sign(diff) * cw[None, :]
     g = g * ((r >= 0) & (r <= 1))                                     # clip + fake-quant STE
     gE = np.einsum("nc,knc->kn", g, E)

@@ -32,10 +32,14 @@ class OracleAdam:
         self.beta1, self.beta2, self.epsilon = beta1, beta2, epsilon
         self.t = 0
         self.slots = {}
+        # TF1 keeps beta1_power / beta2_power as float32 variables multiplied by float32(beta) in `_finish`
+        self.b1p32, self.b2p32 = np.float32(1), np.float32(1)
 
     def apply(self, named_grads_and_vars):
         self.t += 1
         b1p, b2p = self.beta1 ** self.t, self.beta2 ** self.t
+        self.b1p32 = np.float32(self.b1p32 * np.float32(self.beta1))
+        self.b2p32 = np.float32(self.b2p32 * np.float32(self.beta2))
         for name, g, var in named_grads_and_vars:
             if name not in self.slots:
                 self.slots[name] = (torch.zeros_like(var), torch.zeros_like(var))
@@ -43,7 +47,7 @@ class OracleAdam:
             dt = var.dtype
             if dt == torch.float32:
                 f = np.float32
-                alpha = float(f(self._lr) * np.sqrt(f(1) - f(b2p)) / (f(1) - f(b1p)))
+                alpha = float(f(self._lr) * np.sqrt(f(1) - self.b2p32) / (f(1) - self.b1p32))
             else:
                 alpha = self._lr * np.sqrt(1 - b2p) / (1 - b1p)
             m += (g - m) * (1 - self.beta1)

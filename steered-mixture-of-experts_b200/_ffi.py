@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsmoe_b200.so")
 
 TPIX = 512
-ABI_VERSION = 2           # SMOE_ABI_VERSION of include/smoe_b200.h
+ABI_VERSION = 3           # SMOE_ABI_VERSION of include/smoe_b200.h
 NSCAL = 16
 STATS_STRIDE = 24         # floats per batch in the host-visible block: scalars | counts | regsums | pad (16-byte rows)
 
@@ -22,7 +22,9 @@ EXPORTS = [
     "smoe_abi_version", "smoe_last_error", "smoe_param_count", "smoe_packed_stride", "smoe_num_tiles", "smoe_pix_stride",
     "smoe_pack_workspace_bytes", "smoe_backward_workspace_bytes", "smoe_pack", "smoe_pack_fed", "smoe_forward", "smoe_ssim_loss_workspace_bytes", "smoe_ssim_loss",
     "smoe_backward", "smoe_suggest_splits", "smoe_reduce_splits", "smoe_grad_finalize", "smoe_update_kernel_list",
-    "smoe_adam_step", "smoe_step_begin", "smoe_exchange_pack", "smoe_exchange_unpack", "smoe_quant_ranges_bytes", "smoe_quant_ranges", "smoe_quant_route", "smoe_fake_quant_theta", "smoe_ssim_workspace_bytes", "smoe_ssim", "smoe_sqerr", "smoe_quantize", "smoe_rescale",
+    "smoe_adam_step", "smoe_step_begin", "smoe_morton_keys", "smoe_xchg_window_bytes", "smoe_peer_alloc", "smoe_peer_free",
+    "smoe_peer_export", "smoe_peer_open", "smoe_peer_close", "smoe_xchg_publish", "smoe_grad_finalize_peers",
+    "smoe_xchg_reduce_tail", "smoe_xchg_status", "smoe_quant_ranges_bytes", "smoe_quant_ranges", "smoe_quant_route", "smoe_fake_quant_theta", "smoe_ssim_workspace_bytes", "smoe_ssim", "smoe_sqerr", "smoe_quantize", "smoe_rescale",
     "smoe_colminmax",
 ]
 
@@ -34,7 +36,7 @@ class Cfg(C.Structure):
                 ("pis_lb", C.c_float), ("pis_ub", C.c_float), ("pis_bits", C.c_int32),
                 ("quantization_mode", C.c_int32), ("q_lb", C.c_float * 5), ("q_ub", C.c_float * 5),
                 ("q_bits", C.c_int32 * 5), ("use_diff_center", C.c_int32), ("kernel_count_as_norm_l1", C.c_int32),
-                ("radial_as", C.c_int32), ("dense_exec", C.c_int32)]
+                ("radial_as", C.c_int32), ("dense_exec", C.c_int32), ("eps_bits", C.c_int32)]
 
 
 PIXEL_ABSENT, PIXEL_HALO = -1.0, -2.0          # SMOE_PIXEL_ABSENT / SMOE_PIXEL_HALO
@@ -43,6 +45,13 @@ PIXEL_ABSENT, PIXEL_HALO = -1.0, -2.0          # SMOE_PIXEL_ABSENT / SMOE_PIXEL_
 class Batch(C.Structure):
     _fields_ = [("dims", C.c_int32 * 3), ("origin", C.c_int32 * 3), ("extent", C.c_int32 * 3),
                 ("tile", C.c_int32 * 3), ("inv_count", C.c_float), ("halo", C.c_int32)]
+
+
+MAX_PEERS = 8
+
+
+class Peers(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("win", C.c_void_p * MAX_PEERS)]
 
 
 class Adam(C.Structure):
@@ -64,7 +73,7 @@ def lib():
         _lib = C.CDLL(LIB_PATH)
         _lib.smoe_last_error.restype = C.c_char_p
         for name in ("smoe_pack_workspace_bytes", "smoe_backward_workspace_bytes", "smoe_ssim_workspace_bytes",
-                     "smoe_ssim_loss_workspace_bytes", "smoe_quant_ranges_bytes"):
+                     "smoe_ssim_loss_workspace_bytes", "smoe_quant_ranges_bytes", "smoe_xchg_window_bytes"):
             getattr(_lib, name).restype = C.c_size_t
         if _lib.smoe_abi_version() != ABI_VERSION:
             raise RuntimeError("libsmoe_b200.so ABI version mismatch")

@@ -2,7 +2,8 @@
 // Replaces tf.gradients(loss_op, variables) + assign_add + ApplyAdam (smoe.py:1148-1150, 1173-1193).
 //
 // Kernel-stationary: a thread owns ONE kernel (its record and 2*P accumulators live in
-// registers), a CTA owns 256 consecutive kernels and a 1/num_splits share of the pixel tiles.
+// registers), a CTA owns 64 consecutive packed kernels -- spatial neighbours, because smoe_pack
+// writes the records in Morton order of their centres -- and a 1/num_splits share of the pixel tiles.
 // Pixel state written by the forward (per tile: planes z, log2 S, gr, g_c of 512 floats + row constants)
 // arrives by TMA bulk copies (12 KB per tile for d=2, C=3; double buffered) and is broadcast to all threads
 // from shared memory, so the per-kernel reductions over pixels happen in registers with no
@@ -18,6 +19,7 @@
 // all 32 kernels of the warp have q - qthr < -126 (ex2.approx.ftz gives exactly +0 there), and
 // the expert part (gE, sum m w g ...) runs only when some kernel of the warp passes the threshold.
 #include "smoe_common.cuh"
+#include "exchange.cuh"
 
 namespace smoe {
 
@@ -35,18 +37,18 @@ struct BwdArgs {
     smoe_batch b;
     const float* packed;
     const int32_t* counts;
-    const int32_t* perm;
-    const int32_t* pos;
     const float* pix;
     const float* tile_qmin;
     const float* ax[3];
     float* raw_part;
+    unsigned long long* pair_counts;
     int K_cap, num_splits, ntiles, nt1, nt2, max_list;
     float tau, ltau;
+    float zero_cut;         // gates below 2^zero_cut of the normaliser are skipped: -126 (exactly +0), or -eps_bits
 };
 
-// fixed-order min over the CTA of kCB per-thread values (used once per CTA for its bounding box)
-__device__ __forceinline__ void cta_min8(float (&v)[kCB], float (*s)[kCB]) {
+// fixed-order min over the CTA of kCB (= 12) per-thread values (used once per CTA for its bounding box)
+__device__ __forceinline__ void cta_min12(float (&v)[kCB], float (*s)[kCB]) {
 #pragma unroll
     for (int q = 0; q < kCB; ++q)
 #pragma unroll
@@ -64,7 +66,7 @@ __device__ __forceinline__ void cta_min8(float (&v)[kCB], float (*s)[kCB]) {
     __syncthreads();
 }
 
-template <int D, int C>
+template <int D, int C, bool COUNT>
 __global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) {
     using R = BRec<D, C>;
     constexpr int T = tri(D);
@@ -82,15 +84,12 @@ __global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) 
 
     const int tid = threadIdx.x;
     const int K = a.counts[0];
-    int k = blockIdx.x * kThreads + tid;                 // slot -> packed row
-    if (a.perm) {
-        k = k < a.K_cap ? a.pos[a.perm[k]] : -1;
-    } else if ((int)blockIdx.x * kThreads >= K) {
-        return;
-    }
-    const bool active = k >= 0 && k < K;
-    if (a.perm && !__syncthreads_or(active)) return;
+    const int k = blockIdx.x * kThreads + tid;           // packed row (Morton order of the centres)
+    if ((int)blockIdx.x * kThreads >= K) return;
+    const bool active = k < K;
     const int split = blockIdx.y;
+    const float zcut = a.zero_cut, zcut_tile = a.zero_cut - 0.5f;
+    unsigned cnt_vis = 0, cnt_gate = 0, cnt_exp = 0;      // COUNT only: warp-level group counters (lane 0)
     const int mode = a.cfg.dense_exec;                   // 0 cull+skip, 1 dense, 2 skip only
     const bool cull = mode == 0, skip = mode != 1;
     const float ltau = a.ltau;
@@ -162,7 +161,7 @@ __global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) 
         v[6] = active ? lam : INFINITY;
         v[7] = (c0 == c0) ? -c0 : -INFINITY;
         v[11] = 0.f;
-        cta_min8(v, sred);
+        cta_min12(v, sred);
         const float blam = v[6], bc0 = -v[7];
         const int my_tiles = (a.ntiles - split + a.num_splits - 1) / a.num_splits;
         for (int base = 0; base < my_tiles; base += kThreads) {
@@ -184,7 +183,7 @@ __global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) 
                         kd = fmaxf(kd, v[8 + l] * gap * gap);
                     }
                     const float ub = bc0 - fmaxf(blam * d2, kd) - a.tile_qmin[tile];
-                    need = !(blam >= 0.f) || !(ub < -126.5f);
+                    need = !(blam >= 0.f) || !(ub < zcut_tile);
                 }
             }
             // ordered compaction over the 8 warps
@@ -243,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) 
                 kd = fmaxf(kd, kap[l] * gap * gap);
             }
             const float ub = c0 - fmaxf(lam * d2, kd) - a.tile_qmin[tile];
-            need = !(lam >= 0.f) || !(ub < -126.5f);
+            need = !(lam >= 0.f) || !(ub < zcut_tile);
         }
         const bool warp_need = __any_sync(0xffffffffu, need);
 
@@ -339,8 +338,10 @@ __global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) 
                         dq[u] = fmaf(fmaf(qz, z4[u], br), z4[u], cr) - t4[u];
                         dmax = fmaxf(dmax, dq[u]);
                     }
+                    if (COUNT) cnt_vis += 1;
                     // w = 2^dq is exactly +0 for dq < -126 (ex2.approx.ftz): nothing to accumulate
-                    if (__builtin_expect(skip && !__any_sync(0xffffffffu, dmax >= -126.0f), 1)) continue;
+                    if (__builtin_expect(skip && !__any_sync(0xffffffffu, dmax >= zcut), 1)) continue;
+                    if (COUNT) cnt_gate += 1;
                     row_active = true;
                     const float4 grv = *reinterpret_cast<const float4*>(pl + PL_GR * SMOE_TPIX + j0);
                     const float gr4[GRP] = {grv.x, grv.y, grv.z, grv.w};
@@ -356,6 +357,7 @@ __global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) 
                         float t = -w * gr4[u];
                         const bool pass = dq[u] > ltau;              // w > tau
                         if (!skip || __any_sync(0xffffffffu, pass)) {
+                            if (COUNT) cnt_exp += 1;
                             const float wm = pass ? w : 0.f;
                             float gE = 0.f;
 #pragma unroll
@@ -433,6 +435,12 @@ __global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) 
         }
     }
 
+    if (COUNT && (tid & 31) == 0) {
+        // groups of 4 pixels x 32 lanes (vis, gate) and single pixels x 32 lanes (expert part), as issued
+        atomicAdd(&a.pair_counts[4], (unsigned long long)cnt_vis * 128ull);
+        atomicAdd(&a.pair_counts[5], (unsigned long long)cnt_gate * 128ull);
+        atomicAdd(&a.pair_counts[6], (unsigned long long)cnt_exp * 32ull);
+    }
     if (active) {
         float* out = a.raw_part + ((size_t)split * a.K_cap + k) * P;
 #pragma unroll
@@ -463,26 +471,45 @@ __global__ void __launch_bounds__(256) reduce_splits_kernel(const int32_t* __res
 }
 
 
-// statistics -> variable gradients, one thread per active kernel
-template <int D, int C>
+// statistics -> variable gradients, one thread per active kernel.
+// PEERS (pixel-sharded step): the statistics are the sum over the R ranks' published windows, read straight from
+// peer memory in fixed rank order after the flag barrier (exchange.cuh) -- the all-reduce of SURVEY.md 8e fused
+// into its consumer; the same launch reduces the loss scalars and the influence flags.
+template <int D, int C, bool PEERS>
 __global__ void __launch_bounds__(256) grad_finalize_kernel(smoe_cfg cfg, const float* __restrict__ raw, int num_splits,
                                                             int K_cap, const float* __restrict__ theta,
                                                             const int32_t* __restrict__ indices,
                                                             const int32_t* __restrict__ counts, float pis_l1,
                                                             float l1_norm, float u_l1, QuantSet qs_in,
                                                             const QuantDyn* __restrict__ qdyn,
-                                                            float* __restrict__ grads) {
+                                                            float* __restrict__ grads, smoe_peers pr,
+                                                            float* __restrict__ scalars, uint8_t* __restrict__ infl) {
     constexpr int T = tri(D);
     constexpr int P = nparam(D, C);
+    __shared__ float s_stats[PEERS ? 256 * P : 1];
     const int k = blockIdx.x * 256 + threadIdx.x;
-    if (k >= counts[0]) return;
+    const int K = counts[0];
+    int epoch = 0;
+    if (PEERS) {
+        epoch = peer_barrier(pr);
+        const int k0 = blockIdx.x * 256;
+        if (k0 < K) gather_stats(pr, epoch, K_cap, P, k0, min(256, K - k0), s_stats);
+        reduce_tail(pr, epoch, K_cap, P, scalars, infl);
+        peer_epoch_end(pr, epoch);
+    }
+    if (k >= K) return;
     float s[P];
+    if (PEERS) {
 #pragma unroll
-    for (int j = 0; j < P; ++j) s[j] = 0.f;
-    for (int sp = 0; sp < num_splits; ++sp) {
-        const float* r = raw + ((size_t)sp * K_cap + k) * P;
+        for (int j = 0; j < P; ++j) s[j] = s_stats[threadIdx.x * P + j];
+    } else {
 #pragma unroll
-        for (int j = 0; j < P; ++j) s[j] += r[j];
+        for (int j = 0; j < P; ++j) s[j] = 0.f;
+        for (int sp = 0; sp < num_splits; ++sp) {
+            const float* r = raw + ((size_t)sp * K_cap + k) * P;
+#pragma unroll
+            for (int j = 0; j < P; ++j) s[j] += r[j];
+        }
     }
     const int row = indices[k];
     const float* th = theta + (size_t)row * P;
@@ -631,16 +658,18 @@ size_t smoe_backward_workspace_bytes(const smoe_cfg* cfg, int K_cap, int num_spl
 }
 
 int smoe_backward(const smoe_cfg* cfg, const smoe_batch* batch, const float* packed, const int32_t* counts, int K_cap,
-                  const int32_t* perm, const int32_t* pos, const float* pix, const float* tile_qmin, const float* ax0,
-                  const float* ax1, const float* ax2, int num_splits, float* raw_part, void* stream) {
+                  const float* pix, const float* tile_qmin, const float* ax0, const float* ax1, const float* ax2,
+                  int num_splits, float* raw_part, unsigned long long* pair_counts, void* stream) {
     SMOE_REQUIRE(cfg && batch && packed && counts && pix && tile_qmin && ax0 && ax1 && raw_part, "null argument");
-    SMOE_REQUIRE((perm == nullptr) == (pos == nullptr), "perm and pos go together");
     SMOE_REQUIRE(K_cap > 0 && num_splits > 0 && num_splits <= 65535, "bad K_cap / num_splits");
+    SMOE_REQUIRE(cfg->eps_bits == 0 || (cfg->eps_bits >= 24 && cfg->eps_bits <= 126 && cfg->dense_exec == 0),
+                 "eps_bits must be 0 or in [24, 126], with dense_exec == 0");
     BwdArgs a;
     a.cfg = *cfg;
     a.b = *batch;
-    a.packed = packed; a.counts = counts; a.perm = perm; a.pos = pos; a.pix = pix; a.tile_qmin = tile_qmin;
+    a.packed = packed; a.counts = counts; a.pix = pix; a.tile_qmin = tile_qmin;
     a.raw_part = raw_part;
+    a.pair_counts = pair_counts;
     a.ax[0] = ax0; a.ax[1] = ax1; a.ax[2] = ax2 ? ax2 : ax0;
     a.K_cap = K_cap;
     a.num_splits = num_splits;
@@ -649,6 +678,7 @@ int smoe_backward(const smoe_cfg* cfg, const smoe_batch* batch, const float* pac
     a.ntiles = smoe_num_tiles(batch);
     a.tau = 0.5f / (float)(1 << cfg->precision);
     a.ltau = -(float)(cfg->precision + 1);              // log2(tau), exact
+    a.zero_cut = cfg->eps_bits > 0 ? -(float)cfg->eps_bits : -126.0f;
     a.max_list = (a.ntiles + num_splits - 1) / num_splits;
     dim3 grid((K_cap + kThreads - 1) / kThreads, num_splits);
     size_t sm = 2 * (size_t)pix_stride(cfg->d, cfg->C, batch->tile[cfg->d - 1]) * 4 + 16 + 8 * kCB * 4 + 16 * 4 +
@@ -656,13 +686,15 @@ int smoe_backward(const smoe_cfg* cfg, const smoe_batch* batch, const float* pac
     SMOE_REQUIRE(sm <= 100 * 1024, "too many tiles per split for the shared-memory tile list: raise num_splits");
     cudaStream_t st = (cudaStream_t)stream;
     // partial slabs of splits that own no tile, and rows k >= K, are never read
-#define CALL(D, C)                                                                                        \
-    {                                                                                                     \
-        cudaFuncSetAttribute(backward_kernel<D, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
-        backward_kernel<D, C><<<grid, kThreads, sm, st>>>(a);                                             \
+#define LAUNCH(D, C, CNT)                                                                                      \
+    {                                                                                                          \
+        cudaFuncSetAttribute(backward_kernel<D, C, CNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+        backward_kernel<D, C, CNT><<<grid, kThreads, sm, st>>>(a);                                             \
     }
+#define CALL(D, C) if (pair_counts) LAUNCH(D, C, true) else LAUNCH(D, C, false)
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL
+#undef LAUNCH
     return check_launch("smoe_backward");
 }
 
@@ -686,12 +718,35 @@ int smoe_grad_finalize(const smoe_cfg* cfg, const float* raw, int num_splits, in
     const QuantSet qs = make_quantset(cfg);
     int nb = (K_cap + 255) / 256;
     cudaStream_t st = (cudaStream_t)stream;
-#define CALL(D, C)                                                                                              \
-    grad_finalize_kernel<D, C><<<nb, 256, 0, st>>>(*cfg, raw, num_splits, K_cap, theta, indices, counts, pis_l1, \
-                                                   l1_norm, u_l1, qs, (const QuantDyn*)quant_ranges, grads);
+    smoe_peers none = {};
+#define CALL(D, C)                                                                                                     \
+    grad_finalize_kernel<D, C, false><<<nb, 256, 0, st>>>(*cfg, raw, num_splits, K_cap, theta, indices, counts, pis_l1, \
+                                                          l1_norm, u_l1, qs, (const QuantDyn*)quant_ranges, grads,     \
+                                                          none, nullptr, nullptr);
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL
     return check_launch("smoe_grad_finalize");
+}
+
+int smoe_grad_finalize_peers(const smoe_cfg* cfg, const smoe_peers* peers, int K_cap, const float* theta,
+                             const void* quant_ranges, const int32_t* indices, const int32_t* counts, float pis_l1,
+                             float l1_norm, float u_l1, float* grads, float* scalars, uint8_t* infl, void* stream) {
+    SMOE_REQUIRE(cfg && peers && theta && indices && counts && grads && scalars && infl && K_cap > 0, "bad argument");
+    SMOE_REQUIRE(peers->world >= 1 && peers->world <= SMOE_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world,
+                 "bad peer set");
+    for (int r = 0; r < peers->world; ++r) SMOE_REQUIRE(peers->win[r], "null peer window");
+    SMOE_REQUIRE(cfg->quantization_mode != 3 || quant_ranges, "quantization_mode 3 needs quant_ranges");
+    SMOE_REQUIRE(cfg->kernel_count_as_norm_l1 || l1_norm > 0.f, "l1_norm must be positive");
+    const QuantSet qs = make_quantset(cfg);
+    int nb = (K_cap + 255) / 256;
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(D, C)                                                                                                     \
+    grad_finalize_kernel<D, C, true><<<nb, 256, 0, st>>>(*cfg, nullptr, 1, K_cap, theta, indices, counts, pis_l1,       \
+                                                         l1_norm, u_l1, qs, (const QuantDyn*)quant_ranges, grads,      \
+                                                         *peers, scalars, infl);
+    SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
+#undef CALL
+    return check_launch("smoe_grad_finalize_peers");
 }
 
 int smoe_adam_step(const smoe_cfg* cfg, const smoe_adam* hp, const float* alpha_dev, float* theta, const float* grads,

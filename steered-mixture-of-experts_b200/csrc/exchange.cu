@@ -1,0 +1,119 @@
+// Host entry points and stand-alone kernels of the peer-memory exchange (see exchange.cuh for the protocol).
+#include "exchange.cuh"
+
+namespace smoe {
+
+// payload[e & 1] = [sum_s raw_part[s] (K*P, fixed order) | scalars | influence flags as 0/1 floats]
+__global__ void __launch_bounds__(256) xchg_publish_kernel(smoe_peers pr, const int32_t* __restrict__ counts, int K_all,
+                                                           int P, int num_splits, const float* __restrict__ part,
+                                                           const float* __restrict__ scalars,
+                                                           const uint8_t* __restrict__ infl) {
+    int* own = reinterpret_cast<int*>(pr.win[pr.rank]);
+    const int e = own[XW_EPOCH] + 1;
+    float* pay = reinterpret_cast<float*>(own + XW_HDR) + (size_t)(e & 1) * xw_payload_floats(K_all, P);
+    const size_t stride = (size_t)K_all * P;
+    const size_t step = (size_t)gridDim.x * 256, i0 = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (part) {
+        const size_t n = (size_t)counts[0] * P;
+        for (size_t i = i0; i < n; i += step) {
+            float s = 0.f;
+            for (int sp = 0; sp < num_splits; ++sp) s += part[sp * stride + i];
+            pay[i] = s;
+        }
+    }
+    float* tail = pay + stride;
+    for (size_t i = i0; i < (size_t)SMOE_NSCAL + K_all; i += step)
+        tail[i] = i < SMOE_NSCAL ? scalars[i] : (infl[i - SMOE_NSCAL] ? 1.f : 0.f);
+}
+
+__global__ void __launch_bounds__(256) xchg_reduce_tail_kernel(smoe_peers pr, int K_all, int P,
+                                                               float* __restrict__ scalars, uint8_t* __restrict__ infl) {
+    const int e = peer_barrier(pr);
+    reduce_tail(pr, e, K_all, P, scalars, infl);
+    peer_epoch_end(pr, e);
+}
+
+}  // namespace smoe
+
+using namespace smoe;
+
+extern "C" {
+
+size_t smoe_xchg_window_bytes(int K_all, int P) {
+    return (size_t)XW_HDR * sizeof(int32_t) + 2 * xw_payload_floats(K_all, P) * sizeof(float);
+}
+
+// The window must be a dedicated cudaMalloc allocation (cudaIpc exports whole allocations), so the library
+// allocates it: the one documented exception to "the library never allocates".
+int smoe_peer_alloc(size_t bytes, void** ptr) {
+    SMOE_REQUIRE(ptr && bytes > 0, "bad argument");
+    cudaError_t e = cudaMalloc(ptr, bytes);
+    if (e == cudaSuccess) e = cudaMemset(*ptr, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { set_error("smoe_peer_alloc: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+int smoe_peer_free(void* ptr) {
+    cudaError_t e = cudaFree(ptr);
+    if (e != cudaSuccess) { set_error("smoe_peer_free: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+int smoe_peer_export(const void* ptr, void* handle64) {
+    SMOE_REQUIRE(ptr && handle64, "bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaError_t e = cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64, const_cast<void*>(ptr));
+    if (e != cudaSuccess) { set_error("smoe_peer_export: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+int smoe_peer_open(const void* handle64, void** ptr) {
+    SMOE_REQUIRE(ptr && handle64, "bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { set_error("smoe_peer_open: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+int smoe_peer_close(void* ptr) {
+    cudaError_t e = cudaIpcCloseMemHandle(ptr);
+    if (e != cudaSuccess) { set_error("smoe_peer_close: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
+static int check_peers(const smoe_peers* pr) {
+    if (!pr || pr->world < 1 || pr->world > SMOE_MAX_PEERS || pr->rank < 0 || pr->rank >= pr->world) return 0;
+    for (int r = 0; r < pr->world; ++r)
+        if (!pr->win[r]) return 0;
+    return 1;
+}
+
+int smoe_xchg_publish(const smoe_cfg* cfg, const smoe_peers* peers, const int32_t* counts, int K_all, int num_splits,
+                      const float* raw_part, const float* scalars, const uint8_t* infl, void* stream) {
+    SMOE_REQUIRE(cfg && counts && scalars && infl && K_all > 0 && num_splits > 0, "bad argument");
+    SMOE_REQUIRE(check_peers(peers), "bad peer set");
+    const int P = nparam(cfg->d, cfg->C);
+    size_t n = (size_t)K_all * P;
+    int nb = (int)((n + 255) / 256);
+    if (nb > 148 * 8) nb = 148 * 8;
+    xchg_publish_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(*peers, counts, K_all, P, num_splits, raw_part, scalars, infl);
+    return check_launch("smoe_xchg_publish");
+}
+
+int smoe_xchg_reduce_tail(const smoe_cfg* cfg, const smoe_peers* peers, int K_all, float* scalars, uint8_t* infl,
+                          void* stream) {
+    SMOE_REQUIRE(cfg && scalars && infl && K_all > 0, "bad argument");
+    SMOE_REQUIRE(check_peers(peers), "bad peer set");
+    int nb = (K_all + SMOE_NSCAL + 255) / 256;
+    if (nb > 148) nb = 148;             // every CTA spins in the barrier: all of them must be resident
+    xchg_reduce_tail_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(*peers, K_all, nparam(cfg->d, cfg->C), scalars, infl);
+    return check_launch("smoe_xchg_reduce_tail");
+}
+
+int smoe_xchg_status(const smoe_peers* peers, int32_t* epoch_and_error /*[2], host*/) {
+    SMOE_REQUIRE(check_peers(peers) && epoch_and_error, "bad argument");
+    cudaError_t e = cudaMemcpy(epoch_and_error, (const int32_t*)peers->win[peers->rank] + XW_EPOCH, 2 * sizeof(int32_t),
+                               cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_error("smoe_xchg_status: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,130 @@
+// The one exchange step of the pixel-sharded path, written against NVLink peer memory instead of a
+// library collective: every rank PUBLISHES its per-kernel sufficient statistics, loss scalars and influence flags in
+// a window of its own device memory that all peers have mapped (cudaIpc), and the consumer kernels -- the gradient
+// finalisation of a training pass, or a small tail reduction of an evaluation pass -- read the R windows directly
+// and sum them in fixed rank order while they work.  One-shot all-reduce fused into its consumer:
+//   * no NCCL launch, no pack / unpack kernels, no host synchronisation between the halves of a step: the sharded
+//     step is ONE capturable stream of kernels (one CUDA graph), like the single-GPU step;
+//   * every rank adds the same R rows in the same order, so gradients, Adam updates and kernel lists are
+//     bit-identical on all ranks -- replicas cannot drift apart (the desync guard of SURVEY.md 8e by construction).
+// Synchronisation is a flag barrier through the same windows: after publishing epoch e a rank stores e into slot
+// [rank] of every peer's flag block (st.release.sys after __threadfence_system), and a consumer CTA spins until all R
+// slots of its OWN flag block have reached e (ld.acquire.sys).  Two payload buffers alternate with the parity of e:
+// a rank can only publish e+2 after it consumed e+1, which needs every peer to have published e+1, which a peer
+// does only after it finished reading everybody's buffer e -- so no second barrier is needed.  A spin that sees no
+// progress for ~5 s sets an error flag in the window instead of hanging the GPU.
+#pragma once
+#include "smoe_common.cuh"
+
+namespace smoe {
+
+// window = [XW_HDR ints: flags[0..8) | epoch | error | ticket | pad] [payload 0] [payload 1]
+constexpr int XW_HDR = 64;            // ints (256 B)
+constexpr int XW_EPOCH = 16, XW_ERROR = 17, XW_TICKET = 18;
+__host__ __device__ inline size_t xw_payload_floats(int K_all, int P) {
+    return ((size_t)K_all * P + SMOE_NSCAL + (size_t)K_all + 3) / 4 * 4;
+}
+
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_peer(const float* p) {
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_peer4(const float* p) {
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
+
+// Called by every CTA of a consumer kernel.  Block 0 announces this rank's epoch to the peers; thread 0 of every
+// block waits for all ranks.  Returns the epoch (its parity selects the payload buffer).
+__device__ __forceinline__ int peer_barrier(const smoe_peers& pr) {
+    int* own = reinterpret_cast<int*>(pr.win[pr.rank]);
+    const int e = own[XW_EPOCH] + 1;
+    if (blockIdx.x == 0 && (int)threadIdx.x < pr.world) {
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<int*>(pr.win[threadIdx.x]) + pr.rank, e);
+    }
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        for (int r = 0; r < pr.world; ++r) {
+            while (ld_acquire_sys(own + r) - e < 0) {
+                if (clock64() - t0 > 10000000000ll) {          // ~5 s at 2 GHz: a peer died; fail loudly, do not hang
+                    own[XW_ERROR] = 1;
+                    break;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    return e;
+}
+
+// the last CTA of a consumer kernel closes the epoch
+__device__ __forceinline__ void peer_epoch_end(const smoe_peers& pr, int e) {
+    int* own = reinterpret_cast<int*>(pr.win[pr.rank]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(own + XW_TICKET, 1) == (int)gridDim.x - 1) {
+            own[XW_TICKET] = 0;
+            own[XW_EPOCH] = e;
+            __threadfence();
+        }
+    }
+}
+
+// scalars = sum over ranks (rank order), infl = any rank; grid-stride over the tail
+__device__ __forceinline__ void reduce_tail(const smoe_peers& pr, int e, int K_all, int P, float* __restrict__ scalars,
+                                            uint8_t* __restrict__ infl) {
+    const size_t pf = xw_payload_floats(K_all, P), stride = (size_t)K_all * P;
+    const size_t step = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t i = i0; i < (size_t)SMOE_NSCAL + K_all; i += step) {
+        float s = 0.f;
+        for (int r = 0; r < pr.world; ++r) {
+            const float* tail = reinterpret_cast<const float*>(reinterpret_cast<const int*>(pr.win[r]) + XW_HDR) +
+                                (size_t)(e & 1) * pf + stride;
+            s += ld_peer(tail + i);
+        }
+        if (i < SMOE_NSCAL) scalars[i] = s; else infl[i - SMOE_NSCAL] = s > 0.f ? 1 : 0;
+    }
+}
+
+// Sum of the R published statistics rows of kernels [k0, k0 + nk) into shared memory, fixed rank order, coalesced
+// 16-byte peer loads (the range is contiguous in every window).
+__device__ __forceinline__ void gather_stats(const smoe_peers& pr, int e, int K_all, int P, int k0, int nk,
+                                             float* __restrict__ s_stats) {
+    const size_t pf = xw_payload_floats(K_all, P);
+    const size_t beg = (size_t)k0 * P, end = beg + (size_t)nk * P;
+    const size_t abeg = beg & ~(size_t)3;                       // 16-byte aligned start inside the payload
+    const int n4 = (int)((end - abeg + 3) / 4);
+    for (int q = threadIdx.x; q < n4; q += blockDim.x) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < pr.world; ++r) {
+            const float* pay = reinterpret_cast<const float*>(reinterpret_cast<const int*>(pr.win[r]) + XW_HDR) +
+                               (size_t)(e & 1) * pf;
+            const float4 v = ld_peer4(pay + abeg + 4 * (size_t)q);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        const float sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const size_t g = abeg + 4 * (size_t)q + j;
+            if (g >= beg && g < end) s_stats[g - beg] = sv[j];
+        }
+    }
+    __syncthreads();
+}
+
+}  // namespace smoe

@@ -34,16 +34,20 @@ struct Rec {
     static constexpr int T = tri(D);
     static constexpr int GN = T + D + 1;          // qq (upper-tri, off-diagonals doubled) | ql | qc
     static constexpr int EN = C + D * C;          // nu' | gamma
-    static constexpr int RC = (GN + EN + 1 + 3) / 4 * 4;   // + the kernel's active index
+    static constexpr int RC0 = (GN + EN + 1 + 3) / 4 * 4;  // + the kernel's ORIGINAL index
+    // an ODD number of float4 per record: the 8 threads of a quarter-warp then store their records' float4 to 8
+    // different 16-byte bank groups (stride 80 / 48 / 112 B), so the per-thread record writes are conflict-free
+    static constexpr int RC = (RC0 / 4) % 2 == 0 ? RC0 + 4 : RC0;
     static constexpr int NG4 = (GN + 3) / 4;      // float4 loads that cover the geometry part
-    static constexpr int OQ = 0, OL = T, OC = T + D, ONU = GN, OGA = GN + C, OK = RC - 1;
+    static constexpr int OQ = 0, OL = T, OC = T + D, ONU = GN, OGA = GN + C, OK = GN + EN;
 };
 
 // raw packed record + tile centre -> tile-centred compute record
 template <int D, int C>
 __device__ __forceinline__ void transform_record(const float* __restrict__ raw, const float (&mu)[D],
-                                                 const float (&ctr)[3], int kglob, float* __restrict__ out) {
+                                                 const float (&ctr)[3], int korig, float* __restrict__ dst) {
     using R = Rec<D, C>;
+    float out[R::RC];
     float Qm[D][D], v[D];
 #pragma unroll
     for (int l = 0; l < D; ++l)
@@ -76,9 +80,12 @@ __device__ __forceinline__ void transform_record(const float* __restrict__ raw, 
         }
         out[R::ONU + c] = nu;
     }
+    out[R::OK] = __int_as_float(korig);
 #pragma unroll
-    for (int j = R::GN + R::EN; j < R::RC - 1; ++j) out[j] = 0.f;
-    out[R::OK] = __int_as_float(kglob);
+    for (int j = R::OK + 1; j < R::RC; ++j) out[j] = 0.f;
+    float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int j = 0; j < R::RC / 4; ++j) d4[j] = make_float4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
 }
 
 // parabola coefficients of q along x'_0 for fixed x'_1.. : q = c + (b + qq00 z) z
@@ -106,6 +113,7 @@ struct FwdArgs {
     const int32_t* counts;
     const float* chunk_bounds;
     const float* image;
+    const uint8_t* image_u8;
     const float* lossw;
     const float* ax[3];
     float* res;
@@ -117,30 +125,37 @@ struct FwdArgs {
     float* scalars;
     float* partials;
     int32_t* ticket;
+    unsigned long long* pair_counts;
     int ntiles, nt1, nt2, max_chunks;
     float tau, ltau, eps, q_scale, q_inv_scale;
+    float eps_cut;          // eps_bits > 0: terms below 2^-eps_cut of the normaliser may be dropped; 0 = exact
 };
 
-// Ordered compaction helper for a 128-thread CTA: returns this thread's output slot (valid when
-// flag) and the total through *total; `scratch` holds 4 ints.  Contains two __syncthreads.
-__device__ __forceinline__ int cta_compact(bool flag, int* scratch, int* total) {
+// Ordered compaction helper for a 128-thread CTA: returns this thread's output slot (valid when flag) and the
+// total through *total.  `scratch` holds 2 x 4 ints used alternately (`par` flips on every call), so ONE
+// __syncthreads per call is enough: a thread can reach the call after next -- and overwrite this half -- only
+// after every thread has passed the next call's barrier, i.e. has finished reading this half.
+__device__ __forceinline__ int cta_compact(bool flag, int* scratch, int& par, int* total) {
     const unsigned bal = __ballot_sync(0xffffffffu, flag);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) scratch[w] = __popc(bal);
+    int* sc = scratch + 4 * par;
+    par ^= 1;
+    if (lane == 0) sc[w] = __popc(bal);
     __syncthreads();
     int off = 0, tot = 0;
 #pragma unroll
     for (int j = 0; j < kThreadsF / 32; ++j) {
-        const int cnt = scratch[j];
+        const int cnt = sc[j];
         off += (j < w) ? cnt : 0;
         tot += cnt;
     }
-    __syncthreads();
     *total = tot;
     return off + __popc(bal & ((1u << lane) - 1u));
 }
 
-template <int D, int C>
+// COUNT: also count the (pixel, kernel) pairs each sweep evaluates (bench / roofline diagnostics; a separate
+// instantiation, so the product path carries no counter).
+template <int D, int C, bool COUNT>
 __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(const FwdArgs a) {
     using R = Rec<D, C>;
     constexpr int PK = pstride(D, C);
@@ -152,7 +167,7 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
     float* crec = raw1 + kChunk * PK;
     uint64_t* bar = reinterpret_cast<uint64_t*>(crec + kChunk * R::RC);
     float* red = reinterpret_cast<float*>(bar + 2);          // [4 warps][8]
-    int* scratch = reinterpret_cast<int*>(red + 32);         // [8]
+    int* scratch = reinterpret_cast<int*>(red + 32);         // [2][4]
     int* clist = scratch + 8;                                // [max_chunks]
 
     const int tid = threadIdx.x;
@@ -167,6 +182,8 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
     }
     __syncthreads();
     uint32_t phase0 = 0, phase1 = 0;
+    int par = 0;
+    unsigned cntA_vis = 0, cntA_ex = 0, cntB_vis = 0, cntB_ex = 0;     // COUNT only
 
     auto issue = [&](int ci, int buf) {
         int nk = min(kChunk, K - ci * kChunk);
@@ -251,7 +268,7 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
                     }
                 }
                 int tot;
-                const int pos = cta_compact(need, scratch, &tot);
+                const int pos = cta_compact(need, scratch, par, &tot);
                 if (need) clist[n + pos] = ci;
                 n += tot;
             }
@@ -259,7 +276,9 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
             return n;
         };
 
-        // one sweep over the needed chunks; `body(rec)` is called for every kernel that can matter
+        // One sweep over the needed chunks; `body(rec)` is called for every kernel that can matter.  Two CTA
+        // barriers per chunk: the one inside cta_compact (which also orders the previous chunk's reads of `crec`
+        // before this chunk's writes) and the one that publishes the re-centred records.
         auto sweep = [&](int nlist, float thr, auto&& body) {
             if (tid == 0 && nlist > 0) {
                 issue(clist[0], 0);
@@ -287,23 +306,35 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
                     need = !(lam >= 0.f) || !(ub < thr);
                 }
                 int nneed;
-                const int pos = cta_compact(need, scratch, &nneed);
-                if (need) transform_record<D, C>(raw, mu, ctr, ci * kChunk + tid, crec + pos * R::RC);
+                const int pos = cta_compact(need, scratch, par, &nneed);
+                if (need) transform_record<D, C>(raw, mu, ctr, a.indices[ci * kChunk + tid], crec + pos * R::RC);
                 __syncthreads();
                 if (tid == 0 && li + 2 < nlist) issue(clist[li + 2], buf);
 #pragma unroll 2
                 for (int kk = 0; kk < nneed; ++kk) body(crec + kk * R::RC);
-                __syncthreads();
             }
+            __syncthreads();          // the next sweep rebuilds `clist` and re-uses `crec`
         };
 
         // ---- sweep A: normaliser ------------------------------------------------------
+        // Exact mode: a term is skipped only when ex2.approx.ftz returns exactly +0 for it (q < -126).
+        // eps mode (opt-in): with L = the tile's minimum of log2 S from the PREVIOUS pass over this batch, terms
+        // with q < L - 2 - eps_cut are dropped as well; afterwards min log2 S >= L - 2 is verified (the culled sum
+        // is a lower bound of the true one) and the tile is re-swept exactly if the stale L was too optimistic.
         float S[PPT];
+        float cutA = -126.5f;
+        if (a.eps_cut > 0.f && a.tile_qmin) {
+            const float Lprev = a.tile_qmin[tile];
+            cutA = fmaxf(cutA, Lprev - 2.0f - a.eps_cut);
+            if (!(cutA == cutA)) cutA = -126.5f;
+        }
+        float Lneed = cutA > -126.5f ? cutA + a.eps_cut : -INFINITY;      // = Lprev - 2
+        for (int attempt = 0; attempt < 2; ++attempt) {
 #pragma unroll
-        for (int p = 0; p < PPT; ++p) S[p] = 0.f;
-        {
-            const int nlist = build_chunk_list(-126.5f);
-            sweep(nlist, -126.5f, [&](const float* rec) {
+            for (int p = 0; p < PPT; ++p) S[p] = 0.f;
+            const float skipA = cutA + 0.5f;
+            const int nlist = build_chunk_list(cutA);
+            sweep(nlist, cutA, [&](const float* rec) {
                 float f[4 * R::NG4];
                 const float4* r4 = reinterpret_cast<const float4*>(rec);
 #pragma unroll
@@ -320,12 +351,23 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
                     q[p] = fmaf(fmaf(f[R::OQ], x0[p], bq), x0[p], cq);
                     qmax = fmaxf(qmax, q[p]);
                 }
+                if (COUNT) cntA_vis += PPT;
                 // ex2.approx.ftz(q) == +0 exactly for q < -126: adding it would not change S
-                if (__builtin_expect(!skip || __any_sync(0xffffffffu, qmax >= -126.0f), 0)) {
+                if (__builtin_expect(!skip || __any_sync(0xffffffffu, qmax >= skipA), 0)) {
 #pragma unroll
                     for (int p = 0; p < PPT; ++p) S[p] += ex2f(q[p]);
+                    if (COUNT) cntA_ex += PPT;
                 }
             });
+            if (!(Lneed > -INFINITY)) break;                 // exact sweep: done
+            float smin = INFINITY;
+#pragma unroll
+            for (int p = 0; p < PPT; ++p)
+                if (gidx[p] >= 0) smin = fminf(smin, log2f(fmaxf(S[p], kSFloor)));
+            const int bad = __syncthreads_or(smin < Lneed);
+            if (!bad) break;
+            cutA = -126.5f;                                  // stale bound: exact re-sweep
+            Lneed = -INFINITY;
         }
 
         // ---- sweep B: thresholded gates, experts ----------------------------------------
@@ -373,13 +415,15 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
                     q[p] = fmaf(fmaf(f[R::OQ], x0[p], bq), x0[p], cq) - qthr[p];
                     any |= (q[p] > ltau);
                 }
+                if (COUNT) cntB_vis += PPT;
                 if (__builtin_expect(!skip || __any_sync(0xffffffffu, any), 0)) {
+                    if (COUNT) cntB_ex += PPT;
 #pragma unroll
-                    for (int j = R::NG4; j < R::RC / 4; ++j) {
+                    for (int j = R::NG4; j < (R::OK + 4) / 4; ++j) {
                         float4 v = r4[j];
                         f[4 * j] = v.x; f[4 * j + 1] = v.y; f[4 * j + 2] = v.z; f[4 * j + 3] = v.w;
                     }
-                    const int kglob = __float_as_int(f[R::OK]);
+                    const int korig = __float_as_int(f[R::OK]);
                     // expert value E_c(x) = nu'_c + gamma_c . x': the part that does not depend on x'_0 once per
                     // (thread, kernel), one FFMA per pixel and channel
                     float Eb[C];
@@ -397,10 +441,11 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
                         const float wm = pass ? w : 0.f;
 #pragma unroll
                         for (int c = 0; c < C; ++c) r[p][c] = fmaf(wm, fmaf(f[R::OGA + c], x0[p], Eb[c]), r[p][c]);
-                        // tf.argmax keeps the first maximum: kernels arrive in ascending index, so strictly greater
-                        if (pass && w > bestw[p]) { bestw[p] = w; bestk[p] = kglob; }
+                        // tf.argmax keeps the first maximum in ascending kernel index; records arrive in the
+                        // (Morton) packing order, so ties are broken on the original index explicitly
+                        if (pass && (w > bestw[p] || (w == bestw[p] && korig < bestk[p]))) { bestw[p] = w; bestk[p] = korig; }
                     }
-                    if (any && a.infl) a.infl[kglob] = 1;
+                    if (any && a.infl) a.infl[korig] = 1;
                 }
             });
         }
@@ -422,7 +467,9 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
                     const float rc = fminf(fmaxf(rv, 0.f), 1.f);                        // smoe.py:857
                     const float kq = floorf(__fadd_rn(__fmul_rn(rc, a.q_inv_scale), 0.5f));
                     const float rq = __fmul_rn(kq, a.q_scale);                          // smoe.py:899
-                    const float tgt = a.image[gidx[p] * C + c];
+                    // 8-bit feed: the /255 of utils.py:126-128 (float32 division) happens here
+                    const float tgt = a.image_u8 ? __fdiv_rn((float)a.image_u8[gidx[p] * C + c], 255.0f)
+                                                 : a.image[gidx[p] * C + c];
                     const float diff = __fsub_rn(rq, tgt);                              // smoe.py:905
                     const float ad = fabsf(diff) - a.eps;                               // smoe.py:932
                     if (!halo) {
@@ -440,7 +487,7 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
                         if (a.res_pre) a.res_pre[gidx[p] * C + c] = rv;
                     }
                 }
-                if (a.argmax && !halo) a.argmax[gidx[p]] = bestk[p] >= 0 ? a.indices[bestk[p]] : -1;
+                if (a.argmax && !halo) a.argmax[gidx[p]] = bestk[p];
             } else {
 #pragma unroll
                 for (int c = 0; c < C; ++c) g[c] = 0.f;
@@ -463,6 +510,17 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
                     for (int l = 1; l < D - 1; ++l) tp[pix_rowc_offset(C) + l * nrows + row] = xs[l];
                 }
             }
+        }
+    }
+
+    if (COUNT) {
+        // executed-pair counters: lanes x pixels per sweep; integer atomics, order-independent
+        unsigned long long v[4] = {cntA_vis, cntA_ex, cntB_vis, cntB_ex};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_down_sync(0xffffffffu, v[q], o);
+            if ((tid & 31) == 0) atomicAdd(&a.pair_counts[q], v[q]);
         }
     }
 
@@ -516,12 +574,14 @@ using namespace smoe;
 
 extern "C" int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const float* packed, const int32_t* indices,
                             const int32_t* counts, const float* chunk_bounds, int K_cap, const float* image,
-                            const float* loss_weights, const float* ax0, const float* ax1, const float* ax2,
+                            const uint8_t* image_u8, const float* loss_weights, const float* ax0, const float* ax1, const float* ax2,
                             float* res, float* res_pre, int32_t* argmax, uint8_t* infl, float* pix,
-                            float* tile_qmin, float* scalars, float* partials, int32_t* ticket, void* stream) {
-    SMOE_REQUIRE(cfg && batch && packed && indices && counts && chunk_bounds && image && ax0 && ax1 && res && scalars &&
+                            float* tile_qmin, float* scalars, float* partials, int32_t* ticket,
+                            unsigned long long* pair_counts, void* stream) {
+    SMOE_REQUIRE(cfg && batch && packed && indices && counts && chunk_bounds && ax0 && ax1 && res && scalars &&
                      partials && ticket,
                  "null argument");
+    SMOE_REQUIRE((image != nullptr) != (image_u8 != nullptr), "exactly one of image / image_u8");
     SMOE_REQUIRE(K_cap > 0, "K_cap must be positive");
     SMOE_REQUIRE(cfg->d == 2 || ax2, "ax2 required for d == 3");
     SMOE_REQUIRE(batch->tile[0] * batch->tile[1] * batch->tile[2] == SMOE_TPIX, "tile product must be SMOE_TPIX");
@@ -529,6 +589,8 @@ extern "C" int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const 
                  "tile[1]*tile[2] must divide 128 and the last tile extent must be a multiple of 4");
     SMOE_REQUIRE(!pix || tile_qmin, "tile_qmin is required with pix");
     SMOE_REQUIRE(batch->halo >= 0, "negative halo");
+    SMOE_REQUIRE(cfg->eps_bits == 0 || (cfg->eps_bits >= 24 && cfg->eps_bits <= 126), "eps_bits must be 0 or in [24, 126]");
+    SMOE_REQUIRE(cfg->eps_bits == 0 || cfg->dense_exec == 0, "eps_bits needs dense_exec == 0");
     for (int i = 0; i < 3; ++i)
         SMOE_REQUIRE(batch->extent[i] > 0 && batch->origin[i] >= 0 && batch->origin[i] + batch->extent[i] <= batch->dims[i],
                      "batch rectangle outside the image");
@@ -537,10 +599,11 @@ extern "C" int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const 
     a.cfg = *cfg;
     a.b = *batch;
     a.packed = packed; a.indices = indices; a.counts = counts; a.chunk_bounds = chunk_bounds; a.image = image;
+    a.image_u8 = image_u8;
     a.lossw = loss_weights;
     a.ax[0] = ax0; a.ax[1] = ax1; a.ax[2] = ax2 ? ax2 : ax0;
     a.res = res; a.res_pre = res_pre; a.argmax = argmax; a.infl = infl; a.pix = pix; a.tile_qmin = tile_qmin;
-    a.scalars = scalars; a.partials = partials; a.ticket = ticket;
+    a.scalars = scalars; a.partials = partials; a.ticket = ticket; a.pair_counts = pair_counts;
     a.nt1 = (batch->extent[1] + batch->tile[1] - 1) / batch->tile[1];
     a.nt2 = (batch->extent[2] + batch->tile[2] - 1) / batch->tile[2];
     a.ntiles = smoe_num_tiles(batch);
@@ -551,20 +614,23 @@ extern "C" int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const 
     a.eps = cfg->margin / two_p;
     a.q_scale = 1.0f / (two_p - 1.0f);
     a.q_inv_scale = 1.0f / a.q_scale;
+    a.eps_cut = (float)cfg->eps_bits;
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int per_sm = cfg->d == 2 ? 6 : 4;          // resident CTAs per SM (matches __launch_bounds__)
     int grid = a.ntiles < per_sm * sms ? a.ntiles : per_sm * sms;
     cudaStream_t st = (cudaStream_t)stream;
-#define CALL(D, C)                                                                                           \
-    {                                                                                                        \
-        size_t sm = fwd_smem_bytes<D, C>(a.max_chunks);                                                      \
-        SMOE_REQUIRE(sm <= 200 * 1024, "too many kernel chunks for the shared-memory chunk list");           \
-        cudaFuncSetAttribute(forward_kernel<D, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);    \
-        forward_kernel<D, C><<<grid, kThreadsF, sm, st>>>(a);                                                \
+#define LAUNCH(D, C, CNT)                                                                                        \
+    {                                                                                                            \
+        size_t sm = fwd_smem_bytes<D, C>(a.max_chunks);                                                          \
+        SMOE_REQUIRE(sm <= 200 * 1024, "too many kernel chunks for the shared-memory chunk list");               \
+        cudaFuncSetAttribute(forward_kernel<D, C, CNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);   \
+        forward_kernel<D, C, CNT><<<grid, kThreadsF, sm, st>>>(a);                                               \
     }
+#define CALL(D, C) if (pair_counts) LAUNCH(D, C, true) else LAUNCH(D, C, false)
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL
+#undef LAUNCH
     return check_launch("smoe_forward");
 }

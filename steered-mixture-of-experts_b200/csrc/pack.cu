@@ -4,8 +4,12 @@
 // indices, 5x boolean_mask) and 1012 (num_pi).  HBM-bound: reads K_all*(P*4+1) bytes, writes
 // K*(PK*4+4) bytes.  Two launches: (1) per-block flag counts and regulariser partial sums,
 // (2) every block re-derives its exclusive prefix from the <= few-thousand block counts,
-// scans its own flags with warp ballots and scatters records in ascending kernel index
-// (stable, hence bit-exact with numpy boolean masking).  No atomics: sums are fixed-order.
+// scans its own flags with warp ballots and scatters records in the order of `perm` (a stable
+// compaction of the permuted sequence; perm == NULL is ascending kernel index, the order of numpy
+// boolean masking).  Smoe passes the Morton order of the centres, so that 128 consecutive records
+// (a forward chunk) and 64 consecutive records (a backward CTA) are spatial neighbours; the SET of
+// surviving indices is what the reference defines and does not depend on the order.  No atomics:
+// sums are fixed-order.
 #include <math.h>
 #include <stdarg.h>
 #include "smoe_common.cuh"
@@ -32,12 +36,14 @@ struct PackBlk { int32_t count, numpi, nonpos, pad; float sum_pi, sum_diag; };
 
 template <int D, int C>
 __global__ void __launch_bounds__(256) pack_count_kernel(const float* __restrict__ theta,
-                                                         const uint8_t* __restrict__ klist, int K_all,
+                                                         const uint8_t* __restrict__ klist,
+                                                         const int32_t* __restrict__ perm, int K_all,
                                                          int quantize_pis, QuantSet qs_in,
                                                          const QuantDyn* __restrict__ qdyn, PackBlk* __restrict__ blk) {
     const QuantSet qs = qs_in.mode == 3 ? qdyn->qs : qs_in;
     constexpr int P = nparam(D, C);
-    int i = blockIdx.x * 256 + threadIdx.x;
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    const int i = j < K_all ? (perm ? perm[j] : j) : K_all;
     int flag = 0, numpi = 0;
     float spi = 0.f, sdiag = 0.f;
     if (i < K_all) {
@@ -228,7 +234,8 @@ __global__ void __launch_bounds__(kChunk) chunk_bounds_kernel(const float* __res
 template <int D, int C>
 __global__ void __launch_bounds__(256) pack_scatter_kernel(smoe_cfg cfg, const float* __restrict__ theta,
                                                            const float* __restrict__ mus_grid,
-                                                           const uint8_t* __restrict__ klist, int K_all, QuantSet qs_in,
+                                                           const uint8_t* __restrict__ klist,
+                                                           const int32_t* __restrict__ perm, int K_all, QuantSet qs_in,
                                                            const QuantDyn* __restrict__ qdyn,
                                                            const PackBlk* __restrict__ blk, float* __restrict__ packed,
                                                            int32_t* __restrict__ indices, int32_t* __restrict__ pos,
@@ -249,7 +256,8 @@ __global__ void __launch_bounds__(256) pack_scatter_kernel(smoe_cfg cfg, const f
     int prefix = 0;
     for (int j = 0; j < 8; ++j) prefix += s_red[j];
 
-    int i = blockIdx.x * 256 + threadIdx.x;
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    const int i = j < K_all ? (perm ? perm[j] : j) : K_all;
     int flag = 0;
     float pi = 0.f;
     const float* row = theta + (size_t)min(i, K_all - 1) * P;
@@ -317,35 +325,49 @@ __global__ void __launch_bounds__(256) pack_scatter_kernel(smoe_cfg cfg, const f
 template <int D, int C>
 __global__ void __launch_bounds__(256) pack_fed_kernel(smoe_cfg cfg, const float* __restrict__ A_, const float* __restrict__ mus,
                                                        const float* __restrict__ nu, const float* __restrict__ ga,
-                                                       const float* __restrict__ pis, int K, float* __restrict__ packed,
+                                                       const float* __restrict__ pis,
+                                                       const int32_t* __restrict__ order, int K,
+                                                       float* __restrict__ packed, int32_t* __restrict__ indices,
                                                        int32_t* __restrict__ counts) {
     constexpr int PK = pstride(D, C);
-    int i = blockIdx.x * 256 + threadIdx.x;
-    if (i == 0) { counts[0] = K; counts[1] = K; counts[2] = 0; counts[3] = 0; }
-    if (i >= K) return;
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j == 0) { counts[0] = K; counts[1] = K; counts[2] = 0; counts[3] = 0; }
+    if (j >= K) return;
+    const int i = order ? order[j] : j;            // fed row staged at packed row j
+    indices[j] = i;
     float A[D][D];
 #pragma unroll
     for (int l = 0; l < D; ++l)
 #pragma unroll
         for (int m = 0; m < D; ++m) A[l][m] = A_[(size_t)i * D * D + l * D + m];
     stage_record<D, C>(cfg, A, mus + (size_t)i * D, pis[i], nu + (size_t)i * C, ga + (size_t)i * D * C,
-                       packed + (size_t)i * PK);
+                       packed + (size_t)j * PK);
 }
 
-// kernel_list[i] = infl[k] if i == indices[k] for an active k, else 0.  `indices` is ascending (stream compaction
-// keeps the original order), so every original index finds its packed row by bisection: one launch, no clear pass.
-__global__ void __launch_bounds__(256) klist_update_kernel(const int32_t* __restrict__ indices,
-                                                           const int32_t* __restrict__ counts,
-                                                           const uint8_t* __restrict__ infl,
+// Morton (Z-order) key of each kernel centre on a 2^10 grid per axis: the work-assignment order of smoe_pack.
+__global__ void __launch_bounds__(256) morton_keys_kernel(const float* __restrict__ mu, int K, int d, int stride,
+                                                          const float* __restrict__ grid, long long* __restrict__ keys) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= K) return;
+    unsigned long long key = 0;
+    unsigned cell[3] = {0, 0, 0};
+    for (int a = 0; a < d; ++a) {
+        float v = mu[(size_t)i * stride + a];
+        if (grid) v += grid[(size_t)i * d + a];
+        v = v * 1024.f;
+        cell[a] = v >= 1023.f ? 1023u : (v > 0.f ? (unsigned)v : 0u);      // NaN -> 0
+    }
+    for (int b = 0; b < 10; ++b)
+        for (int a = 0; a < d; ++a) key |= (unsigned long long)((cell[a] >> b) & 1u) << (b * d + (d - 1 - a));
+    keys[i] = (long long)key;
+}
+
+// kernel_list[i] = infl[i]: the influence flags are indexed by ORIGINAL kernel index and only active kernels can
+// have theirs set, so this is the reference's "clear, then kernel_list[indices] = influential" (smoe.py:1763-1766).
+__global__ void __launch_bounds__(256) klist_update_kernel(const uint8_t* __restrict__ infl,
                                                            uint8_t* __restrict__ klist, int K_all) {
     const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= K_all) return;
-    int lo = 0, hi = counts[0];
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (indices[mid] < i) lo = mid + 1; else hi = mid;
-    }
-    klist[i] = (lo < counts[0] && indices[lo] == i) ? (infl[lo] ? 1 : 0) : 0;
+    if (i < K_all) klist[i] = infl[i] ? 1 : 0;
 }
 
 // start of a training / evaluation pass: zero the gradient accumulators (zero_op, smoe.py:1612-1613), the scalar
@@ -361,21 +383,6 @@ __global__ void __launch_bounds__(256) step_begin_kernel(float* __restrict__ gra
         scalars[(i / n_scalars) * scalar_stride + i % n_scalars] = 0.f;
     if (infl)
         for (size_t i = i0; i < (size_t)K; i += stride) infl[i] = 0;
-}
-
-// the tail of the buffer a sharded step all-reduces: [scalars | influence flags as floats], and back
-__global__ void __launch_bounds__(256) exchange_pack_kernel(const float* __restrict__ scalars,
-                                                            const uint8_t* __restrict__ infl, int K,
-                                                            float* __restrict__ tail) {
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i < SMOE_NSCAL) tail[i] = scalars[i];
-    if (i < K) tail[SMOE_NSCAL + i] = infl[i] ? 1.f : 0.f;
-}
-__global__ void __launch_bounds__(256) exchange_unpack_kernel(const float* __restrict__ tail, int K,
-                                                              float* __restrict__ scalars, uint8_t* __restrict__ infl) {
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i < SMOE_NSCAL) scalars[i] = tail[i];
-    if (i < K) infl[i] = tail[SMOE_NSCAL + i] > 0.f ? 1 : 0;
 }
 
 
@@ -602,8 +609,8 @@ size_t smoe_pack_workspace_bytes(int K_all) {
 }
 
 int smoe_pack(const smoe_cfg* cfg, const float* theta, const float* mus_grid, const void* quant_ranges,
-              const uint8_t* kernel_list, int K_all, float* packed, int32_t* indices, int32_t* pos, int32_t* counts,
-              float* regsums, float* chunk_bounds, void* workspace, void* stream) {
+              const uint8_t* kernel_list, const int32_t* perm, int K_all, float* packed, int32_t* indices, int32_t* pos,
+              int32_t* counts, float* regsums, float* chunk_bounds, void* workspace, void* stream) {
     SMOE_REQUIRE(!cfg || !cfg->use_diff_center || mus_grid, "use_diff_center needs mus_grid");
     SMOE_REQUIRE(!cfg || cfg->quantization_mode != 3 || quant_ranges, "quantization_mode 3 needs quant_ranges");
     const QuantDyn* qdyn = (const QuantDyn*)quant_ranges;
@@ -616,8 +623,8 @@ int smoe_pack(const smoe_cfg* cfg, const float* theta, const float* mus_grid, co
     int32_t* nonpos_blk = (int32_t*)((char*)workspace + (size_t)nb * sizeof(PackBlk));
     const QuantSet qs = make_quantset(cfg);
 #define CALL(D, C)                                                                                              \
-    pack_count_kernel<D, C><<<nb, 256, 0, st>>>(theta, kernel_list, K_all, cfg->quantize_pis, qs, qdyn, blk);   \
-    pack_scatter_kernel<D, C><<<nb, 256, 0, st>>>(*cfg, theta, mus_grid, kernel_list, K_all, qs, qdyn, blk,     \
+    pack_count_kernel<D, C><<<nb, 256, 0, st>>>(theta, kernel_list, perm, K_all, cfg->quantize_pis, qs, qdyn, blk); \
+    pack_scatter_kernel<D, C><<<nb, 256, 0, st>>>(*cfg, theta, mus_grid, kernel_list, perm, K_all, qs, qdyn, blk, \
                                                   packed, indices, pos, counts, regsums, nonpos_blk);
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL
@@ -671,12 +678,13 @@ int smoe_quant_route(const smoe_cfg* cfg, const float* theta, const void* quant_
 }
 
 int smoe_pack_fed(const smoe_cfg* cfg, const float* A, const float* musX, const float* nu_e, const float* gamma_e,
-                  const float* pis, int K, float* packed, int32_t* counts, float* chunk_bounds, void* stream) {
-    SMOE_REQUIRE(cfg && A && musX && nu_e && gamma_e && pis && packed && counts && chunk_bounds, "null argument");
+                  const float* pis, const int32_t* order, int K, float* packed, int32_t* indices, int32_t* counts,
+                  float* chunk_bounds, void* stream) {
+    SMOE_REQUIRE(cfg && A && musX && nu_e && gamma_e && pis && packed && indices && counts && chunk_bounds, "null argument");
     SMOE_REQUIRE(K > 0, "K must be positive");
     cudaStream_t st = (cudaStream_t)stream;
     int nb = (K + 255) / 256;
-#define CALL(D, C) pack_fed_kernel<D, C><<<nb, 256, 0, st>>>(*cfg, A, musX, nu_e, gamma_e, pis, K, packed, counts);
+#define CALL(D, C) pack_fed_kernel<D, C><<<nb, 256, 0, st>>>(*cfg, A, musX, nu_e, gamma_e, pis, order, K, packed, indices, counts);
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL
     const int nchunks = (K + kChunk - 1) / kChunk;
@@ -686,13 +694,19 @@ int smoe_pack_fed(const smoe_cfg* cfg, const float* A, const float* musX, const 
     return check_launch("smoe_pack_fed");
 }
 
-int smoe_update_kernel_list(const int32_t* indices, const int32_t* counts, const uint8_t* infl, uint8_t* kernel_list,
-                            int K_all, void* stream) {
-    SMOE_REQUIRE(indices && counts && infl && kernel_list && K_all > 0, "bad argument");
+int smoe_update_kernel_list(const uint8_t* infl, uint8_t* kernel_list, int K_all, void* stream) {
+    SMOE_REQUIRE(infl && kernel_list && K_all > 0, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     int nb = (K_all + 255) / 256;
-    klist_update_kernel<<<nb, 256, 0, st>>>(indices, counts, infl, kernel_list, K_all);
+    klist_update_kernel<<<nb, 256, 0, st>>>(infl, kernel_list, K_all);
     return check_launch("smoe_update_kernel_list");
+}
+
+int smoe_morton_keys(const float* centres, int K, int d, int row_stride, const float* grid, long long* keys,
+                     void* stream) {
+    SMOE_REQUIRE(centres && keys && K > 0 && (d == 2 || d == 3) && row_stride >= d, "bad argument");
+    morton_keys_kernel<<<(K + 255) / 256, 256, 0, (cudaStream_t)stream>>>(centres, K, d, row_stride, grid, keys);
+    return check_launch("smoe_morton_keys");
 }
 
 int smoe_step_begin(float* grads, size_t n_grads, float* scalars, int n_rows, int row_stride, uint8_t* infl, int K,
@@ -705,20 +719,6 @@ int smoe_step_begin(float* grads, size_t n_grads, float* scalars, int n_rows, in
     step_begin_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(grads, grads ? n_grads : 0, scalars, SMOE_NSCAL, row_stride,
                                                            n_rows, infl, infl ? K : 0);
     return check_launch("smoe_step_begin");
-}
-
-int smoe_exchange_pack(const float* scalars, const uint8_t* infl, int K, float* tail, void* stream) {
-    SMOE_REQUIRE(scalars && infl && tail && K > 0, "bad argument");
-    const int n = K > SMOE_NSCAL ? K : SMOE_NSCAL;
-    exchange_pack_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(scalars, infl, K, tail);
-    return check_launch("smoe_exchange_pack");
-}
-
-int smoe_exchange_unpack(const float* tail, int K, float* scalars, uint8_t* infl, void* stream) {
-    SMOE_REQUIRE(scalars && infl && tail && K > 0, "bad argument");
-    const int n = K > SMOE_NSCAL ? K : SMOE_NSCAL;
-    exchange_unpack_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(tail, K, scalars, infl);
-    return check_launch("smoe_exchange_unpack");
 }
 
 }  // extern "C"

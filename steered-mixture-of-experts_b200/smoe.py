@@ -28,8 +28,11 @@ from itertools import product
 import numpy as np
 import torch
 
+import os
+import warnings
+
 from . import _ffi
-from ._ffi import Adam, Batch, Cfg, check, lib, ptr, stream_ptr
+from ._ffi import Adam, Batch, Cfg, Peers, check, lib, ptr, stream_ptr
 from .quantizer import quantize_params, rescaler
 
 PARAM_KEYS = ("pis", "musX", "A_diagonal", "A_corr", "gamma_e", "nu_e")
@@ -56,13 +59,27 @@ class AdamOptimizer:
         self._lr = learning_rate
         self._beta1, self._beta2, self._epsilon = beta1, beta2, epsilon
         self._t = 0
+        # TF1 keeps beta1_power / beta2_power as float32 variables, multiplied by float32(beta) after every
+        # apply_gradients (optimizer `_finish`); lr_t uses the powers BEFORE that update, i.e. beta^t at step t
+        self._b1p = np.float32(1.0)
+        self._b2p = np.float32(1.0)
 
     def _step_alpha(self):
         """Advance the beta powers once (one apply_gradients) and return TF's lr_t in float32."""
-        self._t += 1
         f = np.float32
-        b1p, b2p = f(self._beta1 ** self._t), f(self._beta2 ** self._t)
-        return float(f(self._lr) * np.sqrt(f(1) - b2p) / (f(1) - b1p))
+        self._t += 1
+        self._b1p = f(self._b1p * f(self._beta1))
+        self._b2p = f(self._b2p * f(self._beta2))
+        return float(f(self._lr) * np.sqrt(f(1) - self._b2p) / (f(1) - self._b1p))
+
+    def _set_step(self, t):
+        """Restore the step count (checkpoint restore): replays the float32 products."""
+        f = np.float32
+        self._t, self._b1p, self._b2p = 0, f(1.0), f(1.0)
+        for _ in range(int(t)):
+            self._t += 1
+            self._b1p = f(self._b1p * f(self._beta1))
+            self._b2p = f(self._b2p * f(self._beta2))
 
 
 class Smoe:
@@ -74,7 +91,7 @@ class Smoe:
                  overlap_of_batches=0, kernel_count_as_norm_l1=False, train_svs=False, affines=None,
                  train_trafo=False, num_params_model=6, train_inverse_cov=True, init_flag=1,
                  only_rec_from_checkpoint=False, loss_mask=None, device=None, dense_exec=False,
-                 process_group=None, distributed=None, _decoder_only=False):
+                 process_group=None, distributed=None, eps_bits=0, _decoder_only=False, _emulate_shard=None):
         _ffi.require_cuda()
         lib()
         unsupported = {"affines": affines is not None, "train_trafo": train_trafo, "train_svs": train_svs,
@@ -125,6 +142,9 @@ class Smoe:
         self.overlap = int(overlap_of_batches)                # smoe.py:244
         if self.overlap < 0:
             raise ValueError("overlap_of_batches must be >= 0")
+        self.eps_bits = int(eps_bits)
+        if self.eps_bits and not 24 <= self.eps_bits <= 126:
+            raise ValueError("eps_bits must be 0 (exact) or in [24, 126]")
         self.image = image
         self.dim_domain = image.ndim - 1
         self.num_pixel = int(np.prod(image.shape[:self.dim_domain]))
@@ -143,6 +163,10 @@ class Smoe:
                     raise ValueError("Required BatchSize is not compatible to input dimensions")
         else:
             self.batch_size_valued = tuple(self.batch_shape[:-1])
+        if self.overlap > min(self.batch_size_valued):
+            # a window narrower than its halo would count partly-halo rows in the loss (the kernels derive the halo
+            # from the clipped rectangle); the reference has no such configuration either (smoe_test.py:322-325)
+            raise ValueError("overlap_of_batches must not exceed the smallest batch extent")
         self.batch_size = tuple(np.array(self.batch_size_valued) + 2 * self.overlap)
         self.start_batches = int(np.prod(np.ceil(np.array(image.shape[:-1]) / np.array(self.batch_size_valued))))
 
@@ -168,22 +192,30 @@ class Smoe:
         self.kernel_count = self.start_pis
         self.margin = margin
 
-        # --- distributed sharding: contiguous bands of the first domain axis ---
+        # --- distributed sharding: one rectangular block of pixels per rank ---
         self._pg = process_group
         self._world, self._rank = 1, 0
-        if distributed is not False and torch.distributed.is_available() and torch.distributed.is_initialized():
+        self._emulated = _emulate_shard is not None      # profiling aid: the work of rank r of R on one GPU, no exchange
+        if self._emulated:
+            self._rank, self._world = int(_emulate_shard[0]), int(_emulate_shard[1])
+        elif distributed is not False and torch.distributed.is_available() and torch.distributed.is_initialized():
             self._world = torch.distributed.get_world_size(process_group)
             self._rank = torch.distributed.get_rank(process_group)
+        d = self.dim_domain
         if self._world > 1:
+            if self._world > _ffi.MAX_PEERS:
+                raise NotImplementedError(f"at most {_ffi.MAX_PEERS} ranks (one NVSwitch node)")
             if self.start_batches != 1:
                 raise NotImplementedError("pixel sharding over ranks needs start_batches == 1")
             if self.ssim_opt or self.overlap > 0:
-                # SSIM windows and halos cross the band borders: a sharded SSIM loss needs a 5-pixel halo exchange
+                # SSIM windows and halos cross the block borders: a sharded SSIM loss needs a 5-pixel halo exchange
                 raise NotImplementedError("ssim_opt / overlap_of_batches on a sharded model")
-            n0 = image.shape[0]
-            self._band = (n0 * self._rank // self._world, n0 * (self._rank + 1) // self._world)
+            self._blocks = self._choose_blocks(self._world)
+            self._block = self._blocks[self._rank]
         else:
-            self._band = (0, image.shape[0])
+            self._block = tuple((0, image.shape[a]) for a in range(d))
+            self._blocks = [self._block]
+        self._band = self._block[0]
 
         self._init_device(dense_exec)
 
@@ -270,6 +302,72 @@ class Smoe:
         return tuple(int(joint_domain_shape[a] / div[a]) for a in range(nd))
 
     # ------------------------------------------------------------------------------------------
+    # pixel sharding: block decomposition
+    # ------------------------------------------------------------------------------------------
+    def _reach_px(self):
+        """Per axis, the distance in pixels over which a kernel's float32 gate can be non-zero (logit within 126
+        of its peak), estimated from the median initial steering matrix.  A heuristic that only steers the block
+        decomposition and the pixel-split count -- results never depend on it."""
+        d = self.dim_domain
+        A = np.asarray(self.A_init, dtype=np.float64)
+        diag = np.stack([A] * d, 1) if A.ndim == 1 else np.stack([A[:, a, a] for a in range(d)], 1)
+        med = np.maximum(np.median(np.abs(diag), axis=0), 1e-6)
+        q = 0.72134752 * (med if self.train_inverse_cov else med ** 2)          # diagonal of Qm (log2 domain)
+        return [float(np.sqrt(126.0 / q[a]) * max(self.image.shape[a] - 1, 1)) for a in range(d)]
+
+    def _choose_blocks(self, world, halo_weight=0.5):
+        """One rectangular block per rank, rank = row-major index in the block grid.  A rank's work grows with its
+        block PLUS the strip around it that foreign kernels reach into (the backward visits those tiles, the forward
+        sweeps those kernels), so (a) the grid factorisation minimises prod_a (w_a + halo_a) -- 2x4 rather than 8x1
+        bands on a 1080p frame, 2x2x2 rather than frame bands on a video whose kernels span 12 frames -- and (b) the
+        cuts are placed so that blocks with fewer interior sides are wider (work-balanced, not equal, cuts).  Cuts
+        are rounded to the tile grid so that no rank gets partial tiles it would not have had otherwise."""
+        d = self.dim_domain
+        n = self.image.shape[:d]
+        tile = (16, 32) if d == 2 else (8, 8, 8)
+        reach = [halo_weight * r for r in self._reach_px()]
+
+        def factorisations(w, k):
+            if k == 1:
+                yield (w,)
+                return
+            for f in range(1, w + 1):
+                if w % f == 0:
+                    for rest in factorisations(w // f, k - 1):
+                        yield (f,) + rest
+
+        best, best_cost = None, None
+        for fac in factorisations(world, d):
+            if any(n[a] // fac[a] < 1 for a in range(d)):
+                continue
+            cost = 1.0
+            for a in range(d):
+                eff = (n[a] + reach[a] * (2 * fac[a] - 2)) / fac[a]
+                cost *= max(eff, float(tile[a]))                 # a block thinner than a tile still costs a tile
+            if best_cost is None or cost < best_cost * (1 - 1e-9):
+                best, best_cost = fac, cost
+        cuts = []
+        for a in range(d):
+            r = best[a]
+            rc = min(reach[a], n[a] / (2.0 * r))     # the model saturates once the halo is as wide as the block
+            eff = (n[a] + rc * (2 * r - 2)) / r
+            widths = [max(eff - rc * ((i > 0) + (i < r - 1)), 1.0) for i in range(r)]
+            scale = n[a] / sum(widths)
+            edges, acc = [0], 0.0
+            for i in range(r - 1):
+                acc += widths[i] * scale
+                e = int(round(acc / tile[a])) * tile[a] if n[a] >= 2 * r * tile[a] else int(round(acc))
+                e = min(max(e, edges[-1] + 1), n[a] - (r - 1 - i))
+                edges.append(e)
+            edges.append(n[a])
+            cuts.append(edges)
+        self._block_grid = best
+        blocks = []
+        for idx in product(*[range(best[a]) for a in range(d)]):
+            blocks.append(tuple((cuts[a][idx[a]], cuts[a][idx[a] + 1]) for a in range(d)))
+        return blocks
+
+    # ------------------------------------------------------------------------------------------
     # device state
     # ------------------------------------------------------------------------------------------
     def _init_device(self, dense_exec):
@@ -295,7 +393,10 @@ class Smoe:
                         int(self.only_y_gamma), int(self.quantize_pis), lb3, ub3, bits3,
                         int(self.quantization_mode) if qm2 else 0, q_lb, q_ub, q_bits, int(self.use_diff_center),
                         int(self.kernel_count_as_norm_l1), int(bool(self.radial_as)),
-                        int(dense_exec))   # dense_exec: 0 cull+skip, 1 dense, 2 skip only
+                        int(dense_exec),   # dense_exec: 0 cull+skip, 1 dense, 2 skip only
+                        int(self.eps_bits))
+        if self.eps_bits and int(dense_exec) != 0:
+            raise ValueError("eps_bits (opt-in epsilon culling) needs dense_exec == 0")
         # variables
         A0 = np.asarray(self.A_init, dtype=np.float64)
         theta = np.zeros((K, self._P), dtype=np.float32)
@@ -319,22 +420,23 @@ class Smoe:
         self._adam_m = torch.zeros_like(self._theta)
         self._adam_v = torch.zeros_like(self._theta)
         self._group_owner = [None, None, None]
-        # image band resident on this rank + coordinate axes (np.linspace -> float32 feed, smoe.py:545)
-        b0, b1 = self._band
-        self._local_shape = (b1 - b0,) + tuple(self.image.shape[1:d])
+        # image block resident on this rank + coordinate axes (np.linspace -> float32 feed, smoe.py:545)
+        blk = self._block
+        self._local_slices = tuple(slice(lo, hi) for lo, hi in blk)
+        self._local_shape = tuple(hi - lo for lo, hi in blk)
         self._dims3 = tuple(self._local_shape) + (1,) * (3 - d)
-        self._d_image = torch.from_numpy(np.ascontiguousarray(self.image[b0:b1])).to(dev)
+        self._d_image = torch.from_numpy(np.ascontiguousarray(self.image[self._local_slices])).to(dev)
         self._d_image_u8 = None
+        self._use_u8 = False                                 # set_image() fed 8-bit pixels: the forward reads them
         self._d_loss_mask = None
         if self.loss_mask is not None:                       # per-pixel loss weights (smoe.py:550, 932, 1674-1677)
             lm = np.asarray(self.loss_mask, dtype=np.float32).reshape(self.image.shape[:-1])
             if (lm < 0).any():
                 raise ValueError("loss_mask weights must be >= 0")
-            self._d_loss_mask = torch.from_numpy(np.ascontiguousarray(lm[b0:b1])).to(dev)
+            self._d_loss_mask = torch.from_numpy(np.ascontiguousarray(lm[self._local_slices])).to(dev)
         self._d_sample_w = None                              # per-call pixel selection of sampling_percentage < 100
         self.random_sampling_per_batch = None                # None = uniform (smoe.py:271-273)
-        axes = [np.linspace(0, 1, self.image.shape[a]).astype(np.float32) for a in range(d)]
-        axes[0] = axes[0][b0:b1]
+        axes = [np.linspace(0, 1, self.image.shape[a]).astype(np.float32)[blk[a][0]:blk[a][1]] for a in range(d)]
         self._d_axes = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in axes]
         self._h_axes = axes
         npx = int(np.prod(self._local_shape))
@@ -394,7 +496,8 @@ class Smoe:
         self._packed = torch.zeros((K, self._PK), dtype=f32, device=dev)
         self._indices = torch.zeros((K,), dtype=torch.int32, device=dev)
         self._pos = torch.zeros((K,), dtype=torch.int32, device=dev)
-        self._perm = None
+        self._perm = torch.zeros((K,), dtype=torch.int32, device=dev)
+        self._keys = torch.zeros((K,), dtype=torch.int64, device=dev)
         self._refresh_perm()
         # one block per batch [scalars (NSCAL) | counts (4 x int32) | regulariser sums (2) | pad]: a single
         # device->host copy per run_batched call brings back everything the host needs
@@ -404,44 +507,127 @@ class Smoe:
         self._regsums = self._stats[:, _ffi.NSCAL + 4:_ffi.NSCAL + 6]
         self._infl = torch.zeros((K,), dtype=torch.uint8, device=dev)
         self._pix = torch.zeros((max_tiles * L.smoe_pix_stride(d, Cc, C.byref(self._batches[0])),), dtype=f32, device=dev)
-        self._tile_qmin = torch.zeros((max_tiles,), dtype=f32, device=dev)
+        # per batch: the forward's tile minima of log2 S (culling threshold of the backward; with eps_bits also the
+        # PREVIOUS pass's bound for the forward's own sweep A, -inf = "no bound yet, sweep exactly")
+        self._tile_qmin = torch.full((nb, max_tiles), -float("inf"), dtype=f32, device=dev)
+        self._pair_counts = None        # uint64[8] executed-pair counters, enable_pair_counts()
         self._chunk_bounds = torch.zeros(((K + 127) // 128, 12), dtype=f32, device=dev)
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         self._partials = torch.zeros((8 * sms * 8,), dtype=f32, device=dev)
         self._ticket = torch.zeros((4,), dtype=torch.int32, device=dev)
         self._pack_ws = torch.zeros((L.smoe_pack_workspace_bytes(K) + 15) // 4, dtype=torch.int32, device=dev)
-        import os as _os
-        self._splits = int(_os.environ.get("SMOE_SPLITS", 0)) or max(int(L.smoe_suggest_splits(K, C.byref(b)))
-                                                                     for b in self._batches)
+        if self._world > 1:
+            # a rank's block is reached by a fraction of the kernels only: size the pixel splits for the kernel CTAs
+            # that will actually have work, so the (kernel CTA, split) grid still fills the GPU
+            reach = self._reach_px()
+            frac = float(np.prod([min(1.0, (self._local_shape[a] + 2 * reach[a]) / (self.image.shape[a] + 2 * reach[a]))
+                                  for a in range(d)]))
+            k_eff = max(64, int(K * frac))
+        else:
+            k_eff = K
+        self._splits = int(os.environ.get("SMOE_SPLITS", 0)) or max(int(L.smoe_suggest_splits(k_eff, C.byref(b)))
+                                                                    for b in self._batches)
         self._raw_part = None           # allocated on the first training pass
-        # [raw statistics | scalars | influence flags]: the buffer a multi-GPU run all-reduces
-        self._xbuf = torch.zeros((K * self._P + _ffi.NSCAL + K,), dtype=f32, device=dev) if self._world > 1 else None
+        self._peers = None
+        if self._world > 1 and not self._emulated:
+            self._open_peer_windows()
         self._host_stats = torch.zeros((nb, _ffi.STATS_STRIDE), dtype=f32).pin_memory()
         self._alpha_host = torch.zeros((4,), dtype=f32).pin_memory()
         self._alpha_dev = torch.zeros((4,), dtype=f32, device=dev)
         self._graphs = {}
-        # with several ranks the step is two graphs around an eager NCCL all-reduce (capturing the
-        # collective itself hung on this stack)
+        # one CUDA graph per training-step signature, on one GPU and sharded alike (the exchange is stream-ordered
+        # kernels over peer memory)
         self.use_cuda_graphs = True
         self.gpu_launches = 0
 
-    def _refresh_perm(self):
-        """Spatially coherent kernel -> thread-slot assignment for the backward (Morton order of the current
-        centres).  Purely a work-assignment heuristic: any permutation gives bit-identical results, a coherent
-        one makes the kernels of a warp / CTA neighbours so that the tile culling bites."""
-        d = self.dim_domain
-        mu = self._centres().detach().cpu().numpy()
-        bits = 10
-        cell = np.clip((mu * (1 << bits)).astype(np.int64), 0, (1 << bits) - 1)
-        key = np.zeros(mu.shape[0], dtype=np.int64)
-        for b in range(bits):
-            for a in range(d):
-                key |= ((cell[:, a] >> b) & 1) << (b * d + (d - 1 - a))
-        perm = torch.from_numpy(np.argsort(key, kind="stable").astype(np.int32)).to(self.device)
-        if self._perm is None:
-            self._perm = perm
+    def _open_peer_windows(self):
+        """Allocate this rank's exchange window, swap cudaIpc handles with the other ranks of the node (host
+        plumbing: torch.distributed) and map theirs (csrc/exchange.cuh)."""
+        L = lib()
+        nbytes = L.smoe_xchg_window_bytes(self.start_pis, self._P)
+        own = C.c_void_p()
+        check(L.smoe_peer_alloc(C.c_size_t(nbytes), C.byref(own)), "smoe_peer_alloc")
+        handle = (C.c_ubyte * 64)()
+        check(L.smoe_peer_export(own, handle), "smoe_peer_export")
+        handles = [None] * self._world
+        torch.distributed.all_gather_object(handles, bytes(handle), group=self._pg)
+        self._peers = Peers()
+        self._peers.world, self._peers.rank = self._world, self._rank
+        self._peer_own = own
+        for r in range(self._world):
+            if r == self._rank:
+                self._peers.win[r] = own.value
+            else:
+                mapped = C.c_void_p()
+                buf = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+                check(L.smoe_peer_open(buf, C.byref(mapped)), "smoe_peer_open")
+                self._peers.win[r] = mapped.value
+        torch.cuda.synchronize()
+        torch.distributed.barrier(group=self._pg)       # every window exists and is zeroed before anyone signals
+
+    def close(self):
+        """Unmap / free the peer windows of a sharded model (collective: every rank calls it)."""
+        if getattr(self, "_peers", None) is None:
+            return
+        L = lib()
+        torch.cuda.synchronize()
+        torch.distributed.barrier(group=self._pg)
+        for r in range(self._world):
+            if r != self._rank:
+                L.smoe_peer_close(C.c_void_p(self._peers.win[r]))
+        torch.distributed.barrier(group=self._pg)
+        L.smoe_peer_free(self._peer_own)
+        self._peers = None
+
+    def exchange_status(self):
+        """(epoch, error) of this rank's exchange window; error != 0 means a peer never arrived at a barrier."""
+        st = (C.c_int32 * 2)()
+        check(lib().smoe_xchg_status(C.byref(self._peers), st), "smoe_xchg_status")
+        return int(st[0]), int(st[1])
+
+    def enable_pair_counts(self, on=True):
+        """Executed-(pixel, kernel)-pair counters of the two sweep kernels (bench / roofline diagnostics; a separate
+        kernel instantiation, the default path carries none)."""
+        self._pair_counts = torch.zeros((8,), dtype=torch.int64, device=self.device) if on else None
+        self._graphs = {}
+
+    def set_image(self, pixels):
+        """Feed this rank's block of the target for the following passes (the end-to-end path: a frame arrives in
+        host memory every step).  `pixels`: uint8 (as an image file holds them; /255 as utils.py:126-128 happens in
+        the forward kernel's epilogue) or float32 in [0,1], shape of the local block, ideally pinned; the copy is
+        asynchronous on the current stream."""
+        t = pixels if isinstance(pixels, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pixels))
+        if tuple(t.shape) != tuple(self._d_image.shape):
+            raise ValueError(f"expected the local block {tuple(self._d_image.shape)}, got {tuple(t.shape)}")
+        if t.dtype == torch.uint8:
+            if self.ssim_opt:
+                raise NotImplementedError("8-bit feed with ssim_opt: feed float32 pixels")
+            if self._d_image_u8 is None:
+                self._d_image_u8 = torch.empty(self._d_image.shape, dtype=torch.uint8, device=self.device)
+            self._d_image_u8.copy_(t, non_blocking=True)
+            self._use_u8 = True
+        elif t.dtype == torch.float32:
+            self._d_image.copy_(t, non_blocking=True)
+            self._use_u8 = False
         else:
-            self._perm.copy_(perm)      # in place: captured CUDA graphs hold this buffer's address
+            raise ValueError("set_image takes uint8 or float32 pixels")
+        self.valid = self.qvalid = False
+
+    def _refresh_perm(self):
+        """Spatially coherent packing order (Morton order of the current centres): smoe_pack writes the compute
+        records in this order, so a forward chunk (128 records) and a backward CTA (64 records) hold neighbours and
+        the tile culling bites.  Purely a work-assignment choice -- any order gives the same per-kernel results.
+        Keys and sort run on the device (stable sort: ties keep ascending index)."""
+        check(lib().smoe_morton_keys(ptr(self._theta), self.start_pis, self.dim_domain, self._P, ptr(self._mus_grid),
+                                     ptr(self._keys), stream_ptr()), "smoe_morton_keys")
+        # in place: captured CUDA graphs hold the buffer's address
+        self._perm.copy_(torch.sort(self._keys, stable=True).indices.to(torch.int32))
+
+    def get_active_indices(self, batch=0):
+        """The reference's `indices` of the last pass over `batch` (smoe.py:741-742): ascending original indices of
+        the kernels with pi > 0 that are on the batch's kernel list."""
+        K = int(self._counts[batch, 0].item())
+        return np.sort(self._indices[:K].cpu().numpy())
 
     def _enable_res_pre(self):
         """Keep the mixture output before clip / output quantisation (diagnostics and parity tests;
@@ -497,6 +683,11 @@ class Smoe:
         device, so a captured step never bakes a step count into its kernel arguments."""
         opts = [self.optimizer1, self.optimizer2, self.optimizer3]
         trainable = [True, self.train_pis, True]
+        # One apply_gradients per GROUP (smoe.py:1173-1184).  When set_optimizer(opt) aliases one object to all three
+        # groups (smoe.py:1080-1090), TF builds three apply_gradients ops on it and each multiplies the shared
+        # beta1_power / beta2_power once per step -- the powers advance three times per step and the order of the
+        # three ops inside one session.run is unspecified; here they run in group order (1, 2, 3), which is one of
+        # TF's valid serialisations (the test-side restatement pins the same order).
         for g, (opt, tr) in enumerate(zip(opts, trainable)):
             on = tr and not opt._lr == 0
             self._alpha_host[g] = opt._step_alpha() if on else 0.0
@@ -519,7 +710,7 @@ class Smoe:
     # ------------------------------------------------------------------------------------------
     def run_batched(self, pis_l1=0, u_l1=0, sv_l1_sub_l2=0, train=True, update_reconstruction=False,
                     with_quantized_params=False, sampling_percentage=100, with_inc=False, train_inc=False,
-                    thr_sv=None, use_loss_mask=False, _host_image=None):
+                    thr_sv=None, use_loss_mask=False):
         if with_inc or train_inc:
             raise NotImplementedError("inc paths are outside the hot path (D1)")
         if train:
@@ -555,39 +746,39 @@ class Smoe:
         if graphable:
             key = (float(pis_l1), float(u_l1), self.grad_clip_value_abs, id(self.optimizer1), id(self.optimizer2),
                    id(self.optimizer3), self.optimizer1._lr, self.optimizer2._lr, self.optimizer3._lr,
-                   None if _host_image is None else _host_image.data_ptr(), bool(use_loss_mask))
+                   self._use_u8, bool(use_loss_mask))
             state = self._graphs.get(key)
             if state is None:
                 self._graphs[key] = "warm"              # first step with this signature runs eagerly
             else:
                 if state == "warm":
+                    l0 = self.gpu_launches
+                    torch.cuda.synchronize()
                     try:
-                        l0 = self.gpu_launches
-                        torch.cuda.synchronize()
-                        graphs = []
-                        # with several ranks the NCCL all-reduce stays outside: [pre] -> all_reduce -> [post]
-                        for phase in (("all",) if self._world == 1 else ("pre", "post")):
-                            g = torch.cuda.CUDAGraph()
-                            with torch.cuda.graph(g):
-                                self._enqueue(pis_l1, u_l1, True, False, False, _host_image, phase=phase, lossw=lossw)
-                            graphs.append(g)
-                        state = (graphs, self.gpu_launches - l0)
-                        self.gpu_launches = l0
-                        self._graphs[key] = state
-                    except Exception as exc:             # capture unsupported here: stay eager, loudly
-                        print(f"smoe_b200: CUDA graph capture disabled ({exc})")
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            self._enqueue(pis_l1, u_l1, True, False, False, lossw=lossw)
+                        state = (g, self.gpu_launches - l0)
+                    except Exception as exc:
+                        # Loud by default: a silent eager fallback would hide a 2x slower step.  A sharded model
+                        # cannot fall back at all: its peers would replay a graph while this rank runs eagerly --
+                        # same kernels, so still correct, but the failure must be seen.
+                        if os.environ.get("SMOE_ALLOW_EAGER", "0") != "1":
+                            raise RuntimeError(f"smoe_b200: CUDA graph capture of the training step failed ({exc}); "
+                                               "set SMOE_ALLOW_EAGER=1 to run the step eagerly instead") from exc
+                        warnings.warn(f"smoe_b200: CUDA graph capture failed ({exc}); running eagerly")
                         self.use_cuda_graphs = False
                         torch.cuda.synchronize()
                         state = None
+                    self.gpu_launches = l0
+                    if state is not None:
+                        self._graphs[key] = state
                 if state is not None:
-                    state[0][0].replay()
-                    if self._world > 1:
-                        torch.distributed.all_reduce(self._xbuf, group=self._pg)
-                        state[0][1].replay()
+                    state[0].replay()
                     self.gpu_launches += state[1]
                     replayed = True
         if not replayed:
-            self._enqueue(pis_l1, u_l1, train, update_reconstruction, with_quantized_params, _host_image,
+            self._enqueue(pis_l1, u_l1, train, update_reconstruction, with_quantized_params,
                           lossw=lossw, batches=batches)
         torch.cuda.current_stream().synchronize()
         h = self._host_stats.numpy().astype(np.float64)
@@ -617,6 +808,12 @@ class Smoe:
             mse_val += mse_b * frac
             num_pi = int(h[ii, _ffi.NSCAL + 1])
         self._last_nonpos = int(h[:, _ffi.NSCAL + 2].sum())
+        if self._last_nonpos > 0 and not getattr(self, "_warned_nonpos", False):
+            # pi * prod(diag A) < 0 with use_determinant: the reference gives such a kernel a NEGATIVE weight n_w
+            # (smoe.py:809-820); the log-domain kernels evaluate it with |coef| -- say so once
+            warnings.warn(f"smoe_b200: {self._last_nonpos} active kernel(s) have pi * prod(diag A) < 0; they are "
+                          "evaluated with the absolute value of that weight (the reference would subtract them)")
+            self._warned_nonpos = True
         if update_reconstruction:
             self._update_sampling_probabilities()
             rec, amax = self._gather_reconstruction()
@@ -661,6 +858,8 @@ class Smoe:
         if self._world > 1 or self.overlap > 0:
             return
         d, Cc = self.dim_domain, self.image.shape[-1]
+        if self._use_u8:
+            torch.div(self._d_image_u8.to(torch.float32), 255.0, out=self._d_image)
         err = ((self._d_res.reshape(self._local_shape + (Cc,)) - self._d_image) ** 2).mean(dim=-1)
         probs = []
         for org, ext in self._batch_rects():
@@ -668,27 +867,18 @@ class Smoe:
             probs.append(e / e.sum())
         self.random_sampling_per_batch = probs
 
-    def _enqueue(self, pis_l1, u_l1, train, update_reconstruction, with_quantized_params, _host_image, phase="all",
-                 lossw=None, batches=None):
-        """Every launch of one run_batched call, asynchronous on the current stream (capturable).
-        phase "pre" / "post" enqueue only the part before / after the all-reduce of a sharded step."""
+    def _enqueue(self, pis_l1, u_l1, train, update_reconstruction, with_quantized_params, lossw=None, batches=None):
+        """Every launch of one run_batched call, asynchronous on the current stream (capturable, also sharded:
+        the exchange is stream-ordered kernels over peer memory)."""
         L, st = lib(), stream_ptr()
         K = self.start_pis
         batches = self._batches if batches is None else batches
-        pre, post = phase in ("all", "pre"), phase in ("all", "post")
-        if pre:
-            if _host_image is not None:                  # e2e path: this step's pixels come from pinned host memory
-                if _host_image.dtype == torch.uint8:     # 8-bit pixels as read from disk; /255 as utils.py:126-128
-                    if self._d_image_u8 is None:
-                        self._d_image_u8 = torch.empty(self._d_image.shape, dtype=torch.uint8, device=self.device)
-                    self._d_image_u8.copy_(_host_image, non_blocking=True)
-                    torch.div(self._d_image_u8.to(torch.float32), 255.0, out=self._d_image)
-                else:
-                    self._d_image.copy_(_host_image, non_blocking=True)
-            check(L.smoe_step_begin(ptr(self._grads) if train else ptr(None), C.c_size_t(self._grads.numel()),
-                                    ptr(self._stats), len(self._batches), _ffi.STATS_STRIDE, ptr(self._infl), K, st),
-                  "smoe_step_begin")
-            self.gpu_launches += 1
+        sharded = self._world > 1 and not self._emulated
+        pc = ptr(self._pair_counts)
+        check(L.smoe_step_begin(ptr(self._grads) if train else ptr(None), C.c_size_t(self._grads.numel()),
+                                ptr(self._stats), len(self._batches), _ffi.STATS_STRIDE, ptr(self._infl), K, st),
+              "smoe_step_begin")
+        self.gpu_launches += 1
         fed = with_quantized_params and update_reconstruction
         if fed:
             rp = {k: torch.as_tensor(np.ascontiguousarray(np.asarray(v, dtype=np.float32)), device=self.device)
@@ -696,77 +886,88 @@ class Smoe:
             Kf = int(rp["pis"].shape[0])
             if Kf > K:
                 raise ValueError("more fed kernels than model kernels")
+            # the fed rows in Morton order of their centres, like the variables (device keys + device sort)
+            fkeys = torch.empty((Kf,), dtype=torch.int64, device=self.device)
+            check(L.smoe_morton_keys(ptr(rp["musX"]), Kf, self.dim_domain, self.dim_domain, ptr(None), ptr(fkeys), st),
+                  "smoe_morton_keys")
+            forder = torch.sort(fkeys, stable=True).indices.to(torch.int32)
         norm = float(self.start_pis)
-        if pre and self._qdyn is not None and not fed:
+        if self._qdyn is not None and not fed:
             check(L.smoe_quant_ranges(C.byref(self._cfg), ptr(self._theta), K, int(self.train_musx), ptr(self._qdyn), st),
                   "smoe_quant_ranges")
             self.gpu_launches += 1
+        img_f32 = ptr(None) if self._use_u8 else ptr(self._d_image)
+        img_u8 = ptr(self._d_image_u8) if self._use_u8 else ptr(None)
+        ax2 = ptr(self._d_axes[2]) if self.dim_domain == 3 else ptr(None)
         for ii, b in enumerate(batches):
             counts, regs, scal = self._counts[ii], self._regsums[ii], self._scalars[ii]
-            if not pre:
-                pass
-            elif fed:
+            tq = self._tile_qmin[ii]
+            if fed:
                 check(L.smoe_pack_fed(C.byref(self._cfg), ptr(rp["A"]), ptr(rp["musX"]), ptr(rp["nu_e"]),
-                                      ptr(rp["gamma_e"]), ptr(rp["pis"]), Kf, ptr(self._packed), ptr(counts),
-                                      ptr(self._chunk_bounds), st), "smoe_pack_fed")
-                self._indices[:Kf] = torch.arange(Kf, dtype=torch.int32, device=self.device)
+                                      ptr(rp["gamma_e"]), ptr(rp["pis"]), ptr(forder), Kf, ptr(self._packed),
+                                      ptr(self._indices), ptr(counts), ptr(self._chunk_bounds), st), "smoe_pack_fed")
                 regs.zero_()
                 self.gpu_launches += 3
             else:
                 check(L.smoe_pack(C.byref(self._cfg), ptr(self._theta), ptr(self._mus_grid), ptr(self._qdyn),
-                                  ptr(self._klist[ii]), K, ptr(self._packed),
+                                  ptr(self._klist[ii]), ptr(self._perm), K, ptr(self._packed),
                                   ptr(self._indices), ptr(self._pos), ptr(counts), ptr(regs), ptr(self._chunk_bounds),
                                   ptr(self._pack_ws), st), "smoe_pack")
                 self.gpu_launches += 3
-            if pre:
-                if ii > 0:
-                    self._infl.zero_()
-                check(L.smoe_forward(C.byref(self._cfg), C.byref(b), ptr(self._packed), ptr(self._indices), ptr(counts),
-                                     ptr(self._chunk_bounds), K,
-                                     ptr(self._d_image), ptr(lossw), ptr(self._d_axes[0]), ptr(self._d_axes[1]),
-                                     ptr(self._d_axes[2]) if self.dim_domain == 3 else ptr(None),
-                                     ptr(self._d_res), ptr(self._d_res_pre),
-                                     ptr(self._d_argmax) if update_reconstruction else ptr(None),
-                                     ptr(self._infl), ptr(self._pix) if train else ptr(None), ptr(self._tile_qmin),
-                                     ptr(scal), ptr(self._partials), ptr(self._ticket), st), "smoe_forward")
+            if ii > 0:
+                self._infl.zero_()
+            check(L.smoe_forward(C.byref(self._cfg), C.byref(b), ptr(self._packed), ptr(self._indices), ptr(counts),
+                                 ptr(self._chunk_bounds), K, img_f32, img_u8, ptr(lossw), ptr(self._d_axes[0]),
+                                 ptr(self._d_axes[1]), ax2, ptr(self._d_res), ptr(self._d_res_pre),
+                                 ptr(self._d_argmax) if update_reconstruction else ptr(None),
+                                 ptr(self._infl), ptr(self._pix) if train else ptr(None), ptr(tq),
+                                 ptr(scal), ptr(self._partials), ptr(self._ticket), pc, st), "smoe_forward")
+            self.gpu_launches += 1
+            if self._batch_phantom[ii]:
+                pb, halo1 = self._phantom
+                check(L.smoe_forward(C.byref(self._cfg), C.byref(pb), ptr(self._packed), ptr(self._indices),
+                                     ptr(counts), ptr(self._chunk_bounds), K, img_f32, img_u8, ptr(halo1),
+                                     ptr(self._d_axes[0]), ptr(self._d_axes[1]), ax2,
+                                     ptr(self._d_res), ptr(None), ptr(None), ptr(self._infl), ptr(None), ptr(None),
+                                     ptr(scal), ptr(self._partials), ptr(self._ticket), ptr(None), st),
+                      "smoe_forward (phantom)")
                 self.gpu_launches += 1
-                if self._batch_phantom[ii]:
-                    pb, halo1 = self._phantom
-                    check(L.smoe_forward(C.byref(self._cfg), C.byref(pb), ptr(self._packed), ptr(self._indices),
-                                         ptr(counts), ptr(self._chunk_bounds), K, ptr(self._d_image), ptr(halo1),
-                                         ptr(self._d_axes[0]), ptr(self._d_axes[1]),
-                                         ptr(self._d_axes[2]) if self.dim_domain == 3 else ptr(None),
-                                         ptr(self._d_res), ptr(None), ptr(None), ptr(self._infl), ptr(None), ptr(None),
-                                         ptr(scal), ptr(self._partials), ptr(self._ticket), st), "smoe_forward (phantom)")
-                    self.gpu_launches += 1
-                if self.ssim_opt:
-                    check(L.smoe_ssim_loss(C.byref(self._cfg), C.byref(b), ptr(self._d_res), ptr(self._d_image),
-                                           ptr(self._d_res_pre), ptr(self._pix) if train else ptr(None), ptr(scal),
-                                           ptr(self._ssim_ws), st), "smoe_ssim_loss")
-                    self.gpu_launches += 2 * self.dim_domain + 2 if train else self.dim_domain + 1
-            if train and pre:
-                check(L.smoe_backward(C.byref(self._cfg), C.byref(b), ptr(self._packed), ptr(counts), K,
-                                      ptr(self._perm), ptr(self._pos), ptr(self._pix),
-                                      ptr(self._tile_qmin), ptr(self._d_axes[0]), ptr(self._d_axes[1]),
-                                      ptr(self._d_axes[2]) if self.dim_domain == 3 else ptr(None),
-                                      self._splits, ptr(self._raw_part), st), "smoe_backward")
-                self.gpu_launches += 1
-            if self._world > 1:
-                self._exchange(train, counts, scal, phase)
-            if not post:
-                continue
+            if self.ssim_opt:
+                check(L.smoe_ssim_loss(C.byref(self._cfg), C.byref(b), ptr(self._d_res), ptr(self._d_image),
+                                       ptr(self._d_res_pre), ptr(self._pix) if train else ptr(None), ptr(scal),
+                                       ptr(self._ssim_ws), st), "smoe_ssim_loss")
+                self.gpu_launches += 2 * self.dim_domain + 2 if train else self.dim_domain + 1
             if train:
-                raw, ns = (self._xbuf, 1) if self._world > 1 else (self._raw_part, self._splits)
-                check(L.smoe_grad_finalize(C.byref(self._cfg), ptr(raw), ns, K, ptr(self._theta), ptr(self._qdyn),
-                                           ptr(self._indices), ptr(counts), C.c_float(float(pis_l1)), C.c_float(norm),
-                                           C.c_float(float(u_l1)), ptr(self._grads), st), "smoe_grad_finalize")
+                check(L.smoe_backward(C.byref(self._cfg), C.byref(b), ptr(self._packed), ptr(counts), K,
+                                      ptr(self._pix), ptr(tq), ptr(self._d_axes[0]), ptr(self._d_axes[1]), ax2,
+                                      self._splits, ptr(self._raw_part), pc, st), "smoe_backward")
+                self.gpu_launches += 1
+            if sharded:
+                # the one exchange step: publish this rank's sums, then the consumer sums the R
+                # windows over NVLink in rank order -- fused into the gradient finalisation on a training pass
+                check(L.smoe_xchg_publish(C.byref(self._cfg), C.byref(self._peers), ptr(counts), K, self._splits,
+                                          ptr(self._raw_part) if train else ptr(None), ptr(scal), ptr(self._infl), st),
+                      "smoe_xchg_publish")
+                self.gpu_launches += 1
+                if train:
+                    check(L.smoe_grad_finalize_peers(C.byref(self._cfg), C.byref(self._peers), K, ptr(self._theta),
+                                                     ptr(self._qdyn), ptr(self._indices), ptr(counts),
+                                                     C.c_float(float(pis_l1)), C.c_float(norm), C.c_float(float(u_l1)),
+                                                     ptr(self._grads), ptr(scal), ptr(self._infl), st),
+                          "smoe_grad_finalize_peers")
+                else:
+                    check(L.smoe_xchg_reduce_tail(C.byref(self._cfg), C.byref(self._peers), K, ptr(scal),
+                                                  ptr(self._infl), st), "smoe_xchg_reduce_tail")
+                self.gpu_launches += 1
+            elif train:
+                check(L.smoe_grad_finalize(C.byref(self._cfg), ptr(self._raw_part), self._splits, K, ptr(self._theta),
+                                           ptr(self._qdyn), ptr(self._indices), ptr(counts), C.c_float(float(pis_l1)),
+                                           C.c_float(norm), C.c_float(float(u_l1)), ptr(self._grads), st),
+                      "smoe_grad_finalize")
                 self.gpu_launches += 1
             if not with_quantized_params:                 # smoe.py:1763-1766
-                check(L.smoe_update_kernel_list(ptr(self._indices), ptr(counts), ptr(self._infl), ptr(self._klist[ii]),
-                                                K, st), "smoe_update_kernel_list")
+                check(L.smoe_update_kernel_list(ptr(self._infl), ptr(self._klist[ii]), K, st), "smoe_update_kernel_list")
                 self.gpu_launches += 1
-        if not post:
-            return
         if train and self._qdyn is not None:             # clipped gradients of the plain groups -> extreme elements
             check(L.smoe_quant_route(C.byref(self._cfg), ptr(self._theta), ptr(self._qdyn), K, ptr(self._grads), st),
                   "smoe_quant_route")
@@ -776,52 +977,36 @@ class Smoe:
         # one small device->host read per call: scalars, counts, regulariser sums
         self._host_stats.copy_(self._stats, non_blocking=True)
 
-    def _exchange(self, train, counts, scal, phase="all"):
-        """The one exchange step of the sharded path: sum over ranks of the
-        per-kernel statistics, the loss scalars and the influence flags."""
-        L, st = lib(), stream_ptr()
-        K, P = self.start_pis, self._P
-        if phase in ("all", "pre"):
-            if train:
-                check(L.smoe_reduce_splits(C.byref(self._cfg), ptr(counts), K, self._splits, ptr(self._raw_part),
-                                           ptr(self._xbuf), st), "smoe_reduce_splits")
-                self.gpu_launches += 1
-            else:
-                self._xbuf[:K * P].zero_()
-            check(L.smoe_exchange_pack(ptr(scal), ptr(self._infl), K, ptr(self._xbuf[K * P:]), st), "smoe_exchange_pack")
-            self.gpu_launches += 1
-        if phase == "all":
-            torch.distributed.all_reduce(self._xbuf, group=self._pg)
-        if phase in ("all", "post"):
-            check(L.smoe_exchange_unpack(ptr(self._xbuf[K * P:]), K, ptr(scal), ptr(self._infl), st),
-                  "smoe_exchange_unpack")
-            self.gpu_launches += 1
-
     def _gather_reconstruction(self):
         Cc = self.image.shape[-1]
+        d = self.dim_domain
         res = self._d_res.reshape(self._local_shape + (Cc,))
         amax = self._d_argmax.reshape(self._local_shape)
-        if self._world > 1:
-            # bands can differ by one row: gather through a padded buffer
-            n0 = self.image.shape[0]
-            rows = [n0 * (r + 1) // self._world - n0 * r // self._world for r in range(self._world)]
-            mr = max(rows)
-            pad_res = torch.zeros((mr,) + tuple(res.shape[1:]), dtype=res.dtype, device=self.device)
-            pad_res[:res.shape[0]] = res
-            pad_am = torch.zeros((mr,) + tuple(amax.shape[1:]), dtype=amax.dtype, device=self.device)
-            pad_am[:amax.shape[0]] = amax
+        if self._world > 1 and not self._emulated:
+            # blocks differ in shape: gather through buffers padded to the largest block, then place each block
+            mx = tuple(max(hi - lo for lo, hi in (blk[a] for blk in self._blocks)) for a in range(d))
+            pad_res = torch.zeros(mx + (Cc,), dtype=res.dtype, device=self.device)
+            pad_am = torch.zeros(mx, dtype=amax.dtype, device=self.device)
+            own = tuple(slice(0, n) for n in self._local_shape)
+            pad_res[own] = res
+            pad_am[own] = amax
             out_r = [torch.empty_like(pad_res) for _ in range(self._world)]
             out_a = [torch.empty_like(pad_am) for _ in range(self._world)]
             torch.distributed.all_gather(out_r, pad_res, group=self._pg)
             torch.distributed.all_gather(out_a, pad_am, group=self._pg)
-            res = torch.cat([o[:r] for o, r in zip(out_r, rows)], dim=0)
-            amax = torch.cat([o[:r] for o, r in zip(out_a, rows)], dim=0)
+            res = torch.empty(tuple(self.image.shape[:d]) + (Cc,), dtype=res.dtype, device=self.device)
+            amax = torch.empty(tuple(self.image.shape[:d]), dtype=amax.dtype, device=self.device)
+            for blk, o_r, o_a in zip(self._blocks, out_r, out_a):
+                dst = tuple(slice(lo, hi) for lo, hi in blk)
+                src = tuple(slice(0, hi - lo) for lo, hi in blk)
+                res[dst] = o_r[src]
+                amax[dst] = o_a[src]
         rec = res.cpu().numpy()
         am = amax.cpu().numpy().astype(np.float64)
         if (am < 0).any():
             # tf.argmax over the influential kernels returns position 0 when every gate is zero:
             # the lowest-index influential kernel of the batch (smoe.py:833-836, 1716)
-            infl_idx = self._indices[self._infl.to(torch.bool)[:self._indices.shape[0]]]
+            infl_idx = torch.nonzero(self._infl).flatten()
             fill = float(infl_idx.min().item()) if infl_idx.numel() else 0.0
             am[am < 0] = fill
         return rec, am
@@ -869,6 +1054,7 @@ class Smoe:
                         loss_val, mse_val, num_pi, num_sv = self.run_batched(
                             pis_l1=pis_l1, u_l1=u_l1, train=False, update_reconstruction=False)
                 if validate:
+                    self.check_replicas()
                     if self.quantization_mode >= 1:
                         self.qparams = quantize_params(self, self.get_params())
                     if self.quantization_mode == 1:
@@ -915,6 +1101,11 @@ class Smoe:
         pis = self._effective_pis()
         full_axes = [np.linspace(0, 1, self.image.shape[a]) for a in range(d)]
         rects = self._batch_rects()
+        if self._world > 1:
+            # A sharded model is the one-batch model of the whole image: every rank probes the WHOLE image rectangle,
+            # so the lists stay identical on all ranks (a rank-local probe would give every rank another kernel set,
+            # and the exchanged statistics are indexed by packed position).
+            rects = [((0,) * d, tuple(self.image.shape[:d]))]
         for ii, (org, ext) in enumerate(rects):
             pts = []
             ov = self.overlap
@@ -939,9 +1130,27 @@ class Smoe:
     def _batch_rects(self):
         d = self.dim_domain
         if self._world > 1:
-            return [((self._band[0],) + (0,) * (d - 1), self._local_shape)]
+            return [(tuple(lo for lo, _ in self._block), self._local_shape)]
         starts = [range(0, self.image.shape[a], self.batch_size_valued[a]) for a in range(d)]
         return [(org, self.batch_size_valued) for org in product(*starts)]
+
+    def check_replicas(self):
+        """Desync guard of the sharded path: every rank must hold bit-identical parameters, Adam state
+        and kernel lists (the exchange sums in a fixed rank order, so they are by construction).  Collective; raises
+        on any rank that differs from rank 0."""
+        if self._world == 1 or self._emulated:
+            return True
+        sig = torch.stack([t.view(torch.int32).to(torch.int64).sum() for t in
+                           (self._theta, self._adam_m, self._adam_v)] + [self._klist.to(torch.int64).sum()])
+        ref = sig.clone()
+        torch.distributed.broadcast(ref, src=torch.distributed.get_global_rank(self._pg, 0) if self._pg is not None else 0,
+                                    group=self._pg)
+        ok = torch.tensor([1 if bool((ref == sig).all()) else 0], device=self.device)
+        torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN, group=self._pg)
+        epoch, err = self.exchange_status()
+        if ok.item() != 1 or err:
+            raise RuntimeError(f"smoe_b200: replicas out of sync on rank {self._rank} (exchange epoch {epoch}, error {err})")
+        return True
 
     def _assembled_A(self):
         d, K = self.dim_domain, self.start_pis
@@ -1078,7 +1287,7 @@ class Smoe:
         self.iter = cp["iter"]
         for o, t in zip((self.optimizer1, self.optimizer2, self.optimizer3), cp["adam_t"]):
             if o is not None:
-                o._t = t
+                o._set_step(t)
         self.valid = self.qvalid = False
         print("Model restored from file: %s" % path)
 

@@ -1,11 +1,15 @@
 """Multi-GPU parity check, launched with torchrun (one rank per GPU):
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py [--c3]
 
-Every rank builds the row-sharded model and, next to it, an unsharded copy of the same model
-(distributed=False) on its own GPU, runs three training steps on both and compares loss, accumulated
-gradients (<= 1e-4 relative to the tensor max-norm, SURVEY.md 8e: summation order differs with R),
-kernel lists and the gathered reconstruction."""
+Every rank builds the pixel-sharded model (blocks of pixels, peer-memory exchange fused into grad_finalize) and,
+next to it, an unsharded copy of the same model (distributed=False) on its own GPU, and compares
+  * three training steps: loss, accumulated gradients (<= 1e-4 relative to the tensor max-norm, SURVEY.md 8e:
+    summation order differs with R), kernel lists, the gathered reconstruction;
+  * Smoe.train() past the kernel-list cadence with pi-sparsification on a grid where the reference's maha < 800
+    probe is selective: kernel lists, pruned index sets and parameters must stay identical ON EVERY RANK
+    (check_replicas) and agree with the unsharded run;
+  * with --c3: one training step of BASELINE config 3 (1080p RGB, 32,768 kernels) sharded vs unsharded."""
 import os
 import sys
 
@@ -16,69 +20,120 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def compare_steps(Smoe, AdamOptimizer, img, k, rank, steps=3, tag=""):
+    ok = True
+    kw = dict(use_determinant=True, train_inverse_cov=False, use_yuv=False)
+    ms = Smoe(img, kernels_per_dim=k, **kw)
+    m1 = Smoe(img, kernels_per_dim=k, distributed=False, **kw)
+    for m in (ms, m1):
+        m.set_optimizer(AdamOptimizer(1e-3), AdamOptimizer(1e-5), AdamOptimizer(1.0))
+    ms._enable_res_pre()
+    m1._enable_res_pre()
+    for step in range(steps):
+        a = ms.run_batched(pis_l1=0.1, train=True, update_reconstruction=True)
+        b = m1.run_batched(pis_l1=0.1, train=True, update_reconstruction=True)
+        # the two runs tile the pixels differently (different tile centres), so a few pixels that sit within float32
+        # noise of an output rounding boundary round the other way; each such pixel moves the gradient by
+        # ~2/(255 N C).  Forward parity is therefore asserted on the pre-quantisation output, and the gradient
+        # bound is widened per differing pixel.
+        flips = int((np.round(ms.reconstruction_image * 255) != np.round(m1.reconstruction_image * 255)).sum())
+        pre_s = ms._d_res_pre.cpu().numpy().reshape(ms._local_shape + (img.shape[-1],))
+        pre_1 = m1._d_res_pre.cpu().numpy().reshape(img.shape)[ms._local_slices]
+        dpre = np.abs(pre_s - pre_1)
+        # a gate within float32 noise of the threshold (smoe.py:825-827) may pass in one tiling only: such pixels
+        # move by at most ~tau * |expert| and must be rare
+        thr_flips = int((dpre > 1e-5).sum())
+        if dpre.max() > 2 * 0.5 / 256 or thr_flips > 1e-4 * dpre.size + 1 or flips > 1e-3 * img.size:
+            ok = False
+            print(f"{tag} rank {rank} step {step} pre-quant diff {dpre.max():.3e} thr_flips {thr_flips} flips {flips}")
+        flips += 4 * thr_flips
+        ga, gb = ms.get_gradients(), m1.get_gradients()
+        for key in ga:
+            rel = np.abs(ga[key] - gb[key]).max() / max(np.abs(gb[key]).max(), 1e-30)
+            if rel > 1e-4 + 1e-3 * flips:
+                ok = False
+                print(f"{tag} rank {rank} step {step} {key} rel {rel:.3e} (flips {flips})")
+        if abs(a[0] - b[0]) > 1e-6 + 1e-6 * flips or a[2] != b[2]:
+            ok = False
+            print(f"{tag} rank {rank} step {step} loss {a[0]} vs {b[0]}")
+        # keep the two models on identical parameters so that every step is a like-for-like comparison
+        pa, pb = ms.get_params(), m1.get_params()
+        for key in pa:
+            if np.abs(pa[key] - pb[key]).max() > 1e-3 * max(1.0, np.abs(pb[key]).max()):
+                ok = False
+                print(f"{tag} rank {rank} step {step} params {key} diverged {np.abs(pa[key] - pb[key]).max():.3e}")
+        m1.set_params(pa)
+        m1.kernel_list_per_batch = ms.kernel_list_per_batch
+        ms.check_replicas()
+    ms.valid = m1.valid = False          # both hold the image from before the last Adam step
+    ra, rb = ms.get_reconstruction(), m1.get_reconstruction()
+    if ra.shape != rb.shape or (np.round(ra * 255) != np.round(rb * 255)).mean() > 2e-3:
+        ok = False
+        print(f"{tag} rank {rank} reconstruction mismatch")
+    kla, klb = ms.kernel_list_per_batch[0], m1.kernel_list_per_batch[0]
+    if (kla != klb).sum() > 1:
+        ok = False
+        print(f"{tag} rank {rank} kernel list mismatch {(kla != klb).sum()}")
+    epoch, err = ms.exchange_status()
+    if err:
+        ok = False
+        print(f"{tag} rank {rank} exchange error flag set at epoch {epoch}")
+    ms.close()
+    return ok
+
+
+def compare_train(Smoe, AdamOptimizer, img, k, rank):
+    """train() through update_kernel_list with pruning: the probe is selective here (narrow kernels), so a
+    rank-local probe would give every rank another kernel list (the round-1 defect)."""
+    ok = True
+    kw = dict(use_determinant=True, train_inverse_cov=False, use_yuv=False, normalize_pis=True)
+    ms = Smoe(img, kernels_per_dim=k, **kw)
+    m1 = Smoe(img, kernels_per_dim=k, distributed=False, **kw)
+    for m in (ms, m1):
+        m.train(24, val_iter=12, ukl_iter=6, optimizer1=AdamOptimizer(1e-3), optimizer2=AdamOptimizer(2e-5),
+                optimizer3=AdamOptimizer(1.0), pis_l1=50.0)
+    ms.check_replicas()
+    near = m1.kernel_list_per_batch[0]
+    if near.all():
+        print(f"rank {rank} train check: probe not selective on this grid (test would be vacuous)")
+        ok = False
+    ia, ib = ms.get_active_indices(), m1.get_active_indices()
+    if len(set(ia.tolist()) ^ set(ib.tolist())) > max(2, len(ib) // 200):
+        ok = False
+        print(f"rank {rank} train: active sets differ by {len(set(ia.tolist()) ^ set(ib.tolist()))} of {len(ib)}")
+    if ms.num_pis[-1][1] >= ms.start_pis:
+        ok = False
+        print(f"rank {rank} train: nothing was pruned ({ms.num_pis[-1]})")
+    pa, pb = ms.get_params(), m1.get_params()
+    for key in pa:
+        if np.abs(pa[key] - pb[key]).max() > 2e-2 * max(1.0, np.abs(pb[key]).max()):
+            ok = False
+            print(f"rank {rank} train params {key} differ {np.abs(pa[key] - pb[key]).max():.3e}")
+    if abs(ms.losses[-1][1] - m1.losses[-1][1]) > 1e-3 * abs(m1.losses[-1][1]) + 1e-6:
+        ok = False
+        print(f"rank {rank} train loss {ms.losses[-1]} vs {m1.losses[-1]}")
+    ms.close()
+    return ok
+
+
 def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    torch.distributed.barrier()
     import bench
     from smoe_b200 import Smoe, AdamOptimizer
     ok = True
-    for shape, k in (((135, 96, 3), [12, 10]), ((40, 48, 12, 3), [4, 4, 3])):
-        img = bench.synth_image(shape, 77)
-        kw = dict(use_determinant=True, train_inverse_cov=False, use_yuv=False)
-        ms = Smoe(img, kernels_per_dim=k, **kw)
-        m1 = Smoe(img, kernels_per_dim=k, distributed=False, **kw)
-        assert ms._world == world and m1._world == 1
-        for m in (ms, m1):
-            m.set_optimizer(AdamOptimizer(1e-3), AdamOptimizer(1e-5), AdamOptimizer(1.0))
-        ms._enable_res_pre()
-        m1._enable_res_pre()
-        for step in range(3):
-            a = ms.run_batched(pis_l1=0.1, train=True, update_reconstruction=True)
-            b = m1.run_batched(pis_l1=0.1, train=True, update_reconstruction=True)
-            # the two runs tile the pixels differently (different tile centres), so a few pixels that sit
-            # within float32 noise of an output rounding boundary round the other way; each such pixel
-            # moves the gradient by ~2/(255 N C).  Forward parity is therefore asserted on the
-            # pre-quantisation output, and the gradient bound is widened per differing pixel.
-            flips = int((np.round(ms.reconstruction_image * 255) != np.round(m1.reconstruction_image * 255)).sum())
-            b0, b1 = ms._band
-            pre_s = ms._d_res_pre.cpu().numpy().reshape(ms._local_shape + (img.shape[-1],))
-            pre_1 = m1._d_res_pre.cpu().numpy().reshape(img.shape)[b0:b1]
-            dpre = np.abs(pre_s - pre_1)
-            # a gate within float32 noise of the threshold (smoe.py:825-827) may pass in one tiling only:
-            # such pixels move by at most ~tau * |expert| and must be rare
-            thr_flips = int((dpre > 1e-5).sum())
-            if dpre.max() > 2 * 0.5 / 256 or thr_flips > 1e-4 * dpre.size + 1 or flips > 1e-3 * img.size:
-                ok = False
-                print(f"rank {rank} step {step} pre-quant diff {dpre.max():.3e} thr_flips {thr_flips} flips {flips}")
-            flips += 4 * thr_flips
-            ga, gb = ms.get_gradients(), m1.get_gradients()
-            for key in ga:
-                rel = np.abs(ga[key] - gb[key]).max() / max(np.abs(gb[key]).max(), 1e-30)
-                if rel > 1e-4 + 1e-3 * flips:
-                    ok = False
-                    print(f"rank {rank} step {step} {key} rel {rel:.3e}")
-            if abs(a[0] - b[0]) > 1e-6 + 1e-6 * flips or a[2] != b[2]:
-                ok = False
-                print(f"rank {rank} step {step} loss {a[0]} vs {b[0]}")
-            # keep the two models on identical parameters so that every step is a like-for-like comparison
-            pa, pb = ms.get_params(), m1.get_params()
-            for key in pa:
-                if np.abs(pa[key] - pb[key]).max() > 1e-3 * max(1.0, np.abs(pb[key]).max()):
-                    ok = False
-                    print(f"rank {rank} step {step} params {key} diverged {np.abs(pa[key] - pb[key]).max():.3e}")
-            m1.set_params(pa)
-            m1.kernel_list_per_batch = ms.kernel_list_per_batch
-        ms.valid = m1.valid = False          # both hold the image from before the last Adam step
-        ra, rb = ms.get_reconstruction(), m1.get_reconstruction()
-        if ra.shape != rb.shape or (np.round(ra * 255) != np.round(rb * 255)).mean() > 2e-3:
-            ok = False
-            print(f"rank {rank} reconstruction mismatch")
-        kla, klb = ms.kernel_list_per_batch[0], m1.kernel_list_per_batch[0]
-        if (kla != klb).sum() > 1:
-            ok = False
-            print(f"rank {rank} kernel list mismatch {(kla != klb).sum()}")
+    for shape, k in (((135, 96, 3), [12, 10]), ((40, 48, 12, 3), [4, 4, 3]), ((192, 256, 1), [24, 32])):
+        ok &= compare_steps(Smoe, AdamOptimizer, bench.synth_image(shape, 77), k, rank, tag=str(shape))
+    ok &= compare_train(Smoe, AdamOptimizer, bench.synth_image((160, 192, 1), 78), [20, 24], rank)
+    if "--c3" in sys.argv:
+        shape, k, seed, _ = bench.WORKLOADS["c3"]
+        ok &= compare_steps(Smoe, AdamOptimizer, bench.synth_image(shape, seed), k, rank, steps=1, tag="c3")
     t = torch.tensor([1.0 if ok else 0.0], device="cuda")
     torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN)
     if rank == 0:

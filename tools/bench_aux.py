@@ -1,4 +1,4 @@
-"""HBM-bound pieces and the config-5 decoder, timed with CUDA events (python scratch/bench_aux.py)."""
+"""HBM-bound pieces and the config-5 decoder, timed with CUDA events (python tools/bench_aux.py)."""
 import ctypes as C
 import json
 import sys
@@ -38,7 +38,7 @@ K = int(smoe.rparams["pis"].shape[0])
 ms = timeit(lambda: smoe.run_batched(train=False, update_reconstruction=False, with_quantized_params=False) and None, 5)
 # forward with the FED parameters (the decoder path proper), device-resident
 def fed():
-    smoe._enqueue(0, 0, False, True, True, None)
+    smoe._enqueue(0, 0, False, True, True)
 ms_fed = timeit(fed, 5)
 out["c5_decoder"] = {"pixels": H * W, "kernels_fed": K, "grid_kernels": smoe.start_pis, "forward_ms": ms_fed,
                      "mpixel_per_s": H * W / ms_fed / 1e3, "evals_per_s": H * W * K / (ms_fed / 1e3)}
@@ -60,7 +60,7 @@ out["psnr_4k"] = {"ms": ms_sq, "algorithmic_GBps": alg / ms_sq / 1e6, "frac_of_m
 # ---- pi-mask compaction on the 518,400-kernel grid of config 5 ----------------------------------------
 Kall, P, PK = smoe.start_pis, smoe._P, smoe._PK
 smoe._theta[:, smoe._off["pi"]] = torch.where(torch.rand(Kall, device="cuda") < 0.7, 1.0, -1.0)
-ms_pack = timeit(lambda: check(lib().smoe_pack(C.byref(smoe._cfg), ptr(smoe._theta), ptr(smoe._mus_grid), ptr(None), ptr(smoe._klist[0]), Kall, ptr(smoe._packed),
+ms_pack = timeit(lambda: check(lib().smoe_pack(C.byref(smoe._cfg), ptr(smoe._theta), ptr(smoe._mus_grid), ptr(None), ptr(smoe._klist[0]), ptr(smoe._perm), Kall, ptr(smoe._packed),
                                                ptr(smoe._indices), ptr(smoe._pos), ptr(smoe._counts[0]), ptr(smoe._regsums[0]),
                                                ptr(smoe._chunk_bounds), ptr(smoe._pack_ws), stream_ptr()), "pack"))
 Ka = int(smoe._counts[0, 0])

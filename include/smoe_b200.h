@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define SMOE_ABI_VERSION 3   /* 3: Morton-ordered packing (perm argument of smoe_pack, influence flags by ORIGINAL index,
+#define SMOE_ABI_VERSION 3   /* 3: Hilbert-ordered packing (perm argument of smoe_pack, influence flags by ORIGINAL index,
                                 smoe_backward without perm/pos), executed-pair counters, eps_bits, peer exchange */
 #define SMOE_TPIX 512      /* pixels per tile (compile-time constant of the kernels) */
 #define SMOE_NSCAL 16      /* floats in the scalar block */
@@ -132,7 +132,7 @@ size_t      smoe_backward_workspace_bytes(const smoe_cfg* cfg, int K_cap, int nu
  * 732-735 (A assembly), 738-753 (bool_mask = kernel_list & pis>0, indices, 5x boolean_mask) and
  * 1012 (num_pi = count_nonzero(qpis>0)); stable stream compaction of the sequence perm[0..K_all) (perm == NULL:
  * ascending kernel index, the order of the reference's boolean_mask).  The SET {indices[0..K)} is the reference's
- * `indices`; the ORDER is a work-assignment choice: with perm = Morton order of the centres (smoe_morton_keys +
+ * `indices`; the ORDER is a work-assignment choice: with perm = Hilbert order of the centres (smoe_spatial_keys +
  * a sort), 128 consecutive records (one shared-memory chunk of smoe_forward) and 64 consecutive records (one CTA of
  * smoe_backward) are spatial neighbours, which is what the exact tile culling exploits.
  *   counts[0] = K (active), counts[1] = num_pi, counts[2] = kernels with pi*det <= 0 (unsupported
@@ -153,13 +153,15 @@ int smoe_pack(const smoe_cfg* cfg, const float* theta, const float* mus_grid /*[
  * smoe.py:1688-1689: rparams A, musX, nu_e, gamma_e, pis of K rows each); no mask, K given. */
 int smoe_pack_fed(const smoe_cfg* cfg, const float* A /*[K][d][d]*/, const float* musX, const float* nu_e,
                   const float* gamma_e, const float* pis, const int32_t* order /*[K] or NULL: fed row staged at packed
-                  row j (e.g. Morton order)*/, int K, float* packed, int32_t* indices /*[K] out: order, or identity*/,
+                  row j (e.g. Hilbert order)*/, int K, float* packed, int32_t* indices /*[K] out: order, or identity*/,
                   int32_t* counts, float* chunk_bounds, void* stream);
 
-/* Morton (Z-order) keys of the kernel centres on a 2^10 grid per axis (centres[i*row_stride + a] (+ grid[i*d + a])):
- * sorting them gives the `perm` of smoe_pack / the `order` of smoe_pack_fed. */
-int smoe_morton_keys(const float* centres, int K, int d, int row_stride, const float* grid /*or NULL*/, long long* keys,
-                     void* stream);
+/* Hilbert-curve keys of the kernel centres on a 2^10 grid per axis (centres[i*row_stride + a] (+ grid[i*d + a]),
+ * times scale[a] (host array of d floats, or NULL = 1): n_a / max_a n_a makes the curve isotropic in pixels).  Sorting
+ * them gives the `perm` of smoe_pack / the `order` of smoe_pack_fed.  Any run of consecutive Hilbert indices is
+ * spatially compact, which keeps chunks / CTAs compact after stream compaction shifts the run boundaries. */
+int smoe_spatial_keys(const float* centres, int K, int d, int row_stride, const float* grid /*or NULL*/,
+                      const float* scale /*host [d] or NULL*/, long long* keys, void* stream);
 
 /* Fused forward over one batch: Mahalanobis logits, gating with the un-renormalised threshold,
  * experts, clip, output fake-quant, loss partials, per-pixel backward state.  Replaces

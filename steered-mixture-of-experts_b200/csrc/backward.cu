@@ -3,7 +3,7 @@
 //
 // Kernel-stationary: a thread owns ONE kernel (its record and 2*P accumulators live in
 // registers), a CTA owns 64 consecutive packed kernels -- spatial neighbours, because smoe_pack
-// writes the records in Morton order of their centres -- and a 1/num_splits share of the pixel tiles.
+// writes the records in Hilbert order of their centres -- and a 1/num_splits share of the pixel tiles.
 // Pixel state written by the forward (per tile: planes z, log2 S, gr, g_c of 512 floats + row constants)
 // arrives by TMA bulk copies (12 KB per tile for d=2, C=3; double buffered) and is broadcast to all threads
 // from shared memory, so the per-kernel reductions over pixels happen in registers with no
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) 
 
     const int tid = threadIdx.x;
     const int K = a.counts[0];
-    const int k = blockIdx.x * kThreads + tid;           // packed row (Morton order of the centres)
+    const int k = blockIdx.x * kThreads + tid;           // packed row (Hilbert order of the centres)
     if ((int)blockIdx.x * kThreads >= K) return;
     const bool active = k < K;
     const int split = blockIdx.y;

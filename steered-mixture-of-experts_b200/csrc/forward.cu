@@ -155,7 +155,9 @@ __device__ __forceinline__ int cta_compact(bool flag, int* scratch, int& par, in
 
 // COUNT: also count the (pixel, kernel) pairs each sweep evaluates (bench / roofline diagnostics; a separate
 // instantiation, so the product path carries no counter).
-template <int D, int C, bool COUNT>
+// AMAX: track the arg-max gate per pixel (only the reconstruction passes ask for it; the training step does not, and
+// its instantiation saves the 2 x PPT registers).
+template <int D, int C, bool COUNT, bool AMAX>
 __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(const FwdArgs a) {
     using R = Rec<D, C>;
     constexpr int PK = pstride(D, C);
@@ -218,7 +220,8 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
         }
         // the thread's PPT pixels: same (i1, i2), rows i0 = p*step + i0_first
         float x0[PPT], xs[3] = {0.f, 0.f, 0.f};
-        long long gidx[PPT];     // linear pixel index in the image buffer, -1 when outside
+        unsigned okmask = 0;     // bit p: pixel p is inside the batch (and fed); its buffer index is recomputed in the epilogue
+        const int gbase12 = ((tid / e2) % e1 + lo[1]) * a.b.dims[2] + (tid % e2 + lo[2]);
         unsigned hmask = 0;      // bit p: pixel p lies in the overlap halo (forwarded, outside the loss crop)
         {
             const int i2 = tid % e2, i1 = (tid / e2) % e1;
@@ -237,9 +240,10 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
                 const int i0 = j / (e2 * e1);
                 const int g0 = lo[0] + i0;
                 const bool ok = g0 <= hi[0] && g1 <= hi[1] && g2 <= hi[2];
-                gidx[p] = ok ? ((long long)g0 * a.b.dims[1] + g1) * a.b.dims[2] + g2 : -1;
+                bool fed = ok;
                 // a pixel that is not part of this run's feed (random sub-sampling, smoe.py:1664-1667)
-                if (a.lossw && ok && a.lossw[gidx[p]] == SMOE_PIXEL_ABSENT) gidx[p] = -1;
+                if (a.lossw && ok && a.lossw[g0 * a.b.dims[1] * a.b.dims[2] + gbase12] == SMOE_PIXEL_ABSENT) fed = false;
+                if (fed) okmask |= 1u << p;
                 if (a.b.halo > 0 && (h12 || in_halo(0, g0))) hmask |= 1u << p;
                 x0[p] = a.ax[0][min(g0, hi[0])] - ctr[0];
             }
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
             float smin = INFINITY;
 #pragma unroll
             for (int p = 0; p < PPT; ++p)
-                if (gidx[p] >= 0) smin = fminf(smin, log2f(fmaxf(S[p], kSFloor)));
+                if ((okmask >> p) & 1u) smin = fminf(smin, log2f(fmaxf(S[p], kSFloor)));
             const int bad = __syncthreads_or(smin < Lneed);
             if (!bad) break;
             cutA = -126.5f;                                  // stale bound: exact re-sweep
@@ -374,12 +378,14 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
         float qthr[PPT], r[PPT][C], bestw[PPT];
         int bestk[PPT];
         float qmin = INFINITY;
+        unsigned live_mask = 0;          // bit p: S > 1e-11 (smoe.py:821), all that the epilogue needs of S
 #pragma unroll
         for (int p = 0; p < PPT; ++p) {
+            if (S[p] > kSFloor) live_mask |= 1u << p;
             float Sc = fmaxf(S[p], kSFloor);
             // w = e/S = 2^(q - log2 S) > tau  <=>  q - log2 S > log2 tau = -(precision+1); +inf disables pixels
             // outside the batch.  (qthr holds log2 S: the gate needs no multiplication by tau.)
-            qthr[p] = gidx[p] >= 0 ? log2f(Sc) : INFINITY;
+            qthr[p] = ((okmask >> p) & 1u) ? log2f(Sc) : INFINITY;
             qmin = fminf(qmin, qthr[p]);
             bestw[p] = 0.f;
             bestk[p] = -1;
@@ -442,8 +448,8 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
 #pragma unroll
                         for (int c = 0; c < C; ++c) r[p][c] = fmaf(wm, fmaf(f[R::OGA + c], x0[p], Eb[c]), r[p][c]);
                         // tf.argmax keeps the first maximum in ascending kernel index; records arrive in the
-                        // (Morton) packing order, so ties are broken on the original index explicitly
-                        if (pass && (w > bestw[p] || (w == bestw[p] && korig < bestk[p]))) { bestw[p] = w; bestk[p] = korig; }
+                        // (Hilbert) packing order, so ties are broken on the original index explicitly
+                        if (AMAX && pass && (w > bestw[p] || (w == bestw[p] && korig < bestk[p]))) { bestw[p] = w; bestk[p] = korig; }
                     }
                     if (any && a.infl) a.infl[korig] = 1;
                 }
@@ -457,9 +463,12 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
             float g[C], gr = 0.f;
             // per-pixel loss weight (loss_mask, smoe.py:932, 1674-1677); SMOE_PIXEL_HALO marks a pixel of the
             // overlap halo: forwarded (gates, influence list) but outside the loss crop (smoe.py:909-923)
-            const float lwv = (a.lossw && gidx[p] >= 0) ? a.lossw[gidx[p]] : 1.f;
+            const bool inb = (okmask >> p) & 1u;
+            // linear pixel index in the image buffer (< 2^31, checked by the host)
+            const int gpix = (lo[0] + j / (e2 * e1)) * a.b.dims[1] * a.b.dims[2] + gbase12;
+            const float lwv = (a.lossw && inb) ? a.lossw[gpix] : 1.f;
             const bool halo = ((hmask >> p) & 1u) || lwv == SMOE_PIXEL_HALO;
-            if (gidx[p] >= 0) {
+            if (inb) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     const float rv = r[p][c];
@@ -468,8 +477,8 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
                     const float kq = floorf(__fadd_rn(__fmul_rn(rc, a.q_inv_scale), 0.5f));
                     const float rq = __fmul_rn(kq, a.q_scale);                          // smoe.py:899
                     // 8-bit feed: the /255 of utils.py:126-128 (float32 division) happens here
-                    const float tgt = a.image_u8 ? __fdiv_rn((float)a.image_u8[gidx[p] * C + c], 255.0f)
-                                                 : a.image[gidx[p] * C + c];
+                    const size_t gi = (size_t)gpix * C + c;
+                    const float tgt = a.image_u8 ? __fdiv_rn((float)a.image_u8[gi], 255.0f) : a.image[gi];
                     const float diff = __fsub_rn(rq, tgt);                              // smoe.py:905
                     const float ad = fabsf(diff) - a.eps;                               // smoe.py:932
                     if (!halo) {
@@ -483,11 +492,11 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
                     if (a.lossw) g[c] *= lwv;
                     gr = fmaf(g[c], rv, gr);
                     if (!halo) {                 // a halo pixel is the interior of another window, which writes it
-                        a.res[gidx[p] * C + c] = rq;
-                        if (a.res_pre) a.res_pre[gidx[p] * C + c] = rv;
+                        a.res[gi] = rq;
+                        if (a.res_pre) a.res_pre[gi] = rv;
                     }
                 }
-                if (a.argmax && !halo) a.argmax[gidx[p]] = bestk[p];
+                if (AMAX && !halo) a.argmax[gpix] = bestk[p];
             } else {
 #pragma unroll
                 for (int c = 0; c < C; ++c) g[c] = 0.f;
@@ -496,8 +505,8 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
                 // planes [z | qthr | gr | g_c][512] + row constants; coordinates are stored for every slot
                 const int RLf = a.b.tile[D - 1];
                 float* tp = a.pix + (size_t)tile * pix_stride(D, C, RLf);
-                const bool in = gidx[p] >= 0;
-                const bool live = S[p] > kSFloor;                                        // smoe.py:821
+                const bool in = inb;
+                const bool live = (live_mask >> p) & 1u;                                 // smoe.py:821
                 tp[PL_Z * SMOE_TPIX + j] = D == 1 ? x0[p] : xs[D - 1];
                 tp[PL_QTHR * SMOE_TPIX + j] = in ? qthr[p] : INFINITY;   // outside the batch: w = tau * 2^(-inf) = 0
                 tp[PL_GR * SMOE_TPIX + j] = (in && live) ? gr : 0.f;
@@ -595,6 +604,7 @@ extern "C" int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const 
         SMOE_REQUIRE(batch->extent[i] > 0 && batch->origin[i] >= 0 && batch->origin[i] + batch->extent[i] <= batch->dims[i],
                      "batch rectangle outside the image");
     SMOE_REQUIRE(cfg->d == 3 || (batch->dims[2] == 1 && batch->tile[2] == 1), "d == 2 needs dims[2] == tile[2] == 1");
+    SMOE_REQUIRE((long long)batch->dims[0] * batch->dims[1] * batch->dims[2] < (1ll << 31), "more than 2^31 pixels");
     FwdArgs a;
     a.cfg = *cfg;
     a.b = *batch;
@@ -621,14 +631,16 @@ extern "C" int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const 
     const int per_sm = cfg->d == 2 ? 6 : 4;          // resident CTAs per SM (matches __launch_bounds__)
     int grid = a.ntiles < per_sm * sms ? a.ntiles : per_sm * sms;
     cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH(D, C, CNT)                                                                                        \
-    {                                                                                                            \
-        size_t sm = fwd_smem_bytes<D, C>(a.max_chunks);                                                          \
-        SMOE_REQUIRE(sm <= 200 * 1024, "too many kernel chunks for the shared-memory chunk list");               \
-        cudaFuncSetAttribute(forward_kernel<D, C, CNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);   \
-        forward_kernel<D, C, CNT><<<grid, kThreadsF, sm, st>>>(a);                                               \
+#define LAUNCH(D, C, CNT, AM)                                                                                       \
+    {                                                                                                               \
+        size_t sm = fwd_smem_bytes<D, C>(a.max_chunks);                                                             \
+        SMOE_REQUIRE(sm <= 200 * 1024, "too many kernel chunks for the shared-memory chunk list");                  \
+        cudaFuncSetAttribute(forward_kernel<D, C, CNT, AM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);  \
+        forward_kernel<D, C, CNT, AM><<<grid, kThreadsF, sm, st>>>(a);                                              \
     }
-#define CALL(D, C) if (pair_counts) LAUNCH(D, C, true) else LAUNCH(D, C, false)
+#define CALL(D, C)                                                               \
+    if (pair_counts) { if (argmax) LAUNCH(D, C, true, true) else LAUNCH(D, C, true, false) } \
+    else { if (argmax) LAUNCH(D, C, false, true) else LAUNCH(D, C, false, false) }
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL
 #undef LAUNCH

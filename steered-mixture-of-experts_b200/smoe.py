@@ -498,6 +498,8 @@ class Smoe:
         self._pos = torch.zeros((K,), dtype=torch.int32, device=dev)
         self._perm = torch.zeros((K,), dtype=torch.int32, device=dev)
         self._keys = torch.zeros((K,), dtype=torch.int64, device=dev)
+        nmax = float(max(self.image.shape[:d]))
+        self._key_scale = (C.c_float * 3)(*([self.image.shape[a] / nmax for a in range(d)] + [1.0] * (3 - d)))
         self._refresh_perm()
         # one block per batch [scalars (NSCAL) | counts (4 x int32) | regulariser sums (2) | pad]: a single
         # device->host copy per run_batched call brings back everything the host needs
@@ -614,12 +616,12 @@ class Smoe:
         self.valid = self.qvalid = False
 
     def _refresh_perm(self):
-        """Spatially coherent packing order (Morton order of the current centres): smoe_pack writes the compute
+        """Spatially coherent packing order (Hilbert-curve order of the current centres, isotropic in pixels): smoe_pack writes the compute
         records in this order, so a forward chunk (128 records) and a backward CTA (64 records) hold neighbours and
         the tile culling bites.  Purely a work-assignment choice -- any order gives the same per-kernel results.
         Keys and sort run on the device (stable sort: ties keep ascending index)."""
-        check(lib().smoe_morton_keys(ptr(self._theta), self.start_pis, self.dim_domain, self._P, ptr(self._mus_grid),
-                                     ptr(self._keys), stream_ptr()), "smoe_morton_keys")
+        check(lib().smoe_spatial_keys(ptr(self._theta), self.start_pis, self.dim_domain, self._P, ptr(self._mus_grid),
+                                      self._key_scale, ptr(self._keys), stream_ptr()), "smoe_spatial_keys")
         # in place: captured CUDA graphs hold the buffer's address
         self._perm.copy_(torch.sort(self._keys, stable=True).indices.to(torch.int32))
 
@@ -886,10 +888,10 @@ class Smoe:
             Kf = int(rp["pis"].shape[0])
             if Kf > K:
                 raise ValueError("more fed kernels than model kernels")
-            # the fed rows in Morton order of their centres, like the variables (device keys + device sort)
+            # the fed rows in Hilbert order of their centres, like the variables (device keys + device sort)
             fkeys = torch.empty((Kf,), dtype=torch.int64, device=self.device)
-            check(L.smoe_morton_keys(ptr(rp["musX"]), Kf, self.dim_domain, self.dim_domain, ptr(None), ptr(fkeys), st),
-                  "smoe_morton_keys")
+            check(L.smoe_spatial_keys(ptr(rp["musX"]), Kf, self.dim_domain, self.dim_domain, ptr(None), self._key_scale,
+                                      ptr(fkeys), st), "smoe_spatial_keys")
             forder = torch.sort(fkeys, stable=True).indices.to(torch.int32)
         norm = float(self.start_pis)
         if self._qdyn is not None and not fed:

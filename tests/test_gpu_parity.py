@@ -144,7 +144,7 @@ def test_compaction_bit_exact_and_packed_records():
     want = np.nonzero(kl & (p["pis"] > 0))[0]
     assert Kact == want.size and num_pi == int((p["pis"] > 0).sum())
     np.testing.assert_array_equal(m.get_active_indices(), want)
-    # the records are packed in Morton order of the centres: bring them back to ascending index for the comparison
+    # the records are packed in Hilbert order of the centres: bring them back to ascending index for the comparison
     order = np.argsort(m._indices[:Kact].cpu().numpy())
     rec = m._packed[:Kact].cpu().numpy()[order]
     assert (m._pos.cpu().numpy()[want] >= 0).all()
@@ -572,6 +572,38 @@ def test_full_size_config4_culling_is_exact_and_forward_matches_oracle():
     idx = rs.choice(int(np.prod(shape[:-1])), 100, replace=False)
     out = _oracle_at_pixels(img, params0, idx, dict(use_determinant=True, train_inverse_cov=False, use_yuv=False))
     _check_sampled_forward(res[0][3][idx], out)
+
+
+@pytest.mark.parametrize("workload", ["c2", "c4s"])
+def test_epsilon_culling_is_opt_in_and_stays_inside_the_parity_bars(workload):
+    """eps_bits = 48 (OPT-IN; the default is exact): terms below 2^-48 of a pixel's normaliser are dropped.  Against
+    the exact mode on the same model: pre-quantisation reconstruction within 1e-6, gradients within 1e-5 of the tensor
+    max-norm (the parity bars are 1e-5 / 1e-4), identical pruned index sets, over several passes (the forward's bound
+    is the previous pass's tile minimum, re-checked after every sweep)."""
+    import bench
+    shape, kgrid, seed, _ = bench.WORKLOADS[workload]
+    img = bench.synth_image(shape, seed)
+    me = _mk(img, kgrid, eps_bits=48, **bench.SMOE_KW)
+    mx = _mk(img, kgrid, **bench.SMOE_KW)
+    me._enable_res_pre()
+    mx._enable_res_pre()
+    for it in range(3):
+        le = me.run_batched(pis_l1=0.1, train=True, update_reconstruction=True)
+        lx = mx.run_batched(pis_l1=0.1, train=True, update_reconstruction=True)
+        assert abs(le[0] - lx[0]) <= 1e-6 * max(1.0, abs(lx[0])) and le[2] == lx[2]
+        assert np.abs(me._d_res_pre.cpu().numpy() - mx._d_res_pre.cpu().numpy()).max() <= 1e-6
+        ge, gx = me.get_gradients(), mx.get_gradients()
+        for k in PARAM_KEYS:
+            assert _rel(ge[k], gx[k]) < 1e-5, (it, k)
+        np.testing.assert_array_equal(me.get_active_indices(), mx.get_active_indices())
+        # keep both on the exact trajectory -- raw device copies, so that both models also keep the SAME packing order
+        # (set_params would re-derive the Hilbert order of one of them and with it the summation order)
+        me._theta.copy_(mx._theta)
+        me._adam_m.copy_(mx._adam_m)
+        me._adam_v.copy_(mx._adam_v)
+        me._klist.copy_(mx._klist)
+    with pytest.raises(ValueError):
+        _mk(img[:32, :32], [4, 4] + ([2] if img.ndim == 4 else []), eps_bits=8, **bench.SMOE_KW)
 
 
 def test_full_size_decoder_config5():

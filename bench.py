@@ -228,7 +228,7 @@ def kernel_times(m, steps, with_step=True):
     def bwd(pc=None):
         check(L.smoe_backward(C.byref(m._cfg), C.byref(b), ptr(m._packed), ptr(counts), m.start_pis, ptr(m._pix),
                               ptr(m._tile_qmin[0]), ptr(m._d_axes[0]), ptr(m._d_axes[1]), ax2, m._splits,
-                              ptr(m._raw_part), ptr(pc), st), "backward")
+                              ptr(m._raw_part), ptr(m._plan), ptr(pc), st), "backward")
 
     fw, bw = [], []
     for _ in range(steps + 1):

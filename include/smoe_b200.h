@@ -205,7 +205,11 @@ int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const float* pack
 int smoe_backward(const smoe_cfg* cfg, const smoe_batch* batch, const float* packed, const int32_t* counts,
                   int K_cap, const float* pix, const float* tile_qmin,
                   const float* ax0, const float* ax1, const float* ax2, int num_splits, float* raw_part,
+                  int32_t* plan /* smoe_backward_plan_bytes: [groups] reachable-tile counts | [groups] tile bitmasks,
+                  groups of 64 packed kernels; written by a planning pre-pass of this call and read again by
+                  smoe_grad_finalize / smoe_reduce_splits / smoe_xchg_publish */,
                   unsigned long long* pair_counts /* optional, see smoe_forward */, void* stream);
+size_t smoe_backward_plan_bytes(int K_cap, const smoe_batch* batch);
 /*   Thread slot s works on packed row s: the order smoe_pack wrote (any order gives the same per-kernel results;
  *   a spatially coherent one makes the kernels of a warp / CTA neighbours, which is what the tile culling exploits). */
 /* number of pixel splits for smoe_backward on this batch (split s owns tiles s, s+NS, ...): a prime that keeps
@@ -215,13 +219,16 @@ int smoe_suggest_splits(int K_cap, const smoe_batch* batch);
 /* Fixed-order reduction of the pixel splits: raw[k][j] = sum_s raw_part[s][k][j].  (The buffer a
  * multi-GPU run all-reduces with NCCL.) */
 int smoe_reduce_splits(const smoe_cfg* cfg, const int32_t* counts, int K_cap, int num_splits,
-                       const float* raw_part, float* raw, void* stream);
+                       const float* raw_part, const int32_t* plan /* of the smoe_backward call, or NULL: every slab */,
+                       float* raw, void* stream);
 
 /* Statistics -> variable gradients (chain rule through A assembly, pi, determinant; L1 terms of
  * smoe.py:1027, 1044), scattered through `indices` and ACCUMULATED into the K_all-sized `grads`
  * (assign_add, smoe.py:1150).  Also rewrites kernel_list[indices[k]] = infl[k] when infl != NULL
  * (smoe.py:1763-1766). */
-int smoe_grad_finalize(const smoe_cfg* cfg, const float* raw, int num_splits, int K_cap, const float* theta,
+int smoe_grad_finalize(const smoe_cfg* cfg, const float* raw, int num_splits,
+                       const int32_t* plan /* of the smoe_backward call that wrote `raw`, or NULL: every slab */,
+                       int K_cap, const float* theta,
                        const void* quant_ranges /* quantization_mode 3 only */,
                        const int32_t* indices, const int32_t* counts, float pis_l1, float l1_norm /* start_pis */,
                        float u_l1, float* grads, void* stream);
@@ -286,7 +293,8 @@ int smoe_peer_open(const void* handle64, void** ptr);
 int smoe_peer_close(void* ptr);
 /* raw_part may be NULL (evaluation pass: only scalars and flags are exchanged). */
 int smoe_xchg_publish(const smoe_cfg* cfg, const smoe_peers* peers, const int32_t* counts, int K_all, int num_splits,
-                      const float* raw_part, const float* scalars, const uint8_t* infl /*[K_all]*/, void* stream);
+                      const float* raw_part, const int32_t* plan /* of smoe_backward, NULL with raw_part == NULL */,
+                      const float* scalars, const uint8_t* infl /*[K_all]*/, void* stream);
 /* smoe_grad_finalize on the rank-summed statistics; also scalars[0..SMOE_NSCAL) = sum over ranks, infl = any rank. */
 int smoe_grad_finalize_peers(const smoe_cfg* cfg, const smoe_peers* peers, int K_cap, const float* theta,
                              const void* quant_ranges, const int32_t* indices, const int32_t* counts, float pis_l1,

@@ -20,7 +20,7 @@ STATS_STRIDE = 24         # floats per batch in the host-visible block: scalars 
 
 EXPORTS = [
     "smoe_abi_version", "smoe_last_error", "smoe_param_count", "smoe_packed_stride", "smoe_num_tiles", "smoe_pix_stride",
-    "smoe_pack_workspace_bytes", "smoe_backward_workspace_bytes", "smoe_pack", "smoe_pack_fed", "smoe_forward", "smoe_ssim_loss_workspace_bytes", "smoe_ssim_loss",
+    "smoe_pack_workspace_bytes", "smoe_backward_workspace_bytes", "smoe_backward_plan_bytes", "smoe_pack", "smoe_pack_fed", "smoe_forward", "smoe_ssim_loss_workspace_bytes", "smoe_ssim_loss",
     "smoe_backward", "smoe_suggest_splits", "smoe_reduce_splits", "smoe_grad_finalize", "smoe_update_kernel_list",
     "smoe_adam_step", "smoe_step_begin", "smoe_spatial_keys", "smoe_xchg_window_bytes", "smoe_peer_alloc", "smoe_peer_free",
     "smoe_peer_export", "smoe_peer_open", "smoe_peer_close", "smoe_xchg_publish", "smoe_grad_finalize_peers",
@@ -72,7 +72,7 @@ def lib():
                 "smoe_b200 has no CPU or PyTorch fallback.")
         _lib = C.CDLL(LIB_PATH)
         _lib.smoe_last_error.restype = C.c_char_p
-        for name in ("smoe_pack_workspace_bytes", "smoe_backward_workspace_bytes", "smoe_ssim_workspace_bytes",
+        for name in ("smoe_pack_workspace_bytes", "smoe_backward_workspace_bytes", "smoe_backward_plan_bytes", "smoe_ssim_workspace_bytes",
                      "smoe_ssim_loss_workspace_bytes", "smoe_quant_ranges_bytes", "smoe_xchg_window_bytes"):
             getattr(_lib, name).restype = C.c_size_t
         if _lib.smoe_abi_version() != ABI_VERSION:

@@ -3,7 +3,12 @@
 //
 // Kernel-stationary: a thread owns ONE kernel (its record and 2*P accumulators live in
 // registers), a CTA owns 64 consecutive packed kernels -- spatial neighbours, because smoe_pack
-// writes the records in Hilbert order of their centres -- and a 1/num_splits share of the pixel tiles.
+// writes the records in Hilbert order of their centres -- and a 1/num_splits share of the pixel tiles
+// (split s owns tiles s, s+NS, ...: a geometry-fixed rule, so the partial sums group the same way in
+// every execution mode).  Which of its tiles a CTA must visit comes from a planning pre-pass
+// (bwd_plan_kernel: one CTA per group tests every tile of the batch against the group's bounding box and
+// leaves a bitmask), so a CTA spends no time on geometry, and the CTAs of a group that cannot reach the
+// batch at all -- most groups, when the batch is one rank's pixel block -- leave after one load.
 // Pixel state written by the forward (per tile: planes z, log2 S, gr, g_c of 512 floats + row constants)
 // arrives by TMA bulk copies (12 KB per tile for d=2, C=3; double buffered) and is broadcast to all threads
 // from shared memory, so the per-kernel reductions over pixels happen in registers with no
@@ -42,28 +47,107 @@ struct BwdArgs {
     const float* ax[3];
     float* raw_part;
     unsigned long long* pair_counts;
-    int K_cap, num_splits, ntiles, nt1, nt2, max_list;
+    int32_t* plan_cnt;      // [groups] reachable tiles of each group of kGroup packed kernels
+    uint32_t* plan_bits;    // [groups][nwords] bit t: tile t is reachable
+    int K_cap, num_splits, ntiles, nt1, nt2, nwords, max_list;
     float tau, ltau;
     float zero_cut;         // gates below 2^zero_cut of the normaliser are skipped: -126 (exactly +0), or -eps_bits
 };
 
-// fixed-order min over the CTA of kCB (= 12) per-thread values (used once per CTA for its bounding box)
-__device__ __forceinline__ void cta_min12(float (&v)[kCB], float (*s)[kCB]) {
+// tile geometry (as the forward derives it)
+template <int D>
+__device__ __forceinline__ void tile_box_of(const BwdArgs& a, int tile, float (&ctr)[3], float (&half)[3]) {
+    int tt[3];
+    tt[2] = tile % a.nt2;
+    tt[1] = (tile / a.nt2) % a.nt1;
+    tt[0] = tile / (a.nt2 * a.nt1);
 #pragma unroll
-    for (int q = 0; q < kCB; ++q)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v[q] = fminf(v[q], __shfl_xor_sync(0xffffffffu, v[q], o));
-    if ((threadIdx.x & 31) == 0)
-#pragma unroll
-        for (int q = 0; q < kCB; ++q) s[threadIdx.x >> 5][q] = v[q];
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < kCB; ++q) {
-        float m = INFINITY;
-        for (int w = 0; w < kThreads / 32; ++w) m = fminf(m, s[w][q]);
-        v[q] = m;
+    for (int i = 0; i < 3; ++i) {
+        const int lo = a.b.origin[i] + tt[i] * a.b.tile[i];
+        const int hi = min(lo + a.b.tile[i], a.b.origin[i] + a.b.extent[i]) - 1;
+        const float x0 = (i < D) ? a.ax[i][lo] : 0.f, x1 = (i < D) ? a.ax[i][hi] : 0.f;
+        ctr[i] = 0.5f * (x0 + x1);
+        half[i] = 0.5f * (x1 - x0) * 1.0001f + 1e-7f;
     }
+}
+
+// Planning pre-pass: one CTA per group of kGroup consecutive packed kernels.  The group's bounding box (box of
+// the centres, smallest eigenvalue / per-axis bounds, largest c0) is tested against every tile of the batch with
+// the exact-zero criterion (w = 2^(q - qthr) is exactly 0 when q - min qthr < -126, or below the eps cut); the
+// reachable tiles are left as a bitmask.  dense_exec != 0: every tile.
+template <int D, int C>
+__global__ void __launch_bounds__(128) bwd_plan_kernel(const BwdArgs a) {
+    constexpr int P = nparam(D, C), PK = pstride(D, C);
+    __shared__ float sred[4][kCB];
+    __shared__ int s_cnt[4];
+    const int tid = threadIdx.x, g = blockIdx.x;
+    const int K = a.counts[0];
+    if (g * kGroup >= K) {
+        if (tid == 0) a.plan_cnt[g] = 0;
+        return;
+    }
+    const bool cull = a.cfg.dense_exec == 0;
+    float v[kCB];
+    {
+        const int k = g * kGroup + tid;
+        const bool on = tid < kGroup && k < K;
+        const float* rec = a.packed + (size_t)(on ? k : 0) * PK;
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            const float m = (l < D && on) ? rec[off_mu(D, C) + l] : 0.f;
+            v[l] = (l < D && on) ? m : INFINITY;
+            v[3 + l] = (l < D && on) ? -m : INFINITY;
+            v[8 + l] = (l < D && on) ? rec[P + 1 + l] : INFINITY;
+        }
+        v[6] = on ? rec[P] : INFINITY;
+        const float c0 = on ? rec[off_pi(D, C)] : -INFINITY;
+        v[7] = (c0 == c0) ? -c0 : -INFINITY;          // NaN c0: never cull
+        v[11] = 0.f;
+#pragma unroll
+        for (int q = 0; q < kCB; ++q)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[q] = fminf(v[q], __shfl_xor_sync(0xffffffffu, v[q], o));
+        if ((tid & 31) == 0)
+#pragma unroll
+            for (int q = 0; q < kCB; ++q) sred[tid >> 5][q] = v[q];
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kCB; ++q) v[q] = fminf(fminf(sred[0][q], sred[1][q]), fminf(sred[2][q], sred[3][q]));
+        __syncthreads();
+    }
+    const float blam = v[6], bc0 = -v[7];
+    const float zcut_tile = a.zero_cut - 0.5f;
+    uint32_t* bits = a.plan_bits + (size_t)g * a.nwords;
+    int n = 0;
+    for (int base = 0; base < a.ntiles; base += 128) {
+        const int tile = base + tid;
+        bool need = false;
+        if (tile < a.ntiles) {
+            need = true;
+            if (cull) {
+                float ctr[3], half[3];
+                tile_box_of<D>(a, tile, ctr, half);
+                float d2 = 0.f, kd = 0.f;
+#pragma unroll
+                for (int l = 0; l < D; ++l) {
+                    const float mn = v[l] - ctr[l], mx = -v[3 + l] - ctr[l];
+                    const float gap = fmaxf(fmaxf(mn - half[l], -half[l] - mx), 0.f);
+                    d2 = fmaf(gap, gap, d2);
+                    kd = fmaxf(kd, v[8 + l] * gap * gap);
+                }
+                const float ub = bc0 - fmaxf(blam * d2, kd) - a.tile_qmin[tile];
+                need = !(blam >= 0.f) || !(ub < zcut_tile);
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, need);
+        if ((tid & 31) == 0 && base + tid < a.nwords * 32) bits[(base + tid) >> 5] = bal;
+        n += __popc(bal);
+    }
+    // n holds this warp's count: fixed-order sum over the 4 warps
+    if ((tid & 31) == 0) s_cnt[tid >> 5] = n;
     __syncthreads();
+    n = s_cnt[0] + s_cnt[1] + s_cnt[2] + s_cnt[3];
+    if (tid == 0) a.plan_cnt[g] = n;
 }
 
 template <int D, int C, bool COUNT>
@@ -78,14 +162,19 @@ __global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) 
     float* buf0 = reinterpret_cast<float*>(smem_raw);
     float* buf1 = buf0 + tstride;
     uint64_t* bar = reinterpret_cast<uint64_t*>(buf1 + tstride);
-    float (*sred)[kCB] = reinterpret_cast<float (*)[kCB]>(bar + 2);     // [8 warps][kCB]
-    int* scratch = reinterpret_cast<int*>(sred + 8);                // [16]
+    int* scratch = reinterpret_cast<int*>(bar + 2);                 // [16]
     int* tlist = scratch + 16;                                      // [max_list]
 
     const int tid = threadIdx.x;
     const int K = a.counts[0];
-    const int k = blockIdx.x * kThreads + tid;           // packed row (Hilbert order of the centres)
-    if ((int)blockIdx.x * kThreads >= K) return;
+    // kHalves = 2 adjacent lanes share one kernel and take alternate rows of every tile (their partial sums are
+    // added at the end, fixed order): a warp then covers 16 neighbouring kernels x 2 rows instead of 32 kernels,
+    // which tightens the warp-level skip tests, and a group of kernels gets twice the threads -- what a rank's
+    // small pixel block, reached by a hundred groups only, needs to fill the GPU.
+    const int k = blockIdx.x * kGroup + tid / kHalves;   // packed row (Hilbert order of the centres)
+    const int hsel = tid % kHalves;
+    if ((int)blockIdx.x * kGroup >= K) return;
+    if (a.plan_cnt[blockIdx.x] == 0) return;             // the group reaches no tile of this batch
     const bool active = k < K;
     const int split = blockIdx.y;
     const float zcut = a.zero_cut, zcut_tile = a.zero_cut - 0.5f;
@@ -129,64 +218,15 @@ __global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) 
             for (int c = 0; c < C; ++c) ga[l][c] = rec[off_ga(D, C) + l * C + c];
     }
 
-    // tile geometry (as the forward derives it)
-    auto tile_box = [&](int tile, float (&ctr)[3], float (&half)[3]) {
-        int tt[3];
-        tt[2] = tile % a.nt2;
-        tt[1] = (tile / a.nt2) % a.nt1;
-        tt[0] = tile / (a.nt2 * a.nt1);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const int lo = a.b.origin[i] + tt[i] * a.b.tile[i];
-            const int hi = min(lo + a.b.tile[i], a.b.origin[i] + a.b.extent[i]) - 1;
-            const float x0 = (i < D) ? a.ax[i][lo] : 0.f, x1 = (i < D) ? a.ax[i][hi] : 0.f;
-            ctr[i] = 0.5f * (x0 + x1);
-            half[i] = 0.5f * (x1 - x0) * 1.0001f + 1e-7f;
-        }
-    };
-
-    // ---- CTA-level culling: ordered list of this split's tiles that some kernel of the CTA can
-    //      reach (w = tau*2^(q-qthr) is exactly 0 when q - min qthr < -126) --------------------
+    // ordered list of this split's tiles (s, s + NS, ...) that the group can reach, from the plan's bitmask
     int nlist = 0;
     {
-        float v[kCB];
-#pragma unroll
-        for (int l = 0; l < 3; ++l) {
-            v[l] = (l < D && active) ? mu[l] : INFINITY;
-            v[3 + l] = (l < D && active) ? -mu[l] : INFINITY;
-            v[8 + l] = INFINITY;
-        }
-#pragma unroll
-        for (int l = 0; l < D; ++l) v[8 + l] = active ? kap[l] : INFINITY;
-        v[6] = active ? lam : INFINITY;
-        v[7] = (c0 == c0) ? -c0 : -INFINITY;
-        v[11] = 0.f;
-        cta_min12(v, sred);
-        const float blam = v[6], bc0 = -v[7];
+        const uint32_t* bits = a.plan_bits + (size_t)blockIdx.x * a.nwords;
         const int my_tiles = (a.ntiles - split + a.num_splits - 1) / a.num_splits;
         for (int base = 0; base < my_tiles; base += kThreads) {
             const int it = base + tid;
-            bool need = false;
-            int tile = 0;
-            if (it < my_tiles) {
-                tile = split + it * a.num_splits;
-                need = true;
-                if (cull) {
-                    float ctr[3], half[3];
-                    tile_box(tile, ctr, half);
-                    float d2 = 0.f, kd = 0.f;
-#pragma unroll
-                    for (int l = 0; l < D; ++l) {
-                        const float mn = v[l] - ctr[l], mx = -v[3 + l] - ctr[l];
-                        const float gap = fmaxf(fmaxf(mn - half[l], -half[l] - mx), 0.f);
-                        d2 = fmaf(gap, gap, d2);
-                        kd = fmaxf(kd, v[8 + l] * gap * gap);
-                    }
-                    const float ub = bc0 - fmaxf(blam * d2, kd) - a.tile_qmin[tile];
-                    need = !(blam >= 0.f) || !(ub < zcut_tile);
-                }
-            }
-            // ordered compaction over the 8 warps
+            const int tile = split + it * a.num_splits;
+            const bool need = it < my_tiles && ((bits[tile >> 5] >> (tile & 31)) & 1u);
             const unsigned bal = __ballot_sync(0xffffffffu, need);
             const int lane = tid & 31, w = tid >> 5;
             if (lane == 0) scratch[w] = __popc(bal);
@@ -227,7 +267,7 @@ __global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) 
         const int buf = li & 1;
         const int tile = tlist[li];
         float ctr[3], half[3];
-        tile_box(tile, ctr, half);
+        tile_box_of<D>(a, tile, ctr, half);
         float mup[D];
 #pragma unroll
         for (int l = 0; l < D; ++l) mup[l] = mu[l] - ctr[l];
@@ -297,7 +337,7 @@ __global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) 
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, nv[C], nz[C];      // row sums, reset after every folded row
 #pragma unroll
             for (int c = 0; c < C; ++c) nv[c] = nz[c] = 0.f;
-            for (int r0 = 0; r0 < SMOE_TPIX; r0 += RL) {
+            for (int r0 = hsel * RL; r0 < SMOE_TPIX; r0 += kHalves * RL) {
                 // the pixels of a row differ only in their LAST coordinate z: q = cr + (br + qq_last z) z
                 float xr[3] = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -441,7 +481,22 @@ __global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) 
         atomicAdd(&a.pair_counts[5], (unsigned long long)cnt_gate * 128ull);
         atomicAdd(&a.pair_counts[6], (unsigned long long)cnt_exp * 32ull);
     }
-    if (active) {
+    // the kHalves lanes of a kernel are adjacent: add their partial sums (commutative: both lanes get the same bits)
+    {
+        auto pair_sum = [&](float& v) { v += __shfl_xor_sync(0xffffffffu, v, 1); };
+        pair_sum(G0);
+#pragma unroll
+        for (int l = 0; l < D; ++l) pair_sum(G1[l]);
+#pragma unroll
+        for (int q = 0; q < T; ++q) pair_sum(G2[q]);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            pair_sum(GNu[c]);
+#pragma unroll
+            for (int l = 0; l < D; ++l) pair_sum(GGa[l][c]);
+        }
+    }
+    if (active && hsel == 0) {
         float* out = a.raw_part + ((size_t)split * a.K_cap + k) * P;
 #pragma unroll
         for (int l = 0; l < D; ++l) out[off_mu(D, C) + l] = G1[l];
@@ -460,12 +515,14 @@ __global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) 
 // raw[k][j] = sum_s raw_part[s][k][j], fixed order
 __global__ void __launch_bounds__(256) reduce_splits_kernel(const int32_t* __restrict__ counts, int K_cap, int P,
                                                             int num_splits, const float* __restrict__ part,
+                                                            const int32_t* __restrict__ plan_cnt,
                                                             float* __restrict__ raw) {
     size_t n = (size_t)counts[0] * P;
     size_t stride = (size_t)K_cap * P;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int used = plan_cnt ? segments_used(plan_cnt[(i / P) / kGroup], num_splits) : num_splits;
         float s = 0.f;
-        for (int sp = 0; sp < num_splits; ++sp) s += part[sp * stride + i];
+        for (int sp = 0; sp < used; ++sp) s += part[sp * stride + i];
         raw[i] = s;
     }
 }
@@ -483,7 +540,8 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(smoe_cfg cfg, const 
                                                             float l1_norm, float u_l1, QuantSet qs_in,
                                                             const QuantDyn* __restrict__ qdyn,
                                                             float* __restrict__ grads, smoe_peers pr,
-                                                            float* __restrict__ scalars, uint8_t* __restrict__ infl) {
+                                                            float* __restrict__ scalars, uint8_t* __restrict__ infl,
+                                                            const int32_t* __restrict__ plan_cnt) {
     constexpr int T = tri(D);
     constexpr int P = nparam(D, C);
     __shared__ float s_stats[PEERS ? 256 * P : 1];
@@ -493,7 +551,7 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(smoe_cfg cfg, const 
     if (PEERS) {
         epoch = peer_barrier(pr);
         const int k0 = blockIdx.x * 256;
-        if (k0 < K) gather_stats(pr, epoch, K_cap, P, k0, min(256, K - k0), s_stats);
+        if (k0 < K) gather_stats<P>(pr, epoch, K_cap, k0, min(256, K - k0), s_stats);
         reduce_tail(pr, epoch, K_cap, P, scalars, infl);
         peer_epoch_end(pr, epoch);
     }
@@ -505,7 +563,9 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(smoe_cfg cfg, const 
     } else {
 #pragma unroll
         for (int j = 0; j < P; ++j) s[j] = 0.f;
-        for (int sp = 0; sp < num_splits; ++sp) {
+        // segments of the group's tile list that a backward CTA actually processed (others wrote nothing)
+        const int used = plan_cnt ? segments_used(plan_cnt[k / kGroup], num_splits) : num_splits;
+        for (int sp = 0; sp < used; ++sp) {
             const float* r = raw + ((size_t)sp * K_cap + k) * P;
 #pragma unroll
             for (int j = 0; j < P; ++j) s[j] += r[j];
@@ -657,10 +717,16 @@ size_t smoe_backward_workspace_bytes(const smoe_cfg* cfg, int K_cap, int num_spl
     return (size_t)num_splits * K_cap * nparam(cfg->d, cfg->C) * sizeof(float);
 }
 
+size_t smoe_backward_plan_bytes(int K_cap, const smoe_batch* batch) {
+    const size_t groups = (size_t)(K_cap + kGroup - 1) / kGroup;
+    const size_t nwords = ((size_t)smoe_num_tiles(batch) + 127) / 128 * 4;       // whole 128-tile rounds of the plan CTA
+    return (groups + groups * nwords) * sizeof(int32_t);
+}
+
 int smoe_backward(const smoe_cfg* cfg, const smoe_batch* batch, const float* packed, const int32_t* counts, int K_cap,
                   const float* pix, const float* tile_qmin, const float* ax0, const float* ax1, const float* ax2,
-                  int num_splits, float* raw_part, unsigned long long* pair_counts, void* stream) {
-    SMOE_REQUIRE(cfg && batch && packed && counts && pix && tile_qmin && ax0 && ax1 && raw_part, "null argument");
+                  int num_splits, float* raw_part, int32_t* plan, unsigned long long* pair_counts, void* stream) {
+    SMOE_REQUIRE(cfg && batch && packed && counts && pix && tile_qmin && ax0 && ax1 && raw_part && plan, "null argument");
     SMOE_REQUIRE(K_cap > 0 && num_splits > 0 && num_splits <= 65535, "bad K_cap / num_splits");
     SMOE_REQUIRE(cfg->eps_bits == 0 || (cfg->eps_bits >= 24 && cfg->eps_bits <= 126 && cfg->dense_exec == 0),
                  "eps_bits must be 0 or in [24, 126], with dense_exec == 0");
@@ -679,15 +745,18 @@ int smoe_backward(const smoe_cfg* cfg, const smoe_batch* batch, const float* pac
     a.tau = 0.5f / (float)(1 << cfg->precision);
     a.ltau = -(float)(cfg->precision + 1);              // log2(tau), exact
     a.zero_cut = cfg->eps_bits > 0 ? -(float)cfg->eps_bits : -126.0f;
+    const int groups = (K_cap + kGroup - 1) / kGroup;
+    a.plan_cnt = plan;
+    a.plan_bits = reinterpret_cast<uint32_t*>(plan + groups);
+    a.nwords = (a.ntiles + 127) / 128 * 4;
     a.max_list = (a.ntiles + num_splits - 1) / num_splits;
-    dim3 grid((K_cap + kThreads - 1) / kThreads, num_splits);
-    size_t sm = 2 * (size_t)pix_stride(cfg->d, cfg->C, batch->tile[cfg->d - 1]) * 4 + 16 + 8 * kCB * 4 + 16 * 4 +
-                (size_t)a.max_list * 4 + 64;
+    dim3 grid(groups, num_splits);
+    size_t sm = 2 * (size_t)pix_stride(cfg->d, cfg->C, batch->tile[cfg->d - 1]) * 4 + 16 + 16 * 4 + (size_t)a.max_list * 4 + 64;
     SMOE_REQUIRE(sm <= 100 * 1024, "too many tiles per split for the shared-memory tile list: raise num_splits");
     cudaStream_t st = (cudaStream_t)stream;
-    // partial slabs of splits that own no tile, and rows k >= K, are never read
 #define LAUNCH(D, C, CNT)                                                                                      \
     {                                                                                                          \
+        bwd_plan_kernel<D, C><<<groups, 128, 0, st>>>(a);                                                      \
         cudaFuncSetAttribute(backward_kernel<D, C, CNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
         backward_kernel<D, C, CNT><<<grid, kThreads, sm, st>>>(a);                                             \
     }
@@ -699,19 +768,19 @@ int smoe_backward(const smoe_cfg* cfg, const smoe_batch* batch, const float* pac
 }
 
 int smoe_reduce_splits(const smoe_cfg* cfg, const int32_t* counts, int K_cap, int num_splits, const float* raw_part,
-                       float* raw, void* stream) {
+                       const int32_t* plan, float* raw, void* stream) {
     SMOE_REQUIRE(cfg && counts && raw_part && raw && K_cap > 0 && num_splits > 0, "bad argument");
     int P = nparam(cfg->d, cfg->C);
     size_t n = (size_t)K_cap * P;
     int nb = (int)((n + 255) / 256);
     if (nb > 148 * 16) nb = 148 * 16;
-    reduce_splits_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(counts, K_cap, P, num_splits, raw_part, raw);
+    reduce_splits_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(counts, K_cap, P, num_splits, raw_part, plan, raw);
     return check_launch("smoe_reduce_splits");
 }
 
-int smoe_grad_finalize(const smoe_cfg* cfg, const float* raw, int num_splits, int K_cap, const float* theta,
-                       const void* quant_ranges, const int32_t* indices, const int32_t* counts, float pis_l1,
-                       float l1_norm, float u_l1, float* grads, void* stream) {
+int smoe_grad_finalize(const smoe_cfg* cfg, const float* raw, int num_splits, const int32_t* plan, int K_cap,
+                       const float* theta, const void* quant_ranges, const int32_t* indices, const int32_t* counts,
+                       float pis_l1, float l1_norm, float u_l1, float* grads, void* stream) {
     SMOE_REQUIRE(cfg && raw && theta && indices && counts && grads && K_cap > 0 && num_splits > 0, "bad argument");
     SMOE_REQUIRE(cfg->quantization_mode != 3 || quant_ranges, "quantization_mode 3 needs quant_ranges");
     SMOE_REQUIRE(cfg->kernel_count_as_norm_l1 || l1_norm > 0.f, "l1_norm must be positive");
@@ -722,7 +791,7 @@ int smoe_grad_finalize(const smoe_cfg* cfg, const float* raw, int num_splits, in
 #define CALL(D, C)                                                                                                     \
     grad_finalize_kernel<D, C, false><<<nb, 256, 0, st>>>(*cfg, raw, num_splits, K_cap, theta, indices, counts, pis_l1, \
                                                           l1_norm, u_l1, qs, (const QuantDyn*)quant_ranges, grads,     \
-                                                          none, nullptr, nullptr);
+                                                          none, nullptr, nullptr, plan);
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL
     return check_launch("smoe_grad_finalize");
@@ -743,7 +812,7 @@ int smoe_grad_finalize_peers(const smoe_cfg* cfg, const smoe_peers* peers, int K
 #define CALL(D, C)                                                                                                     \
     grad_finalize_kernel<D, C, true><<<nb, 256, 0, st>>>(*cfg, nullptr, 1, K_cap, theta, indices, counts, pis_l1,       \
                                                          l1_norm, u_l1, qs, (const QuantDyn*)quant_ranges, grads,      \
-                                                         *peers, scalars, infl);
+                                                         *peers, scalars, infl, nullptr);
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL
     return check_launch("smoe_grad_finalize_peers");

@@ -6,6 +6,7 @@ namespace smoe {
 // payload[e & 1] = [sum_s raw_part[s] (K*P, fixed order) | scalars | influence flags as 0/1 floats]
 __global__ void __launch_bounds__(256) xchg_publish_kernel(smoe_peers pr, const int32_t* __restrict__ counts, int K_all,
                                                            int P, int num_splits, const float* __restrict__ part,
+                                                           const int32_t* __restrict__ plan_cnt,
                                                            const float* __restrict__ scalars,
                                                            const uint8_t* __restrict__ infl) {
     int* own = reinterpret_cast<int*>(pr.win[pr.rank]);
@@ -16,14 +17,20 @@ __global__ void __launch_bounds__(256) xchg_publish_kernel(smoe_peers pr, const 
     if (part) {
         const size_t n = (size_t)counts[0] * P;
         for (size_t i = i0; i < n; i += step) {
+            const int used = plan_cnt ? segments_used(plan_cnt[(i / P) / kGroup], num_splits) : num_splits;
+            if (used == 0) continue;                       // unreached group: reach flag 0, rows never read
             float s = 0.f;
-            for (int sp = 0; sp < num_splits; ++sp) s += part[sp * stride + i];
+            for (int sp = 0; sp < used; ++sp) s += part[sp * stride + i];
             pay[i] = s;
         }
     }
     float* tail = pay + stride;
     for (size_t i = i0; i < (size_t)SMOE_NSCAL + K_all; i += step)
         tail[i] = i < SMOE_NSCAL ? scalars[i] : (infl[i - SMOE_NSCAL] ? 1.f : 0.f);
+    // reach flags: which groups of kernels this rank's backward had any tile for (their rows above are defined)
+    float* reach = tail + SMOE_NSCAL + K_all;
+    for (size_t g = i0; g < xw_groups(K_all); g += step)
+        reach[g] = (part && (!plan_cnt || plan_cnt[g] > 0) && (int)(g * kGroup) < counts[0]) ? 1.f : 0.f;
 }
 
 __global__ void __launch_bounds__(256) xchg_reduce_tail_kernel(smoe_peers pr, int K_all, int P,
@@ -87,14 +94,15 @@ static int check_peers(const smoe_peers* pr) {
 }
 
 int smoe_xchg_publish(const smoe_cfg* cfg, const smoe_peers* peers, const int32_t* counts, int K_all, int num_splits,
-                      const float* raw_part, const float* scalars, const uint8_t* infl, void* stream) {
+                      const float* raw_part, const int32_t* plan, const float* scalars, const uint8_t* infl,
+                      void* stream) {
     SMOE_REQUIRE(cfg && counts && scalars && infl && K_all > 0 && num_splits > 0, "bad argument");
     SMOE_REQUIRE(check_peers(peers), "bad peer set");
     const int P = nparam(cfg->d, cfg->C);
     size_t n = (size_t)K_all * P;
     int nb = (int)((n + 255) / 256);
     if (nb > 148 * 8) nb = 148 * 8;
-    xchg_publish_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(*peers, counts, K_all, P, num_splits, raw_part, scalars, infl);
+    xchg_publish_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(*peers, counts, K_all, P, num_splits, raw_part, plan, scalars, infl);
     return check_launch("smoe_xchg_publish");
 }
 

@@ -21,8 +21,14 @@ namespace smoe {
 // window = [XW_HDR ints: flags[0..8) | epoch | error | ticket | pad] [payload 0] [payload 1]
 constexpr int XW_HDR = 64;            // ints (256 B)
 constexpr int XW_EPOCH = 16, XW_ERROR = 17, XW_TICKET = 18;
+// payload = [K_all*P statistics | SMOE_NSCAL scalars | K_all influence flags | groups reach flags], groups of kGroup
+__host__ __device__ inline size_t xw_groups(int K_all) { return ((size_t)K_all + kGroup - 1) / kGroup; }
 __host__ __device__ inline size_t xw_payload_floats(int K_all, int P) {
-    return ((size_t)K_all * P + SMOE_NSCAL + (size_t)K_all + 3) / 4 * 4;
+    return ((size_t)K_all * P + SMOE_NSCAL + (size_t)K_all + xw_groups(K_all) + 3) / 4 * 4;
+}
+__device__ __forceinline__ const float* xw_payload(const smoe_peers& pr, int r, int e, int K_all, int P) {
+    return reinterpret_cast<const float*>(reinterpret_cast<const int*>(pr.win[r]) + XW_HDR) +
+           (size_t)(e & 1) * xw_payload_floats(K_all, P);
 }
 
 __device__ __forceinline__ void st_release_sys(int* p, int v) {
@@ -85,44 +91,57 @@ __device__ __forceinline__ void peer_epoch_end(const smoe_peers& pr, int e) {
     }
 }
 
-// scalars = sum over ranks (rank order), infl = any rank; grid-stride over the tail
+// scalars = sum over ranks (rank order), infl = any rank; grid-stride over the tail.  The R remote loads of an
+// element are issued back to back before the first use (a peer load is an NVLink round trip of a few microseconds:
+// dependent loads would serialise R of them).
 __device__ __forceinline__ void reduce_tail(const smoe_peers& pr, int e, int K_all, int P, float* __restrict__ scalars,
                                             uint8_t* __restrict__ infl) {
-    const size_t pf = xw_payload_floats(K_all, P), stride = (size_t)K_all * P;
+    const size_t stride = (size_t)K_all * P;
     const size_t step = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (size_t i = i0; i < (size_t)SMOE_NSCAL + K_all; i += step) {
+        float v[SMOE_MAX_PEERS];
+#pragma unroll
+        for (int r = 0; r < SMOE_MAX_PEERS; ++r) v[r] = r < pr.world ? ld_peer(xw_payload(pr, r, e, K_all, P) + stride + i) : 0.f;
         float s = 0.f;
-        for (int r = 0; r < pr.world; ++r) {
-            const float* tail = reinterpret_cast<const float*>(reinterpret_cast<const int*>(pr.win[r]) + XW_HDR) +
-                                (size_t)(e & 1) * pf + stride;
-            s += ld_peer(tail + i);
-        }
+#pragma unroll
+        for (int r = 0; r < SMOE_MAX_PEERS; ++r) s += v[r];
         if (i < SMOE_NSCAL) scalars[i] = s; else infl[i - SMOE_NSCAL] = s > 0.f ? 1 : 0;
     }
 }
 
-// Sum of the R published statistics rows of kernels [k0, k0 + nk) into shared memory, fixed rank order, coalesced
-// 16-byte peer loads (the range is contiguous in every window).
-__device__ __forceinline__ void gather_stats(const smoe_peers& pr, int e, int K_all, int P, int k0, int nk,
+// Sum of the R published statistics rows of kernels [k0, k0 + nk) into shared memory (k0 a multiple of 256), fixed
+// rank order, coalesced 16-byte peer loads issued R at a time.  A rank whose pixel block is not reached by a group
+// of kernels published a reach flag of 0 for it and its rows are not read at all (they hold nothing defined).
+template <int P>
+__device__ __forceinline__ void gather_stats(const smoe_peers& pr, int e, int K_all, int k0, int nk,
                                              float* __restrict__ s_stats) {
-    const size_t pf = xw_payload_floats(K_all, P);
-    const size_t beg = (size_t)k0 * P, end = beg + (size_t)nk * P;
-    const size_t abeg = beg & ~(size_t)3;                       // 16-byte aligned start inside the payload
-    const int n4 = (int)((end - abeg + 3) / 4);
+    constexpr int F4G = kGroup * P / 4;                       // float4 per group: kGroup * P floats is a multiple of 4
+    static_assert((kGroup * P) % 4 == 0, "group rows must be float4-aligned");
+    __shared__ float s_reach[SMOE_MAX_PEERS][256 / kGroup];
+    const size_t tail = (size_t)K_all * P + SMOE_NSCAL + K_all;
+    constexpr int GPB = 256 / kGroup;                          // groups per 256-kernel block
+    if (threadIdx.x < SMOE_MAX_PEERS * GPB) {
+        const int r = threadIdx.x / GPB, gl = threadIdx.x % GPB;
+        const size_t g = (size_t)k0 / kGroup + gl;
+        s_reach[r][gl] = (r < pr.world && g < xw_groups(K_all)) ? ld_peer(xw_payload(pr, r, e, K_all, P) + tail + g) : 0.f;
+    }
+    __syncthreads();
+    const size_t beg = (size_t)k0 * P;
+    const int n4 = (nk * P + 3) / 4;
     for (int q = threadIdx.x; q < n4; q += blockDim.x) {
+        const int gl = q / F4G;
+        float4 v[SMOE_MAX_PEERS];
+#pragma unroll
+        for (int r = 0; r < SMOE_MAX_PEERS; ++r)
+            v[r] = (r < pr.world && s_reach[r][gl] != 0.f) ? ld_peer4(xw_payload(pr, r, e, K_all, P) + beg + 4 * (size_t)q)
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = 0; r < pr.world; ++r) {
-            const float* pay = reinterpret_cast<const float*>(reinterpret_cast<const int*>(pr.win[r]) + XW_HDR) +
-                               (size_t)(e & 1) * pf;
-            const float4 v = ld_peer4(pay + abeg + 4 * (size_t)q);
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-        }
+#pragma unroll
+        for (int r = 0; r < SMOE_MAX_PEERS; ++r) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
         const float sv[4] = {s.x, s.y, s.z, s.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const size_t g = abeg + 4 * (size_t)q + j;
-            if (g >= beg && g < end) s_stats[g - beg] = sv[j];
-        }
+        for (int j = 0; j < 4; ++j)
+            if (4 * q + j < nk * P) s_stats[4 * q + j] = sv[j];
     }
     __syncthreads();
 }

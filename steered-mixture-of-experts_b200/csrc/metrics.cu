@@ -407,7 +407,7 @@ int smoe_suggest_splits(int K_cap, const smoe_batch* b) {
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int nt[3], ntiles = 1;
     for (int i = 0; i < 3; ++i) { nt[i] = (b->extent[i] + b->tile[i] - 1) / b->tile[i]; ntiles *= nt[i]; }
-    const int kt = (K_cap + kThreads - 1) / kThreads;
+    const int kt = (K_cap + kGroup - 1) / kGroup;
     int want = (2 * 8 * sms + kt - 1) / kt;          // >= ~2 waves of 8 CTAs per SM
     if (want < ntiles / 180) want = ntiles / 180;
     if (want < 8) want = 8;

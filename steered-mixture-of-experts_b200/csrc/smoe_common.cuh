@@ -12,7 +12,9 @@
 
 namespace smoe {
 
-constexpr int kThreads = 64;                        // threads per CTA of the backward (one kernel per thread)
+constexpr int kThreads = 64;                        // threads per CTA of the backward
+constexpr int kHalves = 2;                          // threads per kernel in the backward: each takes every other tile row
+constexpr int kGroup = kThreads / kHalves;          // kernels per backward CTA (= planning group)
 constexpr int kThreadsF = 128;                       // threads per CTA of the forward
 constexpr int kPixPerThread = SMOE_TPIX / kThreadsF; // 4 pixels per thread in the forward
 constexpr int kChunk = 128;                          // kernels staged per shared-memory chunk
@@ -24,6 +26,9 @@ __host__ __device__ constexpr int nparam(int d, int C) { return d + tri(d) + 1 +
 // packed record = P parameters | lam (eigenvalue bound) | kap[d] (per-axis bounds) | pad to a multiple of 4
 __host__ __device__ constexpr int pstride(int d, int C) { return (nparam(d, C) + 1 + d + 3) / 4 * 4; }
 constexpr int kCB = 12;                              // floats per chunk-bounds entry
+// Groups of kernels that reach no tile of the batch are skipped by every backward CTA; their slabs of raw_part are
+// never written and never read.  A group that reaches some tile has all its num_splits slabs written.
+__host__ __device__ inline int segments_used(int n, int num_splits) { return n > 0 ? num_splits : 0; }
 // offsets inside a theta / grads row and inside a packed record (same order)
 __host__ __device__ constexpr int off_mu(int, int) { return 0; }
 __host__ __device__ constexpr int off_A(int d, int) { return d; }

@@ -518,17 +518,17 @@ class Smoe:
         self._partials = torch.zeros((8 * sms * 8,), dtype=f32, device=dev)
         self._ticket = torch.zeros((4,), dtype=torch.int32, device=dev)
         self._pack_ws = torch.zeros((L.smoe_pack_workspace_bytes(K) + 15) // 4, dtype=torch.int32, device=dev)
-        if self._world > 1:
-            # a rank's block is reached by a fraction of the kernels only: size the pixel splits for the kernel CTAs
-            # that will actually have work, so the (kernel CTA, split) grid still fills the GPU
-            reach = self._reach_px()
-            frac = float(np.prod([min(1.0, (self._local_shape[a] + 2 * reach[a]) / (self.image.shape[a] + 2 * reach[a]))
-                                  for a in range(d)]))
-            k_eff = max(64, int(K * frac))
-        else:
-            k_eff = K
+        # Pixel splits of the backward (split s owns tiles s, s+NS, ...): sized for the kernel groups that will have
+        # work -- a rank's block is reached by a fraction of the kernels only, and the groups that do not reach it
+        # leave after one load -- so that the (group, split) grid still fills the GPU a few waves deep.
+        reach = self._reach_px()
+        frac = float(np.prod([min(1.0, (self._local_shape[a] + 2 * reach[a]) / (self.image.shape[a] + 2 * reach[a]))
+                              for a in range(d)]))
+        k_eff = max(64, int(K * frac))
         self._splits = int(os.environ.get("SMOE_SPLITS", 0)) or max(int(L.smoe_suggest_splits(k_eff, C.byref(b)))
                                                                     for b in self._batches)
+        self._plan = torch.zeros((max(L.smoe_backward_plan_bytes(K, C.byref(b)) for b in self._batches) + 3) // 4,
+                                 dtype=torch.int32, device=dev)
         self._raw_part = None           # allocated on the first training pass
         self._peers = None
         if self._world > 1 and not self._emulated:
@@ -942,13 +942,14 @@ class Smoe:
             if train:
                 check(L.smoe_backward(C.byref(self._cfg), C.byref(b), ptr(self._packed), ptr(counts), K,
                                       ptr(self._pix), ptr(tq), ptr(self._d_axes[0]), ptr(self._d_axes[1]), ax2,
-                                      self._splits, ptr(self._raw_part), pc, st), "smoe_backward")
-                self.gpu_launches += 1
+                                      self._splits, ptr(self._raw_part), ptr(self._plan), pc, st), "smoe_backward")
+                self.gpu_launches += 2
             if sharded:
                 # the one exchange step: publish this rank's sums, then the consumer sums the R
                 # windows over NVLink in rank order -- fused into the gradient finalisation on a training pass
                 check(L.smoe_xchg_publish(C.byref(self._cfg), C.byref(self._peers), ptr(counts), K, self._splits,
-                                          ptr(self._raw_part) if train else ptr(None), ptr(scal), ptr(self._infl), st),
+                                          ptr(self._raw_part) if train else ptr(None),
+                                          ptr(self._plan) if train else ptr(None), ptr(scal), ptr(self._infl), st),
                       "smoe_xchg_publish")
                 self.gpu_launches += 1
                 if train:
@@ -962,7 +963,8 @@ class Smoe:
                                                   ptr(self._infl), st), "smoe_xchg_reduce_tail")
                 self.gpu_launches += 1
             elif train:
-                check(L.smoe_grad_finalize(C.byref(self._cfg), ptr(self._raw_part), self._splits, K, ptr(self._theta),
+                check(L.smoe_grad_finalize(C.byref(self._cfg), ptr(self._raw_part), self._splits, ptr(self._plan), K,
+                                           ptr(self._theta),
                                            ptr(self._qdyn), ptr(self._indices), ptr(counts), C.c_float(float(pis_l1)),
                                            C.c_float(norm), C.c_float(float(u_l1)), ptr(self._grads), st),
                       "smoe_grad_finalize")

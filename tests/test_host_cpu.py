@@ -133,14 +133,14 @@ def test_c_abi_argument_errors_are_reported_without_a_device(libpath):
     assert b"null argument" in h.smoe_last_error()
     assert h.smoe_forward(null, null, null, null, null, null, 16, null, null, null, null, null, null, null, null, null,
                           null, null, null, null, null, null, null, null) == -1
-    assert h.smoe_backward(null, null, null, null, 0, null, null, null, null, null, 1, null, null, null) == -1
+    assert h.smoe_backward(null, null, null, null, 0, null, null, null, null, null, 1, null, null, null, null) == -1
     # the peer exchange validates its peer set before touching CUDA
     pr = _ffi.Peers()
     pr.world, pr.rank = 9, 0
-    assert h.smoe_xchg_publish(ctypes.byref(cfg), ctypes.byref(pr), one8 := (ctypes.c_int32 * 8)(), 4, 1, null,
+    assert h.smoe_xchg_publish(ctypes.byref(cfg), ctypes.byref(pr), one8 := (ctypes.c_int32 * 8)(), 4, 1, null, null,
                                (ctypes.c_float * 16)(), (ctypes.c_ubyte * 4)(), null) == -1
     assert b"bad peer set" in h.smoe_last_error()
-    assert h.smoe_xchg_window_bytes(32768, 15) == 256 + 2 * 4 * (32768 * 15 + 16 + 32768)
+    assert h.smoe_xchg_window_bytes(32768, 15) == 256 + 2 * 4 * (32768 * 15 + 16 + 32768 + 512)
     assert h.smoe_adam_step(ctypes.byref(cfg), null, null, null, null, null, null, 0, null) == -1
     assert h.smoe_ssim_loss(ctypes.byref(cfg), ctypes.byref(b), null, null, null, null, null, null, null) == -1
     cfg3 = _ffi.Cfg()

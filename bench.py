@@ -214,47 +214,58 @@ def kernel_times(m, steps, with_step=True):
         m._raw_part = torch.zeros((m._splits * m.start_pis * m._P,), dtype=torch.float32, device=m.device)
     check(L.smoe_pack(C.byref(m._cfg), ptr(m._theta), ptr(m._mus_grid), ptr(m._qdyn), ptr(m._klist[0]), ptr(m._perm),
                       m.start_pis, ptr(m._packed), ptr(m._indices), ptr(m._pos), ptr(counts), ptr(regs),
-                      ptr(m._chunk_bounds), ptr(m._pack_ws), st), "pack")
+                      ptr(m._chunk_bounds), ptr(m._pack_ws), ptr(None), ptr(None), ptr(None), st), "pack")
 
     def fwd(pc=None):
         m._infl.zero_()
         scal.zero_()
         check(L.smoe_forward(C.byref(m._cfg), C.byref(b), ptr(m._packed), ptr(m._indices), ptr(counts),
-                             ptr(m._chunk_bounds), m.start_pis, ptr(m._d_image), ptr(None), ptr(None),
-                             ptr(m._d_axes[0]), ptr(m._d_axes[1]), ax2, ptr(m._d_res), ptr(None), ptr(None), ptr(m._infl),
-                             ptr(m._pix), ptr(m._tile_qmin[0]), ptr(scal), ptr(m._partials), ptr(m._ticket), ptr(pc), st),
+                             ptr(m._chunk_bounds), m.start_pis, ptr(None), ptr(m._d_axes[0]), ptr(m._d_axes[1]), ax2,
+                             ptr(m._d_res_pre), ptr(None), ptr(m._infl), ptr(m._pix), ptr(m._tile_qmin[0]), ptr(pc), st),
               "forward")
+
+    def loss():
+        check(L.smoe_loss(C.byref(m._cfg), C.byref(b), ptr(m._d_res_pre), ptr(m._d_image), ptr(None), ptr(None),
+                          ptr(m._d_res), ptr(m._pix), ptr(scal), ptr(m._partials), ptr(m._ticket), st), "loss")
 
     def bwd(pc=None):
         check(L.smoe_backward(C.byref(m._cfg), C.byref(b), ptr(m._packed), ptr(counts), m.start_pis, ptr(m._pix),
                               ptr(m._tile_qmin[0]), ptr(m._d_axes[0]), ptr(m._d_axes[1]), ax2, m._splits,
                               ptr(m._raw_part), ptr(m._plan), ptr(pc), st), "backward")
 
-    fw, bw = [], []
+    fw, bw, ls = [], [], []
     for _ in range(steps + 1):
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         m._infl.zero_()
         scal.zero_()
         e[0].record()
         fwd()
         e[1].record()
-        bwd()
+        loss()
         e[2].record()
+        bwd()
+        e[3].record()
         torch.cuda.synchronize()
         fw.append(e[0].elapsed_time(e[1]))
-        bw.append(e[1].elapsed_time(e[2]))
-    fw, bw = fw[1:], bw[1:]
+        ls.append(e[1].elapsed_time(e[2]))
+        bw.append(e[2].elapsed_time(e[3]))
+    fw, bw, ls = fw[1:], bw[1:], ls[1:]
     pc = torch.zeros((8,), dtype=torch.int64, device=m.device)
     fwd(pc)
+    loss()
     bwd(pc)
     torch.cuda.synchronize()
     pairs = [int(v) for v in pc.cpu().numpy()]
-    out = {"forward_ms": float(np.mean(fw)), "backward_ms": float(np.mean(bw)), "other_ms": 0.0, "pairs": pairs,
+    # loss stage: elementwise, HBM-bound: r (C f32) + target (C f32) read, res (C f32) + 1 + C planes written, gr plane read
+    Cc = m.image.shape[-1]
+    loss_bytes = float(np.prod(m._local_shape)) * 4 * (3 * Cc + 2 + Cc)
+    out = {"forward_ms": float(np.mean(fw)), "backward_ms": float(np.mean(bw)), "loss_ms": float(np.mean(ls)),
+           "loss_GBps": loss_bytes / (float(np.mean(ls)) / 1e3) / 1e9, "other_ms": 0.0, "pairs": pairs,
            "launches_timed": len(fw)}
     if with_step:
         # everything else in a step: pack, finalize / exchange, list upkeep, Adam, memsets
         step = event_time(lambda: m.run_batched(train=True), 5, warm=2)
-        out["other_ms"] = max(0.0, step - out["forward_ms"] - out["backward_ms"])
+        out["other_ms"] = max(0.0, step - out["forward_ms"] - out["backward_ms"] - out["loss_ms"])
     return out
 
 
@@ -303,7 +314,7 @@ def aux_hbm_pieces(m, img, peaks):
     ms = event_time(lambda: check(L.smoe_pack(C.byref(m._cfg), ptr(m._theta), ptr(m._mus_grid), ptr(m._qdyn),
                                               ptr(m._klist[0]), ptr(m._perm), K, ptr(m._packed), ptr(m._indices),
                                               ptr(m._pos), ptr(m._counts[0]), ptr(m._regsums[0]), ptr(m._chunk_bounds),
-                                              ptr(m._pack_ws), stream_ptr()), "pack"), 10, 2)
+                                              ptr(m._pack_ws), ptr(None), ptr(None), ptr(None), stream_ptr()), "pack"), 10, 2)
     Ka = int(m._counts[0, 0].item())
     alg = K * (P * 4 + 1 + 4) + Ka * (PK * 4 + 4) + K * 4
     out["compaction"] = {"ms": ms, "K_all": K, "K_active": Ka, "GBps": alg / ms / 1e6,
@@ -411,6 +422,7 @@ def run_ours(args):
                                           2: "exact-zero skipping only"}[int(args.dense_exec)] +
                                          (f" + epsilon culling 2^-{args.eps_bits}" if args.eps_bits else ""),
                                  "forward_ms": ker["forward_ms"], "backward_ms": ker["backward_ms"],
+                                 "loss_ms": ker["loss_ms"], "loss_GBps": ker["loss_GBps"],
                                  "other_ms": ker["other_ms"], "launches_timed": ker["launches_timed"]},
                 "executed": executed_roofline(ker, d, C, peak_tflops)}
     # dense_equivalent_speedup: how much faster than a kernel that executes all N*K pairs at 100 % of the FP32 roofline

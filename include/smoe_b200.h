@@ -147,14 +147,18 @@ int smoe_pack(const smoe_cfg* cfg, const float* theta, const float* mus_grid /*[
               float* packed, int32_t* indices /*[K_all]: original index of packed row k*/,
               int32_t* pos /*[K_all]: packed row of each kernel or -1*/,
               int32_t* counts, float* regsums,
-              float* chunk_bounds /*[ceil(K_all/128)][12]*/, void* workspace, void* stream);
+              float* chunk_bounds /*[ceil(K_all/128)][12]*/, void* workspace,
+              float* grads_clear /* optional [K_all][P]: zeroed (zero_op of the accumulators, smoe.py:1612-1613) */,
+              float* scalars_clear /* optional [SMOE_NSCAL]: zeroed */, uint8_t* infl_clear /* optional [K_all]: zeroed */,
+              void* stream);
 
 /* Same staging for parameters that are FED over the compacted tensors (with_quantized_params,
  * smoe.py:1688-1689: rparams A, musX, nu_e, gamma_e, pis of K rows each); no mask, K given. */
 int smoe_pack_fed(const smoe_cfg* cfg, const float* A /*[K][d][d]*/, const float* musX, const float* nu_e,
                   const float* gamma_e, const float* pis, const int32_t* order /*[K] or NULL: fed row staged at packed
                   row j (e.g. Hilbert order)*/, int K, float* packed, int32_t* indices /*[K] out: order, or identity*/,
-                  int32_t* counts, float* chunk_bounds, void* stream);
+                  int32_t* counts, float* chunk_bounds, float* scalars_clear /*optional*/,
+                  uint8_t* infl_clear /*optional [K_all]*/, int K_all, void* stream);
 
 /* Hilbert-curve keys of the kernel centres on a 2^10 grid per axis (centres[i*row_stride + a] (+ grid[i*d + a]),
  * times scale[a] (host array of d floats, or NULL = 1): n_a / max_a n_a makes the curve isotropic in pixels).  Sorting
@@ -163,39 +167,50 @@ int smoe_pack_fed(const smoe_cfg* cfg, const float* A /*[K][d][d]*/, const float
 int smoe_spatial_keys(const float* centres, int K, int d, int row_stride, const float* grid /*or NULL*/,
                       const float* scale /*host [d] or NULL*/, long long* keys, void* stream);
 
-/* Fused forward over one batch: Mahalanobis logits, gating with the un-renormalised threshold,
- * experts, clip, output fake-quant, loss partials, per-pixel backward state.  Replaces
- * smoe.py:777-858 (kernel values, gates, influence list, argmax, mixture, clip) and 899-937, 1053
- * (fake-quant, diff, loss, mse).  The K x N gate matrix is never materialised.
- *   res      [dims..][C]  fake-quantised reconstruction (written inside the batch rectangle)
- *   res_pre  [dims..][C]  optional (may be NULL): mixture output before clip / quantisation
+/* Fused forward over one batch: Mahalanobis logits, gating with the un-renormalised threshold, experts, mixture.
+ * Replaces smoe.py:777-858 (kernel values, gates, influence list, argmax, mixture).  The K x N gate matrix is never
+ * materialised.  The forward reads NO target pixels: clip, output quantisation and the loss live in smoe_loss, so a
+ * step's target may still be on its way from the host while the sweeps run.
+ *   rbuf     [dims..][C]  mixture output r BEFORE clip / quantisation (written inside the batch rectangle, not for
+ *            halo pixels)
  *   argmax   [dims..] int32, optional: original index of the kernel with the largest gate (ties: the lowest
  *            original index, as tf.argmax over the ascending `indices`), -1 where no gate passed the threshold
  *            (host applies tf.argmax's all-zero convention)
  *   infl     [K_all] uint8, optional, indexed by ORIGINAL kernel index: 1 where the kernel's gate passed the
- *            threshold for some pixel (kernel_list_batch, smoe.py:829); must be zeroed by the caller
+ *            threshold for some pixel (kernel_list_batch, smoe.py:829); must be zeroed by the caller (smoe_pack can)
+ *   pix      optional: per-pixel state for smoe_loss / smoe_backward (planes z, qthr = log2 max(S, 1e-11), and the
+ *            "S > 1e-11" flag in the gr plane)
+ *   tile_qmin [tiles] (required with pix): min over the tile of qthr, the culling threshold of the backward; with
+ *            cfg->eps_bits also READ: the previous pass's value bounds this pass's sweep A
+ *   loss_weights [dims..] optional: only its sentinels matter here -- SMOE_PIXEL_ABSENT (the pixel is not fed at all:
+ *            random sub-sampling, smoe.py:1664-1667) and SMOE_PIXEL_HALO (forwarded, no output)
  *   pair_counts [8] uint64, optional (NULL in the product path): executed-work counters for the roofline
  *            report, accumulated with integer atomics -- [0] sweep-A pairs whose logit was evaluated, [1] sweep-A
  *            pairs whose ex2 + add was executed, [2] sweep-B pairs evaluated, [3] sweep-B pairs whose expert part
  *            was executed; smoe_backward adds [4] pairs evaluated, [5] pairs whose gate / moment part was executed,
- *            [6] pairs whose expert part was executed (all in lanes x pixels as issued)
- *   pix      optional: per-pixel state for smoe_backward
- *   tile_qmin [tiles] (required with pix): min over the tile of log2(max(S, 1e-11)), the culling threshold
- *            of the backward
- *   loss_weights [dims..] optional (NULL = every pixel of the rectangle, weight 1): per-pixel weight of the
- *            loss term (the `loss_weights` feed of smoe.py:550, 932, 1674-1677), or one of the sentinels
- *            SMOE_PIXEL_ABSENT (the pixel is not fed at all: random sub-sampling, smoe.py:1664-1667) and
- *            SMOE_PIXEL_HALO (fed, but cropped away before the loss: overlap_of_batches, smoe.py:909-923)
- *   scalars  [SMOE_NSCAL]: [0..C) sum_n (|diff|-eps)^2 per channel, [4] sum diff^2,
- *            [5] non-finite flag; accumulated (+=) so that batches/ranks can be summed; the
- *            caller zeroes it */
+ *            [6] pairs whose expert part was executed (all in lanes x pixels as issued) */
 int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const float* packed, const int32_t* indices,
-                 const int32_t* counts, const float* chunk_bounds, int K_cap, const float* image,
-                 const uint8_t* image_u8 /* exactly one of image / image_u8: 8-bit pixels as an image file holds
-                 them, divided by 255 in float32 as utils.py:126-128 does */,
-                 const float* loss_weights, const float* ax0, const float* ax1, const float* ax2, float* res, float* res_pre,
-                 int32_t* argmax, uint8_t* infl, float* pix, float* tile_qmin /*[tiles]*/, float* scalars,
-                 float* partials /*[num_sms*8][8]*/, int32_t* ticket, unsigned long long* pair_counts, void* stream);
+                 const int32_t* counts, const float* chunk_bounds, int K_cap, const float* loss_weights,
+                 const float* ax0, const float* ax1, const float* ax2, float* rbuf, int32_t* argmax, uint8_t* infl,
+                 float* pix, float* tile_qmin /*[tiles]*/, unsigned long long* pair_counts, void* stream);
+
+/* Loss stage of one batch, after smoe_forward: res = fake_quant(clip(r)) (smoe.py:857, 899), diff = res - target,
+ * loss and squared-error sums (smoe.py:905-937, 1053), and -- when pix != NULL -- dL/dr with the straight-through
+ * masks of clip and fake-quant: g_c and gr = sum_c g_c r_c (0 where S was clamped, smoe.py:821) into the planes of the
+ * backward state.  Elementwise, HBM-bound.
+ *   image / image_u8  exactly one: float32 target, or 8-bit pixels as an image file holds them, divided by 255 in
+ *            float32 as utils.py:126-128 does
+ *   loss_weights [dims..] optional (NULL = weight 1 everywhere): per-pixel weight of the loss term (the `loss_weights`
+ *            feed of smoe.py:550, 932, 1674-1677) or a sentinel (absent / halo pixels take no part)
+ *   res      [dims..][C]  optional: fake-quantised reconstruction (written inside the batch rectangle, not for halo
+ *            pixels); a plain training pass needs only its sums and passes NULL
+ *   scalars  [SMOE_NSCAL]: [0..C) sum_n (|diff|-eps)^2 per channel, [4] sum diff^2, [5] non-finite flag; accumulated
+ *            (+=) so that batches / ranks can be summed; the caller zeroes it (smoe_pack can)
+ *   partials [smoe_loss_partials()][8] scratch, ticket: one int32, zero before the first call */
+int smoe_loss_partials(void);
+int smoe_loss(const smoe_cfg* cfg, const smoe_batch* batch, const float* rbuf, const float* image,
+              const uint8_t* image_u8, const float* loss_weights, float* res, float* pix, float* scalars,
+              float* partials, int32_t* ticket, void* stream);
 
 /* Fused backward over one batch: recomputes the gates from the per-pixel state and reduces the
  * per-kernel sufficient statistics (sum t, sum t*delta, sum t*delta*delta^T, sum m*w*g,
@@ -303,11 +318,21 @@ int smoe_xchg_reduce_tail(const smoe_cfg* cfg, const smoe_peers* peers, int K_al
                           void* stream);
 int smoe_xchg_status(const smoe_peers* peers, int32_t* epoch_and_error /*[2], host memory; synchronous*/);
 
+/* Host -> device feed of a pass's target pixels (pinned host memory) on a dedicated copy stream, overlapping whatever
+ * the main stream does until smoe_loss: the copy is ordered after the work already enqueued on main_stream
+ * (order_event is recorded there and awaited by copy_stream) and done_event fires when the pixels have landed --
+ * make the main stream wait for it right before smoe_loss.  The reference feeds its target through the TF feed dict
+ * on every session.run (smoe.py:1671-1672, 1702). */
+int smoe_feed(void* dst, const void* src_host, size_t bytes, void* main_stream, void* copy_stream,
+              void* order_event /* cudaEvent_t */, void* done_event /* cudaEvent_t */);
+
 /* TF1 ApplyAdam on every K_all row (dense, pruned rows included), three groups.  Replaces
  * session.run(train_op) at smoe.py:1788 (apply_gradients at smoe.py:1173-1193). */
 int smoe_adam_step(const smoe_cfg* cfg, const smoe_adam* hp, const float* alpha_dev /* optional device [3]:
                    overrides hp->alpha, so that a captured CUDA graph carries no step count */,
-                   float* theta, const float* grads, float* adam_m, float* adam_v, int K_all, void* stream);
+                   float* theta, const float* grads, float* adam_m, float* adam_v, int K_all,
+                   const uint8_t* infl, uint8_t* kernel_list /* both optional: the same launch also does
+                   smoe_update_kernel_list (one-batch models, whose list is rewritten once per step) */, void* stream);
 
 /* custom_ssim (ops/image_ops_impl.py:235-293) as evaluated by the loss graph (smoe.py:993-1010):
  * SYMMETRIC pad 5, 11-tap sigma-1.5 Gaussian window, VALID; out[c] = mean SSIM of channel c.
@@ -322,7 +347,7 @@ int    smoe_ssim(int d, const int32_t dims[3], int C, const float* a, const floa
  * divides by the number of positions and forms 1 - sum_c w_c ssim_c); and, when pix != NULL, d loss / d res
  * pushed through the output fake-quant and the clip (straight-through where 0 <= res_pre <= 1) and written
  * over the g_c / gr planes of the backward state that smoe_forward filled for the squared-error loss.
- *   res, image, res_pre: [dims..][C] as in smoe_forward (res_pre is required) */
+ *   res, image: [dims..][C] as in smoe_loss; res_pre: the rbuf of smoe_forward */
 size_t smoe_ssim_loss_workspace_bytes(const smoe_cfg* cfg, const smoe_batch* batch);
 int    smoe_ssim_loss(const smoe_cfg* cfg, const smoe_batch* batch, const float* res, const float* image,
                       const float* res_pre, float* pix, float* scalars, void* workspace, void* stream);

@@ -521,9 +521,7 @@ __global__ void __launch_bounds__(256) reduce_splits_kernel(const int32_t* __res
     size_t stride = (size_t)K_cap * P;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int used = plan_cnt ? segments_used(plan_cnt[(i / P) / kGroup], num_splits) : num_splits;
-        float s = 0.f;
-        for (int sp = 0; sp < used; ++sp) s += part[sp * stride + i];
-        raw[i] = s;
+        raw[i] = slab_sum(part + i, stride, used);
     }
 }
 
@@ -544,33 +542,32 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(smoe_cfg cfg, const 
                                                             const int32_t* __restrict__ plan_cnt) {
     constexpr int T = tri(D);
     constexpr int P = nparam(D, C);
-    __shared__ float s_stats[PEERS ? 256 * P : 1];
-    const int k = blockIdx.x * 256 + threadIdx.x;
+    __shared__ float s_stats[kFin * P];
+    const int k = blockIdx.x * kFin + threadIdx.x;
     const int K = counts[0];
+    const int k0 = blockIdx.x * kFin;
     int epoch = 0;
     if (PEERS) {
         epoch = peer_barrier(pr);
-        const int k0 = blockIdx.x * 256;
-        if (k0 < K) gather_stats<P>(pr, epoch, K_cap, k0, min(256, K - k0), s_stats);
+        if (k0 < K) gather_stats<P>(pr, epoch, K_cap, k0, min(kFin, K - k0), s_stats);
         reduce_tail(pr, epoch, K_cap, P, scalars, infl);
         peer_epoch_end(pr, epoch);
-    }
-    if (k >= K) return;
-    float s[P];
-    if (PEERS) {
-#pragma unroll
-        for (int j = 0; j < P; ++j) s[j] = s_stats[threadIdx.x * P + j];
-    } else {
-#pragma unroll
-        for (int j = 0; j < P; ++j) s[j] = 0.f;
-        // segments of the group's tile list that a backward CTA actually processed (others wrote nothing)
-        const int used = plan_cnt ? segments_used(plan_cnt[k / kGroup], num_splits) : num_splits;
-        for (int sp = 0; sp < used; ++sp) {
-            const float* r = raw + ((size_t)sp * K_cap + k) * P;
-#pragma unroll
-            for (int j = 0; j < P; ++j) s[j] += r[j];
+    } else if (k0 < K) {
+        // sum of the pixel-split slabs of this block's kFin kernels, fixed split order; the block's rows are one
+        // contiguous range of every slab, read with coalesced loads (element e of the range by thread e % 256)
+        const int n = min(kFin, K - k0) * P;
+        const size_t beg = (size_t)k0 * P, stride = (size_t)K_cap * P;
+        for (int e = threadIdx.x; e < n; e += 256) {
+            // slabs of a group of kernels that reaches no tile were never written (and are not read)
+            const int used = plan_cnt ? segments_used(plan_cnt[(k0 + e / P) / kGroup], num_splits) : num_splits;
+            s_stats[e] = slab_sum(raw + beg + e, stride, used);
         }
+        __syncthreads();
     }
+    if (threadIdx.x >= kFin || k >= K) return;
+    float s[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) s[j] = s_stats[threadIdx.x * P + j];
     const int row = indices[k];
     const float* th = theta + (size_t)row * P;
     float* gr = grads + (size_t)row * P;
@@ -683,10 +680,12 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(smoe_cfg cfg, const 
 template <int D, int C>
 __global__ void __launch_bounds__(256) adam_kernel(smoe_adam hp, const float* __restrict__ alpha_dev,
                                                    float* __restrict__ theta, const float* __restrict__ grads,
-                                                   float* __restrict__ am, float* __restrict__ av, size_t n) {
+                                                   float* __restrict__ am, float* __restrict__ av, size_t n,
+                                                   const uint8_t* __restrict__ infl, uint8_t* __restrict__ klist) {
     constexpr int P = nparam(D, C);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int j = (int)(i % P);
+        if (klist && j == 0) klist[i / P] = infl[i / P] ? 1 : 0;      // kernel_list <- influential kernels (smoe.py:1763-1766)
         int grp;
         bool on = true;
         if (j < off_A(D, C)) { grp = 0; on = hp.train_musx != 0; }
@@ -785,7 +784,7 @@ int smoe_grad_finalize(const smoe_cfg* cfg, const float* raw, int num_splits, co
     SMOE_REQUIRE(cfg->quantization_mode != 3 || quant_ranges, "quantization_mode 3 needs quant_ranges");
     SMOE_REQUIRE(cfg->kernel_count_as_norm_l1 || l1_norm > 0.f, "l1_norm must be positive");
     const QuantSet qs = make_quantset(cfg);
-    int nb = (K_cap + 255) / 256;
+    int nb = (K_cap + kFin - 1) / kFin;
     cudaStream_t st = (cudaStream_t)stream;
     smoe_peers none = {};
 #define CALL(D, C)                                                                                                     \
@@ -807,7 +806,7 @@ int smoe_grad_finalize_peers(const smoe_cfg* cfg, const smoe_peers* peers, int K
     SMOE_REQUIRE(cfg->quantization_mode != 3 || quant_ranges, "quantization_mode 3 needs quant_ranges");
     SMOE_REQUIRE(cfg->kernel_count_as_norm_l1 || l1_norm > 0.f, "l1_norm must be positive");
     const QuantSet qs = make_quantset(cfg);
-    int nb = (K_cap + 255) / 256;
+    int nb = (K_cap + kFin - 1) / kFin;
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL(D, C)                                                                                                     \
     grad_finalize_kernel<D, C, true><<<nb, 256, 0, st>>>(*cfg, nullptr, 1, K_cap, theta, indices, counts, pis_l1,       \
@@ -819,13 +818,14 @@ int smoe_grad_finalize_peers(const smoe_cfg* cfg, const smoe_peers* peers, int K
 }
 
 int smoe_adam_step(const smoe_cfg* cfg, const smoe_adam* hp, const float* alpha_dev, float* theta, const float* grads,
-                   float* adam_m, float* adam_v, int K_all, void* stream) {
+                   float* adam_m, float* adam_v, int K_all, const uint8_t* infl, uint8_t* kernel_list, void* stream) {
     SMOE_REQUIRE(cfg && hp && theta && grads && adam_m && adam_v && K_all > 0, "bad argument");
+    SMOE_REQUIRE((infl == nullptr) == (kernel_list == nullptr), "infl and kernel_list go together");
     size_t n = (size_t)K_all * nparam(cfg->d, cfg->C);
     int nb = (int)((n + 255) / 256);
     if (nb > 148 * 8) nb = 148 * 8;
     cudaStream_t st = (cudaStream_t)stream;
-#define CALL(D, C) adam_kernel<D, C><<<nb, 256, 0, st>>>(*hp, alpha_dev, theta, grads, adam_m, adam_v, n);
+#define CALL(D, C) adam_kernel<D, C><<<nb, 256, 0, st>>>(*hp, alpha_dev, theta, grads, adam_m, adam_v, n, infl, kernel_list);
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL
     return check_launch("smoe_adam_step");

@@ -19,9 +19,7 @@ __global__ void __launch_bounds__(256) xchg_publish_kernel(smoe_peers pr, const 
         for (size_t i = i0; i < n; i += step) {
             const int used = plan_cnt ? segments_used(plan_cnt[(i / P) / kGroup], num_splits) : num_splits;
             if (used == 0) continue;                       // unreached group: reach flag 0, rows never read
-            float s = 0.f;
-            for (int sp = 0; sp < used; ++sp) s += part[sp * stride + i];
-            pay[i] = s;
+            pay[i] = slab_sum(part + i, stride, used);
         }
     }
     float* tail = pay + stride;
@@ -114,6 +112,20 @@ int smoe_xchg_reduce_tail(const smoe_cfg* cfg, const smoe_peers* peers, int K_al
     if (nb > 148) nb = 148;             // every CTA spins in the barrier: all of them must be resident
     xchg_reduce_tail_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(*peers, K_all, nparam(cfg->d, cfg->C), scalars, infl);
     return check_launch("smoe_xchg_reduce_tail");
+}
+
+// Host -> device feed of a pass's target pixels on a dedicated copy stream: the copy is ordered after everything
+// already enqueued on `main_stream` (earlier readers of dst) and `done_event` fires when it has landed; the consumer
+// stream waits for that event right before smoe_loss.  Four runtime calls, no synchronisation.
+int smoe_feed(void* dst, const void* src_host, size_t bytes, void* main_stream, void* copy_stream, void* order_event,
+              void* done_event) {
+    SMOE_REQUIRE(dst && src_host && bytes > 0 && copy_stream && order_event && done_event, "bad argument");
+    cudaError_t e = cudaEventRecord((cudaEvent_t)order_event, (cudaStream_t)main_stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent((cudaStream_t)copy_stream, (cudaEvent_t)order_event, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dst, src_host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)copy_stream);
+    if (e == cudaSuccess) e = cudaEventRecord((cudaEvent_t)done_event, (cudaStream_t)copy_stream);
+    if (e != cudaSuccess) { set_error("smoe_feed: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
 }
 
 int smoe_xchg_status(const smoe_peers* peers, int32_t* epoch_and_error /*[2], host*/) {

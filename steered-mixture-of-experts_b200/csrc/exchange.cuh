@@ -109,7 +109,7 @@ __device__ __forceinline__ void reduce_tail(const smoe_peers& pr, int e, int K_a
     }
 }
 
-// Sum of the R published statistics rows of kernels [k0, k0 + nk) into shared memory (k0 a multiple of 256), fixed
+// Sum of the R published statistics rows of kernels [k0, k0 + nk) into shared memory (k0 a multiple of kFin), fixed
 // rank order, coalesced 16-byte peer loads issued R at a time.  A rank whose pixel block is not reached by a group
 // of kernels published a reach flag of 0 for it and its rows are not read at all (they hold nothing defined).
 template <int P>
@@ -117,9 +117,9 @@ __device__ __forceinline__ void gather_stats(const smoe_peers& pr, int e, int K_
                                              float* __restrict__ s_stats) {
     constexpr int F4G = kGroup * P / 4;                       // float4 per group: kGroup * P floats is a multiple of 4
     static_assert((kGroup * P) % 4 == 0, "group rows must be float4-aligned");
-    __shared__ float s_reach[SMOE_MAX_PEERS][256 / kGroup];
+    __shared__ float s_reach[SMOE_MAX_PEERS][kFin / kGroup];
     const size_t tail = (size_t)K_all * P + SMOE_NSCAL + K_all;
-    constexpr int GPB = 256 / kGroup;                          // groups per 256-kernel block
+    constexpr int GPB = kFin / kGroup;                         // groups per finalize block
     if (threadIdx.x < SMOE_MAX_PEERS * GPB) {
         const int r = threadIdx.x / GPB, gl = threadIdx.x % GPB;
         const size_t g = (size_t)k0 / kGroup + gl;

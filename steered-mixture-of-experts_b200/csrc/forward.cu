@@ -1,4 +1,7 @@
-// Fused SMoE forward (smoe_forward).  Replaces smoe.py:777-858, 899-937, 1053.
+// Fused SMoE forward (smoe_forward) and the per-pixel loss stage (smoe_loss).  Replace smoe.py:777-858 and
+// smoe.py:899-937, 1053.  The forward needs no target pixels: it leaves the mixture output r (before clip) and the
+// gate state; smoe_loss then clips, fake-quantises, compares with the target and writes dL/dr for the backward.
+// Keeping the two apart lets a step's target arrive from the host WHILE the sweeps run (the end-to-end path).
 //
 // Pixel-stationary: a CTA (128 threads, 6 resident per SM for images, 4 for video) owns a spatially compact tile of
 // SMOE_TPIX = 512 pixels (4 per thread, in registers) and streams the active kernels past it twice:
@@ -112,22 +115,16 @@ struct FwdArgs {
     const int32_t* indices;
     const int32_t* counts;
     const float* chunk_bounds;
-    const float* image;
-    const uint8_t* image_u8;
     const float* lossw;
     const float* ax[3];
-    float* res;
-    float* res_pre;
+    float* rbuf;
     int32_t* argmax;
     uint8_t* infl;
     float* pix;
     float* tile_qmin;
-    float* scalars;
-    float* partials;
-    int32_t* ticket;
     unsigned long long* pair_counts;
     int ntiles, nt1, nt2, max_chunks;
-    float tau, ltau, eps, q_scale, q_inv_scale;
+    float tau, ltau;
     float eps_cut;          // eps_bits > 0: terms below 2^-eps_cut of the normaliser may be dropped; 0 = exact
 };
 
@@ -194,12 +191,6 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
         mbar_expect_tx(&bar[buf], bytes);
         tma_load_1d(buf ? raw1 : raw0, a.packed + (size_t)ci * kChunk * PK, bytes, &bar[buf]);
     };
-
-    float lsum[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) lsum[c] = 0.f;
-    float sqsum = 0.f;
-    int nonfinite = 0;
 
     const int e1 = a.b.tile[1], e2 = a.b.tile[2];
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
@@ -456,62 +447,28 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
             });
         }
 
-        // ---- epilogue: clip, output fake-quant, loss, backward state -----------------------
+        // ---- epilogue: mixture output and gate state for the loss stage / the backward ---------
 #pragma unroll
         for (int p = 0; p < PPT; ++p) {
             const int j = p * kThreadsF + tid;
-            float g[C], gr = 0.f;
-            // per-pixel loss weight (loss_mask, smoe.py:932, 1674-1677); SMOE_PIXEL_HALO marks a pixel of the
-            // overlap halo: forwarded (gates, influence list) but outside the loss crop (smoe.py:909-923)
             const bool inb = (okmask >> p) & 1u;
             // linear pixel index in the image buffer (< 2^31, checked by the host)
             const int gpix = (lo[0] + j / (e2 * e1)) * a.b.dims[1] * a.b.dims[2] + gbase12;
-            const float lwv = (a.lossw && inb) ? a.lossw[gpix] : 1.f;
-            const bool halo = ((hmask >> p) & 1u) || lwv == SMOE_PIXEL_HALO;
-            if (inb) {
+            // a pixel of the overlap halo (smoe.py:909-923) is the interior of another window, which writes it
+            const bool halo = ((hmask >> p) & 1u) || (a.lossw && inb && a.lossw[gpix] == SMOE_PIXEL_HALO);
+            if (inb && !halo) {
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const float rv = r[p][c];
-                    if (!(fabsf(rv) <= 3.0e38f)) nonfinite = 1;
-                    const float rc = fminf(fmaxf(rv, 0.f), 1.f);                        // smoe.py:857
-                    const float kq = floorf(__fadd_rn(__fmul_rn(rc, a.q_inv_scale), 0.5f));
-                    const float rq = __fmul_rn(kq, a.q_scale);                          // smoe.py:899
-                    // 8-bit feed: the /255 of utils.py:126-128 (float32 division) happens here
-                    const size_t gi = (size_t)gpix * C + c;
-                    const float tgt = a.image_u8 ? __fdiv_rn((float)a.image_u8[gi], 255.0f) : a.image[gi];
-                    const float diff = __fsub_rn(rq, tgt);                              // smoe.py:905
-                    const float ad = fabsf(diff) - a.eps;                               // smoe.py:932
-                    if (!halo) {
-                        sqsum = fmaf(diff, diff, sqsum);
-                        lsum[c] = a.lossw ? fmaf(ad * ad, lwv, lsum[c]) : fmaf(ad, ad, lsum[c]);
-                    }
-                    const float cw = a.cfg.use_yuv ? (c == 0 ? 0.75f : 0.125f) : (1.0f / C);
-                    const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
-                    const bool ste = (rv >= 0.f) && (rv <= 1.f) && !halo;               // clip + fake-quant STE
-                    g[c] = ste ? 2.f * ad * sgn * cw * a.b.inv_count : 0.f;
-                    if (a.lossw) g[c] *= lwv;
-                    gr = fmaf(g[c], rv, gr);
-                    if (!halo) {                 // a halo pixel is the interior of another window, which writes it
-                        a.res[gi] = rq;
-                        if (a.res_pre) a.res_pre[gi] = rv;
-                    }
-                }
-                if (AMAX && !halo) a.argmax[gpix] = bestk[p];
-            } else {
-#pragma unroll
-                for (int c = 0; c < C; ++c) g[c] = 0.f;
+                for (int c = 0; c < C; ++c) a.rbuf[(size_t)gpix * C + c] = r[p][c];
+                if (AMAX) a.argmax[gpix] = bestk[p];
             }
             if (a.pix) {
-                // planes [z | qthr | gr | g_c][512] + row constants; coordinates are stored for every slot
+                // planes [z | qthr | live][512] + row constants; coordinates are stored for every slot.  The gr plane
+                // carries "S > 1e-11" (smoe.py:821) to smoe_loss, which replaces it by gr and fills the g_c planes.
                 const int RLf = a.b.tile[D - 1];
                 float* tp = a.pix + (size_t)tile * pix_stride(D, C, RLf);
-                const bool in = inb;
-                const bool live = (live_mask >> p) & 1u;                                 // smoe.py:821
                 tp[PL_Z * SMOE_TPIX + j] = D == 1 ? x0[p] : xs[D - 1];
-                tp[PL_QTHR * SMOE_TPIX + j] = in ? qthr[p] : INFINITY;   // outside the batch: w = tau * 2^(-inf) = 0
-                tp[PL_GR * SMOE_TPIX + j] = (in && live) ? gr : 0.f;
-#pragma unroll
-                for (int c = 0; c < C; ++c) tp[(PL_G + c) * SMOE_TPIX + j] = in ? g[c] : 0.f;
+                tp[PL_QTHR * SMOE_TPIX + j] = inb ? qthr[p] : INFINITY;   // outside the batch: w = 2^(-inf) = 0
+                tp[PL_GR * SMOE_TPIX + j] = (inb && ((live_mask >> p) & 1u)) ? 1.f : 0.f;
                 if (D > 1 && j % RLf == 0) {
                     const int row = j / RLf, nrows = SMOE_TPIX / RLf;
                     tp[pix_rowc_offset(C) + row] = x0[p];
@@ -533,7 +490,109 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
         }
     }
 
-    // ---- loss partials: warp shuffle -> CTA -> fixed-order sum by the last CTA -------------
+}
+
+// ---- loss stage -------------------------------------------------------------------------------------------
+// Per pixel of the batch (smoe.py:857, 899-937, 1053): res = fake_quant(clip(r)), diff = res - target, the loss and
+// squared-error partial sums, and dL/dr (straight-through where 0 <= r <= 1) for the backward: g_c and gr = sum_c g_c r_c
+// into the pixel-state planes the forward prepared.  Elementwise and HBM-bound: reads r (C floats), the target (C bytes
+// or floats), writes res (C floats) and 1 + C plane values per pixel.  Persistent grid, one fixed-order partial per CTA,
+// summed by the last CTA -- no float atomics, deterministic.
+struct LossArgs {
+    smoe_cfg cfg;
+    smoe_batch b;
+    const float* rbuf;
+    const float* image;
+    const uint8_t* image_u8;
+    const float* lossw;
+    float* res;
+    float* pix;
+    float* scalars;
+    float* partials;
+    int32_t* ticket;
+    int ntiles, nt1, nt2, pix_tstride;
+    float eps, q_scale, q_inv_scale;
+};
+
+template <int C>
+__global__ void __launch_bounds__(256) loss_kernel(const LossArgs a) {
+    const int tid = threadIdx.x;
+    const int e1 = a.b.tile[1], e2 = a.b.tile[2];
+    const int D = a.cfg.d;
+    float lsum[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) lsum[c] = 0.f;
+    float sqsum = 0.f;
+    int nonfinite = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        int tt[3], lo[3], hi[3];
+        tt[2] = tile % a.nt2;
+        tt[1] = (tile / a.nt2) % a.nt1;
+        tt[0] = tile / (a.nt2 * a.nt1);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            lo[i] = a.b.origin[i] + tt[i] * a.b.tile[i];
+            hi[i] = min(lo[i] + a.b.tile[i], a.b.origin[i] + a.b.extent[i]) - 1;
+        }
+        auto in_halo = [&](int ax, int g) {
+            const int o = a.b.origin[ax], e = o + a.b.extent[ax];
+            return ax < D && ((o > 0 && g < o + a.b.halo) || (e < a.b.dims[ax] && g >= e - a.b.halo));
+        };
+        float* tp = a.pix ? a.pix + (size_t)tile * a.pix_tstride : nullptr;
+        // slot j = i0 * (e1 e2) + i1 * e2 + i2 of the tile, as the forward numbers them; 256 is a multiple of e1 e2,
+        // so a thread keeps its (i1, i2) and steps through i0
+        const int i2 = tid % e2, i1 = (tid / e2) % e1;
+        const int g1 = lo[1] + i1, g2 = lo[2] + i2;
+        const bool in12 = g1 <= hi[1] && g2 <= hi[2];
+        const bool halo12 = a.b.halo > 0 && (in_halo(1, g1) || in_halo(2, g2));
+        const int rows_per_pass = 256 / (e1 * e2);
+        int g0 = lo[0] + tid / (e1 * e2);
+        for (int j = tid; j < SMOE_TPIX; j += 256, g0 += rows_per_pass) {
+            bool inb = in12 && g0 <= hi[0];
+            const int gpix = inb ? (g0 * a.b.dims[1] + g1) * a.b.dims[2] + g2 : 0;
+            // per-pixel loss weight (loss_mask, smoe.py:932, 1674-1677), or a sentinel: pixel not fed at all (random
+            // sub-sampling, smoe.py:1664-1667) / fed but cropped away before the loss (overlap halo, smoe.py:909-923)
+            const float lwv = (a.lossw && inb) ? a.lossw[gpix] : 1.f;
+            if (lwv == SMOE_PIXEL_ABSENT) inb = false;
+            const bool halo = lwv == SMOE_PIXEL_HALO || halo12 || (a.b.halo > 0 && in_halo(0, g0));
+            float g[C], gr = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) g[c] = 0.f;
+            if (inb && !halo) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const size_t gi = (size_t)gpix * C + c;
+                    const float rv = a.rbuf[gi];
+                    if (!(fabsf(rv) <= 3.0e38f)) nonfinite = 1;
+                    const float rc = fminf(fmaxf(rv, 0.f), 1.f);                        // smoe.py:857
+                    const float kq = floorf(__fadd_rn(__fmul_rn(rc, a.q_inv_scale), 0.5f));
+                    const float rq = __fmul_rn(kq, a.q_scale);                          // smoe.py:899
+                    // 8-bit feed: the /255 of utils.py:126-128 (float32 division) happens here
+                    const float tgt = a.image_u8 ? __fdiv_rn((float)a.image_u8[gi], 255.0f) : a.image[gi];
+                    const float diff = __fsub_rn(rq, tgt);                              // smoe.py:905
+                    const float ad = fabsf(diff) - a.eps;                               // smoe.py:932
+                    sqsum = fmaf(diff, diff, sqsum);
+                    lsum[c] = a.lossw ? fmaf(ad * ad, lwv, lsum[c]) : fmaf(ad, ad, lsum[c]);
+                    const float cw = a.cfg.use_yuv ? (c == 0 ? 0.75f : 0.125f) : (1.0f / C);
+                    const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+                    const bool ste = (rv >= 0.f) && (rv <= 1.f);                        // clip + fake-quant STE
+                    g[c] = ste ? 2.f * ad * sgn * cw * a.b.inv_count : 0.f;
+                    if (a.lossw) g[c] *= lwv;
+                    gr = fmaf(g[c], rv, gr);
+                    if (a.res) a.res[gi] = rq;
+                }
+            }
+            if (tp) {
+                const bool live = tp[PL_GR * SMOE_TPIX + j] != 0.f;                      // S > 1e-11, left by the forward
+                tp[PL_GR * SMOE_TPIX + j] = live ? gr : 0.f;
+#pragma unroll
+                for (int c = 0; c < C; ++c) tp[(PL_G + c) * SMOE_TPIX + j] = g[c];
+            }
+        }
+    }
+    // partials: warp shuffle -> CTA -> fixed-order sum by the last CTA
+    __shared__ float red[8][8];
+    __shared__ int s_last;
     float vals[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) vals[q] = 0.f;
@@ -545,15 +604,13 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
     for (int q = 0; q < 6; ++q)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) vals[q] += __shfl_down_sync(0xffffffffu, vals[q], o);
-    __syncthreads();
     if ((tid & 31) == 0)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) red[(tid >> 5) * 8 + q] = vals[q];
+        for (int q = 0; q < 8; ++q) red[tid >> 5][q] = vals[q];
     __syncthreads();
-    __shared__ int s_last;
     if (tid < 8) {
         float s = 0.f;
-        for (int wv = 0; wv < kThreadsF / 32; ++wv) s += red[wv * 8 + tid];
+        for (int wv = 0; wv < 8; ++wv) s += red[wv][tid];
         a.partials[(size_t)blockIdx.x * 8 + tid] = s;
     }
     __threadfence();
@@ -582,15 +639,10 @@ static size_t fwd_smem_bytes(int max_chunks) {
 using namespace smoe;
 
 extern "C" int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const float* packed, const int32_t* indices,
-                            const int32_t* counts, const float* chunk_bounds, int K_cap, const float* image,
-                            const uint8_t* image_u8, const float* loss_weights, const float* ax0, const float* ax1, const float* ax2,
-                            float* res, float* res_pre, int32_t* argmax, uint8_t* infl, float* pix,
-                            float* tile_qmin, float* scalars, float* partials, int32_t* ticket,
-                            unsigned long long* pair_counts, void* stream) {
-    SMOE_REQUIRE(cfg && batch && packed && indices && counts && chunk_bounds && ax0 && ax1 && res && scalars &&
-                     partials && ticket,
-                 "null argument");
-    SMOE_REQUIRE((image != nullptr) != (image_u8 != nullptr), "exactly one of image / image_u8");
+                            const int32_t* counts, const float* chunk_bounds, int K_cap, const float* loss_weights,
+                            const float* ax0, const float* ax1, const float* ax2, float* rbuf, int32_t* argmax,
+                            uint8_t* infl, float* pix, float* tile_qmin, unsigned long long* pair_counts, void* stream) {
+    SMOE_REQUIRE(cfg && batch && packed && indices && counts && chunk_bounds && ax0 && ax1 && rbuf, "null argument");
     SMOE_REQUIRE(K_cap > 0, "K_cap must be positive");
     SMOE_REQUIRE(cfg->d == 2 || ax2, "ax2 required for d == 3");
     SMOE_REQUIRE(batch->tile[0] * batch->tile[1] * batch->tile[2] == SMOE_TPIX, "tile product must be SMOE_TPIX");
@@ -608,12 +660,11 @@ extern "C" int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const 
     FwdArgs a;
     a.cfg = *cfg;
     a.b = *batch;
-    a.packed = packed; a.indices = indices; a.counts = counts; a.chunk_bounds = chunk_bounds; a.image = image;
-    a.image_u8 = image_u8;
+    a.packed = packed; a.indices = indices; a.counts = counts; a.chunk_bounds = chunk_bounds;
     a.lossw = loss_weights;
     a.ax[0] = ax0; a.ax[1] = ax1; a.ax[2] = ax2 ? ax2 : ax0;
-    a.res = res; a.res_pre = res_pre; a.argmax = argmax; a.infl = infl; a.pix = pix; a.tile_qmin = tile_qmin;
-    a.scalars = scalars; a.partials = partials; a.ticket = ticket; a.pair_counts = pair_counts;
+    a.rbuf = rbuf; a.argmax = argmax; a.infl = infl; a.pix = pix; a.tile_qmin = tile_qmin;
+    a.pair_counts = pair_counts;
     a.nt1 = (batch->extent[1] + batch->tile[1] - 1) / batch->tile[1];
     a.nt2 = (batch->extent[2] + batch->tile[2] - 1) / batch->tile[2];
     a.ntiles = smoe_num_tiles(batch);
@@ -621,9 +672,6 @@ extern "C" int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const 
     const float two_p = (float)(1 << cfg->precision);
     a.tau = 0.5f / two_p;
     a.ltau = -(float)(cfg->precision + 1);          // log2(tau), exact
-    a.eps = cfg->margin / two_p;
-    a.q_scale = 1.0f / (two_p - 1.0f);
-    a.q_inv_scale = 1.0f / a.q_scale;
     a.eps_cut = (float)cfg->eps_bits;
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
@@ -645,4 +693,38 @@ extern "C" int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const 
 #undef CALL
 #undef LAUNCH
     return check_launch("smoe_forward");
+}
+
+extern "C" int smoe_loss_partials(void) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms * 8;                 // CTAs of the loss stage at most; 8 floats each
+}
+
+extern "C" int smoe_loss(const smoe_cfg* cfg, const smoe_batch* batch, const float* rbuf, const float* image,
+                         const uint8_t* image_u8, const float* loss_weights, float* res, float* pix, float* scalars,
+                         float* partials, int32_t* ticket, void* stream) {
+    SMOE_REQUIRE(cfg && batch && rbuf && scalars && partials && ticket, "null argument");
+    SMOE_REQUIRE((image != nullptr) != (image_u8 != nullptr), "exactly one of image / image_u8");
+    SMOE_REQUIRE(batch->tile[0] * batch->tile[1] * batch->tile[2] == SMOE_TPIX, "tile product must be SMOE_TPIX");
+    SMOE_REQUIRE(cfg->C == 1 || cfg->C == 3, "1 or 3 channels");
+    SMOE_REQUIRE(256 % (batch->tile[1] * batch->tile[2]) == 0, "tile[1]*tile[2] must divide 256");
+    LossArgs a;
+    a.cfg = *cfg;
+    a.b = *batch;
+    a.rbuf = rbuf; a.image = image; a.image_u8 = image_u8; a.lossw = loss_weights; a.res = res; a.pix = pix;
+    a.scalars = scalars; a.partials = partials; a.ticket = ticket;
+    a.nt1 = (batch->extent[1] + batch->tile[1] - 1) / batch->tile[1];
+    a.nt2 = (batch->extent[2] + batch->tile[2] - 1) / batch->tile[2];
+    a.ntiles = smoe_num_tiles(batch);
+    a.pix_tstride = pix_stride(cfg->d, cfg->C, batch->tile[cfg->d - 1]);
+    const float two_p = (float)(1 << cfg->precision);
+    a.eps = cfg->margin / two_p;
+    a.q_scale = 1.0f / (two_p - 1.0f);
+    a.q_inv_scale = 1.0f / a.q_scale;
+    const int cap = smoe_loss_partials();
+    const int grid = a.ntiles < cap ? a.ntiles : cap;
+    if (cfg->C == 1) loss_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    else loss_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    return check_launch("smoe_loss");
 }

@@ -39,10 +39,20 @@ __global__ void __launch_bounds__(256) pack_count_kernel(const float* __restrict
                                                          const uint8_t* __restrict__ klist,
                                                          const int32_t* __restrict__ perm, int K_all,
                                                          int quantize_pis, QuantSet qs_in,
-                                                         const QuantDyn* __restrict__ qdyn, PackBlk* __restrict__ blk) {
+                                                         const QuantDyn* __restrict__ qdyn, PackBlk* __restrict__ blk,
+                                                         float* __restrict__ grads_clear,
+                                                         float* __restrict__ scalars_clear,
+                                                         uint8_t* __restrict__ infl_clear) {
     const QuantSet qs = qs_in.mode == 3 ? qdyn->qs : qs_in;
     constexpr int P = nparam(D, C);
     const int j = blockIdx.x * 256 + threadIdx.x;
+    // start-of-pass clears folded into this launch (zero_op of smoe.py:1612-1613, scalar block, influence flags)
+    if (grads_clear) {
+        const size_t n = (size_t)K_all * P;
+        for (size_t q = (size_t)j; q < n; q += (size_t)gridDim.x * 256) grads_clear[q] = 0.f;
+    }
+    if (scalars_clear && j < SMOE_NSCAL) scalars_clear[j] = 0.f;
+    if (infl_clear && j < K_all) infl_clear[j] = 0;
     const int i = j < K_all ? (perm ? perm[j] : j) : K_all;
     int flag = 0, numpi = 0;
     float spi = 0.f, sdiag = 0.f;
@@ -328,9 +338,13 @@ __global__ void __launch_bounds__(256) pack_fed_kernel(smoe_cfg cfg, const float
                                                        const float* __restrict__ pis,
                                                        const int32_t* __restrict__ order, int K,
                                                        float* __restrict__ packed, int32_t* __restrict__ indices,
-                                                       int32_t* __restrict__ counts) {
+                                                       int32_t* __restrict__ counts, float* __restrict__ scalars_clear,
+                                                       uint8_t* __restrict__ infl_clear, int K_all) {
     constexpr int PK = pstride(D, C);
     const int j = blockIdx.x * 256 + threadIdx.x;
+    if (scalars_clear && j < SMOE_NSCAL) scalars_clear[j] = 0.f;
+    if (infl_clear)
+        for (int q = j; q < K_all; q += gridDim.x * 256) infl_clear[q] = 0;
     if (j == 0) { counts[0] = K; counts[1] = K; counts[2] = 0; counts[3] = 0; }
     if (j >= K) return;
     const int i = order ? order[j] : j;            // fed row staged at packed row j
@@ -632,7 +646,8 @@ size_t smoe_pack_workspace_bytes(int K_all) {
 
 int smoe_pack(const smoe_cfg* cfg, const float* theta, const float* mus_grid, const void* quant_ranges,
               const uint8_t* kernel_list, const int32_t* perm, int K_all, float* packed, int32_t* indices, int32_t* pos,
-              int32_t* counts, float* regsums, float* chunk_bounds, void* workspace, void* stream) {
+              int32_t* counts, float* regsums, float* chunk_bounds, void* workspace, float* grads_clear,
+              float* scalars_clear, uint8_t* infl_clear, void* stream) {
     SMOE_REQUIRE(!cfg || !cfg->use_diff_center || mus_grid, "use_diff_center needs mus_grid");
     SMOE_REQUIRE(!cfg || cfg->quantization_mode != 3 || quant_ranges, "quantization_mode 3 needs quant_ranges");
     const QuantDyn* qdyn = (const QuantDyn*)quant_ranges;
@@ -645,7 +660,8 @@ int smoe_pack(const smoe_cfg* cfg, const float* theta, const float* mus_grid, co
     int32_t* nonpos_blk = (int32_t*)((char*)workspace + (size_t)nb * sizeof(PackBlk));
     const QuantSet qs = make_quantset(cfg);
 #define CALL(D, C)                                                                                              \
-    pack_count_kernel<D, C><<<nb, 256, 0, st>>>(theta, kernel_list, perm, K_all, cfg->quantize_pis, qs, qdyn, blk); \
+    pack_count_kernel<D, C><<<nb, 256, 0, st>>>(theta, kernel_list, perm, K_all, cfg->quantize_pis, qs, qdyn, blk,  \
+                                                grads_clear, scalars_clear, infl_clear);                          \
     pack_scatter_kernel<D, C><<<nb, 256, 0, st>>>(*cfg, theta, mus_grid, kernel_list, perm, K_all, qs, qdyn, blk, \
                                                   packed, indices, pos, counts, regsums, nonpos_blk);
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
@@ -701,12 +717,13 @@ int smoe_quant_route(const smoe_cfg* cfg, const float* theta, const void* quant_
 
 int smoe_pack_fed(const smoe_cfg* cfg, const float* A, const float* musX, const float* nu_e, const float* gamma_e,
                   const float* pis, const int32_t* order, int K, float* packed, int32_t* indices, int32_t* counts,
-                  float* chunk_bounds, void* stream) {
+                  float* chunk_bounds, float* scalars_clear, uint8_t* infl_clear, int K_all, void* stream) {
     SMOE_REQUIRE(cfg && A && musX && nu_e && gamma_e && pis && packed && indices && counts && chunk_bounds, "null argument");
     SMOE_REQUIRE(K > 0, "K must be positive");
     cudaStream_t st = (cudaStream_t)stream;
     int nb = (K + 255) / 256;
-#define CALL(D, C) pack_fed_kernel<D, C><<<nb, 256, 0, st>>>(*cfg, A, musX, nu_e, gamma_e, pis, order, K, packed, indices, counts);
+#define CALL(D, C) pack_fed_kernel<D, C><<<nb, 256, 0, st>>>(*cfg, A, musX, nu_e, gamma_e, pis, order, K, packed, indices, counts, \
+                                                              scalars_clear, infl_clear, infl_clear ? K_all : 0);
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL
     const int nchunks = (K + kChunk - 1) / kChunk;

@@ -15,6 +15,7 @@ namespace smoe {
 constexpr int kThreads = 64;                        // threads per CTA of the backward
 constexpr int kHalves = 2;                          // threads per kernel in the backward: each takes every other tile row
 constexpr int kGroup = kThreads / kHalves;          // kernels per backward CTA (= planning group)
+constexpr int kFin = 64;                            // kernels per CTA of grad_finalize (256 threads gather, 64 apply the chain rule)
 constexpr int kThreadsF = 128;                       // threads per CTA of the forward
 constexpr int kPixPerThread = SMOE_TPIX / kThreadsF; // 4 pixels per thread in the forward
 constexpr int kChunk = 128;                          // kernels staged per shared-memory chunk
@@ -122,6 +123,20 @@ __device__ __forceinline__ bool quant_in_range(float x, Nudged n) {
 __device__ __forceinline__ float ste_mask(float x, Nudged n) {
     if (n.flags & (QF_IDENT | QF_ZERO | QF_PASS | QF_ROUTE)) return 1.f;
     return quant_in_range(x, n) ? 1.f : 0.f;
+}
+// sum_{sp < used} p[sp * stride] in split order; the loads of 8 slabs are issued before the first add (a dependent
+// load-add chain would serialise one memory latency per slab)
+__device__ __forceinline__ float slab_sum(const float* __restrict__ p, size_t stride, int used) {
+    float acc = 0.f;
+    for (int sp = 0; sp < used; sp += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (sp + u < used) ? p[(size_t)(sp + u) * stride] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (sp + u < used) acc += v[u];
+    }
+    return acc;
 }
 __device__ __forceinline__ float ex2f(float x) {
     float y;

@@ -318,10 +318,9 @@ class Smoe:
     def _choose_blocks(self, world, halo_weight=0.5):
         """One rectangular block per rank, rank = row-major index in the block grid.  A rank's work grows with its
         block PLUS the strip around it that foreign kernels reach into (the backward visits those tiles, the forward
-        sweeps those kernels), so (a) the grid factorisation minimises prod_a (w_a + halo_a) -- 2x4 rather than 8x1
-        bands on a 1080p frame, 2x2x2 rather than frame bands on a video whose kernels span 12 frames -- and (b) the
-        cuts are placed so that blocks with fewer interior sides are wider (work-balanced, not equal, cuts).  Cuts
-        are rounded to the tile grid so that no rank gets partial tiles it would not have had otherwise."""
+        sweeps those kernels), so the grid factorisation minimises prod_a (w_a + halo_a) -- 2x4 rather than 8x1 bands
+        on a 1080p frame.  The cuts themselves are equal and rounded to the tile grid (no rank gets partial tiles it
+        would not have had otherwise): the time of a rank follows its pixel count."""
         d = self.dim_domain
         n = self.image.shape[:d]
         tile = (16, 32) if d == 2 else (8, 8, 8)
@@ -337,7 +336,12 @@ class Smoe:
                         yield (f,) + rest
 
         best, best_cost = None, None
-        for fac in factorisations(world, d):
+        forced = os.environ.get("SMOE_BLOCK_GRID")              # e.g. "2,4": override the factorisation (experiments)
+        if forced:
+            best = tuple(int(v) for v in forced.split(","))
+            if len(best) != d or int(np.prod(best)) != world:
+                raise ValueError("SMOE_BLOCK_GRID must have one factor per domain axis and multiply to the world size")
+        for fac in ([] if forced else factorisations(world, d)):
             if any(n[a] // fac[a] < 1 for a in range(d)):
                 continue
             cost = 1.0
@@ -349,9 +353,9 @@ class Smoe:
         cuts = []
         for a in range(d):
             r = best[a]
-            rc = min(reach[a], n[a] / (2.0 * r))     # the model saturates once the halo is as wide as the block
-            eff = (n[a] + rc * (2 * r - 2)) / r
-            widths = [max(eff - rc * ((i > 0) + (i < r - 1)), 1.0) for i in range(r)]
+            # equal cuts: measured on configs 3 and 4, a rank's time follows its pixel count far more closely than
+            # the number of kernels that reach in from outside (a corner block 1.5x as wide ran 1.7x as long)
+            widths = [1.0] * r
             scale = n[a] / sum(widths)
             edges, acc = [0], 0.0
             for i in range(r - 1):
@@ -427,7 +431,9 @@ class Smoe:
         self._dims3 = tuple(self._local_shape) + (1,) * (3 - d)
         self._d_image = torch.from_numpy(np.ascontiguousarray(self.image[self._local_slices])).to(dev)
         self._d_image_u8 = None
-        self._use_u8 = False                                 # set_image() fed 8-bit pixels: the forward reads them
+        self._use_u8 = False                                 # set_image() fed 8-bit pixels: the loss stage reads them
+        self._copy_stream = self._img_event = None           # set_image()'s host->device copy, overlapped with the forward
+        self._img_pending = False
         self._d_loss_mask = None
         if self.loss_mask is not None:                       # per-pixel loss weights (smoe.py:550, 932, 1674-1677)
             lm = np.asarray(self.loss_mask, dtype=np.float32).reshape(self.image.shape[:-1])
@@ -441,7 +447,7 @@ class Smoe:
         self._h_axes = axes
         npx = int(np.prod(self._local_shape))
         self._d_res = torch.zeros((npx, Cc), dtype=f32, device=dev)
-        self._d_res_pre = None
+        self._d_res_pre = torch.zeros((npx, Cc), dtype=f32, device=dev)      # mixture output before clip (the forward's rbuf)
         self._d_argmax = torch.zeros((npx,), dtype=torch.int32, device=dev)
         # batches (smoe.py:1643: sliding_window order, first axis outermost)
         self._tile = self._choose_tile()
@@ -487,7 +493,6 @@ class Smoe:
             self._phantom = (pb, torch.full((1,), _ffi.PIXEL_HALO, dtype=f32, device=dev))
         self._ssim_ws = None
         if self.ssim_opt:
-            self._d_res_pre = torch.zeros_like(self._d_res)      # the SSIM gradient needs the pre-clip values (STE)
             nbytes = max(L.smoe_ssim_loss_workspace_bytes(C.byref(self._cfg), C.byref(b)) for b in self._batches)
             self._ssim_ws = torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=dev)
         nb = len(self._batches)
@@ -515,7 +520,7 @@ class Smoe:
         self._pair_counts = None        # uint64[8] executed-pair counters, enable_pair_counts()
         self._chunk_bounds = torch.zeros(((K + 127) // 128, 12), dtype=f32, device=dev)
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        self._partials = torch.zeros((8 * sms * 8,), dtype=f32, device=dev)
+        self._partials = torch.zeros((8 * int(L.smoe_loss_partials()),), dtype=f32, device=dev)
         self._ticket = torch.zeros((4,), dtype=torch.int32, device=dev)
         self._pack_ws = torch.zeros((L.smoe_pack_workspace_bytes(K) + 15) // 4, dtype=torch.int32, device=dev)
         # Pixel splits of the backward (split s owns tiles s, s+NS, ...): sized for the kernel groups that will have
@@ -534,7 +539,10 @@ class Smoe:
         if self._world > 1 and not self._emulated:
             self._open_peer_windows()
         self._host_stats = torch.zeros((nb, _ffi.STATS_STRIDE), dtype=f32).pin_memory()
+        self._host_f32 = self._host_stats.numpy()                       # views of the pinned block
+        self._host_i32 = self._host_stats.view(torch.int32).numpy()
         self._alpha_host = torch.zeros((4,), dtype=f32).pin_memory()
+        self._alpha_np = self._alpha_host.numpy()
         self._alpha_dev = torch.zeros((4,), dtype=f32, device=dev)
         self._graphs = {}
         # one CUDA graph per training-step signature, on one GPU and sharded alike (the exchange is stream-ordered
@@ -599,20 +607,35 @@ class Smoe:
         the forward kernel's epilogue) or float32 in [0,1], shape of the local block, ideally pinned; the copy is
         asynchronous on the current stream."""
         t = pixels if isinstance(pixels, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pixels))
-        if tuple(t.shape) != tuple(self._d_image.shape):
+        if t.shape != self._d_image.shape:
             raise ValueError(f"expected the local block {tuple(self._d_image.shape)}, got {tuple(t.shape)}")
         if t.dtype == torch.uint8:
             if self.ssim_opt:
                 raise NotImplementedError("8-bit feed with ssim_opt: feed float32 pixels")
             if self._d_image_u8 is None:
                 self._d_image_u8 = torch.empty(self._d_image.shape, dtype=torch.uint8, device=self.device)
-            self._d_image_u8.copy_(t, non_blocking=True)
-            self._use_u8 = True
+            dst, self._use_u8 = self._d_image_u8, True
         elif t.dtype == torch.float32:
-            self._d_image.copy_(t, non_blocking=True)
-            self._use_u8 = False
+            dst, self._use_u8 = self._d_image, False
         else:
             raise ValueError("set_image takes uint8 or float32 pixels")
+        if t.is_cuda or not t.is_contiguous():
+            raise ValueError("set_image takes a contiguous host tensor (pinned for an asynchronous copy)")
+        # The copy runs on its own stream: the next pass's pack and forward sweeps need no target pixels and overlap
+        # it; only the loss stage waits for the event (run_batched).  smoe_feed orders it after earlier readers.
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._img_event = torch.cuda.Event()
+            self._order_event = torch.cuda.Event()
+            for ev in (self._img_event, self._order_event):      # torch creates the CUDA event lazily: force it
+                ev.record()
+            self._feed_handles = (C.c_void_p(self._copy_stream.cuda_stream), C.c_void_p(self._order_event.cuda_event),
+                                  C.c_void_p(self._img_event.cuda_event))
+        self._feed_src = t                                        # keep the host buffer alive until the copy is consumed
+        cs, oe, de = self._feed_handles
+        check(lib().smoe_feed(C.c_void_p(dst.data_ptr()), C.c_void_p(t.data_ptr()), C.c_size_t(t.numel() * t.element_size()),
+                              stream_ptr(), cs, oe, de), "smoe_feed")
+        self._img_pending = True
         self.valid = self.qvalid = False
 
     def _refresh_perm(self):
@@ -632,10 +655,9 @@ class Smoe:
         return np.sort(self._indices[:K].cpu().numpy())
 
     def _enable_res_pre(self):
-        """Keep the mixture output before clip / output quantisation (diagnostics and parity tests;
-        SURVEY.md decision D4 compares reconstructions pre-quantisation)."""
-        if self._d_res_pre is None:
-            self._d_res_pre = torch.zeros_like(self._d_res)
+        """The mixture output before clip / output quantisation is always kept (it is what smoe_forward hands to
+        smoe_loss; SURVEY.md decision D4 compares reconstructions pre-quantisation).  Kept for callers of round 1."""
+        return None
 
     def get_pre_clip_reconstruction(self):
         self._enable_res_pre()
@@ -692,9 +714,9 @@ class Smoe:
         # TF's valid serialisations (the test-side restatement pins the same order).
         for g, (opt, tr) in enumerate(zip(opts, trainable)):
             on = tr and not opt._lr == 0
-            self._alpha_host[g] = opt._step_alpha() if on else 0.0
+            self._alpha_np[g] = opt._step_alpha() if on else 0.0
 
-    def _adam_launch(self):
+    def _adam_launch(self, fuse_klist=False):
         hp = Adam()
         for g, opt in enumerate([self.optimizer1, self.optimizer2, self.optimizer3]):
             hp.alpha[g] = 0.0
@@ -704,7 +726,8 @@ class Smoe:
         self._alpha_dev.copy_(self._alpha_host, non_blocking=True)
         check(lib().smoe_adam_step(C.byref(self._cfg), C.byref(hp), ptr(self._alpha_dev), ptr(self._theta),
                                    ptr(self._grads), ptr(self._adam_m), ptr(self._adam_v), self.start_pis,
-                                   stream_ptr()), "smoe_adam_step")
+                                   ptr(self._infl) if fuse_klist else ptr(None),
+                                   ptr(self._klist[0]) if fuse_klist else ptr(None), stream_ptr()), "smoe_adam_step")
         self.gpu_launches += 1
 
     # ------------------------------------------------------------------------------------------
@@ -755,12 +778,23 @@ class Smoe:
             else:
                 if state == "warm":
                     l0 = self.gpu_launches
+                    if self._img_pending:               # an event of another stream cannot be awaited inside a capture
+                        torch.cuda.current_stream().wait_event(self._img_event)
+                        self._img_pending = False
                     torch.cuda.synchronize()
                     try:
-                        g = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(g):
+                        # two graphs, split where the target pixels are first needed (before the loss stage): a
+                        # pending set_image() copy is awaited BETWEEN them, so it overlaps pack + forward
+                        graphs = []
+                        for phase in (("pre", "post") if len(self._batches) == 1 else ()):
+                            g = torch.cuda.CUDAGraph()
+                            with torch.cuda.graph(g):
+                                self._enqueue(pis_l1, u_l1, True, False, False, lossw=lossw, phase=phase)
+                            graphs.append(g)
+                        gall = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(gall):
                             self._enqueue(pis_l1, u_l1, True, False, False, lossw=lossw)
-                        state = (g, self.gpu_launches - l0)
+                        state = (gall, graphs, (self.gpu_launches - l0) // (2 if graphs else 1))
                     except Exception as exc:
                         # Loud by default: a silent eager fallback would hide a 2x slower step.  A sharded model
                         # cannot fall back at all: its peers would replay a graph while this rank runs eagerly --
@@ -776,15 +810,27 @@ class Smoe:
                     if state is not None:
                         self._graphs[key] = state
                 if state is not None:
-                    state[0].replay()
-                    self.gpu_launches += state[1]
+                    if self._img_pending and state[1]:
+                        state[1][0].replay()
+                        torch.cuda.current_stream().wait_event(self._img_event)
+                        self._img_pending = False
+                        state[1][1].replay()
+                    else:
+                        if self._img_pending:
+                            torch.cuda.current_stream().wait_event(self._img_event)
+                            self._img_pending = False
+                        state[0].replay()
+                    self.gpu_launches += state[2]
                     replayed = True
         if not replayed:
             self._enqueue(pis_l1, u_l1, train, update_reconstruction, with_quantized_params,
                           lossw=lossw, batches=batches)
         torch.cuda.current_stream().synchronize()
-        h = self._host_stats.numpy().astype(np.float64)
-        h[:, _ffi.NSCAL:_ffi.NSCAL + 4] = self._host_stats.view(torch.int32).numpy()[:, _ffi.NSCAL:_ffi.NSCAL + 4]
+        # plain Python lists: this runs after every step, and NumPy temporaries would cost more than the arithmetic
+        h = self._host_f32.tolist()
+        hi = self._host_i32.tolist()
+        for row, irow in zip(h, hi):
+            row[_ffi.NSCAL:_ffi.NSCAL + 4] = irow[_ffi.NSCAL:_ffi.NSCAL + 4]
         norm = float(self.start_pis)
         Cc = self.image.shape[-1]
         loss_val = mse_val = 0.0
@@ -792,24 +838,24 @@ class Smoe:
         for ii, b in enumerate(batches):
             inv_n = float(b.inv_count)
             if self.ssim_opt:                              # smoe.py:1006-1010
-                per = [h[ii, 8 + c] / self._batch_npix[ii] for c in range(Cc)]
+                per = [h[ii][8 + c] / self._batch_npix[ii] for c in range(Cc)]
                 ssim = (sum(p * wgt for p, wgt in zip(per, (6, 1, 1))) / 8 if Cc == 3 else per[0]) if self.use_yuv \
                     else sum(per) / Cc
                 lp = 1 - ssim
             elif self.use_yuv:                             # smoe.py:933-935
-                lp = 6 / 8 * h[ii, 0] * inv_n + 1 / 8 * sum(h[ii, c] * inv_n for c in range(1, Cc))
+                lp = 6 / 8 * h[ii][0] * inv_n + 1 / 8 * sum(h[ii][c] * inv_n for c in range(1, Cc))
             else:
-                lp = sum(h[ii, c] for c in range(Cc)) * inv_n / Cc
-            l1n = max(h[ii, _ffi.NSCAL + 1], 1.0) if self.kernel_count_as_norm_l1 else norm      # smoe.py:1022-1025
-            loss_b = lp + pis_l1 * h[ii, _ffi.NSCAL + 4] / l1n + u_l1 * h[ii, _ffi.NSCAL + 5]
-            mse_b = h[ii, 4] * inv_n / Cc * ((2 ** self.precision) ** 2)
-            if h[ii, 5] > 0:
+                lp = sum(h[ii][c] for c in range(Cc)) * inv_n / Cc
+            l1n = max(h[ii][_ffi.NSCAL + 1], 1.0) if self.kernel_count_as_norm_l1 else norm      # smoe.py:1022-1025
+            loss_b = lp + pis_l1 * h[ii][_ffi.NSCAL + 4] / l1n + u_l1 * h[ii][_ffi.NSCAL + 5]
+            mse_b = h[ii][4] * inv_n / Cc * ((2 ** self.precision) ** 2)
+            if h[ii][5] > 0:
                 loss_b = float("nan")
             frac = 1.0 if self._world > 1 else self._batch_npix[ii] / self.num_pixel
             loss_val += loss_b * frac                       # smoe.py:1758-1759
             mse_val += mse_b * frac
-            num_pi = int(h[ii, _ffi.NSCAL + 1])
-        self._last_nonpos = int(h[:, _ffi.NSCAL + 2].sum())
+            num_pi = int(h[ii][_ffi.NSCAL + 1])
+        self._last_nonpos = int(sum(row[_ffi.NSCAL + 2] for row in h))
         if self._last_nonpos > 0 and not getattr(self, "_warned_nonpos", False):
             # pi * prod(diag A) < 0 with use_determinant: the reference gives such a kernel a NEGATIVE weight n_w
             # (smoe.py:809-820); the log-domain kernels evaluate it with |coef| -- say so once
@@ -869,18 +915,20 @@ class Smoe:
             probs.append(e / e.sum())
         self.random_sampling_per_batch = probs
 
-    def _enqueue(self, pis_l1, u_l1, train, update_reconstruction, with_quantized_params, lossw=None, batches=None):
+    def _enqueue(self, pis_l1, u_l1, train, update_reconstruction, with_quantized_params, lossw=None, batches=None,
+                 phase="all"):
         """Every launch of one run_batched call, asynchronous on the current stream (capturable, also sharded:
-        the exchange is stream-ordered kernels over peer memory)."""
+        the exchange is stream-ordered kernels over peer memory).  phase "pre" = everything that needs no target
+        pixels (staging, forward), "post" = the rest (loss stage, backward, exchange, finalize, Adam); only one-batch
+        passes are split, so that a pending set_image() copy can be awaited between the halves."""
         L, st = lib(), stream_ptr()
         K = self.start_pis
         batches = self._batches if batches is None else batches
         sharded = self._world > 1 and not self._emulated
         pc = ptr(self._pair_counts)
-        check(L.smoe_step_begin(ptr(self._grads) if train else ptr(None), C.c_size_t(self._grads.numel()),
-                                ptr(self._stats), len(self._batches), _ffi.STATS_STRIDE, ptr(self._infl), K, st),
-              "smoe_step_begin")
-        self.gpu_launches += 1
+        pre, post = phase in ("all", "pre"), phase in ("all", "post")
+        assert phase == "all" or len(batches) == 1
+        # (the start-of-pass clears -- gradient accumulators, scalar blocks, influence flags -- ride in smoe_pack)
         fed = with_quantized_params and update_reconstruction
         if fed:
             rp = {k: torch.as_tensor(np.ascontiguousarray(np.asarray(v, dtype=np.float32)), device=self.device)
@@ -894,46 +942,55 @@ class Smoe:
                                       ptr(fkeys), st), "smoe_spatial_keys")
             forder = torch.sort(fkeys, stable=True).indices.to(torch.int32)
         norm = float(self.start_pis)
-        if self._qdyn is not None and not fed:
+        if pre and self._qdyn is not None and not fed:
             check(L.smoe_quant_ranges(C.byref(self._cfg), ptr(self._theta), K, int(self.train_musx), ptr(self._qdyn), st),
                   "smoe_quant_ranges")
             self.gpu_launches += 1
-        img_f32 = ptr(None) if self._use_u8 else ptr(self._d_image)
-        img_u8 = ptr(self._d_image_u8) if self._use_u8 else ptr(None)
         ax2 = ptr(self._d_axes[2]) if self.dim_domain == 3 else ptr(None)
         for ii, b in enumerate(batches):
             counts, regs, scal = self._counts[ii], self._regsums[ii], self._scalars[ii]
             tq = self._tile_qmin[ii]
-            if fed:
-                check(L.smoe_pack_fed(C.byref(self._cfg), ptr(rp["A"]), ptr(rp["musX"]), ptr(rp["nu_e"]),
-                                      ptr(rp["gamma_e"]), ptr(rp["pis"]), ptr(forder), Kf, ptr(self._packed),
-                                      ptr(self._indices), ptr(counts), ptr(self._chunk_bounds), st), "smoe_pack_fed")
-                regs.zero_()
-                self.gpu_launches += 3
-            else:
-                check(L.smoe_pack(C.byref(self._cfg), ptr(self._theta), ptr(self._mus_grid), ptr(self._qdyn),
-                                  ptr(self._klist[ii]), ptr(self._perm), K, ptr(self._packed),
-                                  ptr(self._indices), ptr(self._pos), ptr(counts), ptr(regs), ptr(self._chunk_bounds),
-                                  ptr(self._pack_ws), st), "smoe_pack")
-                self.gpu_launches += 3
-            if ii > 0:
-                self._infl.zero_()
-            check(L.smoe_forward(C.byref(self._cfg), C.byref(b), ptr(self._packed), ptr(self._indices), ptr(counts),
-                                 ptr(self._chunk_bounds), K, img_f32, img_u8, ptr(lossw), ptr(self._d_axes[0]),
-                                 ptr(self._d_axes[1]), ax2, ptr(self._d_res), ptr(self._d_res_pre),
-                                 ptr(self._d_argmax) if update_reconstruction else ptr(None),
-                                 ptr(self._infl), ptr(self._pix) if train else ptr(None), ptr(tq),
-                                 ptr(scal), ptr(self._partials), ptr(self._ticket), pc, st), "smoe_forward")
-            self.gpu_launches += 1
-            if self._batch_phantom[ii]:
-                pb, halo1 = self._phantom
-                check(L.smoe_forward(C.byref(self._cfg), C.byref(pb), ptr(self._packed), ptr(self._indices),
-                                     ptr(counts), ptr(self._chunk_bounds), K, img_f32, img_u8, ptr(halo1),
-                                     ptr(self._d_axes[0]), ptr(self._d_axes[1]), ax2,
-                                     ptr(self._d_res), ptr(None), ptr(None), ptr(self._infl), ptr(None), ptr(None),
-                                     ptr(scal), ptr(self._partials), ptr(self._ticket), ptr(None), st),
-                      "smoe_forward (phantom)")
+            if pre:
+                if fed:
+                    check(L.smoe_pack_fed(C.byref(self._cfg), ptr(rp["A"]), ptr(rp["musX"]), ptr(rp["nu_e"]),
+                                          ptr(rp["gamma_e"]), ptr(rp["pis"]), ptr(forder), Kf, ptr(self._packed),
+                                          ptr(self._indices), ptr(counts), ptr(self._chunk_bounds), ptr(scal),
+                                          ptr(self._infl), K, st), "smoe_pack_fed")
+                    regs.zero_()
+                    self.gpu_launches += 3
+                else:
+                    check(L.smoe_pack(C.byref(self._cfg), ptr(self._theta), ptr(self._mus_grid), ptr(self._qdyn),
+                                      ptr(self._klist[ii]), ptr(self._perm), K, ptr(self._packed),
+                                      ptr(self._indices), ptr(self._pos), ptr(counts), ptr(regs), ptr(self._chunk_bounds),
+                                      ptr(self._pack_ws), ptr(self._grads) if (train and ii == 0) else ptr(None),
+                                      ptr(scal), ptr(self._infl), st), "smoe_pack")
+                    self.gpu_launches += 3
+                check(L.smoe_forward(C.byref(self._cfg), C.byref(b), ptr(self._packed), ptr(self._indices), ptr(counts),
+                                     ptr(self._chunk_bounds), K, ptr(lossw), ptr(self._d_axes[0]), ptr(self._d_axes[1]),
+                                     ax2, ptr(self._d_res_pre), ptr(self._d_argmax) if update_reconstruction else ptr(None),
+                                     ptr(self._infl), ptr(self._pix) if train else ptr(None), ptr(tq), pc, st),
+                      "smoe_forward")
                 self.gpu_launches += 1
+                if self._batch_phantom[ii]:
+                    pb, halo1 = self._phantom
+                    check(L.smoe_forward(C.byref(self._cfg), C.byref(pb), ptr(self._packed), ptr(self._indices),
+                                         ptr(counts), ptr(self._chunk_bounds), K, ptr(halo1), ptr(self._d_axes[0]),
+                                         ptr(self._d_axes[1]), ax2, ptr(self._d_res_pre), ptr(None), ptr(self._infl),
+                                         ptr(None), ptr(None), ptr(None), st), "smoe_forward (phantom)")
+                    self.gpu_launches += 1
+            if not post:
+                continue
+            if phase == "all" and self._img_pending:      # eager pass right after set_image(): the loss needs the pixels
+                torch.cuda.current_stream().wait_event(self._img_event)
+                self._img_pending = False
+            check(L.smoe_loss(C.byref(self._cfg), C.byref(b), ptr(self._d_res_pre),
+                              ptr(None) if self._use_u8 else ptr(self._d_image),
+                              ptr(self._d_image_u8) if self._use_u8 else ptr(None), ptr(lossw),
+                              # the quantised reconstruction itself is only needed by callers that read it
+                              ptr(self._d_res) if (update_reconstruction or self.ssim_opt or not train) else ptr(None),
+                              ptr(self._pix) if train else ptr(None), ptr(scal), ptr(self._partials), ptr(self._ticket),
+                              st), "smoe_loss")
+            self.gpu_launches += 1
             if self.ssim_opt:
                 check(L.smoe_ssim_loss(C.byref(self._cfg), C.byref(b), ptr(self._d_res), ptr(self._d_image),
                                        ptr(self._d_res_pre), ptr(self._pix) if train else ptr(None), ptr(scal),
@@ -969,15 +1026,18 @@ class Smoe:
                                            C.c_float(norm), C.c_float(float(u_l1)), ptr(self._grads), st),
                       "smoe_grad_finalize")
                 self.gpu_launches += 1
-            if not with_quantized_params:                 # smoe.py:1763-1766
+            # kernel_list <- influential kernels (smoe.py:1763-1766); a one-batch training pass does it inside the Adam launch
+            if not with_quantized_params and not (train and len(batches) == 1):
                 check(L.smoe_update_kernel_list(ptr(self._infl), ptr(self._klist[ii]), K, st), "smoe_update_kernel_list")
                 self.gpu_launches += 1
+        if not post:
+            return
         if train and self._qdyn is not None:             # clipped gradients of the plain groups -> extreme elements
             check(L.smoe_quant_route(C.byref(self._cfg), ptr(self._theta), ptr(self._qdyn), K, ptr(self._grads), st),
                   "smoe_quant_route")
             self.gpu_launches += 1
         if train:
-            self._adam_launch()
+            self._adam_launch(fuse_klist=len(batches) == 1 and not with_quantized_params)
         # one small device->host read per call: scalars, counts, regulariser sums
         self._host_stats.copy_(self._stats, non_blocking=True)
 

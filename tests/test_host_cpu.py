@@ -129,10 +129,13 @@ def test_c_abi_argument_errors_are_reported_without_a_device(libpath):
     cfg.d, cfg.C, cfg.precision = 2, 3, 8
     b = _ffi.Batch()
     assert h.smoe_pack(ctypes.byref(cfg), null, null, null, null, null, 16, null, null, null, null, null, null, null,
-                       null) == -1
+                       null, null, null, null) == -1
     assert b"null argument" in h.smoe_last_error()
     assert h.smoe_forward(null, null, null, null, null, null, 16, null, null, null, null, null, null, null, null, null,
-                          null, null, null, null, null, null, null, null) == -1
+                          null, null) == -1
+    assert h.smoe_loss(ctypes.byref(cfg), ctypes.byref(b), one16 := (ctypes.c_float * 16)(), one16, one16, null, one16,
+                       null, one16, one16, (ctypes.c_int32 * 1)(), null) == -1
+    assert b"exactly one of image" in h.smoe_last_error()
     assert h.smoe_backward(null, null, null, null, 0, null, null, null, null, null, 1, null, null, null, null) == -1
     # the peer exchange validates its peer set before touching CUDA
     pr = _ffi.Peers()
@@ -140,17 +143,18 @@ def test_c_abi_argument_errors_are_reported_without_a_device(libpath):
     assert h.smoe_xchg_publish(ctypes.byref(cfg), ctypes.byref(pr), one8 := (ctypes.c_int32 * 8)(), 4, 1, null, null,
                                (ctypes.c_float * 16)(), (ctypes.c_ubyte * 4)(), null) == -1
     assert b"bad peer set" in h.smoe_last_error()
-    assert h.smoe_xchg_window_bytes(32768, 15) == 256 + 2 * 4 * (32768 * 15 + 16 + 32768 + 512)
-    assert h.smoe_adam_step(ctypes.byref(cfg), null, null, null, null, null, null, 0, null) == -1
+    assert h.smoe_xchg_window_bytes(32768, 15) == 256 + 2 * 4 * (32768 * 15 + 16 + 32768 + 1024)
+    assert h.smoe_adam_step(ctypes.byref(cfg), null, null, null, null, null, null, 0, null, null, null) == -1
     assert h.smoe_ssim_loss(ctypes.byref(cfg), ctypes.byref(b), null, null, null, null, null, null, null) == -1
     cfg3 = _ffi.Cfg()
     cfg3.d, cfg3.C, cfg3.quantization_mode = 2, 3, 3
     one = (ctypes.c_float * 64)()
-    assert h.smoe_pack(ctypes.byref(cfg3), one, null, null, one, null, 4, one, one, one, one, one, one, one, null) == -1
+    assert h.smoe_pack(ctypes.byref(cfg3), one, null, null, one, null, 4, one, one, one, one, one, one, one, null, null,
+                       null, null) == -1
     assert b"quant_ranges" in h.smoe_last_error()
     assert h.smoe_quant_ranges(ctypes.byref(cfg), one, 4, 1, one, null) == -1      # only meaningful for mode 3
     assert h.smoe_quant_ranges_bytes() > 0
     # the host mirror raises with the library's message
     with pytest.raises(RuntimeError, match="null argument"):
         _ffi.check(h.smoe_pack(ctypes.byref(cfg), null, null, null, null, null, 16, null, null, null, null, null, null,
-                               null, null), "smoe_pack")
+                               null, null, null, null, null), "smoe_pack")

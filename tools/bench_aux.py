@@ -62,7 +62,7 @@ Kall, P, PK = smoe.start_pis, smoe._P, smoe._PK
 smoe._theta[:, smoe._off["pi"]] = torch.where(torch.rand(Kall, device="cuda") < 0.7, 1.0, -1.0)
 ms_pack = timeit(lambda: check(lib().smoe_pack(C.byref(smoe._cfg), ptr(smoe._theta), ptr(smoe._mus_grid), ptr(None), ptr(smoe._klist[0]), ptr(smoe._perm), Kall, ptr(smoe._packed),
                                                ptr(smoe._indices), ptr(smoe._pos), ptr(smoe._counts[0]), ptr(smoe._regsums[0]),
-                                               ptr(smoe._chunk_bounds), ptr(smoe._pack_ws), stream_ptr()), "pack"))
+                                               ptr(smoe._chunk_bounds), ptr(smoe._pack_ws), ptr(None), ptr(None), ptr(None), stream_ptr()), "pack"))
 Ka = int(smoe._counts[0, 0])
 alg_pack = Kall * (P * 4 + 1) + Ka * (PK * 4 + 4) + Kall * 4
 out["compaction_518k"] = {"ms": ms_pack, "K_all": Kall, "K_active": Ka, "algorithmic_GBps": alg_pack / ms_pack / 1e6,

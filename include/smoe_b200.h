@@ -318,6 +318,20 @@ int smoe_xchg_reduce_tail(const smoe_cfg* cfg, const smoe_peers* peers, int K_al
                           void* stream);
 int smoe_xchg_status(const smoe_peers* peers, int32_t* epoch_and_error /*[2], host memory; synchronous*/);
 
+/* Halo pull for SSIM as the loss on a pixel-sharded model ("a 5-pixel halo across shards"; the
+ * ring is 10 pixels wide because both the windows of the ring's inner 5 positions and their own 5-pixel support are
+ * needed for the gradient of the block's pixels): every rank's `res` buffer covers its block plus the ring and lives
+ * in peer-mapped memory (smoe_peer_alloc / _export / _open); after smoe_loss, smoe_halo_pull waits until all ranks
+ * have written their blocks (second flag barrier of the windows) and copies the ring from the owners' buffers.
+ * Geometry in image coordinates, unused axes [0,1). */
+typedef struct smoe_halo_map {
+    int32_t world, rank, d, C;
+    int32_t blk_lo[SMOE_MAX_PEERS][3], blk_hi[SMOE_MAX_PEERS][3];     /* each rank's block                         */
+    int32_t buf_lo[SMOE_MAX_PEERS][3], buf_dims[SMOE_MAX_PEERS][3];   /* each rank's resident buffer: origin, extents */
+    void*   res[SMOE_MAX_PEERS];                                      /* each rank's res buffer as mapped here      */
+} smoe_halo_map;
+int smoe_halo_pull(const smoe_peers* peers, const smoe_halo_map* map, void* stream);
+
 /* Host -> device feed of a pass's target pixels (pinned host memory) on a dedicated copy stream, overlapping whatever
  * the main stream does until smoe_loss: the copy is ordered after the work already enqueued on main_stream
  * (order_event is recorded there and awaited by copy_stream) and done_event fires when the pixels have landed --
@@ -346,11 +360,22 @@ int    smoe_ssim(int d, const int32_t dims[3], int C, const float* a, const floa
  * (res, image), SYMMETRIC-padded by 5 at the rectangle's borders, ACCUMULATED into scalars[8 + c] (the caller
  * divides by the number of positions and forms 1 - sum_c w_c ssim_c); and, when pix != NULL, d loss / d res
  * pushed through the output fake-quant and the clip (straight-through where 0 <= res_pre <= 1) and written
- * over the g_c / gr planes of the backward state that smoe_forward filled for the squared-error loss.
- *   res, image: [dims..][C] as in smoe_loss; res_pre: the rbuf of smoe_forward */
+ * over the g_c / gr planes of the backward state that smoe_loss filled for the squared-error loss.
+ *   res, image: [dims..][C] as in smoe_loss; res_pre: the rbuf of smoe_forward
+ *   region   optional (NULL: the batch's loss rectangle, as above).  Pixel-sharded SSIM: the resident buffers hold the
+ *            rank's block PLUS a ring of 10 halo pixels (res pulled from the neighbours by smoe_halo_pull, the target
+ *            static); the windows are centred on the positions of `region` (block + ring, clipped to the image, so the
+ *            symmetric padding only ever reflects at true image borders), while the SSIM sum and the gradient run over
+ *            the batch rectangle only -- every position of the image is counted by exactly one rank, and a window
+ *            that straddles a block border sees the neighbour's pixels.  inv_count = 1 / positions of the WHOLE image. */
+typedef struct smoe_ssim_region {
+    int32_t lo[3], n[3];     /* compute rectangle inside the resident buffer (contains the batch rectangle) */
+    float   inv_count;
+} smoe_ssim_region;
 size_t smoe_ssim_loss_workspace_bytes(const smoe_cfg* cfg, const smoe_batch* batch);
-int    smoe_ssim_loss(const smoe_cfg* cfg, const smoe_batch* batch, const float* res, const float* image,
-                      const float* res_pre, float* pix, float* scalars, void* workspace, void* stream);
+int    smoe_ssim_loss(const smoe_cfg* cfg, const smoe_batch* batch, const smoe_ssim_region* region, const float* res,
+                      const float* image, const float* res_pre, float* pix, float* scalars, void* workspace,
+                      void* stream);
 
 /* sum over all elements of (a-b)^2 -> out[0] (double accumulation in fixed order);
  * PSNR = 10 log10((2^p)^2 / (mean * (2^p)^2)) on the host (plotter.py:14-15, smoe.py:1053). */

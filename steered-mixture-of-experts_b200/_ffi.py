@@ -24,7 +24,7 @@ EXPORTS = [
     "smoe_backward", "smoe_suggest_splits", "smoe_reduce_splits", "smoe_grad_finalize", "smoe_update_kernel_list",
     "smoe_adam_step", "smoe_step_begin", "smoe_spatial_keys", "smoe_xchg_window_bytes", "smoe_peer_alloc", "smoe_peer_free",
     "smoe_peer_export", "smoe_peer_open", "smoe_peer_close", "smoe_xchg_publish", "smoe_grad_finalize_peers",
-    "smoe_xchg_reduce_tail", "smoe_xchg_status", "smoe_feed", "smoe_quant_ranges_bytes", "smoe_quant_ranges", "smoe_quant_route", "smoe_fake_quant_theta", "smoe_ssim_workspace_bytes", "smoe_ssim", "smoe_sqerr", "smoe_quantize", "smoe_rescale",
+    "smoe_xchg_reduce_tail", "smoe_xchg_status", "smoe_feed", "smoe_halo_pull", "smoe_quant_ranges_bytes", "smoe_quant_ranges", "smoe_quant_route", "smoe_fake_quant_theta", "smoe_ssim_workspace_bytes", "smoe_ssim", "smoe_sqerr", "smoe_quantize", "smoe_rescale",
     "smoe_colminmax",
 ]
 
@@ -52,6 +52,17 @@ MAX_PEERS = 8
 
 class Peers(C.Structure):
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("win", C.c_void_p * MAX_PEERS)]
+
+
+class HaloMap(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("d", C.c_int32), ("C", C.c_int32),
+                ("blk_lo", (C.c_int32 * 3) * MAX_PEERS), ("blk_hi", (C.c_int32 * 3) * MAX_PEERS),
+                ("buf_lo", (C.c_int32 * 3) * MAX_PEERS), ("buf_dims", (C.c_int32 * 3) * MAX_PEERS),
+                ("res", C.c_void_p * MAX_PEERS)]
+
+
+class SsimRegion(C.Structure):
+    _fields_ = [("lo", C.c_int32 * 3), ("n", C.c_int32 * 3), ("inv_count", C.c_float)]
 
 
 class Adam(C.Structure):

@@ -38,6 +38,38 @@ __global__ void __launch_bounds__(256) xchg_reduce_tail_kernel(smoe_peers pr, in
     peer_epoch_end(pr, e);
 }
 
+// Halo pull of a pixel-sharded SSIM loss: after every rank's loss stage has written the quantised reconstruction of
+// its own block, each rank copies the ring of pixels around its block from the ranks that own them (peer loads over
+// NVLink), so that SSIM windows which straddle a block border see the neighbour's pixels.  One flag barrier (slot 1)
+// in front; the next writer of any res buffer is the next pass's loss stage, which every rank reaches only after the
+// statistics exchange of this pass -- i.e. after everybody's pull -- so no second barrier is needed.
+__global__ void __launch_bounds__(256) halo_pull_kernel(smoe_peers pr, smoe_halo_map hm) {
+    const int e = peer_barrier(pr, 1);
+    const int me = hm.rank;
+    const size_t n = (size_t)hm.buf_dims[me][0] * hm.buf_dims[me][1] * hm.buf_dims[me][2];
+    float* own = reinterpret_cast<float*>(hm.res[me]);
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        int g[3];
+        g[2] = (int)(i % hm.buf_dims[me][2]) + hm.buf_lo[me][2];
+        g[1] = (int)((i / hm.buf_dims[me][2]) % hm.buf_dims[me][1]) + hm.buf_lo[me][1];
+        g[0] = (int)(i / ((size_t)hm.buf_dims[me][2] * hm.buf_dims[me][1])) + hm.buf_lo[me][0];
+        bool mine = true;
+        for (int a = 0; a < 3; ++a) mine = mine && g[a] >= hm.blk_lo[me][a] && g[a] < hm.blk_hi[me][a];
+        if (mine) continue;
+        for (int r = 0; r < hm.world; ++r) {
+            bool in = true;
+            for (int a = 0; a < 3; ++a) in = in && g[a] >= hm.blk_lo[r][a] && g[a] < hm.blk_hi[r][a];
+            if (!in) continue;
+            const size_t src = (((size_t)(g[0] - hm.buf_lo[r][0]) * hm.buf_dims[r][1] + (g[1] - hm.buf_lo[r][1])) *
+                                hm.buf_dims[r][2] + (g[2] - hm.buf_lo[r][2])) * hm.C;
+            const float* peer = reinterpret_cast<const float*>(hm.res[r]);
+            for (int c = 0; c < hm.C; ++c) own[i * hm.C + c] = ld_peer(peer + src + c);
+            break;
+        }
+    }
+    peer_epoch_end(pr, e, 1);
+}
+
 }  // namespace smoe
 
 using namespace smoe;
@@ -126,6 +158,17 @@ int smoe_feed(void* dst, const void* src_host, size_t bytes, void* main_stream, 
     if (e == cudaSuccess) e = cudaEventRecord((cudaEvent_t)done_event, (cudaStream_t)copy_stream);
     if (e != cudaSuccess) { set_error("smoe_feed: %s", cudaGetErrorString(e)); return (int)e; }
     return 0;
+}
+
+int smoe_halo_pull(const smoe_peers* peers, const smoe_halo_map* map, void* stream) {
+    SMOE_REQUIRE(check_peers(peers) && map, "bad argument");
+    SMOE_REQUIRE(map->world == peers->world && map->rank == peers->rank && (map->C == 1 || map->C == 3), "bad halo map");
+    for (int r = 0; r < map->world; ++r) SMOE_REQUIRE(map->res[r], "null res buffer in the halo map");
+    const size_t n = (size_t)map->buf_dims[map->rank][0] * map->buf_dims[map->rank][1] * map->buf_dims[map->rank][2];
+    int nb = (int)((n + 255) / 256);
+    if (nb > 148 * 4) nb = 148 * 4;
+    halo_pull_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(*peers, *map);
+    return check_launch("smoe_halo_pull");
 }
 
 int smoe_xchg_status(const smoe_peers* peers, int32_t* epoch_and_error /*[2], host*/) {

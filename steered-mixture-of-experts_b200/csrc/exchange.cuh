@@ -18,9 +18,14 @@
 
 namespace smoe {
 
-// window = [XW_HDR ints: flags[0..8) | epoch | error | ticket | pad] [payload 0] [payload 1]
+// window = [XW_HDR ints: barrier slot 0 {flags[0..8) | epoch 16 | ticket 18}, error 17,
+//                       barrier slot 1 {flags[32..40) | epoch 20 | ticket 21}, pad] [payload 0] [payload 1]
+// slot 0 is the per-pass statistics exchange, slot 1 the halo pull of a pixel-sharded SSIM loss.
 constexpr int XW_HDR = 64;            // ints (256 B)
 constexpr int XW_EPOCH = 16, XW_ERROR = 17, XW_TICKET = 18;
+__device__ __forceinline__ int xw_flags(int slot) { return slot ? 32 : 0; }
+__device__ __forceinline__ int xw_epoch(int slot) { return slot ? 20 : XW_EPOCH; }
+__device__ __forceinline__ int xw_ticket(int slot) { return slot ? 21 : XW_TICKET; }
 // payload = [K_all*P statistics | SMOE_NSCAL scalars | K_all influence flags | groups reach flags], groups of kGroup
 __host__ __device__ inline size_t xw_groups(int K_all) { return ((size_t)K_all + kGroup - 1) / kGroup; }
 __host__ __device__ inline size_t xw_payload_floats(int K_all, int P) {
@@ -55,17 +60,17 @@ __device__ __forceinline__ float4 ld_peer4(const float* p) {
 
 // Called by every CTA of a consumer kernel.  Block 0 announces this rank's epoch to the peers; thread 0 of every
 // block waits for all ranks.  Returns the epoch (its parity selects the payload buffer).
-__device__ __forceinline__ int peer_barrier(const smoe_peers& pr) {
+__device__ __forceinline__ int peer_barrier(const smoe_peers& pr, int slot = 0) {
     int* own = reinterpret_cast<int*>(pr.win[pr.rank]);
-    const int e = own[XW_EPOCH] + 1;
+    const int e = own[xw_epoch(slot)] + 1;
     if (blockIdx.x == 0 && (int)threadIdx.x < pr.world) {
         __threadfence_system();
-        st_release_sys(reinterpret_cast<int*>(pr.win[threadIdx.x]) + pr.rank, e);
+        st_release_sys(reinterpret_cast<int*>(pr.win[threadIdx.x]) + xw_flags(slot) + pr.rank, e);
     }
     if (threadIdx.x == 0) {
         const long long t0 = clock64();
         for (int r = 0; r < pr.world; ++r) {
-            while (ld_acquire_sys(own + r) - e < 0) {
+            while (ld_acquire_sys(own + xw_flags(slot) + r) - e < 0) {
                 if (clock64() - t0 > 10000000000ll) {          // ~5 s at 2 GHz: a peer died; fail loudly, do not hang
                     own[XW_ERROR] = 1;
                     break;
@@ -78,14 +83,14 @@ __device__ __forceinline__ int peer_barrier(const smoe_peers& pr) {
 }
 
 // the last CTA of a consumer kernel closes the epoch
-__device__ __forceinline__ void peer_epoch_end(const smoe_peers& pr, int e) {
+__device__ __forceinline__ void peer_epoch_end(const smoe_peers& pr, int e, int slot = 0) {
     int* own = reinterpret_cast<int*>(pr.win[pr.rank]);
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(own + XW_TICKET, 1) == (int)gridDim.x - 1) {
-            own[XW_TICKET] = 0;
-            own[XW_EPOCH] = e;
+        if (atomicAdd(own + xw_ticket(slot), 1) == (int)gridDim.x - 1) {
+            own[xw_ticket(slot)] = 0;
+            own[xw_epoch(slot)] = e;
             __threadfence();
         }
     }

@@ -30,10 +30,17 @@ __device__ __forceinline__ int refl(int i, int n) {
 
 struct LRect {
     int dims[3];      // resident image extents
-    int lo[3];        // loss rectangle inside the image
-    int n[3];         // its extents
+    int lo[3];        // compute rectangle inside the image buffer: SSIM windows are centred on its positions and the
+    int n[3];         // symmetric padding reflects at its borders
+    int clo[3];       // count rectangle (relative to lo): positions whose SSIM values enter the sum and whose pixels
+    int cn[3];        // receive a gradient.  Equal to the compute rectangle unless the caller set a region.
+    float inv_np;     // 1 / number of positions of the mean
     int C;
 };
+__device__ __forceinline__ bool in_count(const LRect& r, const int (&id)[3]) {
+    return id[0] >= r.clo[0] && id[0] < r.clo[0] + r.cn[0] && id[1] >= r.clo[1] && id[1] < r.clo[1] + r.cn[1] &&
+           id[2] >= r.clo[2] && id[2] < r.clo[2] + r.cn[2];
+}
 
 __device__ __forceinline__ size_t rect_global(const LRect& r, int i0, int i1, int i2, int c) {
     return (((size_t)(r.lo[0] + i0) * r.dims[1] + (r.lo[1] + i1)) * r.dims[2] + (r.lo[2] + i2)) * r.C + c;
@@ -54,6 +61,7 @@ __global__ void __launch_bounds__(256) sl_fwd_pass(LRect r, const float* __restr
         const size_t pix = i / r.C;
         int id[3] = {(int)(pix / ((size_t)r.n[2] * r.n[1])), (int)((pix / r.n[2]) % r.n[1]), (int)(pix % r.n[2])};
         const int n = r.n[axis], pos = id[axis];
+        const bool counted = in_count(r, id);
         const size_t stride = axis == 0 ? (size_t)r.n[1] * r.n[2] * r.C : (axis == 1 ? (size_t)r.n[2] * r.C : (size_t)r.C);
         const size_t base = i - (size_t)pos * stride;
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -86,6 +94,7 @@ __global__ void __launch_bounds__(256) sl_fwd_pass(LRect r, const float* __restr
             dst[i] = 2.f * cs * (my - lum * mx) / Dl + 2.f * lum * (cs * mx - my) / Dc;
             dst[total + i] = -ssim / Dc;
             dst[2 * total + i] = 2.f * lum / Dc;
+            if (!counted) ssim = 0.f;             // a position of the halo ring: another rank's (the sum is per owner)
         } else {
 #pragma unroll
             for (int p = 0; p < 4; ++p) dst[(size_t)p * total + i] = acc[p];
@@ -164,10 +173,14 @@ __global__ void __launch_bounds__(256) sl_apply(smoe_cfg cfg, smoe_batch b, LRec
                                                 const float* __restrict__ res, const float* __restrict__ image,
                                                 const float* __restrict__ res_pre, float* __restrict__ pix,
                                                 int nt1, int nt2, float tau) {
-    const size_t total = (size_t)r.n[0] * r.n[1] * r.n[2];
-    const size_t ip = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (ip >= total) return;
-    const int i2 = (int)(ip % r.n[2]), i1 = (int)((ip / r.n[2]) % r.n[1]), i0 = (int)(ip / ((size_t)r.n[2] * r.n[1]));
+    const size_t total = (size_t)r.n[0] * r.n[1] * r.n[2];            // positions of the compute rectangle (plane size)
+    const size_t ncount = (size_t)r.cn[0] * r.cn[1] * r.cn[2];
+    const size_t iq = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (iq >= ncount) return;
+    // position inside the count rectangle -> inside the compute rectangle (the planes' index space)
+    const int i2 = r.clo[2] + (int)(iq % r.cn[2]), i1 = r.clo[1] + (int)((iq / r.cn[2]) % r.cn[1]),
+              i0 = r.clo[0] + (int)(iq / ((size_t)r.cn[2] * r.cn[1]));
+    const size_t ip = ((size_t)i0 * r.n[1] + i1) * r.n[2] + i2;
     // position inside the batch (forward) rectangle -> tile and slot
     const int f[3] = {r.lo[0] + i0 - b.origin[0], r.lo[1] + i1 - b.origin[1], r.lo[2] + i2 - b.origin[2]};
     const int t0 = f[0] / b.tile[0], t1 = f[1] / b.tile[1], t2 = f[2] / b.tile[2];
@@ -175,7 +188,7 @@ __global__ void __launch_bounds__(256) sl_apply(smoe_cfg cfg, smoe_batch b, LRec
     const int j = ((f[0] % b.tile[0]) * b.tile[1] + (f[1] % b.tile[1])) * b.tile[2] + (f[2] % b.tile[2]);
     float* tp = pix + (size_t)tile * pix_stride(D, C, b.tile[D - 1]);
     const size_t nC = total * C;
-    const float inv_np = 1.0f / (float)total;
+    const float inv_np = r.inv_np;
     float gr = 0.f;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
@@ -194,7 +207,7 @@ __global__ void __launch_bounds__(256) sl_apply(smoe_cfg cfg, smoe_batch b, LRec
     tp[PL_GR * SMOE_TPIX + j] = live ? gr : 0.f;
 }
 
-static LRect loss_rect(const smoe_cfg* cfg, const smoe_batch* b) {
+static LRect loss_rect(const smoe_cfg* cfg, const smoe_batch* b, const smoe_ssim_region* reg) {
     LRect r;
     for (int a = 0; a < 3; ++a) {
         r.dims[a] = b->dims[a];
@@ -205,7 +218,15 @@ static LRect loss_rect(const smoe_cfg* cfg, const smoe_batch* b) {
         }
         r.lo[a] = lo;
         r.n[a] = hi - lo;
+        r.clo[a] = 0;
+        r.cn[a] = r.n[a];
+        if (reg) {                                 // compute rectangle given by the caller; the batch is the count rectangle
+            r.clo[a] = lo - reg->lo[a];
+            r.lo[a] = reg->lo[a];
+            r.n[a] = reg->n[a];
+        }
     }
+    r.inv_np = reg ? reg->inv_count : 1.0f / (float)((size_t)r.n[0] * r.n[1] * r.n[2]);
     r.C = cfg->C;
     return r;
 }
@@ -216,21 +237,28 @@ using namespace smoe;
 
 extern "C" size_t smoe_ssim_loss_workspace_bytes(const smoe_cfg* cfg, const smoe_batch* batch) {
     if (!cfg || !batch) return 0;
-    const size_t total = (size_t)batch->extent[0] * batch->extent[1] * batch->extent[2] * cfg->C;
+    // sized for the whole resident buffer, so that a caller-given compute region (batch + halo ring) fits too
+    const size_t total = (size_t)batch->dims[0] * batch->dims[1] * batch->dims[2] * cfg->C;
     const size_t nblocks = (total + 255) / 256;
     return 2 * 4 * total * sizeof(float) + 256 + nblocks * 4 * sizeof(double) + 256;
 }
 
-extern "C" int smoe_ssim_loss(const smoe_cfg* cfg, const smoe_batch* batch, const float* res, const float* image,
-                              const float* res_pre, float* pix, float* scalars, void* workspace, void* stream) {
+extern "C" int smoe_ssim_loss(const smoe_cfg* cfg, const smoe_batch* batch, const smoe_ssim_region* region,
+                              const float* res, const float* image, const float* res_pre, float* pix, float* scalars,
+                              void* workspace, void* stream) {
     SMOE_REQUIRE(cfg && batch && res && image && res_pre && scalars && workspace, "null argument");
     SMOE_REQUIRE(cfg->d == 2 || cfg->d == 3, "unsupported d");
-    const LRect r = loss_rect(cfg, batch);
-    for (int a = 0; a < 3; ++a) SMOE_REQUIRE(r.n[a] > 0, "overlap halo swallows the batch");
+    SMOE_REQUIRE(!region || batch->halo == 0, "a compute region and an overlap halo cannot be combined");
+    const LRect r = loss_rect(cfg, batch, region);
+    for (int a = 0; a < 3; ++a) {
+        SMOE_REQUIRE(r.n[a] > 0 && r.cn[a] > 0, "overlap halo swallows the batch");
+        SMOE_REQUIRE(r.lo[a] >= 0 && r.lo[a] + r.n[a] <= r.dims[a] && r.clo[a] >= 0 && r.clo[a] + r.cn[a] <= r.n[a],
+                     "compute region must lie inside the buffer and contain the batch");
+    }
     cudaStream_t st = (cudaStream_t)stream;
     const size_t npos = (size_t)r.n[0] * r.n[1] * r.n[2];
     const size_t total = npos * r.C;
-    const size_t cap = (size_t)batch->extent[0] * batch->extent[1] * batch->extent[2] * cfg->C;
+    const size_t cap = (size_t)batch->dims[0] * batch->dims[1] * batch->dims[2] * cfg->C;
     const int nblocks = (int)((total + 255) / 256);
     float* p0 = (float*)workspace;
     float* p1 = p0 + 4 * cap;
@@ -259,7 +287,7 @@ extern "C" int smoe_ssim_loss(const smoe_cfg* cfg, const smoe_batch* batch, cons
         const int nt1 = (batch->extent[1] + batch->tile[1] - 1) / batch->tile[1];
         const int nt2 = (batch->extent[2] + batch->tile[2] - 1) / batch->tile[2];
         const float tau = 0.5f / (float)(1 << cfg->precision);
-        const int nb = (int)((npos + 255) / 256);
+        const int nb = (int)(((size_t)r.cn[0] * r.cn[1] * r.cn[2] + 255) / 256);
 #define CALL(D, C) sl_apply<D, C><<<nb, 256, 0, st>>>(*cfg, *batch, r, src, res, image, res_pre, pix, nt1, nt2, tau);
         SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL

@@ -10,8 +10,7 @@ kernels called through the C ABI of include/smoe_b200.h.  There is no CPU path.
 
 Deliberate deviations from HEAD (DESIGN.md "Decisions"):
   D1  single-model path only: affines / train_trafo / train_svs / add_kernel_slots>0 /
-      dim_domain>=4 raise NotImplementedError (so do radial_as with quantization_mode 3, and
-      ssim_opt / overlap_of_batches / sampling_percentage<100 on a row-sharded model);
+      dim_domain>=4 raise NotImplementedError (so does radial_as with quantization_mode 3);
       quantization_mode 0-3, quantize_pis, use_diff_center, radial_as, kernel_count_as_norm_l1,
       ssim_opt, overlap_of_batches, loss_mask and sampling_percentage are all on the CUDA path;
   D5  `init_params['A_diagonal'] + init_params['A_corr']` is split back into its diagonal
@@ -207,9 +206,8 @@ class Smoe:
                 raise NotImplementedError(f"at most {_ffi.MAX_PEERS} ranks (one NVSwitch node)")
             if self.start_batches != 1:
                 raise NotImplementedError("pixel sharding over ranks needs start_batches == 1")
-            if self.ssim_opt or self.overlap > 0:
-                # SSIM windows and halos cross the block borders: a sharded SSIM loss needs a 5-pixel halo exchange
-                raise NotImplementedError("ssim_opt / overlap_of_batches on a sharded model")
+            # (overlap_of_batches is a no-op here: a sharded model is ONE batch, and a single window has no halo;
+            # ssim_opt pulls a ring of neighbour pixels over NVLink, see _init_halo)
             self._blocks = self._choose_blocks(self._world)
             self._block = self._blocks[self._rank]
         else:
@@ -428,8 +426,15 @@ class Smoe:
         blk = self._block
         self._local_slices = tuple(slice(lo, hi) for lo, hi in blk)
         self._local_shape = tuple(hi - lo for lo, hi in blk)
-        self._dims3 = tuple(self._local_shape) + (1,) * (3 - d)
-        self._d_image = torch.from_numpy(np.ascontiguousarray(self.image[self._local_slices])).to(dev)
+        # The resident buffers cover the block, plus -- for SSIM as the loss on a sharded model -- a ring of 10 pixels
+        # around it (clipped to the image): windows that straddle a block border need the neighbours' pixels.
+        ring = 10 if (self.ssim_opt and self._world > 1 and not self._emulated) else 0
+        self._buf = tuple((max(lo - ring, 0), min(hi + ring, self.image.shape[a])) for a, (lo, hi) in enumerate(blk))
+        self._buf_slices = tuple(slice(lo, hi) for lo, hi in self._buf)
+        self._buf_shape = tuple(hi - lo for lo, hi in self._buf)
+        self._blk_in_buf = tuple(slice(blk[a][0] - self._buf[a][0], blk[a][1] - self._buf[a][0]) for a in range(d))
+        self._dims3 = tuple(self._buf_shape) + (1,) * (3 - d)
+        self._d_image = torch.from_numpy(np.ascontiguousarray(self.image[self._buf_slices])).to(dev)
         self._d_image_u8 = None
         self._use_u8 = False                                 # set_image() fed 8-bit pixels: the loss stage reads them
         self._copy_stream = self._img_event = None           # set_image()'s host->device copy, overlapped with the forward
@@ -439,26 +444,32 @@ class Smoe:
             lm = np.asarray(self.loss_mask, dtype=np.float32).reshape(self.image.shape[:-1])
             if (lm < 0).any():
                 raise ValueError("loss_mask weights must be >= 0")
-            self._d_loss_mask = torch.from_numpy(np.ascontiguousarray(lm[self._local_slices])).to(dev)
+            self._d_loss_mask = torch.from_numpy(np.ascontiguousarray(lm[self._buf_slices])).to(dev)
         self._d_sample_w = None                              # per-call pixel selection of sampling_percentage < 100
         self.random_sampling_per_batch = None                # None = uniform (smoe.py:271-273)
-        axes = [np.linspace(0, 1, self.image.shape[a]).astype(np.float32)[blk[a][0]:blk[a][1]] for a in range(d)]
+        axes = [np.linspace(0, 1, self.image.shape[a]).astype(np.float32)[self._buf[a][0]:self._buf[a][1]] for a in range(d)]
         self._d_axes = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in axes]
         self._h_axes = axes
-        npx = int(np.prod(self._local_shape))
-        self._d_res = torch.zeros((npx, Cc), dtype=f32, device=dev)
+        npx = int(np.prod(self._buf_shape))
+        self._res_peer = None
+        if ring:
+            # the neighbours read this buffer over NVLink: a dedicated, exportable allocation (smoe_peer_alloc)
+            self._res_peer = _PeerBuffer(npx * Cc * 4)
+            self._d_res = self._res_peer.as_tensor((npx, Cc), dev)
+        else:
+            self._d_res = torch.zeros((npx, Cc), dtype=f32, device=dev)
         self._d_res_pre = torch.zeros((npx, Cc), dtype=f32, device=dev)      # mixture output before clip (the forward's rbuf)
         self._d_argmax = torch.zeros((npx,), dtype=torch.int32, device=dev)
         # batches (smoe.py:1643: sliding_window order, first axis outermost)
         self._tile = self._choose_tile()
         self._batches = []
         if self._world > 1:
-            rects = [((0,) * d, self._local_shape)]
+            rects = [(tuple(sl.start for sl in self._blk_in_buf), self._local_shape)]
         else:
             starts = [range(0, self.image.shape[a], self.batch_size_valued[a]) for a in range(d)]
             rects = [(org, self.batch_size_valued) for org in product(*starts)]
         max_tiles = 0
-        ov = self.overlap
+        ov = self.overlap if self._world == 1 else 0        # a sharded model is one batch: no window halo
         self._batch_npix, self._batch_phantom = [], []
         for org, ext in rects:
             b = Batch()
@@ -536,8 +547,11 @@ class Smoe:
                                  dtype=torch.int32, device=dev)
         self._raw_part = None           # allocated on the first training pass
         self._peers = None
+        self._halo = self._ssim_region = None
         if self._world > 1 and not self._emulated:
             self._open_peer_windows()
+            if self._res_peer is not None:
+                self._init_halo()
         self._host_stats = torch.zeros((nb, _ffi.STATS_STRIDE), dtype=f32).pin_memory()
         self._host_f32 = self._host_stats.numpy()                       # views of the pinned block
         self._host_i32 = self._host_stats.view(torch.int32).numpy()
@@ -575,6 +589,30 @@ class Smoe:
         torch.cuda.synchronize()
         torch.distributed.barrier(group=self._pg)       # every window exists and is zeroed before anyone signals
 
+    def _init_halo(self):
+        """Geometry and peer mappings of the halo pull (smoe_halo_pull) of a sharded SSIM loss."""
+        d, Cc = self.dim_domain, self.image.shape[-1]
+        handles = [None] * self._world
+        torch.distributed.all_gather_object(handles, self._res_peer.handle(), group=self._pg)
+        hm = _ffi.HaloMap()
+        hm.world, hm.rank, hm.d, hm.C = self._world, self._rank, d, Cc
+        for r, blk in enumerate(self._blocks):
+            for a in range(3):
+                lo, hi = blk[a] if a < d else (0, 1)
+                blo = max(lo - 10, 0) if a < d else 0
+                bhi = min(hi + 10, self.image.shape[a]) if a < d else 1
+                hm.blk_lo[r][a], hm.blk_hi[r][a] = lo, hi
+                hm.buf_lo[r][a], hm.buf_dims[r][a] = blo, bhi - blo
+            hm.res[r] = self._res_peer.ptr.value if r == self._rank else self._res_peer.open_peer(handles[r])
+        self._halo = hm
+        reg = _ffi.SsimRegion()
+        for a in range(3):
+            reg.lo[a], reg.n[a] = 0, self._dims3[a]           # windows centred on every position of the resident buffer
+        reg.inv_count = 1.0 / self.num_pixel
+        self._ssim_region = reg
+        torch.cuda.synchronize()
+        torch.distributed.barrier(group=self._pg)
+
     def close(self):
         """Unmap / free the peer windows of a sharded model (collective: every rank calls it)."""
         if getattr(self, "_peers", None) is None:
@@ -587,6 +625,9 @@ class Smoe:
                 L.smoe_peer_close(C.c_void_p(self._peers.win[r]))
         torch.distributed.barrier(group=self._pg)
         L.smoe_peer_free(self._peer_own)
+        if self._res_peer is not None:
+            self._d_res = None
+            self._res_peer.close()
         self._peers = None
 
     def exchange_status(self):
@@ -662,7 +703,7 @@ class Smoe:
     def get_pre_clip_reconstruction(self):
         self._enable_res_pre()
         self.run_batched(train=False, update_reconstruction=True)
-        return self._d_res_pre.reshape(self._local_shape + (self.image.shape[-1],)).cpu().numpy()
+        return self._d_res_pre.reshape(self._buf_shape + (self.image.shape[-1],))[self._blk_in_buf].cpu().numpy()
 
     def _choose_tile(self):
         d = self.dim_domain
@@ -746,8 +787,6 @@ class Smoe:
         if sampling and use_loss_mask:
             raise ValueError("loss_mask and sampling_percentage < 100 cannot be combined (the reference feeds a "
                              "full-batch mask against the sampled pixels, smoe.py:1666-1677)")
-        if sampling and self._world > 1:
-            raise NotImplementedError("sampling_percentage < 100 on a sharded model")
         if self.overlap > 0 and (sampling or use_loss_mask):
             # smoe_test.py:322-325: sampling is "only working if ... batch overlap equal 0"; the mask is sliced
             # with the un-padded window coordinates (smoe.py:1674-1676)
@@ -863,8 +902,8 @@ class Smoe:
                           "evaluated with the absolute value of that weight (the reference would subtract them)")
             self._warned_nonpos = True
         if update_reconstruction:
-            self._update_sampling_probabilities()
             rec, amax = self._gather_reconstruction()
+            self._update_sampling_probabilities(rec)
             if with_quantized_params:
                 self.qreconstruction_image, self.qweight_matrix_argmax, self.qvalid = rec, amax, True
             else:
@@ -876,13 +915,30 @@ class Smoe:
         pixels drawn without replacement by np.random.choice (the global NumPy generator, as the reference) with
         the error-proportional probabilities of the last reconstruction pass (smoe.py:906-907, 1768-1769).
         Returns the per-pixel selection (1 = fed, SMOE_PIXEL_ABSENT = not fed) and batches whose loss means run
-        over the drawn pixels."""
+        over the drawn pixels.  A sharded model is the one-batch model of the whole image: every rank draws the SAME
+        global sample (same generator state and probabilities on every rank -- seed NumPy identically) and feeds the
+        drawn pixels of its own block."""
         d = self.dim_domain
         if self._d_sample_w is None:
-            self._d_sample_w = torch.empty(self._local_shape, dtype=torch.float32, device=self.device)
-        w = np.full(self._local_shape, _ffi.PIXEL_ABSENT, dtype=np.float32)
+            self._d_sample_w = torch.empty(self._buf_shape, dtype=torch.float32, device=self.device)
+        w = np.full(self._buf_shape, _ffi.PIXEL_ABSENT, dtype=np.float32)
         batches = []
         self.last_samples = []
+        if self._world > 1:
+            n = self.num_pixel
+            num_samples = int(np.uint32(np.round(n * sampling_percentage / 100)))
+            p = self.random_sampling_per_batch[0] if self.random_sampling_per_batch is not None else None
+            p = np.ones((n,), dtype=np.float32) / n if p is None else np.asarray(p)
+            samples = np.random.choice(n, (num_samples,), replace=False, p=p)
+            self.last_samples.append(samples)
+            sel = np.full((n,), _ffi.PIXEL_ABSENT, dtype=np.float32)
+            sel[samples] = 1.0
+            w[self._blk_in_buf] = sel.reshape(self.image.shape[:d])[self._local_slices]
+            nb = Batch.from_buffer_copy(self._batches[0])
+            nb.inv_count = 1.0 / max(num_samples, 1)
+            batches.append(nb)
+            self._d_sample_w.copy_(torch.from_numpy(w))
+            return self._d_sample_w, batches
         for ii, ((org, ext), b) in enumerate(zip(self._batch_rects(), self._batches)):
             n = int(np.prod(ext))
             num_samples = int(np.uint32(np.round(n * sampling_percentage / 100)))
@@ -900,12 +956,19 @@ class Smoe:
         self._d_sample_w.copy_(torch.from_numpy(w))
         return self._d_sample_w, batches
 
-    def _update_sampling_probabilities(self):
+    def _update_sampling_probabilities(self, rec=None):
         """sampl_prob = err_map / sum(err_map) per batch, err_map = mean_c (resq - target)^2 (smoe.py:906-907),
-        kept on the device; replaces `random_sampling_per_batch[ii] = results[-1]` (smoe.py:1768-1769)."""
-        if self._world > 1 or self.overlap > 0:
+        kept on the device; replaces `random_sampling_per_batch[ii] = results[-1]` (smoe.py:1768-1769).  Sharded: from
+        the gathered reconstruction, on the host (identical on every rank)."""
+        if self.overlap > 0 and self._world == 1:
             return
         d, Cc = self.dim_domain, self.image.shape[-1]
+        if self._world > 1:
+            if rec is None or self._emulated:
+                return
+            err = ((np.asarray(rec, np.float32) - self.image) ** 2).mean(axis=-1).reshape(-1)
+            self.random_sampling_per_batch = [err / err.sum()]
+            return
         if self._use_u8:
             torch.div(self._d_image_u8.to(torch.float32), 255.0, out=self._d_image)
         err = ((self._d_res.reshape(self._local_shape + (Cc,)) - self._d_image) ** 2).mean(dim=-1)
@@ -992,7 +1055,12 @@ class Smoe:
                               st), "smoe_loss")
             self.gpu_launches += 1
             if self.ssim_opt:
-                check(L.smoe_ssim_loss(C.byref(self._cfg), C.byref(b), ptr(self._d_res), ptr(self._d_image),
+                if self._halo is not None:      # sharded: the ring of neighbour pixels around the block, over NVLink
+                    check(L.smoe_halo_pull(C.byref(self._peers), C.byref(self._halo), st), "smoe_halo_pull")
+                    self.gpu_launches += 1
+                check(L.smoe_ssim_loss(C.byref(self._cfg), C.byref(b),
+                                       C.byref(self._ssim_region) if self._ssim_region is not None else ptr(None),
+                                       ptr(self._d_res), ptr(self._d_image),
                                        ptr(self._d_res_pre), ptr(self._pix) if train else ptr(None), ptr(scal),
                                        ptr(self._ssim_ws), st), "smoe_ssim_loss")
                 self.gpu_launches += 2 * self.dim_domain + 2 if train else self.dim_domain + 1
@@ -1044,8 +1112,8 @@ class Smoe:
     def _gather_reconstruction(self):
         Cc = self.image.shape[-1]
         d = self.dim_domain
-        res = self._d_res.reshape(self._local_shape + (Cc,))
-        amax = self._d_argmax.reshape(self._local_shape)
+        res = self._d_res.reshape(self._buf_shape + (Cc,))[self._blk_in_buf]
+        amax = self._d_argmax.reshape(self._buf_shape)[self._blk_in_buf]
         if self._world > 1 and not self._emulated:
             # blocks differ in shape: gather through buffers padded to the largest block, then place each block
             mx = tuple(max(hi - lo for lo, hi in (blk[a] for blk in self._blocks)) for a in range(d))
@@ -1462,6 +1530,44 @@ class Smoe:
         from .ops.image_ops_impl import smoe_ssim
         rec = self.get_qreconstruction() if quantized else self.get_reconstruction()
         return smoe_ssim(rec, self.image, use_yuv=self.use_yuv, device=self.device)
+
+
+class _PeerBuffer:
+    """A dedicated device allocation that other ranks of the node can map (cudaIpc exports whole allocations, so it
+    cannot come from torch's caching allocator): smoe_peer_alloc / _export / _open.  Exposed to torch through the
+    CUDA array interface; torch does not own the memory."""
+
+    def __init__(self, nbytes):
+        self.nbytes = int(nbytes)
+        self.ptr = C.c_void_p()
+        check(lib().smoe_peer_alloc(C.c_size_t(self.nbytes), C.byref(self.ptr)), "smoe_peer_alloc")
+        self.mapped = []
+
+    def as_tensor(self, shape, device):
+        holder = type("_CAI", (), {})()
+        holder.__cuda_array_interface__ = {"shape": tuple(int(v) for v in shape), "typestr": "<f4",
+                                           "data": (int(self.ptr.value), False), "version": 2, "strides": None}
+        self._holder = holder
+        return torch.as_tensor(holder, device=device)
+
+    def handle(self):
+        h = (C.c_ubyte * 64)()
+        check(lib().smoe_peer_export(self.ptr, h), "smoe_peer_export")
+        return bytes(h)
+
+    def open_peer(self, handle):
+        mapped = C.c_void_p()
+        check(lib().smoe_peer_open((C.c_ubyte * 64).from_buffer_copy(handle), C.byref(mapped)), "smoe_peer_open")
+        self.mapped.append(mapped)
+        return mapped.value
+
+    def close(self):
+        for m in self.mapped:
+            lib().smoe_peer_close(m)
+        self.mapped = []
+        if self.ptr:
+            lib().smoe_peer_free(self.ptr)
+            self.ptr = C.c_void_p()
 
 
 def _fake_quant_torch(x, mn, mx, bits):

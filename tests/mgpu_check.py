@@ -9,6 +9,7 @@ next to it, an unsharded copy of the same model (distributed=False) on its own G
   * Smoe.train() past the kernel-list cadence with pi-sparsification on a grid where the reference's maha < 800
     probe is selective: kernel lists, pruned index sets and parameters must stay identical ON EVERY RANK
     (check_replicas) and agree with the unsharded run;
+  * SSIM as the loss (halo pull over NVLink) and random pixel sub-sampling, sharded vs unsharded;
   * with --c3: one training step of BASELINE config 3 (1080p RGB, 32,768 kernels) sharded vs unsharded."""
 import os
 import sys
@@ -116,6 +117,67 @@ def compare_train(Smoe, AdamOptimizer, img, k, rank):
     return ok
 
 
+def compare_ssim(Smoe, AdamOptimizer, img, k, rank):
+    """SSIM as the loss on a sharded model: every rank's windows see the neighbours' pixels through the halo pull
+    (smoe_halo_pull), so loss and gradients match the unsharded model (float32 SSIM: 1e-3 on the gradients, as in the
+    single-GPU SSIM tests)."""
+    ok = True
+    kw = dict(use_determinant=True, train_inverse_cov=False, use_yuv=img.shape[-1] == 3, ssim_opt=True)
+    ms = Smoe(img, kernels_per_dim=k, **kw)
+    m1 = Smoe(img, kernels_per_dim=k, distributed=False, **kw)
+    for m in (ms, m1):
+        m.set_optimizer(AdamOptimizer(1e-3), AdamOptimizer(1e-5), AdamOptimizer(1.0))
+    for step in range(2):
+        a = ms.run_batched(train=True, update_reconstruction=True)
+        b = m1.run_batched(train=True, update_reconstruction=True)
+        flips = int((np.round(ms.reconstruction_image * 255) != np.round(m1.reconstruction_image * 255)).sum())
+        if abs(a[0] - b[0]) > 2e-5 + 1e-5 * flips:
+            ok = False
+            print(f"ssim rank {rank} step {step} loss {a[0]} vs {b[0]} (flips {flips})")
+        ga, gb = ms.get_gradients(), m1.get_gradients()
+        for key in ga:
+            rel = np.abs(ga[key] - gb[key]).max() / max(np.abs(gb[key]).max(), 1e-30)
+            if rel > 2e-3 + 2e-3 * flips:
+                ok = False
+                print(f"ssim rank {rank} step {step} {key} rel {rel:.3e} (flips {flips})")
+        m1.set_params(ms.get_params())
+        m1.kernel_list_per_batch = ms.kernel_list_per_batch
+        ms.check_replicas()
+    ms.close()
+    return ok
+
+
+def compare_sampling(Smoe, AdamOptimizer, img, k, rank):
+    """sampling_percentage < 100 on a sharded model: all ranks draw the same global sample and feed their own part."""
+    ok = True
+    kw = dict(use_determinant=True, train_inverse_cov=False, use_yuv=False)
+    ms = Smoe(img, kernels_per_dim=k, **kw)
+    m1 = Smoe(img, kernels_per_dim=k, distributed=False, **kw)
+    for m in (ms, m1):
+        m.set_optimizer(AdamOptimizer(1e-3), AdamOptimizer(1e-5), AdamOptimizer(1.0))
+        m.run_batched(train=False, update_reconstruction=True)       # error-proportional probabilities
+    res = []
+    for m in (ms, m1):
+        np.random.seed(11)
+        res.append(m.run_batched(train=True, sampling_percentage=35))
+    sa, sb = set(ms.last_samples[0].tolist()), set(m1.last_samples[0].tolist())
+    if len(sa) != len(sb) or len(sa ^ sb) > 0.01 * len(sa):
+        ok = False
+        print(f"sampling rank {rank}: samples differ ({len(sa ^ sb)} of {len(sa)})")
+    if abs(res[0][0] - res[1][0]) > 1e-3 * abs(res[1][0]) + 1e-6:
+        ok = False
+        print(f"sampling rank {rank}: loss {res[0][0]} vs {res[1][0]}")
+    ga, gb = ms.get_gradients(), m1.get_gradients()
+    for key in ga:
+        rel = np.abs(ga[key] - gb[key]).max() / max(np.abs(gb[key]).max(), 1e-30)
+        if rel > 5e-2 and len(sa ^ sb) == 0:
+            ok = False
+            print(f"sampling rank {rank} {key} rel {rel:.3e}")
+    ms.check_replicas()
+    ms.close()
+    return ok
+
+
 def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -131,6 +193,9 @@ def main():
     for shape, k in (((135, 96, 3), [12, 10]), ((40, 48, 12, 3), [4, 4, 3]), ((192, 256, 1), [24, 32])):
         ok &= compare_steps(Smoe, AdamOptimizer, bench.synth_image(shape, 77), k, rank, tag=str(shape))
     ok &= compare_train(Smoe, AdamOptimizer, bench.synth_image((256, 256, 1), 78), [64, 64], rank)
+    ok &= compare_ssim(Smoe, AdamOptimizer, bench.synth_image((96, 128, 3), 79), [8, 10], rank)
+    ok &= compare_ssim(Smoe, AdamOptimizer, bench.synth_image((40, 48, 24, 1), 80), [4, 4, 3], rank)
+    ok &= compare_sampling(Smoe, AdamOptimizer, bench.synth_image((96, 128, 1), 81), [10, 12], rank)
     if "--c3" in sys.argv:
         shape, k, seed, _ = bench.WORKLOADS["c3"]
         ok &= compare_steps(Smoe, AdamOptimizer, bench.synth_image(shape, seed), k, rank, steps=1, tag="c3")

@@ -11,6 +11,7 @@ aliases `np.int`, `np.bool` restored):
   * quantizer.quantize_params, quantizer.rescaler, utils.reduce_params
   * smoe.Smoe.gen_domain, generate_kernel_grid, generate_experts, generate_pis,
     get_batch_shape and smoe.sliding_window
+  * utils.save_model (a checkpoint pickle written by the reference itself: ref_saved_model_*.pkl)
 The TensorFlow graph itself cannot be executed here (no TensorFlow, no network); the graph
 fixtures (graph_*.npz) are therefore produced by the float64 restatement in oracle/graph.py and
 are marked `pinned=False` inside the file.
@@ -272,9 +273,60 @@ def golden_graph():
     np.savez_compressed(os.path.join(OUT, "graph_cases.npz"), **out)
 
 
+def golden_saved_model(ref_smoe, ref_quantizer, ref_utils):
+    """A checkpoint pickle written by the REFERENCE's own `utils.save_model` (utils.py:18-59) -- with its
+    `reduce_params` and `quantizer.quantize_params` -- from a shim holding reference-initialised parameters, plus the
+    image it belongs to.  tests load it through the product's load_params / smoe_reconstruction.main (SURVEY.md 8 f-2:
+    existing parameter files must work unchanged)."""
+    Smoe = ref_smoe.Smoe
+    img = synth_image((48, 64, 3), 1201)
+    s = object.__new__(Smoe)
+    s.image, s.dim_domain, s.train_inverse_cov = img, 2, False
+    s.musX_init = s.A_init = None
+    s.generate_kernel_grid([6, 8])
+    s.generate_experts()
+    s.generate_pis(False)
+    rs = np.random.RandomState(7)
+    K = s.musX_init.shape[0]
+    A = np.asarray(s.A_init, np.float32)
+    A_diag = np.zeros_like(A)
+    A_corr = np.zeros_like(A)
+    for i in range(2):
+        A_diag[:, i, i] = A[:, i, i] * rs.uniform(0.8, 1.2, K)
+    A_corr[:, 1, 0] = rs.normal(0, 3, K)
+    pis = np.ones(K, np.float32)
+    pis[rs.choice(K, 9, replace=False)] = 0.0          # pruned kernels: reduce_params drops them
+    params = {"pis": pis, "musX": np.asarray(s.musX_init, np.float32) + rs.normal(0, 0.004, (K, 2)).astype(np.float32),
+              "A_diagonal": A_diag, "A_corr": A_corr,
+              "gamma_e": rs.normal(0, 0.2, (K, 2, 3)).astype(np.float32), "nu_e": np.asarray(s.nu_e_init, np.float32)}
+    shim = _Shim()
+    shim.quantization_mode, shim.quantize_pis = 1, False
+    shim.bit_depths = [20, 18, 6, 10, 10]
+    shim.lower_bounds, shim.upper_bounds = [-2500, -.3, -5, 0, -32], [2500, 1.3, 5, 2, 32]
+    shim.use_yuv, shim.only_y_gamma, shim.ssim_opt = True, False, False
+    shim.use_determinant, shim.use_diff_center, shim.radial_as = True, False, False
+    shim.train_gammas, shim.train_musx, shim.train_pis = True, True, True
+    shim.dim_domain, shim.image, shim.train_trafo, shim.affines = 2, img, False, None
+    shim.musX_init = np.asarray(s.musX_init)
+    shim.qparams = ref_quantizer.quantize_params(shim, copy.deepcopy(params))
+    shim.get_params = lambda: copy.deepcopy(params)
+    shim.get_best_params = shim.get_params
+    shim.get_mses = lambda: [(0, 812.5), (100, 301.25)]
+    shim.get_losses = lambda: [(0, 0.0123), (100, 0.0045)]
+    shim.get_num_pis = lambda: [(0, K), (100, K - 9)]
+    path = os.path.join(OUT, "ref_saved_model_00000100_params.pkl")
+    ref_utils.save_model(shim, path, best=False, reduce=True, quantize=True)
+    np.save(os.path.join(OUT, "ref_saved_model_image.npy"), np.round(img * 255).astype(np.uint8))
+    print("wrote", path)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
-    ref_smoe, ref_quantizer, _ = import_reference()
+    ref_smoe, ref_quantizer, ref_utils = import_reference()
+    if "--saved-model-only" in sys.argv:
+        golden_saved_model(ref_smoe, ref_quantizer, ref_utils)
+        return
+    golden_saved_model(ref_smoe, ref_quantizer, ref_utils)
     golden_init(ref_smoe)
     golden_quant(ref_quantizer)
     golden_quant_radial(ref_quantizer)

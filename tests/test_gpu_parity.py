@@ -415,6 +415,28 @@ def test_reconstruction_entry_point_round_trip(tmp_path):
     np.testing.assert_array_equal(p_saved["A_diagonal"], p_loaded["A_diagonal"])
 
 
+def test_reference_written_checkpoint_loads_and_reconstructs(tmp_path):
+    """a checkpoint pickle written by the REFERENCE's utils.save_model (tests/golden/, made by
+    oracle/make_golden.py from the real code) goes through the product's smoe_reconstruction.main unchanged, and the
+    reconstruction from its parameters matches the float64 oracle."""
+    import shutil
+    from smoe_b200 import smoe_reconstruction
+    from smoe_b200.utils import load_params
+    pkl = os.path.join(GOLDEN, "ref_saved_model_00000100_params.pkl")
+    shutil.copy(pkl, str(tmp_path / "00000100_params.pkl"))
+    shutil.copy(os.path.join(GOLDEN, "ref_saved_model_image.npy"), str(tmp_path / "img.npy"))
+    s2, loss, mse, path = smoe_reconstruction.main(str(tmp_path / "img.npy"), str(tmp_path / "out"),
+                                                   str(tmp_path / "00000100_params.pkl"))
+    assert os.path.exists(path + ".png") and s2.start_pis == 39 and s2.use_yuv and s2.use_determinant
+    params = load_params(pkl)
+    img = np.load(os.path.join(GOLDEN, "ref_saved_model_image.npy")).astype(np.float32) / 255.
+    pre = s2.get_pre_clip_reconstruction().reshape(-1, 3)
+    idx = np.arange(img.shape[0] * img.shape[1])
+    out = _oracle_at_pixels(img, params, idx, dict(use_determinant=True, train_inverse_cov=False, use_yuv=True))
+    _check_sampled_forward(pre, out, tol_frac=0.9)
+    assert abs(loss - float(out["loss"])) < 2e-5 and abs(mse / float(out["mse_op"]) - 1) < 2e-3
+
+
 def _oracle_at_pixels(img, params, flat_idx, cfgkw, feed=None):
     """float64 oracle forward at a sample of pixels (each pixel's output depends on no other pixel)."""
     from oracle.graph import GraphCfg, graph_forward

@@ -263,8 +263,8 @@ int smoe_grad_finalize(const smoe_cfg* cfg, const float* raw, int num_splits,
 size_t smoe_quant_ranges_bytes(void);
 int smoe_quant_ranges(const smoe_cfg* cfg, const float* theta, int K_all, int train_musx, void* quant_ranges,
                       void* stream);
-int smoe_quant_route(const smoe_cfg* cfg, const float* theta, const void* quant_ranges, int K_all, float* grads,
-                     void* stream);
+int smoe_quant_route(const smoe_cfg* cfg, const float* theta, const void* quant_ranges /* its scratch part is written */,
+                     int K_all, float* grads, void* stream);
 int smoe_fake_quant_theta(const smoe_cfg* cfg, const float* theta, const void* quant_ranges, int K_all, float* out,
                           float* structural /*[2]*/, void* stream);
 

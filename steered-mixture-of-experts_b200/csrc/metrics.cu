@@ -12,7 +12,11 @@
 
 namespace smoe {
 
-__constant__ float c_win[11];
+// exp(-(k-5)^2 / (2 * 1.5^2)) / sum, rounded to float32 (ops/image_ops_impl.py:131-151): a compile-time initialiser,
+// so smoe_ssim needs no host-to-device copy (and can be captured into a CUDA graph)
+__constant__ float c_win[11] = {1.028380124e-03f, 7.598758209e-03f, 3.600077331e-02f, 1.093606874e-01f, 2.130055428e-01f,
+                                2.660117149e-01f, 2.130055428e-01f, 1.093606874e-01f, 3.600077331e-02f, 7.598758209e-03f,
+                                1.028380124e-03f};
 
 __device__ __forceinline__ int reflect_sym(int i, int n) {
     // numpy / tf "SYMMETRIC": -1 -> 0, -2 -> 1, n -> n-1, n+1 -> n-2
@@ -208,18 +212,34 @@ __global__ void ssim_final_kernel(const double* __restrict__ partial, int nblock
 
 __global__ void __launch_bounds__(256) sqerr_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n,
                                                     double* __restrict__ partial) {
-    // float32 products summed in short float runs, runs and everything above them in double
+    // float32 products summed in short float runs, runs and everything above them in double.  16-byte loads, four of
+    // them per array in flight per thread (HBM-bound: 2 * n * 4 bytes read).
     double acc = 0.0;
     const size_t stride = (size_t)gridDim.x * 256;
-    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-    while (i < n) {
+    const size_t tid0 = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const bool vec = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+    const size_t n4 = vec ? n / 4 : 0;
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    for (size_t i = tid0; i < n4; i += 4 * stride) {
+        float4 x[4], y[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const size_t j = i + u * stride;
+            x[u] = j < n4 ? __ldg(a4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            y[u] = j < n4 ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         float run = 0.f;
-#pragma unroll 8
-        for (int r = 0; r < 8 && i < n; ++r, i += stride) {
-            const float d = a[i] - b[i];
-            run = fmaf(d, d, run);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float d0 = x[u].x - y[u].x, d1 = x[u].y - y[u].y, d2 = x[u].z - y[u].z, d3 = x[u].w - y[u].w;
+            run = fmaf(d0, d0, run); run = fmaf(d1, d1, run); run = fmaf(d2, d2, run); run = fmaf(d3, d3, run);
         }
         acc += (double)run;
+    }
+    for (size_t i = 4 * n4 + tid0; i < n; i += stride) {           // tail (or everything, when unaligned)
+        const float d = a[i] - b[i];
+        acc += (double)(d * d);
     }
     __shared__ double s[256];
     s[threadIdx.x] = acc;
@@ -231,11 +251,11 @@ __global__ void __launch_bounds__(256) sqerr_kernel(const float* __restrict__ a,
     if (threadIdx.x == 0) partial[blockIdx.x] = s[0];
 }
 __global__ void sqerr_final_kernel(const double* __restrict__ partial, int nb, double* __restrict__ out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double t = 0.0;
-        for (int i = 0; i < nb; ++i) t += partial[i];
-        out[0] = t;
-    }
+    // fixed order: lane l sums partials l, l+32, ...; then a fixed shuffle tree
+    double t = 0.0;
+    for (int i = threadIdx.x; i < nb; i += 32) t += partial[i];
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) out[0] = t;
 }
 
 // ---- quantiser --------------------------------------------------------------------------------
@@ -326,16 +346,7 @@ int smoe_ssim(int d, const int32_t dims[3], int C, const float* a, const float* 
               void* stream) {
     SMOE_REQUIRE(a && b && out && workspace && dims, "null argument");
     SMOE_REQUIRE((d == 2 || d == 3) && C >= 1 && C <= 4, "unsupported d / C");
-    static bool win_set = false;
     cudaStream_t st = (cudaStream_t)stream;
-    float w[11];
-    {
-        double s = 0.0, g[11];
-        for (int k = 0; k < 11; ++k) { g[k] = exp(-0.5 * (k - 5.0) * (k - 5.0) / (1.5 * 1.5)); s += g[k]; }
-        for (int k = 0; k < 11; ++k) w[k] = (float)(g[k] / s);
-    }
-    (void)win_set;
-    cudaMemcpyToSymbolAsync(c_win, w, sizeof(w), 0, cudaMemcpyHostToDevice, st);
     const int n0 = dims[0], n1 = dims[1], n2 = (d == 3) ? dims[2] : 1;
     const size_t total = (size_t)n0 * n1 * n2 * C;
     const int nblocks = (int)((total + 255) / 256);
@@ -362,7 +373,8 @@ int smoe_ssim(int d, const int32_t dims[3], int C, const float* a, const float* 
 
 int smoe_sqerr(const float* a, const float* b, size_t n, double* out, void* workspace, void* stream) {
     SMOE_REQUIRE(a && b && out && workspace && n > 0, "bad argument");
-    int nb = (int)((n + 255) / 256);
+    int nb = (int)((n / 16 + 255) / 256);       // a thread covers 16 elements per round
+    if (nb < 1) nb = 1;
     if (nb > 1024) nb = 1024;          // workspace holds 1024 doubles
     cudaStream_t st = (cudaStream_t)stream;
     sqerr_kernel<<<nb, 256, 0, st>>>(a, b, n, (double*)workspace);

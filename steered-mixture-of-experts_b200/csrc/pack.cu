@@ -429,16 +429,22 @@ __global__ void __launch_bounds__(256) step_begin_kernel(float* __restrict__ gra
 //   A_corr, musX, gamma_e : q = fq(x; min, max)                    (plain; clipped gradients go to the extremes)
 // A_corr's reduce_min / reduce_max run over the whole (d, d) blocks of the variable, whose diagonal and upper
 // entries are structural zeros, so 0 always takes part.
+// Two stages, so that the scan over the K_all rows uses the whole GPU: (1) every CTA reduces a slice of the rows to
+// min / max per group (exact, order-independent), (2) one warp combines the CTA results and applies TF's Nudge().
+constexpr int kQBlocks = 256;                 // stage-1 CTAs at most
+struct QuantPart { float mn[6], mx[6]; int kept; int pad[3]; };
+struct QuantRoutePart { float sum[6]; int cnt[6]; };
+struct QuantWork { QuantDyn dyn; QuantPart part[kQBlocks]; QuantRoutePart rpart[kQBlocks]; float share[8]; };
+
 template <int D, int C>
-__global__ void __launch_bounds__(1024) quant_ranges_kernel(smoe_cfg cfg, QuantSet qs_static, int train_musx,
-                                                            const float* __restrict__ theta, int K_all,
-                                                            QuantDyn* __restrict__ out) {
+__global__ void __launch_bounds__(256) quant_ranges_stage1(QuantSet qs_static, const float* __restrict__ theta, int K_all,
+                                                           QuantWork* __restrict__ wk) {
     constexpr int P = nparam(D, C);
     float mn[6], mx[6];
 #pragma unroll
     for (int g = 0; g < 6; ++g) { mn[g] = INFINITY; mx[g] = -INFINITY; }
     int kept = 0;
-    for (int i = threadIdx.x; i < K_all; i += 1024) {
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < K_all; i += gridDim.x * 256) {
         const float* row = theta + (size_t)i * P;
         if (!(fake_quant(row[off_pi(D, C)], qs_static.g[QG_PI]) > 0.f)) continue;          // pis_mask, smoe.py:480
         kept = 1;
@@ -455,8 +461,8 @@ __global__ void __launch_bounds__(1024) quant_ranges_kernel(smoe_cfg cfg, QuantS
 #pragma unroll
         for (int j = 0; j < D * C; ++j) upd(QG_GA, row[off_ga(D, C) + j]);
     }
-    __shared__ float s_mn[32][6], s_mx[32][6];
-    __shared__ int s_kept[32];
+    __shared__ float s_mn[8][6], s_mx[8][6];
+    __shared__ int s_kept[8];
 #pragma unroll
     for (int g = 0; g < 6; ++g)
 #pragma unroll
@@ -472,12 +478,38 @@ __global__ void __launch_bounds__(1024) quant_ranges_kernel(smoe_cfg cfg, QuantS
     }
     __syncthreads();
     if (threadIdx.x != 0) return;
-    kept = 0;
-    for (int w = 0; w < 32; ++w) {
-        kept |= s_kept[w];
+    QuantPart p;
+    p.kept = 0;
+    for (int g = 0; g < 6; ++g) { p.mn[g] = INFINITY; p.mx[g] = -INFINITY; }
+    for (int w = 0; w < 8; ++w) {
+        p.kept |= s_kept[w];
 #pragma unroll
-        for (int g = 0; g < 6; ++g) { mn[g] = fminf(mn[g], s_mn[w][g]); mx[g] = fmaxf(mx[g], s_mx[w][g]); }
+        for (int g = 0; g < 6; ++g) { p.mn[g] = fminf(p.mn[g], s_mn[w][g]); p.mx[g] = fmaxf(p.mx[g], s_mx[w][g]); }
     }
+    wk->part[blockIdx.x] = p;
+}
+
+__global__ void __launch_bounds__(32) quant_ranges_stage2(smoe_cfg cfg, QuantSet qs_static, int train_musx, int nblocks,
+                                                          QuantWork* __restrict__ wk) {
+    float mn[6], mx[6];
+#pragma unroll
+    for (int g = 0; g < 6; ++g) { mn[g] = INFINITY; mx[g] = -INFINITY; }
+    int kept = 0;
+    for (int b = threadIdx.x; b < nblocks; b += 32) {
+        const QuantPart p = wk->part[b];
+        kept |= p.kept;
+#pragma unroll
+        for (int g = 0; g < 6; ++g) { mn[g] = fminf(mn[g], p.mn[g]); mx[g] = fmaxf(mx[g], p.mx[g]); }
+    }
+#pragma unroll
+    for (int g = 0; g < 6; ++g)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[g] = fminf(mn[g], __shfl_xor_sync(0xffffffffu, mn[g], o));
+            mx[g] = fmaxf(mx[g], __shfl_xor_sync(0xffffffffu, mx[g], o));
+        }
+    kept = __any_sync(0xffffffffu, kept);
+    if (threadIdx.x != 0) return;
     QuantDyn q;
     q.qs = qs_static;
     q.qs.mode = 3;
@@ -500,7 +532,7 @@ __global__ void __launch_bounds__(1024) quant_ranges_kernel(smoe_cfg cfg, QuantS
         }
         q.qs.g[g] = n;
     }
-    *out = q;
+    wk->dyn = q;
 }
 
 // The variables as the graph uses them (the q* tensors, smoe.py:482-538; what get_params returns, smoe.py:1796-1798)
@@ -543,44 +575,46 @@ __global__ void __launch_bounds__(256) fake_quant_theta_kernel(smoe_cfg cfg, Qua
 // reduce_min / reduce_max (equal shares among ties), to the extreme elements of the kept kernels.  When the
 // extreme of A_corr is one of its structural zeros, that share lands on a variable entry the graph never reads;
 // it is dropped here (deviation from HEAD, which would start moving that unused entry).
+template <int D, int C, typename FN>
+__device__ __forceinline__ void route_visit(const float* __restrict__ row, float* __restrict__ gr, FN&& fn) {
+#pragma unroll
+    for (int l = 0; l < D; ++l) {
+        fn(1, row[off_mu(D, C) + l], gr[off_mu(D, C) + l]);
+#pragma unroll
+        for (int m = 0; m < l; ++m) fn(0, row[off_A(D, C) + lt(l, m)], gr[off_A(D, C) + lt(l, m)]);
+    }
+#pragma unroll
+    for (int j = 0; j < D * C; ++j) fn(2, row[off_ga(D, C) + j], gr[off_ga(D, C) + j]);
+}
+
+// stage 1: per CTA, the clipped gradient mass below / above the nudged range of each plain group and the number of
+// elements tied at the group's min / max (fixed-order reductions)
 template <int D, int C>
-__global__ void __launch_bounds__(1024) quant_route_kernel(QuantSet qs_static, const QuantDyn* __restrict__ qdyn,
-                                                           const float* __restrict__ theta, int K_all,
-                                                           float* __restrict__ grads) {
+__global__ void __launch_bounds__(256) quant_route_stage1(QuantSet qs_static, const float* __restrict__ theta, int K_all,
+                                                          float* __restrict__ grads, QuantWork* __restrict__ wk) {
     constexpr int P = nparam(D, C);
+    const QuantDyn* qdyn = &wk->dyn;
     const QuantSet qs = qdyn->qs;
     const int groups[3] = {QG_AC, QG_MU, QG_GA};
-    __shared__ float s_sum[32][6];
-    __shared__ int s_cnt[32][6];
-    __shared__ float s_share[6];
     float sum[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // [2*j]: below, [2*j+1]: above
     int cnt[6] = {0, 0, 0, 0, 0, 0};                    // ties at min / max
-    auto visit = [&](auto&& fn) {
-        for (int i = threadIdx.x; i < K_all; i += 1024) {
-            const float* row = theta + (size_t)i * P;
-            if (!(fake_quant(row[off_pi(D, C)], qs_static.g[QG_PI]) > 0.f)) continue;
-            float* gr = grads + (size_t)i * P;
-#pragma unroll
-            for (int l = 0; l < D; ++l) {
-                fn(1, row[off_mu(D, C) + l], gr[off_mu(D, C) + l]);
-#pragma unroll
-                for (int m = 0; m < l; ++m) fn(0, row[off_A(D, C) + lt(l, m)], gr[off_A(D, C) + lt(l, m)]);
-            }
-#pragma unroll
-            for (int j = 0; j < D * C; ++j) fn(2, row[off_ga(D, C) + j], gr[off_ga(D, C) + j]);
-            // structural zeros of A_corr take part in the ties at min / max
-            if (qdyn->mn[QG_AC] == 0.f) cnt[0] += D * D - D * (D - 1) / 2;
-            if (qdyn->mx[QG_AC] == 0.f) cnt[1] += D * D - D * (D - 1) / 2;
-        }
-    };
-    visit([&](int j, float x, float& g) {
-        const Nudged n = qs.g[groups[j]];
-        if (!(n.flags & QF_ROUTE)) return;
-        if (x < n.nmin) sum[2 * j] += g;
-        if (x > n.nmax) sum[2 * j + 1] += g;
-        if (x == qdyn->mn[groups[j]]) cnt[2 * j] += 1;
-        if (x == qdyn->mx[groups[j]]) cnt[2 * j + 1] += 1;
-    });
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < K_all; i += gridDim.x * 256) {
+        const float* row = theta + (size_t)i * P;
+        if (!(fake_quant(row[off_pi(D, C)], qs_static.g[QG_PI]) > 0.f)) continue;
+        route_visit<D, C>(row, grads + (size_t)i * P, [&](int j, float x, float& g) {
+            const Nudged n = qs.g[groups[j]];
+            if (!(n.flags & QF_ROUTE)) return;
+            if (x < n.nmin) sum[2 * j] += g;
+            if (x > n.nmax) sum[2 * j + 1] += g;
+            if (x == qdyn->mn[groups[j]]) cnt[2 * j] += 1;
+            if (x == qdyn->mx[groups[j]]) cnt[2 * j + 1] += 1;
+        });
+        // structural zeros of A_corr take part in the ties at min / max
+        if (qdyn->mn[QG_AC] == 0.f) cnt[0] += D * D - D * (D - 1) / 2;
+        if (qdyn->mx[QG_AC] == 0.f) cnt[1] += D * D - D * (D - 1) / 2;
+    }
+    __shared__ float s_sum[8][6];
+    __shared__ int s_cnt[8][6];
 #pragma unroll
     for (int q = 0; q < 6; ++q)
 #pragma unroll
@@ -595,31 +629,45 @@ __global__ void __launch_bounds__(1024) quant_route_kernel(QuantSet qs_static, c
     if (threadIdx.x < 6) {
         float t = 0.f;
         int c = 0;
-        for (int w = 0; w < 32; ++w) { t += s_sum[w][threadIdx.x]; c += s_cnt[w][threadIdx.x]; }
-        s_share[threadIdx.x] = c > 0 ? t / (float)c : 0.f;
+        for (int w = 0; w < 8; ++w) { t += s_sum[w][threadIdx.x]; c += s_cnt[w][threadIdx.x]; }
+        wk->rpart[blockIdx.x].sum[threadIdx.x] = t;
+        wk->rpart[blockIdx.x].cnt[threadIdx.x] = c;
     }
-    __syncthreads();
-    // second sweep: mask + shares (cnt / sum are dead from here on)
-    for (int i = threadIdx.x; i < K_all; i += 1024) {
+}
+
+// stage 2: equal shares of the clipped mass for the tied extreme elements
+__global__ void __launch_bounds__(32) quant_route_stage2(int nblocks, QuantWork* __restrict__ wk) {
+    if (threadIdx.x >= 6) return;
+    float t = 0.f;
+    int c = 0;
+    for (int b = 0; b < nblocks; ++b) { t += wk->rpart[b].sum[threadIdx.x]; c += wk->rpart[b].cnt[threadIdx.x]; }
+    wk->share[threadIdx.x] = c > 0 ? t / (float)c : 0.f;
+}
+
+// stage 3: in-range mask + shares.  Mode-3 gradient routing for the plain groups (A_corr, musX, gamma_e), applied once
+// to the accumulated gradient before Adam: in-range elements keep their gradient; the gradients of elements below
+// nudged_min / above nudged_max go to the `min` / `max` inputs of fake_quant_with_min_max_vars and from there, through
+// reduce_min / reduce_max (equal shares among ties), to the extreme elements of the kept kernels.  When the extreme
+// of A_corr is one of its structural zeros, that share lands on a variable entry the graph never reads; it is
+// dropped here (deviation from HEAD, which would start moving that unused entry).
+template <int D, int C>
+__global__ void __launch_bounds__(256) quant_route_stage3(QuantSet qs_static, const float* __restrict__ theta, int K_all,
+                                                          float* __restrict__ grads, const QuantWork* __restrict__ wk) {
+    constexpr int P = nparam(D, C);
+    const QuantDyn* qdyn = &wk->dyn;
+    const QuantSet qs = qdyn->qs;
+    const int groups[3] = {QG_AC, QG_MU, QG_GA};
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < K_all; i += gridDim.x * 256) {
         const float* row = theta + (size_t)i * P;
         if (!(fake_quant(row[off_pi(D, C)], qs_static.g[QG_PI]) > 0.f)) continue;
-        float* gr = grads + (size_t)i * P;
-        auto fix = [&](int j, float x, float& g) {
+        route_visit<D, C>(row, grads + (size_t)i * P, [&](int j, float x, float& g) {
             const Nudged n = qs.g[groups[j]];
             if (!(n.flags & QF_ROUTE)) return;
             float v = (x >= n.nmin && x <= n.nmax) ? g : 0.f;
-            if (x == qdyn->mn[groups[j]]) v += s_share[2 * j];
-            if (x == qdyn->mx[groups[j]]) v += s_share[2 * j + 1];
+            if (x == qdyn->mn[groups[j]]) v += wk->share[2 * j];
+            if (x == qdyn->mx[groups[j]]) v += wk->share[2 * j + 1];
             g = v;
-        };
-#pragma unroll
-        for (int l = 0; l < D; ++l) {
-            fix(1, row[off_mu(D, C) + l], gr[off_mu(D, C) + l]);
-#pragma unroll
-            for (int m = 0; m < l; ++m) fix(0, row[off_A(D, C) + lt(l, m)], gr[off_A(D, C) + lt(l, m)]);
-        }
-#pragma unroll
-        for (int j = 0; j < D * C; ++j) fix(2, row[off_ga(D, C) + j], gr[off_ga(D, C) + j]);
+        });
     }
 }
 
@@ -673,7 +721,7 @@ int smoe_pack(const smoe_cfg* cfg, const float* theta, const float* mus_grid, co
     return check_launch("smoe_pack");
 }
 
-size_t smoe_quant_ranges_bytes(void) { return sizeof(QuantDyn); }
+size_t smoe_quant_ranges_bytes(void) { return sizeof(QuantWork); }      // QuantDyn first, then the two-stage scratch
 
 int smoe_quant_ranges(const smoe_cfg* cfg, const float* theta, int K_all, int train_musx, void* quant_ranges,
                       void* stream) {
@@ -682,9 +730,12 @@ int smoe_quant_ranges(const smoe_cfg* cfg, const float* theta, int K_all, int tr
     QuantSet qs = make_quantset(cfg);
     qs.g[QG_PI] = nudge(cfg->pis_lb, cfg->pis_ub, cfg->pis_bits);
     cudaStream_t st = (cudaStream_t)stream;
-#define CALL(D, C) quant_ranges_kernel<D, C><<<1, 1024, 0, st>>>(*cfg, qs, train_musx, theta, K_all, (QuantDyn*)quant_ranges);
+    int nb = (K_all + 255) / 256;
+    if (nb > kQBlocks) nb = kQBlocks;
+#define CALL(D, C) quant_ranges_stage1<D, C><<<nb, 256, 0, st>>>(qs, theta, K_all, (QuantWork*)quant_ranges);
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL
+    quant_ranges_stage2<<<1, 32, 0, st>>>(*cfg, qs, train_musx, nb, (QuantWork*)quant_ranges);
     return check_launch("smoe_quant_ranges");
 }
 
@@ -709,7 +760,13 @@ int smoe_quant_route(const smoe_cfg* cfg, const float* theta, const void* quant_
     QuantSet qs = make_quantset(cfg);
     qs.g[QG_PI] = nudge(cfg->pis_lb, cfg->pis_ub, cfg->pis_bits);
     cudaStream_t st = (cudaStream_t)stream;
-#define CALL(D, C) quant_route_kernel<D, C><<<1, 1024, 0, st>>>(qs, (const QuantDyn*)quant_ranges, theta, K_all, grads);
+    int nb = (K_all + 255) / 256;
+    if (nb > kQBlocks) nb = kQBlocks;
+    QuantWork* wk = (QuantWork*)const_cast<void*>(quant_ranges);       // the scratch part of the opaque block
+#define CALL(D, C)                                                                 \
+    quant_route_stage1<D, C><<<nb, 256, 0, st>>>(qs, theta, K_all, grads, wk);     \
+    quant_route_stage2<<<1, 32, 0, st>>>(nb, wk);                                  \
+    quant_route_stage3<D, C><<<nb, 256, 0, st>>>(qs, theta, K_all, grads, wk);
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL
     return check_launch("smoe_quant_route");

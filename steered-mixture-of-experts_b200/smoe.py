@@ -1008,7 +1008,7 @@ class Smoe:
         if pre and self._qdyn is not None and not fed:
             check(L.smoe_quant_ranges(C.byref(self._cfg), ptr(self._theta), K, int(self.train_musx), ptr(self._qdyn), st),
                   "smoe_quant_ranges")
-            self.gpu_launches += 1
+            self.gpu_launches += 2
         ax2 = ptr(self._d_axes[2]) if self.dim_domain == 3 else ptr(None)
         for ii, b in enumerate(batches):
             counts, regs, scal = self._counts[ii], self._regsums[ii], self._scalars[ii]
@@ -1103,7 +1103,7 @@ class Smoe:
         if train and self._qdyn is not None:             # clipped gradients of the plain groups -> extreme elements
             check(L.smoe_quant_route(C.byref(self._cfg), ptr(self._theta), ptr(self._qdyn), K, ptr(self._grads), st),
                   "smoe_quant_route")
-            self.gpu_launches += 1
+            self.gpu_launches += 3
         if train:
             self._adam_launch(fuse_klist=len(batches) == 1 and not with_quantized_params)
         # one small device->host read per call: scalars, counts, regulariser sums

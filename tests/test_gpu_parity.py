@@ -415,6 +415,23 @@ def test_reconstruction_entry_point_round_trip(tmp_path):
     np.testing.assert_array_equal(p_saved["A_diagonal"], p_loaded["A_diagonal"])
 
 
+def test_negative_determinant_weight_is_reported():
+    """pi * prod(diag A) < 0 under use_determinant: the reference would give the kernel a NEGATIVE weight (smoe.py:809-820);
+    the log-domain kernels evaluate |weight| and the host says so (counts[2] -> one warning per model)."""
+    rs = np.random.RandomState(2)
+    img = rs.uniform(0, 1, (32, 32, 1)).astype(np.float32)
+    m = _mk(img, [4, 4], use_determinant=True, train_inverse_cov=False, use_yuv=False)
+    p = m.get_params()
+    p["A_diagonal"][5, 0, 0] *= -1
+    m.set_params(p)
+    with pytest.warns(UserWarning, match="pi \\* prod"):
+        m.run_batched(train=False)
+    assert m._last_nonpos == 1
+    m2 = _mk(img, [4, 4], use_determinant=True, train_inverse_cov=False, use_yuv=False)
+    m2.run_batched(train=False)
+    assert m2._last_nonpos == 0
+
+
 def test_reference_written_checkpoint_loads_and_reconstructs(tmp_path):
     """a checkpoint pickle written by the REFERENCE's utils.save_model (tests/golden/, made by
     oracle/make_golden.py from the real code) goes through the product's smoe_reconstruction.main unchanged, and the

@@ -206,8 +206,8 @@ int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const float* pack
  *            pixels); a plain training pass needs only its sums and passes NULL
  *   scalars  [SMOE_NSCAL]: [0..C) sum_n (|diff|-eps)^2 per channel, [4] sum diff^2, [5] non-finite flag; accumulated
  *            (+=) so that batches / ranks can be summed; the caller zeroes it (smoe_pack can)
- *   partials [smoe_loss_partials()][8] scratch, ticket: one int32, zero before the first call */
-int smoe_loss_partials(void);
+ *   partials [smoe_loss_partials(batch)][8] scratch, ticket: one int32, zero before the first call */
+int smoe_loss_partials(const smoe_batch* batch);
 int smoe_loss(const smoe_cfg* cfg, const smoe_batch* batch, const float* rbuf, const float* image,
               const uint8_t* image_u8, const float* loss_weights, float* res, float* pix, float* scalars,
               float* partials, int32_t* ticket, void* stream);

@@ -118,32 +118,65 @@ __global__ void __launch_bounds__(128) bwd_plan_kernel(const BwdArgs a) {
     const float blam = v[6], bc0 = -v[7];
     const float zcut_tile = a.zero_cut - 0.5f;
     uint32_t* bits = a.plan_bits + (size_t)g * a.nwords;
+    extern __shared__ uint32_t s_bits[];                      // [nwords]
+    for (int w = tid; w < a.nwords; w += 128) s_bits[w] = (cull && blam >= 0.f) ? 0u : 0xffffffffu;
+    __syncthreads();
     int n = 0;
-    for (int base = 0; base < a.ntiles; base += 128) {
-        const int tile = base + tid;
-        bool need = false;
-        if (tile < a.ntiles) {
-            need = true;
-            if (cull) {
-                float ctr[3], half[3];
-                tile_box_of<D>(a, tile, ctr, half);
-                float d2 = 0.f, kd = 0.f;
+    if (cull && blam >= 0.f) {
+        // Conservative tile rectangle: a tile further than r_l = sqrt((c0_max - cut - qthr_min) / kap_l) from the group's
+        // box along axis l cannot pass the test below, and qthr >= log2(1e-11) > -36.6 everywhere (smoe.py:821).  Only the
+        // tiles inside the rectangle are tested -- a few dozen instead of every tile of the batch.
+        int tlo[3] = {0, 0, 0}, tn[3] = {1, 1, 1};
+        const int ntile[3] = {(a.ntiles / (a.nt1 * a.nt2)), a.nt1, a.nt2};
 #pragma unroll
-                for (int l = 0; l < D; ++l) {
-                    const float mn = v[l] - ctr[l], mx = -v[3 + l] - ctr[l];
-                    const float gap = fmaxf(fmaxf(mn - half[l], -half[l] - mx), 0.f);
-                    d2 = fmaf(gap, gap, d2);
-                    kd = fmaxf(kd, v[8 + l] * gap * gap);
+        for (int l = 0; l < 3; ++l) {
+            tn[l] = ntile[l];
+            if (l < D) {
+                const int o = a.b.origin[l], e = a.b.extent[l];
+                const float x0 = a.ax[l][o], dx = e > 1 ? (a.ax[l][o + e - 1] - x0) / (float)(e - 1) : 1.f;
+                const float kap = v[8 + l];
+                if (kap > 0.f && dx > 0.f) {
+                    const float r = sqrtf(fmaxf(bc0 - zcut_tile + 36.6f, 0.f) / kap) * 1.001f + dx;
+                    const float plo = (v[l] - r - x0) / dx, phi = (-v[3 + l] + r - x0) / dx;       // pixel range, batch-relative
+                    int lo_t = (int)floorf(fmaxf(plo, 0.f)) / a.b.tile[l] - 1;
+                    int hi_t = (int)ceilf(fminf(fmaxf(phi, 0.f), (float)(e - 1))) / a.b.tile[l] + 1;
+                    lo_t = max(lo_t, 0);
+                    hi_t = min(hi_t, ntile[l] - 1);
+                    if (!(plo <= (float)e) || !(phi >= 0.f)) hi_t = lo_t - 1;                       // misses the batch
+                    tlo[l] = lo_t;
+                    tn[l] = max(hi_t - lo_t + 1, 0);
                 }
-                const float ub = bc0 - fmaxf(blam * d2, kd) - a.tile_qmin[tile];
-                need = !(blam >= 0.f) || !(ub < zcut_tile);
             }
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, need);
-        if ((tid & 31) == 0 && base + tid < a.nwords * 32) bits[(base + tid) >> 5] = bal;
-        n += __popc(bal);
+        const int ncand = tn[0] * tn[1] * tn[2];
+        for (int it = tid; it < ncand; it += 128) {
+            const int c2 = it % tn[2], c1 = (it / tn[2]) % tn[1], c0i = it / (tn[2] * tn[1]);
+            const int tile = ((tlo[0] + c0i) * a.nt1 + (tlo[1] + c1)) * a.nt2 + (tlo[2] + c2);
+            float ctr[3], half[3];
+            tile_box_of<D>(a, tile, ctr, half);
+            float d2 = 0.f, kd = 0.f;
+#pragma unroll
+            for (int l = 0; l < D; ++l) {
+                const float mn = v[l] - ctr[l], mx = -v[3 + l] - ctr[l];
+                const float gap = fmaxf(fmaxf(mn - half[l], -half[l] - mx), 0.f);
+                d2 = fmaf(gap, gap, d2);
+                kd = fmaxf(kd, v[8 + l] * gap * gap);
+            }
+            const float ub = bc0 - fmaxf(blam * d2, kd) - a.tile_qmin[tile];
+            if (!(ub < zcut_tile)) atomicOr(&s_bits[tile >> 5], 1u << (tile & 31));
+        }
+        __syncthreads();
     }
-    // n holds this warp's count: fixed-order sum over the 4 warps
+    for (int w = tid; w < a.nwords; w += 128) {
+        uint32_t b = s_bits[w];
+        const int base = w * 32;
+        if (base + 32 > a.ntiles) b &= (base < a.ntiles) ? ((1u << (a.ntiles - base)) - 1u) : 0u;     // no bits beyond the batch
+        bits[w] = b;
+        n += __popc(b);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_down_sync(0xffffffffu, n, o);
+    // fixed-order sum over the 4 warps
     if ((tid & 31) == 0) s_cnt[tid >> 5] = n;
     __syncthreads();
     n = s_cnt[0] + s_cnt[1] + s_cnt[2] + s_cnt[3];
@@ -365,6 +398,9 @@ __global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) 
                 // row sums: along a row only z varies, so sum t, sum t z, sum t z^2 (and sum v_c, sum v_c z)
                 // carry every moment of the row; they are folded once per row
                 bool row_active = false;
+                // (the two lanes of a kernel read rows RL floats apart, i.e. the same banks when RL = 32: a 2-way conflict
+                // on these broadcast loads; measured, walking the second row rotated by half a row costs more
+                // instructions than the conflicts cost LSU cycles -- the LSU pipe is at 16 %)
                 for (int j0 = r0; j0 < r0 + RL; j0 += GRP) {
                     const float4 zv = *reinterpret_cast<const float4*>(pl + PL_Z * SMOE_TPIX + j0);
                     const float4 tv = *reinterpret_cast<const float4*>(pl + PL_QTHR * SMOE_TPIX + j0);
@@ -755,7 +791,7 @@ int smoe_backward(const smoe_cfg* cfg, const smoe_batch* batch, const float* pac
     cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(D, C, CNT)                                                                                      \
     {                                                                                                          \
-        bwd_plan_kernel<D, C><<<groups, 128, 0, st>>>(a);                                                      \
+        bwd_plan_kernel<D, C><<<groups, 128, (size_t)a.nwords * 4, st>>>(a);                                                      \
         cudaFuncSetAttribute(backward_kernel<D, C, CNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
         backward_kernel<D, C, CNT><<<grid, kThreads, sm, st>>>(a);                                             \
     }

@@ -524,11 +524,13 @@ __global__ void __launch_bounds__(256) loss_kernel(const LossArgs a) {
     for (int c = 0; c < C; ++c) lsum[c] = 0.f;
     float sqsum = 0.f;
     int nonfinite = 0;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    {
+        // one tile per CTA: blockIdx.y = first tile coordinate, blockIdx.x = the other two (no per-pixel divisions)
         int tt[3], lo[3], hi[3];
-        tt[2] = tile % a.nt2;
-        tt[1] = (tile / a.nt2) % a.nt1;
-        tt[0] = tile / (a.nt2 * a.nt1);
+        tt[0] = blockIdx.y;
+        tt[1] = a.nt2 == 1 ? (int)blockIdx.x : (int)blockIdx.x / a.nt2;
+        tt[2] = a.nt2 == 1 ? 0 : (int)blockIdx.x % a.nt2;
+        const int tile = (tt[0] * a.nt1 + tt[1]) * a.nt2 + tt[2];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             lo[i] = a.b.origin[i] + tt[i] * a.b.tile[i];
@@ -590,9 +592,12 @@ __global__ void __launch_bounds__(256) loss_kernel(const LossArgs a) {
             }
         }
     }
-    // partials: warp shuffle -> CTA -> fixed-order sum by the last CTA
+    // partials: warp shuffle -> CTA -> fixed-order sum by the last CTA (thread t adds the CTA partials t, t+256, ...
+    // in order, then a fixed tree over the 256 threads)
     __shared__ float red[8][8];
+    __shared__ float tree[256];
     __shared__ int s_last;
+    const int nblk = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
     float vals[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) vals[q] = 0.f;
@@ -611,18 +616,25 @@ __global__ void __launch_bounds__(256) loss_kernel(const LossArgs a) {
     if (tid < 8) {
         float s = 0.f;
         for (int wv = 0; wv < 8; ++wv) s += red[wv][tid];
-        a.partials[(size_t)blockIdx.x * 8 + tid] = s;
+        a.partials[(size_t)bid * 8 + tid] = s;
     }
     __threadfence();
     __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(a.ticket, 1) == (int)gridDim.x - 1);
+    if (tid == 0) s_last = (atomicAdd(a.ticket, 1) == nblk - 1);
     __syncthreads();
     if (s_last) {
         __threadfence();
-        if (tid < 8) {
+        for (int q = 0; q < 6; ++q) {
             float s = 0.f;
-            for (int bq = 0; bq < (int)gridDim.x; ++bq) s += __ldcg(&a.partials[(size_t)bq * 8 + tid]);
-            a.scalars[tid] += s;
+            for (int bq = tid; bq < nblk; bq += 256) s += __ldcg(&a.partials[(size_t)bq * 8 + q]);
+            tree[tid] = s;
+            __syncthreads();
+            for (int o = 128; o > 0; o >>= 1) {
+                if (tid < o) tree[tid] += tree[tid + o];
+                __syncthreads();
+            }
+            if (tid == 0) a.scalars[q] += tree[0];
+            __syncthreads();
         }
         if (tid == 0) *a.ticket = 0;
     }
@@ -695,10 +707,8 @@ extern "C" int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const 
     return check_launch("smoe_forward");
 }
 
-extern "C" int smoe_loss_partials(void) {
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return sms * 8;                 // CTAs of the loss stage at most; 8 floats each
+extern "C" int smoe_loss_partials(const smoe_batch* batch) {
+    return batch ? smoe_num_tiles(batch) : 0;          // one CTA per tile; 8 floats each
 }
 
 extern "C" int smoe_loss(const smoe_cfg* cfg, const smoe_batch* batch, const float* rbuf, const float* image,
@@ -722,8 +732,9 @@ extern "C" int smoe_loss(const smoe_cfg* cfg, const smoe_batch* batch, const flo
     a.eps = cfg->margin / two_p;
     a.q_scale = 1.0f / (two_p - 1.0f);
     a.q_inv_scale = 1.0f / a.q_scale;
-    const int cap = smoe_loss_partials();
-    const int grid = a.ntiles < cap ? a.ntiles : cap;
+    const int nt0 = a.ntiles / (a.nt1 * a.nt2);
+    SMOE_REQUIRE(nt0 <= 65535, "too many tiles along the first axis");
+    const dim3 grid(a.nt1 * a.nt2, nt0);
     if (cfg->C == 1) loss_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
     else loss_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
     return check_launch("smoe_loss");

@@ -531,7 +531,8 @@ class Smoe:
         self._pair_counts = None        # uint64[8] executed-pair counters, enable_pair_counts()
         self._chunk_bounds = torch.zeros(((K + 127) // 128, 12), dtype=f32, device=dev)
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        self._partials = torch.zeros((8 * int(L.smoe_loss_partials()),), dtype=f32, device=dev)
+        self._partials = torch.zeros((8 * max(int(L.smoe_loss_partials(C.byref(b))) for b in self._batches),),
+                                     dtype=f32, device=dev)
         self._ticket = torch.zeros((4,), dtype=torch.int32, device=dev)
         self._pack_ws = torch.zeros((L.smoe_pack_workspace_bytes(K) + 15) // 4, dtype=torch.int32, device=dev)
         # Pixel splits of the backward (split s owns tiles s, s+NS, ...): sized for the kernel groups that will have

@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(128) bwd_plan_kernel(const BwdArgs a) {
     if (tid == 0) a.plan_cnt[g] = n;
 }
 
-template <int D, int C, bool COUNT>
+// DENSE: the dense_exec = 1 instantiation (every pair executed in full) carries none of the skip tests.
+template <int D, int C, bool COUNT, bool DENSE>
 __global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) {
     using R = BRec<D, C>;
     constexpr int T = tri(D);
@@ -213,7 +214,8 @@ __global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) 
     const float zcut = a.zero_cut, zcut_tile = a.zero_cut - 0.5f;
     unsigned cnt_vis = 0, cnt_gate = 0, cnt_exp = 0;      // COUNT only: warp-level group counters (lane 0)
     const int mode = a.cfg.dense_exec;                   // 0 cull+skip, 1 dense, 2 skip only
-    const bool cull = mode == 0, skip = mode != 1;
+    const bool cull = !DENSE && mode == 0;
+    constexpr bool skip = !DENSE;
     const float ltau = a.ltau;
 
     if (tid == 0) {
@@ -421,6 +423,28 @@ __global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) 
                     row_active = true;
                     const float4 grv = *reinterpret_cast<const float4*>(pl + PL_GR * SMOE_TPIX + j0);
                     const float gr4[GRP] = {grv.x, grv.y, grv.z, grv.w};
+                    // does any gate of the group pass the threshold for any kernel of the warp?  Most groups that
+                    // reach this point only carry sub-threshold gates (w < tau): they need neither the g_c planes nor
+                    // the expert part, only t = -w gr and its moments.
+                    bool gpass = true;
+                    if (skip) {
+                        gpass = false;
+#pragma unroll
+                        for (int u = 0; u < GRP; ++u) gpass |= dq[u] > ltau;
+                        gpass = __any_sync(0xffffffffu, gpass);
+                    }
+                    if (!gpass) {
+#pragma unroll
+                        for (int u = 0; u < GRP; ++u) {
+                            const float w = ex2f(dq[u]);             // e / S: the plane holds log2 S
+                            const float t = -w * gr4[u];
+                            const float uz = t * z4[u];
+                            s0 += t;
+                            s1 += uz;
+                            s2 = fmaf(uz, z4[u], s2);
+                        }
+                        continue;
+                    }
                     float g4[C][GRP];
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
@@ -789,13 +813,15 @@ int smoe_backward(const smoe_cfg* cfg, const smoe_batch* batch, const float* pac
     size_t sm = 2 * (size_t)pix_stride(cfg->d, cfg->C, batch->tile[cfg->d - 1]) * 4 + 16 + 16 * 4 + (size_t)a.max_list * 4 + 64;
     SMOE_REQUIRE(sm <= 100 * 1024, "too many tiles per split for the shared-memory tile list: raise num_splits");
     cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH(D, C, CNT)                                                                                      \
-    {                                                                                                          \
-        bwd_plan_kernel<D, C><<<groups, 128, (size_t)a.nwords * 4, st>>>(a);                                                      \
-        cudaFuncSetAttribute(backward_kernel<D, C, CNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
-        backward_kernel<D, C, CNT><<<grid, kThreads, sm, st>>>(a);                                             \
+#define LAUNCH(D, C, CNT, DN)                                                                                       \
+    {                                                                                                               \
+        bwd_plan_kernel<D, C><<<groups, 128, (size_t)a.nwords * 4, st>>>(a);                                        \
+        cudaFuncSetAttribute(backward_kernel<D, C, CNT, DN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+        backward_kernel<D, C, CNT, DN><<<grid, kThreads, sm, st>>>(a);                                              \
     }
-#define CALL(D, C) if (pair_counts) LAUNCH(D, C, true) else LAUNCH(D, C, false)
+#define CALL(D, C)                                                                                        \
+    if (cfg->dense_exec == 1) { if (pair_counts) LAUNCH(D, C, true, true) else LAUNCH(D, C, false, true) } \
+    else { if (pair_counts) LAUNCH(D, C, true, false) else LAUNCH(D, C, false, false) }
     SMOE_DISPATCH_DC(cfg->d, cfg->C, CALL)
 #undef CALL
 #undef LAUNCH

@@ -95,7 +95,7 @@ ms_s = None
 mS, ms_s = step_ms(ssim_opt=True)
 out["c3_step_ms"]["ssim_opt"] = ms_s
 b = mS._batches[0]
-ms_sl = timeit(lambda: check(lib().smoe_ssim_loss(C.byref(mS._cfg), C.byref(b), ptr(mS._d_res), ptr(mS._d_image),
+ms_sl = timeit(lambda: check(lib().smoe_ssim_loss(C.byref(mS._cfg), C.byref(b), ptr(None), ptr(mS._d_res), ptr(mS._d_image),
                                                   ptr(mS._d_res_pre), ptr(mS._pix), ptr(mS._scalars[0]), ptr(mS._ssim_ws),
                                                   stream_ptr()), "ssim_loss"))
 npx = mS.num_pixel

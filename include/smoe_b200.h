@@ -133,7 +133,7 @@ size_t      smoe_backward_workspace_bytes(const smoe_cfg* cfg, int K_cap, int nu
  * 1012 (num_pi = count_nonzero(qpis>0)); stable stream compaction of the sequence perm[0..K_all) (perm == NULL:
  * ascending kernel index, the order of the reference's boolean_mask).  The SET {indices[0..K)} is the reference's
  * `indices`; the ORDER is a work-assignment choice: with perm = Hilbert order of the centres (smoe_spatial_keys +
- * a sort), 128 consecutive records (one shared-memory chunk of smoe_forward) and 64 consecutive records (one CTA of
+ * a sort), 128 consecutive records (one shared-memory chunk of smoe_forward) and 32 consecutive records (one CTA of
  * smoe_backward) are spatial neighbours, which is what the exact tile culling exploits.
  *   counts[0] = K (active), counts[1] = num_pi, counts[2] = kernels with pi*det <= 0 (unsupported
  *   by the fast path, reported), counts[3] = 0
@@ -221,7 +221,7 @@ int smoe_backward(const smoe_cfg* cfg, const smoe_batch* batch, const float* pac
                   int K_cap, const float* pix, const float* tile_qmin,
                   const float* ax0, const float* ax1, const float* ax2, int num_splits, float* raw_part,
                   int32_t* plan /* smoe_backward_plan_bytes: [groups] reachable-tile counts | [groups] tile bitmasks,
-                  groups of 64 packed kernels; written by a planning pre-pass of this call and read again by
+                  groups of 32 packed kernels; written by a planning pre-pass of this call and read again by
                   smoe_grad_finalize / smoe_reduce_splits / smoe_xchg_publish */,
                   unsigned long long* pair_counts /* optional, see smoe_forward */, void* stream);
 size_t smoe_backward_plan_bytes(int K_cap, const smoe_batch* batch);

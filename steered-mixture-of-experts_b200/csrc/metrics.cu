@@ -5,10 +5,11 @@
 // SYMMETRIC pad by 5 on every domain axis, 11-tap sigma-1.5 Gaussian window (the reference's
 // softmax-normalised 11^d window is the outer product of the normalised 1-D windows), VALID
 // correlation of x, y, x*x+y*y, x*y, K1=.01, K2=.03, mean over positions per channel.
-// Implemented as separable passes (innermost axis first) over a 4-plane workspace; the last
-// pass fuses the SSIM formula and a fixed-order block reduction (no atomics).
+// 2-D: one shared-memory tile kernel (ssim_tile.cuh).  3-D: separable passes (innermost axis first) over a 4-plane
+// workspace; the last pass fuses the SSIM formula and a fixed-order block reduction (no atomics).
 #include <math.h>
 #include "smoe_common.cuh"
+#include "ssim_tile.cuh"
 
 namespace smoe {
 
@@ -83,113 +84,6 @@ __global__ void __launch_bounds__(256) ssim_pass_kernel(const float* __restrict_
                 if (s_c[t] == (int)threadIdx.x) s += (double)s_v[t];
             partial[(size_t)blockIdx.x * 4 + threadIdx.x] = s;
         }
-    }
-}
-
-// Fused 2-D SSIM: one CTA per 32x32 output tile, all channels.  The (32+10)^2 x C input tiles of both
-// images are staged in shared memory with the SYMMETRIC reflection folded into the load, then per
-// channel a horizontal and a vertical 11-tap pass run out of shared memory and the SSIM map is reduced
-// in fixed order.  HBM traffic = 2 * 1.72 * N*C*4 bytes (halo re-reads mostly hit L2).
-constexpr int ST = 32, SH = ST + 10, SHP = SH + 1, SEG = 8;
-__global__ void __launch_bounds__(256) ssim2d_fused_kernel(const float* __restrict__ a, const float* __restrict__ b,
-                                                           int n0, int n1, int C, float c1, float c2,
-                                                           double* __restrict__ partial) {
-    extern __shared__ float sm[];
-    float* ta = sm;                          // [C][SH][SHP]  planar, padded rows
-    float* tb = ta + C * SH * SHP;           // [C][SH][SHP]
-    float* hb = tb + C * SH * SHP;           // [4][SH][ST]
-    const int tid = threadIdx.x;
-    const int y0 = blockIdx.y * ST, x0 = blockIdx.x * ST;
-    for (int i = tid; i < SH * SH * C; i += 256) {
-        const int c = i % C, xx = (i / C) % SH, yy = i / (C * SH);
-        const int gy = reflect_sym(y0 + yy - 5, n0), gx = reflect_sym(x0 + xx - 5, n1);
-        const size_t g = ((size_t)gy * n1 + gx) * C + c;
-        ta[(c * SH + yy) * SHP + xx] = a[g];
-        tb[(c * SH + yy) * SHP + xx] = b[g];
-    }
-    __syncthreads();
-    float w[11];
-#pragma unroll
-    for (int k = 0; k < 11; ++k) w[k] = c_win[k];
-    float acc_c[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int c = 0; c < C; ++c) {
-        // horizontal pass: each item = SEG consecutive outputs of one row (sliding window in registers)
-        for (int it = tid; it < SH * (ST / SEG); it += 256) {
-            const int yy = it / (ST / SEG), xs = (it % (ST / SEG)) * SEG;
-            float h[4][SEG];
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int u = 0; u < SEG; ++u) h[q][u] = 0.f;
-            const float* ra = ta + (c * SH + yy) * SHP + xs;
-            const float* rb = tb + (c * SH + yy) * SHP + xs;
-#pragma unroll
-            for (int j = 0; j < SEG + 10; ++j) {
-                const float x = ra[j], y = rb[j];
-                const float s2 = fmaf(x, x, y * y), xy = x * y;
-#pragma unroll
-                for (int u = 0; u < SEG; ++u) {
-                    const int k = j - u;
-                    if (k >= 0 && k < 11) {
-                        h[0][u] = fmaf(w[k], x, h[0][u]);
-                        h[1][u] = fmaf(w[k], y, h[1][u]);
-                        h[2][u] = fmaf(w[k], s2, h[2][u]);
-                        h[3][u] = fmaf(w[k], xy, h[3][u]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int u = 0; u < SEG; ++u) hb[(q * SH + yy) * ST + xs + u] = h[q][u];
-        }
-        __syncthreads();
-        // vertical pass + SSIM: each item = SEG consecutive outputs of one column
-        float acc = 0.f;
-        for (int it = tid; it < ST * (ST / SEG); it += 256) {
-            const int xx = it % ST, ys = (it / ST) * SEG;
-            float v[4][SEG];
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int u = 0; u < SEG; ++u) v[q][u] = 0.f;
-#pragma unroll
-            for (int j = 0; j < SEG + 10; ++j) {
-                float in[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) in[q] = hb[(q * SH + ys + j) * ST + xx];
-#pragma unroll
-                for (int u = 0; u < SEG; ++u) {
-                    const int k = j - u;
-                    if (k >= 0 && k < 11) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) v[q][u] = fmaf(w[k], in[q], v[q][u]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < SEG; ++u) {
-                if (y0 + ys + u < n0 && x0 + xx < n1) {
-                    const float num0 = v[0][u] * v[1][u] * 2.0f;
-                    const float den0 = v[0][u] * v[0][u] + v[1][u] * v[1][u];
-                    const float lum = (num0 + c1) / (den0 + c1);
-                    const float cs = (v[3][u] * 2.0f - num0 + c2) / (v[2][u] - den0 + c2);
-                    acc += lum * cs;
-                }
-            }
-        }
-        acc_c[c] = acc;
-        __syncthreads();
-    }
-    // fixed-order block reduction per channel
-    __shared__ float red[4][256];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) red[c][tid] = acc_c[c];
-    __syncthreads();
-    if (tid < 4) {
-        double s = 0.0;
-        for (int t = 0; t < 256; ++t) s += (double)red[tid][t];
-        partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 4 + tid] = s;
     }
 }
 
@@ -356,11 +250,21 @@ int smoe_ssim(int d, const int32_t dims[3], int C, const float* a, const float* 
     double* partial = (double*)((char*)workspace + off);
     const float c1 = 0.01f * 0.01f, c2 = 0.03f * 0.03f;
     if (d == 2) {
-        dim3 grid((n1 + ST - 1) / ST, (n0 + ST - 1) / ST);
-        const size_t smb = (size_t)(2 * C * SH * SHP + 4 * SH * ST) * sizeof(float);
-        cudaFuncSetAttribute(ssim2d_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
-        ssim2d_fused_kernel<<<grid, 256, smb, st>>>(a, b, n0, n1, C, c1, c2, partial);
-        ssim_final_kernel<<<1, 256, 0, st>>>(partial, (int)(grid.x * grid.y), C, 1.0 / (double)((size_t)n0 * n1), out);
+        // shared-memory tile kernel (ssim_tile.cuh): one launch, HBM traffic = the two images once (+ halo re-reads in L2)
+        tile2d::MomentArgs g;
+        g.x = a; g.y = b; g.pitch = n1; g.n0 = n0; g.n1 = n1;
+        g.clo0 = g.clo1 = 0; g.cn0 = n0; g.cn1 = n1;
+        g.c1 = c1; g.c2 = c2; g.maps = nullptr; g.partial = partial;
+        int nb = 0;
+        cudaError_t e = cudaSuccess;
+        switch (C) {
+            case 1: e = tile2d::launch_moments<1, false>(g, st, &nb); break;
+            case 2: e = tile2d::launch_moments<2, false>(g, st, &nb); break;
+            case 3: e = tile2d::launch_moments<3, false>(g, st, &nb); break;
+            default: e = tile2d::launch_moments<4, false>(g, st, &nb); break;
+        }
+        if (e != cudaSuccess) { set_error("smoe_ssim: %s", cudaGetErrorString(e)); return (int)e; }
+        ssim_final_kernel<<<1, 256, 0, st>>>(partial, nb, C, 1.0 / (double)((size_t)n0 * n1), out);
         return check_launch("smoe_ssim");
     } else {
         ssim_pass_kernel<true, false><<<nblocks, 256, 0, st>>>(a, b, nullptr, p0, n0, n1, n2, C, 2, c1, c2, nullptr);

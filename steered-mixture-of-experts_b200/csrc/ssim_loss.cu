@@ -14,8 +14,17 @@
 // where P is "symmetric pad, then VALID correlation" and P^T its adjoint.  P is separable, so both P and
 // P^T run as one 11-tap pass per axis over planes local to the batch's loss rectangle.  HBM-bound
 // elementwise / stencil work; no atomics, fixed-order reductions.
+//
+// Images (d = 2) take two shared-memory tile kernels instead of the six global-memory passes: ssim2d_tile_kernel
+// (ssim_tile.cuh) computes the window moments, the SSIM sum and the maps a, b, c of a 32x32 tile of positions;
+// sl_adj_apply_tile applies P^T to a 32x32 tile of pixels out of shared memory and writes the backward state.  Both
+// accumulate every sum in the order of the separable passes (kept for video and for rectangles below 16 pixels),
+// so the two routes give the same bits (tested).
+#include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 #include "smoe_common.cuh"
+#include "ssim_tile.cuh"
 
 namespace smoe {
 
@@ -207,6 +216,166 @@ __global__ void __launch_bounds__(256) sl_apply(smoe_cfg cfg, smoe_batch b, LRec
     tp[PL_GR * SMOE_TPIX + j] = live ? gr : 0.f;
 }
 
+// P^T of the maps a, b, c and d loss / d res -> the g_c / gr planes, for one 32x32 tile of pixels of the count
+// rectangle.  The maps of the tile plus a ring of 5 are staged in shared memory (0 outside the compute rectangle); a
+// pixel within 5 of a border of the compute rectangle also collects the windows centred on its mirror image in the
+// symmetric padding (the one position jp outside [0, n) with reflect(jp) = pos; n >= 16 makes it unique).
+struct AdjArgs {
+    smoe_cfg cfg;
+    smoe_batch b;
+    LRect r;
+    const float* maps;        // [3][n0 * n1 * C]
+    const float* res;
+    const float* image;
+    const float* res_pre;
+    float* pix;
+    int nt1, nt2;
+};
+
+template <int D, int C>
+__global__ void __launch_bounds__(tile2d::NT) sl_adj_apply_tile(AdjArgs g) {
+    using namespace tile2d;
+    extern __shared__ float sm[];
+    float* tm = sm;                           // [3][C][H][HP]   maps of the tile + ring
+    float* hb = tm + 3 * C * H * HP;          // [3][T][HP]      after the pass along y (same axis order as sl_adj_pass)
+    const int tid = threadIdx.x;
+    const LRect& r = g.r;
+    const int n0 = r.n[0], n1 = r.n[1];
+    const int y0 = r.clo[0] + blockIdx.y * T, x0 = r.clo[1] + blockIdx.x * T;     // in compute-rectangle coordinates
+    const size_t total = (size_t)n0 * n1 * C;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) load_tile<C, false>(tm + p * C * H * HP, g.maps + p * total, n1, y0, x0, n0, n1, tid);
+    __syncthreads();
+    float w[11];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) w[k] = c_gauss11[k];
+    // the mirror image of position pos (if it has one): centre of the extra windows
+    auto mirror = [](int pos, int n) { return pos < 5 ? -pos - 1 : (pos >= n - 5 ? 2 * n - 1 - pos : INT_MIN); };
+    const int prow = tid / (T / SEGV), pxs = (tid % (T / SEGV)) * SEGV;     // this thread's pixels: SEGV along x
+    float gr[SEGV];
+#pragma unroll
+    for (int u = 0; u < SEGV; ++u) gr[u] = 0.f;
+    for (int c = 0; c < C; ++c) {
+        // adjoint along y: SEGH consecutive rows of one column (of the tile + ring) per thread
+        if (tid < H * (T / SEGH)) {
+            const int xx = tid % H, ys = (tid / H) * SEGH;
+            float h[3][SEGH];
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+#pragma unroll
+                for (int u = 0; u < SEGH; ++u) h[p][u] = 0.f;
+            const float* col = tm + c * H * HP + xx;
+#pragma unroll
+            for (int j = 0; j < SEGH + 10; ++j) {
+                float in[3];
+#pragma unroll
+                for (int p = 0; p < 3; ++p) in[p] = col[p * C * H * HP + (ys + j) * HP];
+#pragma unroll
+                for (int u = 0; u < SEGH; ++u) {
+                    const int k = j - u;
+                    if (k >= 0 && k < 11) {
+#pragma unroll
+                        for (int p = 0; p < 3; ++p) h[p][u] = fmaf(w[k], in[p], h[p][u]);
+                    }
+                }
+            }
+            if (y0 + ys < 5 || y0 + ys + SEGH > n0 - 5) {          // some row of the segment has a mirror image
+#pragma unroll
+                for (int u = 0; u < SEGH; ++u) {
+                    const int gy = y0 + ys + u;
+                    const int jp = gy < n0 ? mirror(gy, n0) : INT_MIN;
+                    if (jp == INT_MIN) continue;
+                    for (int k = 0; k < 11; ++k) {
+                        const int q = jp + k - 5;
+                        if (q >= 0 && q < n0) {
+#pragma unroll
+                            for (int p = 0; p < 3; ++p)
+                                h[p][u] = fmaf(c_gauss11[k], col[p * C * H * HP + (q - (y0 - 5)) * HP], h[p][u]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+#pragma unroll
+                for (int u = 0; u < SEGH; ++u) hb[(p * T + ys + u) * HP + xx] = h[p][u];
+        }
+        __syncthreads();
+        // adjoint along x: SEGV consecutive pixels of one row per thread, then the pixels' gradient
+        {
+            float v[3][SEGV];
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+#pragma unroll
+                for (int u = 0; u < SEGV; ++u) v[p][u] = 0.f;
+            const float* row = hb + prow * HP;
+#pragma unroll
+            for (int j = 0; j < SEGV + 10; ++j) {
+                float in[3];
+#pragma unroll
+                for (int p = 0; p < 3; ++p) in[p] = row[p * T * HP + pxs + j];
+#pragma unroll
+                for (int u = 0; u < SEGV; ++u) {
+                    const int k = j - u;
+                    if (k >= 0 && k < 11) {
+#pragma unroll
+                        for (int p = 0; p < 3; ++p) v[p][u] = fmaf(w[k], in[p], v[p][u]);
+                    }
+                }
+            }
+            if (x0 + pxs < 5 || x0 + pxs + SEGV > n1 - 5) {
+#pragma unroll
+                for (int u = 0; u < SEGV; ++u) {
+                    const int gx = x0 + pxs + u;
+                    const int jp = gx < n1 ? mirror(gx, n1) : INT_MIN;
+                    if (jp == INT_MIN) continue;
+                    for (int k = 0; k < 11; ++k) {
+                        const int q = jp + k - 5;
+                        if (q >= 0 && q < n1) {
+#pragma unroll
+                            for (int p = 0; p < 3; ++p)
+                                v[p][u] = fmaf(c_gauss11[k], row[p * T * HP + q - (x0 - 5)], v[p][u]);
+                        }
+                    }
+                }
+            }
+            const int gy = y0 + prow;
+#pragma unroll
+            for (int u = 0; u < SEGV; ++u) {
+                const int gx = x0 + pxs + u;
+                if (gy >= r.clo[0] + r.cn[0] || gx >= r.clo[1] + r.cn[1]) continue;
+                const size_t gi = rect_global(r, gy, gx, 0, c);
+                const float x = g.res[gi], y = g.image[gi], rv = g.res_pre[gi];
+                const float cw = g.cfg.use_yuv ? (C == 3 ? (c == 0 ? 0.75f : 0.125f) : 1.0f) : (1.0f / C);   // smoe.py:1006-1009
+                const float dS = fmaf(y, v[2][u], fmaf(2.f * x, v[1][u], v[0][u])) * r.inv_np;
+                const bool ste = (rv >= 0.f) && (rv <= 1.f);
+                const float gc = ste ? -cw * dS : 0.f;                    // loss_pixel = 1 - ssim
+                gr[u] = fmaf(gc, rv, gr[u]);
+                // position inside the batch (forward) rectangle -> tile and slot
+                const int f0 = r.lo[0] + gy - g.b.origin[0], f1 = r.lo[1] + gx - g.b.origin[1];
+                const int tile = ((f0 / g.b.tile[0]) * g.nt1 + f1 / g.b.tile[1]) * g.nt2;
+                const int j = ((f0 % g.b.tile[0]) * g.b.tile[1] + (f1 % g.b.tile[1])) * g.b.tile[2];
+                float* tp = g.pix + (size_t)tile * pix_stride(D, C, g.b.tile[D - 1]);
+                tp[(PL_G + c) * SMOE_TPIX + j] = gc;
+            }
+        }
+        __syncthreads();
+    }
+    const int gy = y0 + prow;
+#pragma unroll
+    for (int u = 0; u < SEGV; ++u) {
+        const int gx = x0 + pxs + u;
+        if (gy >= r.clo[0] + r.cn[0] || gx >= r.clo[1] + r.cn[1]) continue;
+        const int f0 = r.lo[0] + gy - g.b.origin[0], f1 = r.lo[1] + gx - g.b.origin[1];
+        const int tile = ((f0 / g.b.tile[0]) * g.nt1 + f1 / g.b.tile[1]) * g.nt2;
+        const int j = ((f0 % g.b.tile[0]) * g.b.tile[1] + (f1 % g.b.tile[1])) * g.b.tile[2];
+        float* tp = g.pix + (size_t)tile * pix_stride(D, C, g.b.tile[D - 1]);
+        // S > 1e-11 (smoe.py:821): the forward stored log2f(max(S, floor)), same device log2f here
+        const bool live = tp[PL_QTHR * SMOE_TPIX + j] > log2f(kSFloor);
+        tp[PL_GR * SMOE_TPIX + j] = live ? gr[u] : 0.f;
+    }
+}
+
 static LRect loss_rect(const smoe_cfg* cfg, const smoe_batch* b, const smoe_ssim_region* reg) {
     LRect r;
     for (int a = 0; a < 3; ++a) {
@@ -264,6 +433,38 @@ extern "C" int smoe_ssim_loss(const smoe_cfg* cfg, const smoe_batch* batch, cons
     float* p1 = p0 + 4 * cap;
     double* partial = (double*)((char*)workspace + (2 * 4 * cap * sizeof(float) + 255) / 256 * 256);
     const float c1 = 0.01f * 0.01f, c2 = 0.03f * 0.03f;
+    const int nt1 = (batch->extent[1] + batch->tile[1] - 1) / batch->tile[1];
+    const int nt2 = (batch->extent[2] + batch->tile[2] - 1) / batch->tile[2];
+    // images: two shared-memory tile kernels; video, tiny rectangles and SMOE_SSIM_GENERIC=1: separable global passes
+    const bool tiled = cfg->d == 2 && r.n[2] == 1 && r.n[0] >= 16 && r.n[1] >= 16 && !getenv("SMOE_SSIM_GENERIC");
+    if (tiled) {
+        tile2d::MomentArgs g;
+        const size_t org = ((size_t)r.lo[0] * r.dims[1] + r.lo[1]) * r.C;
+        g.x = res + org; g.y = image + org; g.pitch = r.dims[1]; g.n0 = r.n[0]; g.n1 = r.n[1];
+        g.clo0 = r.clo[0]; g.clo1 = r.clo[1]; g.cn0 = r.cn[0]; g.cn1 = r.cn[1];
+        g.c1 = c1; g.c2 = c2; g.maps = p0; g.partial = partial;
+        int nb = 0;
+        cudaError_t e = cfg->C == 1 ? (pix ? tile2d::launch_moments<1, true>(g, st, &nb) : tile2d::launch_moments<1, false>(g, st, &nb))
+                                    : (pix ? tile2d::launch_moments<3, true>(g, st, &nb) : tile2d::launch_moments<3, false>(g, st, &nb));
+        if (e != cudaSuccess) { set_error("smoe_ssim_loss: %s", cudaGetErrorString(e)); return (int)e; }
+        sl_final<<<1, 256, 0, st>>>(partial, nb, r.C, scalars);
+        if (pix) {
+            AdjArgs a;
+            a.cfg = *cfg; a.b = *batch; a.r = r; a.maps = p0; a.res = res; a.image = image; a.res_pre = res_pre;
+            a.pix = pix; a.nt1 = nt1; a.nt2 = nt2;
+            dim3 grid((r.cn[1] + tile2d::T - 1) / tile2d::T, (r.cn[0] + tile2d::T - 1) / tile2d::T);
+            const size_t smb = (size_t)(3 * r.C * tile2d::H * tile2d::HP + 3 * tile2d::T * tile2d::HP) * sizeof(float);
+            if (cfg->C == 1) {
+                e = cudaFuncSetAttribute(sl_adj_apply_tile<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
+                if (e == cudaSuccess) sl_adj_apply_tile<2, 1><<<grid, tile2d::NT, smb, st>>>(a);
+            } else {
+                e = cudaFuncSetAttribute(sl_adj_apply_tile<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb);
+                if (e == cudaSuccess) sl_adj_apply_tile<2, 3><<<grid, tile2d::NT, smb, st>>>(a);
+            }
+            if (e != cudaSuccess) { set_error("smoe_ssim_loss: %s", cudaGetErrorString(e)); return (int)e; }
+        }
+        return check_launch("smoe_ssim_loss");
+    }
     float* src = nullptr;
     float* dst = p0;
     for (int axis = cfg->d - 1; axis >= 0; --axis) {
@@ -284,8 +485,6 @@ extern "C" int smoe_ssim_loss(const smoe_cfg* cfg, const smoe_batch* batch, cons
             src = dst;
             dst = (dst == p0) ? p1 : p0;
         }
-        const int nt1 = (batch->extent[1] + batch->tile[1] - 1) / batch->tile[1];
-        const int nt2 = (batch->extent[2] + batch->tile[2] - 1) / batch->tile[2];
         const float tau = 0.5f / (float)(1 << cfg->precision);
         const int nb = (int)(((size_t)r.cn[0] * r.cn[1] * r.cn[2] + 255) / 256);
 #define CALL(D, C) sl_apply<D, C><<<nb, 256, 0, st>>>(*cfg, *batch, r, src, res, image, res_pre, pix, nt1, nt2, tau);

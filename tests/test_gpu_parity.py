@@ -1128,3 +1128,65 @@ def test_radial_kernels(case):
         lq, _, _, _ = m.run_batched(train=False, update_reconstruction=True, with_quantized_params=True)
         l0, _, _, _ = m.run_batched(train=False, update_reconstruction=True)
         assert abs(lq - l0) < 0.2 * l0 + 1e-3
+
+
+@pytest.mark.parametrize("case", ["rgb_whole", "gray_halo", "rgb_region", "rgb_small"])
+def test_ssim_tile_kernels_match_the_separable_passes(case, monkeypatch):
+    """smoe_ssim_loss on images runs as two shared-memory tile kernels (csrc/ssim_tile.cuh); the separable
+    global-memory passes (video path, SMOE_SSIM_GENERIC=1) are the same arithmetic in the same order: identical
+    gradient planes, SSIM sums equal up to the order of the block sums.  Sizes with interior and border tiles,
+    an overlap halo, and a caller-given compute region (the sharded SSIM of SURVEY.md 8 f-4)."""
+    import ctypes as C
+    from smoe_b200 import _ffi
+    L = _ffi.lib()
+    dev = torch.device("cuda:0")
+    Hh, Ww, Cc = {"rgb_whole": (150, 203, 3), "gray_halo": (131, 97, 1), "rgb_region": (120, 140, 3),
+                  "rgb_small": (37, 21, 3)}[case]
+    cfg = _ffi.Cfg()
+    cfg.d, cfg.C, cfg.precision, cfg.use_yuv = 2, Cc, 8, 1
+    b = _ffi.Batch()
+    b.dims[:] = [Hh, Ww, 1]
+    b.tile[:] = [16, 32, 1]
+    region = None
+    if case == "gray_halo":                       # a window in the middle of the image: its halo is cropped on all sides
+        b.origin[:] = [16, 32, 0]
+        b.extent[:] = [96, 64, 1]
+        b.halo = 3
+    elif case == "rgb_region":                    # block + ring inside a larger resident buffer
+        b.origin[:] = [10, 0, 0]
+        b.extent[:] = [80, 96, 1]
+        region = _ffi.SsimRegion()
+        region.lo[:] = [0, 0, 0]
+        region.n[:] = [100, 106, 1]
+        region.inv_count = 1.0 / (300 * 400)
+    else:
+        b.origin[:] = [0, 0, 0]
+        b.extent[:] = [Hh, Ww, 1]
+    b.inv_count = 1.0 / (b.extent[0] * b.extent[1])
+    g = torch.Generator(device="cpu").manual_seed(5)
+    img = torch.rand((Hh, Ww, Cc), generator=g)
+    pre = img + 0.1 * torch.randn((Hh, Ww, Cc), generator=g)          # some values leave [0, 1]: clip mask
+    res = (pre.clamp(0, 1) * 255).round() / 255
+    img, pre, res = img.to(dev), pre.to(dev), res.to(dev)
+    ntiles = L.smoe_num_tiles(C.byref(b))
+    stride = L.smoe_pix_stride(2, Cc, C.byref(b))
+    L.smoe_ssim_loss_workspace_bytes.restype = C.c_size_t
+    ws = torch.zeros(L.smoe_ssim_loss_workspace_bytes(C.byref(cfg), C.byref(b)) // 4 + 64, dtype=torch.float32, device=dev)
+    pix0 = torch.randn((ntiles * stride,), generator=g).to(dev) * 30       # qthr plane: some pixels below log2(1e-11)
+    out = {}
+    for mode in ("tile", "generic"):
+        if mode == "generic":
+            monkeypatch.setenv("SMOE_SSIM_GENERIC", "1")
+        else:
+            monkeypatch.delenv("SMOE_SSIM_GENERIC", raising=False)
+        pix = pix0.clone()
+        scal = torch.zeros(16, dtype=torch.float32, device=dev)
+        _ffi.check(L.smoe_ssim_loss(C.byref(cfg), C.byref(b), C.byref(region) if region is not None else None,
+                                    _ffi.ptr(res), _ffi.ptr(img), _ffi.ptr(pre), _ffi.ptr(pix), _ffi.ptr(scal),
+                                    _ffi.ptr(ws), _ffi.stream_ptr()), "smoe_ssim_loss")
+        torch.cuda.synchronize()
+        out[mode] = (pix.cpu().numpy(), scal.cpu().numpy())
+    assert np.abs(out["generic"][0] - pix0.cpu().numpy()).max() > 0          # the call wrote gradient planes
+    np.testing.assert_array_equal(out["tile"][0], out["generic"][0])
+    np.testing.assert_allclose(out["tile"][1][8:8 + Cc], out["generic"][1][8:8 + Cc], rtol=2e-6)
+    assert np.all(out["generic"][1][8:8 + Cc] > 0)

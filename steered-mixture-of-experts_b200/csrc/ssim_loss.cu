@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(tile2d::NT) sl_adj_apply_tile(AdjArgs g) {
     const size_t total = (size_t)n0 * n1 * C;
 #pragma unroll
     for (int p = 0; p < 3; ++p) load_tile<C, false>(tm + p * C * H * HP, g.maps + p * total, n1, y0, x0, n0, n1, tid);
+    cp_async_wait_all();
     __syncthreads();
     float w[11];
 #pragma unroll
@@ -252,9 +253,25 @@ __global__ void __launch_bounds__(tile2d::NT) sl_adj_apply_tile(AdjArgs g) {
     // the mirror image of position pos (if it has one): centre of the extra windows
     auto mirror = [](int pos, int n) { return pos < 5 ? -pos - 1 : (pos >= n - 5 ? 2 * n - 1 - pos : INT_MIN); };
     const int prow = tid / (T / SEGV), pxs = (tid % (T / SEGV)) * SEGV;     // this thread's pixels: SEGV along x
+    // this thread's pixels: slot in the backward state and index in the resident buffers, -1 outside the count rectangle
     float gr[SEGV];
+    int slot[SEGV], gidx[SEGV];
+    {
+        const int gy = y0 + prow;
+        const int f0 = r.lo[0] + gy - g.b.origin[0];
+        const int pstr = pix_stride(D, C, g.b.tile[D - 1]);
 #pragma unroll
-    for (int u = 0; u < SEGV; ++u) gr[u] = 0.f;
+        for (int u = 0; u < SEGV; ++u) {
+            gr[u] = 0.f;
+            const int gx = x0 + pxs + u;
+            const bool in = gy < r.clo[0] + r.cn[0] && gx < r.clo[1] + r.cn[1];
+            const int f1 = r.lo[1] + gx - g.b.origin[1];
+            const int tile = ((f0 / g.b.tile[0]) * g.nt1 + f1 / g.b.tile[1]) * g.nt2;
+            const int j = ((f0 % g.b.tile[0]) * g.b.tile[1] + (f1 % g.b.tile[1])) * g.b.tile[2];
+            slot[u] = in ? tile * pstr + j : -1;
+            gidx[u] = ((r.lo[0] + gy) * r.dims[1] + (r.lo[1] + gx)) * C;
+        }
+    }
     for (int c = 0; c < C; ++c) {
         // adjoint along y: SEGH consecutive rows of one column (of the tile + ring) per thread
         if (tid < H * (T / SEGH)) {
@@ -339,40 +356,28 @@ __global__ void __launch_bounds__(tile2d::NT) sl_adj_apply_tile(AdjArgs g) {
                     }
                 }
             }
-            const int gy = y0 + prow;
 #pragma unroll
             for (int u = 0; u < SEGV; ++u) {
-                const int gx = x0 + pxs + u;
-                if (gy >= r.clo[0] + r.cn[0] || gx >= r.clo[1] + r.cn[1]) continue;
-                const size_t gi = rect_global(r, gy, gx, 0, c);
+                if (slot[u] < 0) continue;
+                const int gi = gidx[u] + c;
                 const float x = g.res[gi], y = g.image[gi], rv = g.res_pre[gi];
                 const float cw = g.cfg.use_yuv ? (C == 3 ? (c == 0 ? 0.75f : 0.125f) : 1.0f) : (1.0f / C);   // smoe.py:1006-1009
                 const float dS = fmaf(y, v[2][u], fmaf(2.f * x, v[1][u], v[0][u])) * r.inv_np;
                 const bool ste = (rv >= 0.f) && (rv <= 1.f);
                 const float gc = ste ? -cw * dS : 0.f;                    // loss_pixel = 1 - ssim
                 gr[u] = fmaf(gc, rv, gr[u]);
-                // position inside the batch (forward) rectangle -> tile and slot
-                const int f0 = r.lo[0] + gy - g.b.origin[0], f1 = r.lo[1] + gx - g.b.origin[1];
-                const int tile = ((f0 / g.b.tile[0]) * g.nt1 + f1 / g.b.tile[1]) * g.nt2;
-                const int j = ((f0 % g.b.tile[0]) * g.b.tile[1] + (f1 % g.b.tile[1])) * g.b.tile[2];
-                float* tp = g.pix + (size_t)tile * pix_stride(D, C, g.b.tile[D - 1]);
-                tp[(PL_G + c) * SMOE_TPIX + j] = gc;
+                g.pix[(size_t)slot[u] + (PL_G + c) * SMOE_TPIX] = gc;
             }
         }
         __syncthreads();
     }
-    const int gy = y0 + prow;
 #pragma unroll
     for (int u = 0; u < SEGV; ++u) {
-        const int gx = x0 + pxs + u;
-        if (gy >= r.clo[0] + r.cn[0] || gx >= r.clo[1] + r.cn[1]) continue;
-        const int f0 = r.lo[0] + gy - g.b.origin[0], f1 = r.lo[1] + gx - g.b.origin[1];
-        const int tile = ((f0 / g.b.tile[0]) * g.nt1 + f1 / g.b.tile[1]) * g.nt2;
-        const int j = ((f0 % g.b.tile[0]) * g.b.tile[1] + (f1 % g.b.tile[1])) * g.b.tile[2];
-        float* tp = g.pix + (size_t)tile * pix_stride(D, C, g.b.tile[D - 1]);
+        if (slot[u] < 0) continue;
+        float* tp = g.pix + (size_t)slot[u];
         // S > 1e-11 (smoe.py:821): the forward stored log2f(max(S, floor)), same device log2f here
-        const bool live = tp[PL_QTHR * SMOE_TPIX + j] > log2f(kSFloor);
-        tp[PL_GR * SMOE_TPIX + j] = live ? gr[u] : 0.f;
+        const bool live = tp[PL_QTHR * SMOE_TPIX] > log2f(kSFloor);
+        tp[PL_GR * SMOE_TPIX] = live ? gr[u] : 0.f;
     }
 }
 

@@ -25,6 +25,13 @@ static __constant__ float c_gauss11[11] = {1.028380124e-03f, 7.598758209e-03f, 3
                                            2.130055428e-01f, 2.660117149e-01f, 2.130055428e-01f, 1.093606874e-01f,
                                            3.600077331e-02f, 7.598758209e-03f, 1.028380124e-03f};
 
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+// wait for this thread's asynchronous copies; the CTA barrier that follows makes everybody's visible
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ int reflect_sym(int i, int n) {
     // numpy / tf "SYMMETRIC": -1 -> 0, -2 -> 1, n -> n-1, n+1 -> n-2
     while (i < 0 || i >= n) i = i < 0 ? -i - 1 : 2 * n - 1 - i;
@@ -38,27 +45,43 @@ __device__ __forceinline__ void load_tile(float* __restrict__ dst, const float* 
                                           int x0, int n0, int n1, int tid) {
     constexpr int ROW = H * C;
     const bool interior = y0 >= 5 && x0 >= 5 && y0 + T + 5 <= n0 && x0 + T + 5 <= n1;
-    if (interior) {
-        const float* s0 = src + ((size_t)(y0 - 5) * pitch + (x0 - 5)) * C;
-        for (int i = tid; i < H * ROW; i += NT) {
-            const int yy = i / ROW, e = i - yy * ROW;
-            const int xx = e / C, c = e - xx * C;
-            dst[(c * H + yy) * HP + xx] = s0[(size_t)yy * pitch * C + e];
-        }
-    } else {
-        for (int i = tid; i < H * ROW; i += NT) {
-            const int yy = i / ROW, e = i - yy * ROW;
-            const int xx = e / C, c = e - xx * C;
-            int gy = y0 - 5 + yy, gx = x0 - 5 + xx;
-            float v = 0.f;
-            if (REFLECT) {
-                gy = reflect_sym(gy, n0);
-                gx = reflect_sym(gx, n1);
-                v = src[((size_t)gy * pitch + gx) * C + c];
-            } else if (gy >= 0 && gy < n0 && gx >= 0 && gx < n1) {
-                v = src[((size_t)gy * pitch + gx) * C + c];
+    const int lane = tid & 31;
+    // one warp per tile row: the row is ROW contiguous floats in global memory (interior tiles), no division per element
+    for (int yy = tid >> 5; yy < H; yy += NT / 32) {
+        float* drow = dst + yy * HP;
+        if (interior) {
+            // asynchronous 4-byte copies (LDGSTS): every copy of the tile is in flight before the first one is awaited,
+            // and the planar transposition is just the destination address
+            const float* srow = src + ((size_t)(y0 - 5 + yy) * pitch + (x0 - 5)) * C;
+#pragma unroll
+            for (int e0 = 0; e0 < ROW; e0 += 32) {
+                const int e = e0 + lane;
+                if (e < ROW) {
+                    const int xx = e / C, c = e - xx * C;
+                    cp_async4(drow + c * H * HP + xx, srow + e);
+                }
             }
-            dst[(c * H + yy) * HP + xx] = v;
+        } else {
+            int gy = y0 - 5 + yy;
+            const bool yin = gy >= 0 && gy < n0;
+            gy = REFLECT ? reflect_sym(gy, n0) : (yin ? gy : 0);
+            const float* srow = src + (size_t)gy * pitch * C;
+#pragma unroll
+            for (int e0 = 0; e0 < ROW; e0 += 32) {
+                const int e = e0 + lane;
+                if (e < ROW) {
+                    const int xx = e / C, c = e - xx * C;
+                    int gx = x0 - 5 + xx;
+                    float v = 0.f;
+                    if (REFLECT) {
+                        gx = reflect_sym(gx, n1);
+                        v = srow[gx * C + c];
+                    } else if (yin && gx >= 0 && gx < n1) {
+                        v = srow[gx * C + c];
+                    }
+                    drow[c * H * HP + xx] = v;
+                }
+            }
         }
     }
 }
@@ -104,6 +127,7 @@ __global__ void __launch_bounds__(NT) ssim2d_tile_kernel(MomentArgs g) {
     const int y0 = blockIdx.y * T, x0 = blockIdx.x * T;
     load_tile<C, true>(ta, g.x, g.pitch, y0, x0, g.n0, g.n1, tid);
     load_tile<C, true>(tb, g.y, g.pitch, y0, x0, g.n0, g.n1, tid);
+    cp_async_wait_all();
     __syncthreads();
     float w[11];
 #pragma unroll

@@ -154,8 +154,15 @@ __device__ __forceinline__ int cta_compact(bool flag, int* scratch, int& par, in
 // instantiation, so the product path carries no counter).
 // AMAX: track the arg-max gate per pixel (only the reconstruction passes ask for it; the training step does not, and
 // its instantiation saves the 2 x PPT registers).
+#ifndef SMOE_FWD_CTAS_2D
+#define SMOE_FWD_CTAS_2D 6
+#endif
+#ifndef SMOE_FWD_UNROLL
+#define SMOE_FWD_UNROLL 2
+#endif
+constexpr int kBodyUnroll = SMOE_FWD_UNROLL;
 template <int D, int C, bool COUNT, bool AMAX>
-__global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(const FwdArgs a) {
+__global__ void __launch_bounds__(kThreadsF, (D == 2) ? SMOE_FWD_CTAS_2D : 4) forward_kernel(const FwdArgs a) {
     using R = Rec<D, C>;
     constexpr int PK = pstride(D, C);
     constexpr int PPT = kPixPerThread;
@@ -305,7 +312,7 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? 6 : 4) forward_kernel(co
                 if (need) transform_record<D, C>(raw, mu, ctr, a.indices[ci * kChunk + tid], crec + pos * R::RC);
                 __syncthreads();
                 if (tid == 0 && li + 2 < nlist) issue(clist[li + 2], buf);
-#pragma unroll 2
+#pragma unroll kBodyUnroll
                 for (int kk = 0; kk < nneed; ++kk) body(crec + kk * R::RC);
             }
             __syncthreads();          // the next sweep rebuilds `clist` and re-uses `crec`
@@ -688,7 +695,7 @@ extern "C" int smoe_forward(const smoe_cfg* cfg, const smoe_batch* batch, const 
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int per_sm = cfg->d == 2 ? 6 : 4;          // resident CTAs per SM (matches __launch_bounds__)
+    const int per_sm = cfg->d == 2 ? SMOE_FWD_CTAS_2D : 4;          // resident CTAs per SM (matches __launch_bounds__)
     int grid = a.ntiles < per_sm * sms ? a.ntiles : per_sm * sms;
     cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(D, C, CNT, AM)                                                                                       \

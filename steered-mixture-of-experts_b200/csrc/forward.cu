@@ -247,24 +247,28 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? SMOE_FWD_CTAS_2D : 4) fo
             }
         }
 
-        // chunk-level culling: ordered list of the chunks whose bound reaches `thr` over this tile
-        auto build_chunk_list = [&](float thr) -> int {
+        // chunk-level culling: ordered list of the chunks whose bound reaches `thr` over this tile.  `part` selects the
+        // chunks whose box of centres overlaps the tile's box (1, "near"), the others (2, "far") or all of them (0): a
+        // purely geometric split, the same in every execution mode, so that the order of summation does not depend
+        // on the mode.
+        auto build_chunk_list = [&](float thr, int part) -> int {
             int n = 0;
             for (int base = 0; base < nchunks; base += kThreadsF) {
                 const int ci = base + tid;
                 bool need = false;
                 if (ci < nchunks) {
-                    need = true;
-                    if (cull) {
-                        const float* cb = a.chunk_bounds + (size_t)ci * kCB;
-                        float d2 = 0.f, kd = 0.f;
+                    const float* cb = a.chunk_bounds + (size_t)ci * kCB;
+                    float d2 = 0.f, kd = 0.f;
 #pragma unroll
-                        for (int l = 0; l < D; ++l) {
-                            const float mn = cb[l] - ctr[l], mx = cb[3 + l] - ctr[l];
-                            const float gap = fmaxf(fmaxf(mn - half[l], -half[l] - mx), 0.f);
-                            d2 = fmaf(gap, gap, d2);
-                            kd = fmaxf(kd, cb[8 + l] * gap * gap);
-                        }
+                    for (int l = 0; l < D; ++l) {
+                        const float mn = cb[l] - ctr[l], mx = cb[3 + l] - ctr[l];
+                        const float gap = fmaxf(fmaxf(mn - half[l], -half[l] - mx), 0.f);
+                        d2 = fmaf(gap, gap, d2);
+                        kd = fmaxf(kd, cb[8 + l] * gap * gap);
+                    }
+                    const bool near = d2 == 0.f;
+                    need = part == 0 || (part == 1) == near;
+                    if (cull && need) {
                         const float lam = cb[6], ub = cb[7] - fmaxf(lam * d2, kd);
                         need = !(lam >= 0.f) || !(ub < thr);
                     }
@@ -334,9 +338,8 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? SMOE_FWD_CTAS_2D : 4) fo
         for (int attempt = 0; attempt < 2; ++attempt) {
 #pragma unroll
             for (int p = 0; p < PPT; ++p) S[p] = 0.f;
-            const float skipA = cutA + 0.5f;
-            const int nlist = build_chunk_list(cutA);
-            sweep(nlist, cutA, [&](const float* rec) {
+            float skipA = cutA + 0.5f;
+            auto bodyA = [&](const float* rec) {
                 float f[4 * R::NG4];
                 const float4* r4 = reinterpret_cast<const float4*>(rec);
 #pragma unroll
@@ -354,13 +357,40 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? SMOE_FWD_CTAS_2D : 4) fo
                     qmax = fmaxf(qmax, q[p]);
                 }
                 if (COUNT) cntA_vis += PPT;
-                // ex2.approx.ftz(q) == +0 exactly for q < -126: adding it would not change S
+                // adding ex2(q) would not change S: it is +0 exactly (q < -126), or -- second part of the sweep --
+                // below half an ulp of the running sum (see below)
                 if (__builtin_expect(!skip || __any_sync(0xffffffffu, qmax >= skipA), 0)) {
 #pragma unroll
                     for (int p = 0; p < PPT; ++p) S[p] += ex2f(q[p]);
                     if (COUNT) cntA_ex += PPT;
                 }
-            });
+            };
+            // Part 1: the chunks whose centres' box overlaps the tile -- they carry (nearly) all of S.
+            sweep(build_chunk_list(cutA, 1), cutA, bodyA);
+            // Part 2: all other chunks.  S only grows, and float32 addition absorbs a term below half an ulp of the
+            // running sum: with L <= log2 S (now), a term 2^q with q < L - 25 leaves S bit-for-bit unchanged, whether
+            // it is added (dense_exec = 1 adds them all, in this same order) or not.  So the remaining chunks are
+            // culled against L - 25.5 over the tile instead of -126.5, and a warp skips a kernel when every pixel
+            // of it is below its own thread's bound: exact, and most of the far field of sweep A disappears.
+            {
+                float Lt = INFINITY;
+#pragma unroll
+                for (int p = 0; p < PPT; ++p)
+                    if ((okmask >> p) & 1u) Lt = fminf(Lt, log2f(S[p]));             // log2f(0) = -inf: no bound
+                float Lmin = Lt;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) Lmin = fminf(Lmin, __shfl_xor_sync(0xffffffffu, Lmin, o));
+                if ((tid & 31) == 0) red[tid >> 5] = Lmin;
+                __syncthreads();
+                Lmin = fminf(fminf(red[0], red[1]), fminf(red[2], red[3]));
+                __syncthreads();
+                float cut2 = cutA;
+                if (skip && Lmin == Lmin) {
+                    cut2 = fmaxf(cutA, Lmin - 25.5f);
+                    if (Lt == Lt) skipA = fmaxf(skipA, Lt - 25.0f);
+                }
+                sweep(build_chunk_list(cut2, 2), cut2, bodyA);
+            }
             if (!(Lneed > -INFINITY)) break;                 // exact sweep: done
             float smin = INFINITY;
 #pragma unroll
@@ -401,7 +431,7 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? SMOE_FWD_CTAS_2D : 4) fo
         {
             const float ltau = a.ltau;                           // log2(tau), an integer
             const float thrB = qmin + ltau - 0.01f;
-            const int nlist = build_chunk_list(thrB);
+            const int nlist = build_chunk_list(thrB, 0);
             sweep(nlist, thrB, [&](const float* rec) {
                 float f[R::RC];
                 const float4* r4 = reinterpret_cast<const float4*>(rec);

@@ -161,6 +161,10 @@ __device__ __forceinline__ int cta_compact(bool flag, int* scratch, int& par, in
 #define SMOE_FWD_UNROLL 2
 #endif
 constexpr int kBodyUnroll = SMOE_FWD_UNROLL;
+#ifndef SMOE_FWD_NEARCUT
+#define SMOE_FWD_NEARCUT 8.0f
+#endif
+constexpr float kNearCut = SMOE_FWD_NEARCUT;      // sweep A, part 1: see build_chunk_list
 template <int D, int C, bool COUNT, bool AMAX>
 __global__ void __launch_bounds__(kThreadsF, (D == 2) ? SMOE_FWD_CTAS_2D : 4) forward_kernel(const FwdArgs a) {
     using R = Rec<D, C>;
@@ -247,10 +251,12 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? SMOE_FWD_CTAS_2D : 4) fo
             }
         }
 
-        // chunk-level culling: ordered list of the chunks whose bound reaches `thr` over this tile.  `part` selects the
-        // chunks whose box of centres overlaps the tile's box (1, "near"), the others (2, "far") or all of them (0): a
-        // purely geometric split, the same in every execution mode, so that the order of summation does not depend
-        // on the mode.
+        // chunk-level culling: ordered list of the chunks whose bound reaches `thr` over this tile.  Sweep A runs in two
+        // parts (see there): part 1 takes the NEAR kernels -- those whose logit, by the culling bound, falls by at most
+        // kNearCut (log2 units) between the centre and the closest point of the tile's box, a rule that scales with the
+        // kernel's own width -- and therefore only the chunks whose bound says they may hold one; part 2 takes all other
+        // kernels (any chunk); part 0 = everything.  The split depends on the records and the tile geometry only, not on
+        // the execution mode, so the order of summation is the same in every mode.
         auto build_chunk_list = [&](float thr, int part) -> int {
             int n = 0;
             for (int base = 0; base < nchunks; base += kThreadsF) {
@@ -266,12 +272,9 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? SMOE_FWD_CTAS_2D : 4) fo
                         d2 = fmaf(gap, gap, d2);
                         kd = fmaxf(kd, cb[8 + l] * gap * gap);
                     }
-                    const bool near = d2 == 0.f;
-                    need = part == 0 || (part == 1) == near;
-                    if (cull && need) {
-                        const float lam = cb[6], ub = cb[7] - fmaxf(lam * d2, kd);
-                        need = !(lam >= 0.f) || !(ub < thr);
-                    }
+                    const float lam = cb[6], drop = fmaxf(lam * d2, kd);
+                    need = part != 1 || !(lam >= 0.f) || !(drop > kNearCut);
+                    if (cull && need) need = !(lam >= 0.f) || !(cb[7] - drop < thr);
                 }
                 int tot;
                 const int pos = cta_compact(need, scratch, par, &tot);
@@ -285,7 +288,7 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? SMOE_FWD_CTAS_2D : 4) fo
         // One sweep over the needed chunks; `body(rec)` is called for every kernel that can matter.  Two CTA
         // barriers per chunk: the one inside cta_compact (which also orders the previous chunk's reads of `crec`
         // before this chunk's writes) and the one that publishes the re-centred records.
-        auto sweep = [&](int nlist, float thr, auto&& body) {
+        auto sweep = [&](int nlist, float thr, int part, auto&& body) {
             if (tid == 0 && nlist > 0) {
                 issue(clist[0], 0);
                 if (nlist > 1) issue(clist[1], 1);
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? SMOE_FWD_CTAS_2D : 4) fo
                 float mu[D];
 #pragma unroll
                 for (int l = 0; l < D; ++l) mu[l] = need ? raw[off_mu(D, C) + l] - ctr[l] : 0.f;
-                if (need && cull) {
+                if (need && (cull || part != 0)) {
                     float d2 = 0.f, kd = 0.f;
 #pragma unroll
                     for (int l = 0; l < D; ++l) {
@@ -308,8 +311,9 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? SMOE_FWD_CTAS_2D : 4) fo
                         d2 = fmaf(gap, gap, d2);
                         kd = fmaxf(kd, raw[nparam(D, C) + 1 + l] * gap * gap);
                     }
-                    const float lam = raw[nparam(D, C)], ub = raw[off_pi(D, C)] - fmaxf(lam * d2, kd);
-                    need = !(lam >= 0.f) || !(ub < thr);
+                    const float lam = raw[nparam(D, C)], drop = fmaxf(lam * d2, kd);
+                    if (part != 0) need = (part == 1) == (!(lam >= 0.f) || !(drop > kNearCut));
+                    if (need && cull) need = !(lam >= 0.f) || !(raw[off_pi(D, C)] - drop < thr);
                 }
                 int nneed;
                 const int pos = cta_compact(need, scratch, par, &nneed);
@@ -365,11 +369,11 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? SMOE_FWD_CTAS_2D : 4) fo
                     if (COUNT) cntA_ex += PPT;
                 }
             };
-            // Part 1: the chunks whose centres' box overlaps the tile -- they carry (nearly) all of S.
-            sweep(build_chunk_list(cutA, 1), cutA, bodyA);
+            // Part 1: the kernels centred in or right around the tile -- they carry (nearly) all of S.
+            sweep(build_chunk_list(cutA, 1), cutA, 1, bodyA);
             // Part 2: all other chunks.  S only grows, and float32 addition absorbs a term below half an ulp of the
             // running sum: with L <= log2 S (now), a term 2^q with q < L - 25 leaves S bit-for-bit unchanged, whether
-            // it is added (dense_exec = 1 adds them all, in this same order) or not.  So the remaining chunks are
+            // it is added (dense_exec = 1 adds them all, in this same order) or not.  So the remaining kernels are
             // culled against L - 25.5 over the tile instead of -126.5, and a warp skips a kernel when every pixel
             // of it is below its own thread's bound: exact, and most of the far field of sweep A disappears.
             {
@@ -389,7 +393,7 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? SMOE_FWD_CTAS_2D : 4) fo
                     cut2 = fmaxf(cutA, Lmin - 25.5f);
                     if (Lt == Lt) skipA = fmaxf(skipA, Lt - 25.0f);
                 }
-                sweep(build_chunk_list(cut2, 2), cut2, bodyA);
+                sweep(build_chunk_list(cut2, 2), cut2, 2, bodyA);
             }
             if (!(Lneed > -INFINITY)) break;                 // exact sweep: done
             float smin = INFINITY;
@@ -432,7 +436,7 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? SMOE_FWD_CTAS_2D : 4) fo
             const float ltau = a.ltau;                           // log2(tau), an integer
             const float thrB = qmin + ltau - 0.01f;
             const int nlist = build_chunk_list(thrB, 0);
-            sweep(nlist, thrB, [&](const float* rec) {
+            sweep(nlist, thrB, 0, [&](const float* rec) {
                 float f[R::RC];
                 const float4* r4 = reinterpret_cast<const float4*>(rec);
 #pragma unroll

@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(128) bwd_plan_kernel(const BwdArgs a) {
 
 // DENSE: the dense_exec = 1 instantiation (every pair executed in full) carries none of the skip tests.
 template <int D, int C, bool COUNT, bool DENSE>
-__global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(kThreads, 512 / kThreads) backward_kernel(const BwdArgs a) {
     using R = BRec<D, C>;
     constexpr int T = tri(D);
     constexpr int P = nparam(D, C), PK = pstride(D, C);
@@ -543,7 +543,10 @@ __global__ void __launch_bounds__(kThreads, 8) backward_kernel(const BwdArgs a) 
     }
     // the kHalves lanes of a kernel are adjacent: add their partial sums (commutative: both lanes get the same bits)
     {
-        auto pair_sum = [&](float& v) { v += __shfl_xor_sync(0xffffffffu, v, 1); };
+        auto pair_sum = [&](float& v) {
+#pragma unroll
+            for (int o = 1; o < kHalves; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        };
         pair_sum(G0);
 #pragma unroll
         for (int l = 0; l < D; ++l) pair_sum(G1[l]);

@@ -12,8 +12,14 @@
 
 namespace smoe {
 
-constexpr int kThreads = 64;                        // threads per CTA of the backward
-constexpr int kHalves = 2;                          // threads per kernel in the backward: each takes every other tile row
+#ifndef SMOE_BWD_THREADS
+#define SMOE_BWD_THREADS 64
+#endif
+#ifndef SMOE_BWD_HALVES
+#define SMOE_BWD_HALVES 2
+#endif
+constexpr int kThreads = SMOE_BWD_THREADS;                        // threads per CTA of the backward
+constexpr int kHalves = SMOE_BWD_HALVES;                          // threads per kernel in the backward: each takes every other tile row
 constexpr int kGroup = kThreads / kHalves;          // kernels per backward CTA (= planning group)
 constexpr int kFin = 64;                            // kernels per CTA of grad_finalize (256 threads gather, 64 apply the chain rule)
 constexpr int kThreadsF = 128;                       // threads per CTA of the forward

@@ -372,7 +372,8 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? SMOE_FWD_CTAS_2D : 4) fo
             // Part 1: the kernels centred in or right around the tile -- they carry (nearly) all of S.
             sweep(build_chunk_list(cutA, 1), cutA, 1, bodyA);
             // Part 2: all other chunks.  S only grows, and float32 addition absorbs a term below half an ulp of the
-            // running sum: with L <= log2 S (now), a term 2^q with q < L - 25 leaves S bit-for-bit unchanged, whether
+            // running sum: with L <= log2 S (now), a term 2^q with q < L - 25 is below 2^(floor(log2 S) - 24), half an ulp of S
+            // (the cuts keep 0.25 / 0.5 in hand for the errors of log2f and ex2.approx), and leaves S bit-for-bit unchanged, whether
             // it is added (dense_exec = 1 adds them all, in this same order) or not.  So the remaining kernels are
             // culled against L - 25.5 over the tile instead of -126.5, and a warp skips a kernel when every pixel
             // of it is below its own thread's bound: exact, and most of the far field of sweep A disappears.
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(kThreadsF, (D == 2) ? SMOE_FWD_CTAS_2D : 4) fo
                 float cut2 = cutA;
                 if (skip && Lmin == Lmin) {
                     cut2 = fmaxf(cutA, Lmin - 25.5f);
-                    if (Lt == Lt) skipA = fmaxf(skipA, Lt - 25.0f);
+                    if (Lt == Lt) skipA = fmaxf(skipA, Lt - 25.25f);
                 }
                 sweep(build_chunk_list(cut2, 2), cut2, 2, bodyA);
             }

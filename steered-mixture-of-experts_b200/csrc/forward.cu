@@ -23,11 +23,16 @@
 //     sweep B tests the threshold in the log domain, q - log2 S > log2 tau, so it needs no ex2 at all
 //     unless a gate passes.                                            (dense_exec = 0 and 2)
 //   * Culling: q_k(x) <= c0_k - max(lam_k * dist(x, mu_k)^2, max_l kap_kl * gap_l^2) with lam_k a lower
-//     bound of the smallest eigenvalue of Qm_k and kap_kl = 1/(Qm_k^-1)_ll the per-axis bounds.  A chunk of 128 kernels whose bound over the tile's box says "all zero"
+//     bound of the smallest eigenvalue of Qm_k and kap_kl = 1/(Qm_k^-1)_ll the per-axis bounds.  A chunk of 128
+//     kernels whose bound over the tile's box says "all zero"
 //     (sweep A: < -126.5; sweep B: < min_n qthr - 0.01) is never loaded, and inside a loaded chunk
 //     only the kernels that can matter are re-centred and swept (ordered compaction, so sums keep
 //     the order of the dense sweep).  The 0.5 / 0.01 margins cover the rounding of the evaluated
 //     logit, which is < 1e-4 there.                                          (dense_exec = 0)
+//   * Absorbed terms: sweep A adds the kernels around the tile first (part 1, a geometric rule that is the same in
+//     every mode) and everything else afterwards (part 2).  By then S is nearly complete, and a term below half an
+//     ulp of the running float32 sum leaves it bit-for-bit unchanged whether it is added or not -- so part 2 is
+//     culled against log2 S - 25.5 instead of -126.5.                         (dense_exec = 0 and 2)
 #include "smoe_common.cuh"
 
 namespace smoe {

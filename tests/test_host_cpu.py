@@ -158,3 +158,24 @@ def test_c_abi_argument_errors_are_reported_without_a_device(libpath):
     with pytest.raises(RuntimeError, match="null argument"):
         _ffi.check(h.smoe_pack(ctypes.byref(cfg), null, null, null, null, null, 16, null, null, null, null, null, null,
                                null, null, null, null, null), "smoe_pack")
+
+
+def test_absorbed_terms_leave_a_float32_sum_unchanged():
+    """The exactness argument of the forward's sweep A, part 2 (csrc/forward.cu): S only grows, and a term 2^q with
+    q < log2(S) - 25.25 is below half an ulp of S, so adding it -- as the dense mode does -- returns S bit for bit.
+    Checked in numpy float32 for sums of any magnitude, with the term at the very edge of the cut (and 2 ulp of
+    ex2.approx error on top), and for a whole tail of such terms added one by one."""
+    rs = np.random.RandomState(0)
+    S = np.exp2(rs.uniform(-100, 100, 200000)).astype(np.float32)
+    S = np.concatenate([S, np.exp2(np.arange(-100, 100)).astype(np.float32),                  # exact powers of two
+                        np.nextafter(np.exp2(np.arange(-100, 100)).astype(np.float32), np.float32(0))])   # just below
+    L = np.log2(S.astype(np.float64))
+    t = (np.exp2(L - 25.25) * (1 + 2.0 ** -21)).astype(np.float32)
+    assert np.array_equal(S + t, S)
+    acc = S.copy()
+    for _ in range(64):                        # many absorbed terms in a row never add up
+        acc = acc + t
+    assert np.array_equal(acc, S)
+    # the bound is about as tight as it can be: two binades up, the term does change some of the sums
+    t_big = np.exp2(L - 23.0).astype(np.float32)
+    assert not np.array_equal(S + t_big, S)
